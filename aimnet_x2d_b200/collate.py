@@ -1,0 +1,351 @@
+"""Batch collation that emits CSR / segment offsets.
+
+Mirrors ``MyBatch.from_data_list`` (reference ``src/datasets/molecular.py:339-458``): same input
+objects (anything with the reference ``Data`` attributes), same output field names, dtypes and layouts,
+plus a :class:`GraphIndex` with the int32 artefacts the CUDA kernels consume.  The Python loops of the
+reference (``molecular.py:352-438``) are replaced by vectorised numpy and the C functions
+``ax2d_host_csr_build`` / ``ax2d_host_tile_plan`` (include/ax2d.h).  All integer results are exact.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+DEFAULT_TILE_ROWS = 32          # rows of x staged per CTA by the aggregation kernel (QM9: <= 29 atoms/molecule)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _np(t, dtype=None) -> np.ndarray:
+    if isinstance(t, torch.Tensor):
+        t = t.detach().cpu().numpy()
+    a = np.asarray(t)
+    return a if dtype is None else a.astype(dtype, copy=False)
+
+
+class GraphIndex:
+    """Integer artefacts of one batch (all int32, built once at collation):
+
+    ``rowptr/col``      forward CSR: rows = target, stable in edge order  (layers.py:154-163)
+    ``rowptr_t/col_t``  transposed CSR: rows = src mod N                 (its CPU backward order)
+    ``seg_ptr``         molecule row offsets from the sorted batch_indices (molecular.py:406-410)
+    ``tile_ptr``        whole-molecule row tiles for the shared-memory aggregation kernel
+    ``collapsed``       True when every target < N (quirk Q1: the shipped collation never offsets hops)
+    ``tile_local``      True when no edge leaves its tile (no edge leaves its molecule, molecular.py:429-433)
+    """
+
+    _TENSORS = ("rowptr", "col", "rowptr_t", "col_t", "seg_ptr", "tile_ptr")
+
+    def __init__(self):
+        self.num_atoms = 0
+        self.num_graphs = 0
+        self.num_edges = 0
+        self.num_hops = 0
+        self.num_rows = 0              # rows of the forward CSR: N if collapsed else H*N
+        self.collapsed = True
+        self.tile_local = False
+        self.n_tiles = 0
+        self.max_tile_rows = 0
+        self.max_seg = 0
+        self.rowptr = self.col = self.rowptr_t = self.col_t = self.seg_ptr = self.tile_ptr = None
+        self.embed: Dict[str, tuple] = {}      # name -> (order int32 [N], ptr int32 [vocab+1], vocab)
+        self.tetra = None                      # (idx int32 [M,4], slot_ptr int32 [N+1], slot_idx int32 [4M], M)
+        self.cistrans = None                   # (src int32, tgt int32, sign f32, n_upd)
+
+    # ------------------------------------------------------------------ construction (host, exact integers)
+    @staticmethod
+    def build(edges, batch_indices, num_graphs: int, num_hops: int,
+              atom_features: Optional[Dict[str, torch.Tensor]] = None,
+              feature_sizes: Optional[Dict[str, int]] = None,
+              tetra=None, cis=None, trans=None, tile_rows: int = DEFAULT_TILE_ROWS) -> "GraphIndex":
+        lib = _lib.load()
+        gi = GraphIndex()
+        bi = _np(batch_indices, np.int64)
+        N = int(bi.shape[0])
+        B = int(num_graphs)
+        gi.num_atoms, gi.num_graphs, gi.num_hops = N, B, int(num_hops)
+        if N and (np.any(np.diff(bi) < 0) or bi[0] < 0 or bi[-1] >= B):
+            raise ValueError("batch_indices must be sorted and within [0, num_graphs)")
+        seg = np.zeros(B + 1, dtype=np.int32)
+        if N:
+            seg[1:] = np.cumsum(np.bincount(bi, minlength=B)).astype(np.int32)
+        gi.max_seg = int(np.max(np.diff(seg))) if B else 0
+
+        if isinstance(edges, torch.Tensor):
+            e_np = edges.detach().cpu().numpy()          # keeps the (possibly transposed) strides
+        else:
+            e_np = np.asarray(edges)
+        if e_np.dtype != np.int64:
+            e_np = e_np.astype(np.int64)
+        E = int(e_np.shape[0]) if e_np.ndim == 2 else 0
+        gi.num_edges = E
+        if E:
+            tmax = int(e_np[:, 0].max())
+            if tmax >= max(num_hops, 1) * N or int(e_np.min()) < 0:
+                raise ValueError("edge index out of range for message_passing (target must be < num_hops * N)")
+            gi.collapsed = tmax < N
+        R = N if gi.collapsed else num_hops * N
+        gi.num_rows = R
+        rowptr = np.zeros(R + 1, dtype=np.int32)
+        col = np.zeros(max(E, 1), dtype=np.int32)
+        rowptr_t = np.zeros(N + 1, dtype=np.int32)
+        col_t = np.zeros(max(E, 1), dtype=np.int32)
+        if E:
+            se, sc = (s // 8 for s in e_np.strides)
+            _lib.check(lib.ax2d_host_csr_build(_ptr(e_np), E, se, sc, N, R, 0, _ptr(rowptr), _ptr(col), None),
+                       "ax2d_host_csr_build")
+            _lib.check(lib.ax2d_host_csr_build(_ptr(e_np), E, se, sc, N, N, 1, _ptr(rowptr_t), _ptr(col_t), None),
+                       "ax2d_host_csr_build(transposed)")
+        tile_ptr = np.zeros(B + 1, dtype=np.int32)
+        n_tiles, max_rows, local = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        cap = max(int(tile_rows), gi.max_seg)
+        use_csr = gi.collapsed and E > 0
+        _lib.check(lib.ax2d_host_tile_plan(_ptr(seg), B, cap, _ptr(rowptr) if use_csr else None,
+                                           _ptr(col) if use_csr else None, _ptr(tile_ptr),
+                                           C.byref(n_tiles), C.byref(max_rows), C.byref(local)), "ax2d_host_tile_plan")
+        gi.n_tiles, gi.max_tile_rows = int(n_tiles.value), int(max_rows.value)
+        gi.tile_local = bool(local.value) and gi.collapsed
+        if gi.tile_local and E:
+            # the transposed CSR must be tile-local too (true whenever the forward one is: same edge set)
+            t2, m2, l2 = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+            tp2 = np.zeros(B + 1, dtype=np.int32)
+            _lib.check(lib.ax2d_host_tile_plan(_ptr(seg), B, cap, _ptr(rowptr_t), _ptr(col_t), _ptr(tp2),
+                                               C.byref(t2), C.byref(m2), C.byref(l2)), "ax2d_host_tile_plan")
+            gi.tile_local = bool(l2.value)
+        gi.rowptr, gi.col = torch.from_numpy(rowptr), torch.from_numpy(col)
+        gi.rowptr_t, gi.col_t = torch.from_numpy(rowptr_t), torch.from_numpy(col_t)
+        gi.seg_ptr = torch.from_numpy(seg)
+        gi.tile_ptr = torch.from_numpy(tile_ptr[: gi.n_tiles + 1].copy())
+
+        if atom_features is not None:
+            sizes = feature_sizes or {}
+            for name, idx in atom_features.items():
+                gi.add_embedding_index(name, idx, sizes.get(name))
+        gi.set_stereo(tetra, cis, trans)
+        return gi
+
+    def add_embedding_index(self, name: str, idx, vocab: Optional[int] = None) -> None:
+        """Atoms sorted (stably) by table row: the CPU ``index_add`` order of the embedding backward."""
+        a = _np(idx, np.int64)
+        v = int(vocab) if vocab is not None else (int(a.max()) + 1 if a.size else 1)
+        if a.size and (a.min() < 0 or a.max() >= v):
+            raise ValueError(f"feature index '{name}' out of range [0, {v})")
+        order = np.argsort(a, kind="stable").astype(np.int32)
+        ptr = np.zeros(v + 1, dtype=np.int32)
+        if a.size:
+            ptr[1:] = np.cumsum(np.bincount(a, minlength=v)).astype(np.int32)
+        self.embed[name] = (torch.from_numpy(order), torch.from_numpy(ptr), v)
+
+    def set_stereo(self, tetra, cis, trans) -> None:
+        N = self.num_atoms
+        if tetra is not None:
+            t = _np(tetra, np.int64).reshape(-1, 4)
+            M = int(t.shape[0])
+            if M:
+                if t.min() < 0 or t.max() >= N:
+                    raise ValueError("tetrahedral index out of range")
+                flat = t.reshape(-1)
+                slot_idx = np.argsort(flat, kind="stable").astype(np.int32)       # index_add_ order, gnn.py:449-453
+                slot_ptr = np.zeros(N + 1, dtype=np.int32)
+                slot_ptr[1:] = np.cumsum(np.bincount(flat, minlength=N)).astype(np.int32)
+                self.tetra = (torch.from_numpy(t.astype(np.int32)), torch.from_numpy(slot_ptr),
+                              torch.from_numpy(slot_idx), M)
+        src, tgt, sign = [], [], []
+        for arr, s in ((cis, -1.0), (trans, 1.0)):                                # gnn.py:478-497 (quirk Q3)
+            if arr is None:
+                continue
+            a = _np(arr, np.int64)
+            if a.size == 0:
+                continue
+            if a.ndim != 2 or a.shape[0] < 2:
+                raise ValueError("cis/trans index tensors must be [2K,2] with K >= 1")
+            src.extend(int(v) for v in a[0])
+            tgt.extend(int(v) for v in a[1])
+            sign.extend([s] * a.shape[1])
+        if src:
+            if min(src + tgt) < 0 or max(src + tgt) >= N:
+                raise ValueError("cis/trans index out of range")
+            self.cistrans = (torch.tensor(src, dtype=torch.int32), torch.tensor(tgt, dtype=torch.int32),
+                             torch.tensor(sign, dtype=torch.float32), len(src))
+
+    # ------------------------------------------------------------------ movement
+    def to(self, device, non_blocking: bool = False) -> "GraphIndex":
+        out = GraphIndex()
+        out.__dict__.update(self.__dict__)
+        mv = lambda t: t.to(device, non_blocking=non_blocking)
+        for k in self._TENSORS:
+            setattr(out, k, mv(getattr(self, k)))
+        out.embed = {k: (mv(o), mv(p), v) for k, (o, p, v) in self.embed.items()}
+        if self.tetra is not None:
+            i, sp, si, M = self.tetra
+            out.tetra = (mv(i), mv(sp), mv(si), M)
+        if self.cistrans is not None:
+            s, t, g, n = self.cistrans
+            out.cistrans = (mv(s), mv(t), mv(g), n)
+        return out
+
+    def pin_memory(self) -> "GraphIndex":
+        out = GraphIndex()
+        out.__dict__.update(self.__dict__)
+        for k in self._TENSORS:
+            setattr(out, k, getattr(self, k).pin_memory())
+        out.embed = {k: (o.pin_memory(), p.pin_memory(), v) for k, (o, p, v) in self.embed.items()}
+        if self.tetra is not None:
+            i, sp, si, M = self.tetra
+            out.tetra = (i.pin_memory(), sp.pin_memory(), si.pin_memory(), M)
+        if self.cistrans is not None:
+            s, t, g, n = self.cistrans
+            out.cistrans = (s.pin_memory(), t.pin_memory(), g.pin_memory(), n)
+        return out
+
+    def nbytes(self) -> int:
+        n = sum(getattr(self, k).numel() * 4 for k in self._TENSORS)
+        n += sum((o.numel() + p.numel()) * 4 for o, p, _ in self.embed.values())
+        if self.tetra is not None:
+            n += sum(t.numel() * 4 for t in self.tetra[:3])
+        if self.cistrans is not None:
+            n += sum(t.numel() * 4 for t in self.cistrans[:3])
+        return n
+
+
+class MolData:
+    """Attribute bag with the reference's per-molecule ``Data`` fields (molecular.py:349-433)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class MolBatch:
+    """Output of collation: the reference ``Batch`` fields (molecular.py:441-456) + ``graph_index``."""
+
+    FIELDS = ("x", "multi_hop_edge_indices", "batch_indices", "targets", "total_charges",
+              "final_tetrahedral_chiral_tensor", "final_cis_tensor", "final_trans_tensor", "atomic_numbers")
+
+    def __init__(self):
+        self.x = None
+        self.multi_hop_edge_indices = None
+        self.batch_indices = None
+        self.batch = None
+        self.atom_features_map: Dict[str, torch.Tensor] = {}
+        self.targets = None
+        self.total_charges = None
+        self.final_tetrahedral_chiral_tensor = None
+        self.final_cis_tensor = None
+        self.final_trans_tensor = None
+        self.smiles_list: List[str] = []
+        self.atomic_numbers = None
+        self.graph_index: Optional[GraphIndex] = None
+
+    @staticmethod
+    def from_data_list(data_list: Sequence, feature_sizes: Optional[Dict[str, int]] = None,
+                       tile_rows: int = DEFAULT_TILE_ROWS) -> "MolBatch":
+        batch = MolBatch()
+        B = len(data_list)
+        if B == 0:                                                         # molecular.py:346-347
+            return batch
+        num_hops = len(data_list[0].multi_hop_edges)
+        n_atoms = np.array([int(d.x.shape[0]) for d in data_list], dtype=np.int64)
+        offsets = np.zeros(B, dtype=np.int64)
+        np.cumsum(n_atoms[:-1], out=offsets[1:])
+
+        def shifted(attr, width, keep=None):
+            rows = []
+            for d, off in zip(data_list, offsets):
+                for t in getattr(d, attr, []) or []:
+                    a = _np(t, np.int64)
+                    if keep is None or a.shape[0] == keep:                 # 4-neighbour filter, molecular.py:365
+                        rows.append(a + off)
+            return np.stack(rows, 0) if rows else np.empty((0, width), np.int64)
+
+        tetra = shifted("chiral_tensors", 4, keep=4)
+        cis = shifted("cis_bonds_tensors", 2)
+        trans = shifted("trans_bonds_tensors", 2)
+        final_cis = np.concatenate([cis, cis[:, ::-1]], 0) if cis.size else np.empty((0, 2), np.int64)
+        final_trans = np.concatenate([trans, trans[:, ::-1]], 0) if trans.size else np.empty((0, 2), np.int64)
+
+        keys = list(data_list[0].atom_features_map.keys())
+        feats = {k: torch.from_numpy(np.concatenate([_np(d.atom_features_map[k], np.int64) for d in data_list]))
+                 for k in keys}
+        batch_indices = np.repeat(np.arange(B, dtype=np.int64), n_atoms)
+
+        tdim = data_list[0].target.shape[0]
+        if all(d.target.shape[0] == tdim for d in data_list):              # molecular.py:413-418
+            targets = torch.from_numpy(np.stack([_np(d.target, np.float32) for d in data_list], 0))
+        else:
+            targets = [torch.as_tensor(d.target) for d in data_list]
+        total_charges = torch.from_numpy(np.concatenate([_np(d.total_charge, np.float32).reshape(-1) for d in data_list]))
+
+        # [2, E_total] block written molecule by molecule, hop by hop, then handed out transposed -- the
+        # same memory layout (and strides) as ``torch.cat(..., dim=1).t()`` at molecular.py:435-436
+        pieces = []
+        for d, off in zip(data_list, offsets):
+            for h in range(num_hops):
+                e = _np(d.multi_hop_edges[h], np.int64)
+                if e.size:
+                    pieces.append(e + off)
+        if pieces:
+            edges = torch.from_numpy(np.ascontiguousarray(np.concatenate(pieces, 1))).t()
+        else:
+            edges = torch.empty((0, 2), dtype=torch.long)
+
+        batch.x = torch.cat([torch.as_tensor(d.x) for d in data_list], 0)
+        batch.multi_hop_edge_indices = edges
+        batch.batch_indices = torch.from_numpy(batch_indices)
+        batch.batch = batch.batch_indices
+        batch.atom_features_map = feats
+        batch.targets = targets
+        batch.total_charges = total_charges
+        batch.final_tetrahedral_chiral_tensor = torch.from_numpy(tetra)
+        batch.final_cis_tensor = torch.from_numpy(np.ascontiguousarray(final_cis))
+        batch.final_trans_tensor = torch.from_numpy(np.ascontiguousarray(final_trans))
+        batch.smiles_list = [getattr(d, "smiles", "") for d in data_list]
+        if hasattr(data_list[0], "atomic_numbers"):
+            batch.atomic_numbers = torch.cat([torch.as_tensor(d.atomic_numbers) for d in data_list], 0)
+        batch.graph_index = GraphIndex.build(edges, batch_indices, B, num_hops, feats, feature_sizes,
+                                             tetra, final_cis, final_trans, tile_rows)
+        return batch
+
+    # ------------------------------------------------------------------ movement
+    def _apply(self, fn_t, fn_g) -> "MolBatch":
+        out = MolBatch()
+        out.__dict__.update(self.__dict__)
+        for k in self.FIELDS:
+            v = getattr(self, k)
+            if isinstance(v, torch.Tensor):
+                setattr(out, k, fn_t(v))
+        out.batch = out.batch_indices
+        out.atom_features_map = {k: fn_t(v) for k, v in self.atom_features_map.items()}
+        if self.graph_index is not None:
+            out.graph_index = fn_g(self.graph_index)
+        return out
+
+    def to(self, device, non_blocking: bool = False) -> "MolBatch":
+        return self._apply(lambda t: t.to(device, non_blocking=non_blocking),
+                           lambda g: g.to(device, non_blocking=non_blocking))
+
+    def pin_memory(self) -> "MolBatch":
+        return self._apply(lambda t: t.contiguous().pin_memory() if t.numel() else t, lambda g: g.pin_memory())
+
+    def nbytes(self) -> int:
+        n = 0
+        for k in self.FIELDS:
+            v = getattr(self, k)
+            if isinstance(v, torch.Tensor):
+                n += v.numel() * v.element_size()
+        n += sum(v.numel() * v.element_size() for v in self.atom_features_map.values())
+        if self.graph_index is not None:
+            n += self.graph_index.nbytes()
+        return n
+
+
+def collate_fn(data_list):
+    """Drop-in for ``iterable_collate_fn`` (datasets/loaders.py:10-15)."""
+    kept = [d for d in data_list if d is not None]
+    return MolBatch.from_data_list(kept) if kept else None

@@ -1,0 +1,244 @@
+// a6 embedding lookups (models/gnn.py:262-274), a10/a11 post-allreduce clip + Adam on the flat arena
+// (training/trainer.py:164-165), a12 weighted L1 / MSE loss (models/losses.py:14-87).
+#include "common.cuh"
+
+namespace ax2d {
+
+constexpr int kMaxTables = 8;
+struct EmbedArgs {
+  const float* table[kMaxTables];
+  const int64_t* index[kMaxTables];
+};
+
+__global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedArgs a, int n_tables, int E4, int64_t N,
+                                                        float* __restrict__ out, int64_t ldo) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int per_row = n_tables * E4;
+  if (t >= N * per_row) return;
+  const int64_t n = t / per_row;
+  const int c = static_cast<int>(t % per_row);
+  const int tb = c / E4, k = c % E4;
+  const int64_t row = a.index[tb][n];
+  reinterpret_cast<float4*>(out + n * ldo)[c] = __ldg(reinterpret_cast<const float4*>(a.table[tb] + row * E4 * 4) + k);
+}
+
+// Two-level fixed-order segment sum over atoms sorted (stably) by table row.
+// grid = (vocab, splits): CTA (v, s) sums its slice of the segment; 16 lanes x float4 cover emb_dim <= 64*...
+__global__ void __launch_bounds__(128) embed_bwd_partial_kernel(const float* __restrict__ g_out, int64_t ldg,
+                                                                int col0, int E4, const int32_t* __restrict__ order,
+                                                                const int32_t* __restrict__ ptr, int splits,
+                                                                float* __restrict__ partial) {
+  const int v = blockIdx.x, s = blockIdx.y;
+  const int beg = ptr[v], end = ptr[v + 1];
+  const int len = end - beg;
+  const int chunk = (len + splits - 1) / splits;
+  const int lo = beg + s * chunk;
+  const int hi = lo + chunk < end ? lo + chunk : end;
+  for (int c = threadIdx.x; c < E4; c += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = lo; k < hi; ++k) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(g_out + static_cast<int64_t>(order[k]) * ldg + col0) + c);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    reinterpret_cast<float4*>(partial + (static_cast<int64_t>(v) * splits + s) * E4 * 4)[c] = acc;
+  }
+}
+__global__ void embed_bwd_final_kernel(const float* __restrict__ partial, int splits, int E, int64_t vocab,
+                                       float* __restrict__ g_table) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= vocab * E) return;
+  const int64_t v = t / E;
+  const int c = static_cast<int>(t % E);
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += partial[(v * splits + k) * E + c];
+  g_table[t] = s;
+}
+
+// ----------------------------------------------------------------------------------------- optimiser
+constexpr int kNormBlocks = 1024;
+__global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __restrict__ g, int64_t n,
+                                                             float* __restrict__ partial) {
+  __shared__ float red[8];
+  float s = 0.f;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float v = g[(n4 << 2) + threadIdx.x];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) sqnorm_final_kernel(const float* __restrict__ partial, int n_part,
+                                                           float* __restrict__ norm2) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n_part; i += blockDim.x) s += partial[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    norm2[0] = t;
+  }
+}
+
+__global__ void step_inc_kernel(int64_t* step) { step[0] += 1; }
+
+__global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                        const float* __restrict__ norm2, float grad_scale,
+                                                        float max_norm, float lr, float beta1, float beta2, float eps,
+                                                        const int64_t* __restrict__ step) {
+  __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double t = static_cast<double>(step[0]);
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), t);
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), t);
+    s_step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+    s_bc2_sqrt = static_cast<float>(sqrt(bc2));
+    float coef = grad_scale;
+    if (max_norm > 0.f) {                                   // clip_grad_norm_: coef = clamp(max/(norm+1e-6), max=1)
+      const float total = sqrtf(norm2[0]) * grad_scale;
+      const float c = max_norm / (total + 1e-6f);
+      coef *= c < 1.f ? c : 1.f;
+    }
+    s_coef = coef;
+  }
+  __syncthreads();
+  const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float w1 = 1.f - beta1, w2 = 1.f - beta2;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = m[i] + (gi - m[i]) * w1;               // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * beta2 + w2 * gi * gi;           // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);                 // param.addcdiv_(exp_avg, denom, value=-step_size)
+  }
+}
+
+// ----------------------------------------------------------------------------------------- loss
+__global__ void __launch_bounds__(1024) weighted_loss_kernel(const float* __restrict__ pred,
+                                                             const float* __restrict__ target,
+                                                             const float* __restrict__ weights, int64_t B, int T,
+                                                             int kind, float* __restrict__ loss,
+                                                             float* __restrict__ g_pred) {
+  __shared__ float red[32];
+  const float invB = 1.f / static_cast<float>(B);
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < B * T; i += blockDim.x) {
+    const float d = pred[i] - target[i];
+    const float w = weights[i % T];
+    if (kind == 0) {
+      s += fabsf(d) * w;
+      if (g_pred != nullptr) g_pred[i] = (d > 0.f ? w : (d < 0.f ? -w : 0.f)) * invB;
+    } else {
+      s += d * d * w;
+      if (g_pred != nullptr) g_pred[i] = 2.f * d * w * invB;
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    loss[0] = t * invB;
+  }
+}
+
+}  // namespace ax2d
+
+using namespace ax2d;
+
+extern "C" int ax2d_embed_fwd(const float* const* tables, const int64_t* const* indices, int n_tables, int emb_dim,
+                              int64_t N, float* out, int64_t ldo, ax2d_stream_t stream) {
+  AX2D_CHECK_ARG(n_tables >= 1 && n_tables <= kMaxTables, "ax2d_embed_fwd: n_tables=%d not in [1,%d]", n_tables, kMaxTables);
+  AX2D_CHECK_ARG(emb_dim > 0 && emb_dim % 4 == 0 && ldo % 4 == 0, "ax2d_embed_fwd: emb_dim and ldo must be multiples of 4");
+  AX2D_CHECK_ALIGN(out);
+  if (N <= 0) return AX2D_OK;
+  EmbedArgs a;
+  for (int t = 0; t < n_tables; ++t) {
+    AX2D_CHECK_ALIGN(tables[t]);
+    a.table[t] = tables[t];
+    a.index[t] = indices[t];
+  }
+  const int64_t total = N * n_tables * (emb_dim / 4);
+  embed_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      a, n_tables, emb_dim / 4, N, out, ldo);
+  return launch_status("ax2d_embed_fwd");
+}
+
+constexpr int kEmbedSplits = 64;
+extern "C" int64_t ax2d_embed_bwd_workspace(int64_t vocab, int emb_dim) {
+  return vocab * kEmbedSplits * static_cast<int64_t>(emb_dim) * 4;
+}
+extern "C" int ax2d_embed_bwd(const float* g_out, int64_t ldg, int table, int emb_dim, int64_t vocab,
+                              const int32_t* order, const int32_t* ptr, float* g_table, void* workspace,
+                              ax2d_stream_t stream) {
+  AX2D_CHECK_ARG(emb_dim > 0 && emb_dim % 4 == 0 && ldg % 4 == 0, "ax2d_embed_bwd: emb_dim and ldg must be multiples of 4");
+  AX2D_CHECK_ARG(workspace != nullptr && vocab > 0, "ax2d_embed_bwd: workspace required");
+  AX2D_CHECK_ALIGN(g_out);
+  AX2D_CHECK_ALIGN(workspace);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(static_cast<unsigned>(vocab), kEmbedSplits);
+  embed_bwd_partial_kernel<<<grid, 32, 0, st>>>(g_out, ldg, table * emb_dim, emb_dim / 4, order, ptr, kEmbedSplits,
+                                                static_cast<float*>(workspace));
+  int rc = launch_status("ax2d_embed_bwd(partial)");
+  if (rc != AX2D_OK) return rc;
+  const int64_t total = vocab * emb_dim;
+  embed_bwd_final_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      static_cast<const float*>(workspace), kEmbedSplits, emb_dim, vocab, g_table);
+  return launch_status("ax2d_embed_bwd(final)");
+}
+
+extern "C" int64_t ax2d_sqnorm_workspace(int64_t n) {
+  (void)n;
+  return kNormBlocks * 4;
+}
+extern "C" int ax2d_sqnorm(const float* g, int64_t n, float* norm2, int64_t* step_inc, void* workspace,
+                           ax2d_stream_t stream) {
+  AX2D_CHECK_ARG(n >= 0 && workspace != nullptr, "ax2d_sqnorm: bad arguments");
+  AX2D_CHECK_ALIGN(g);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int64_t blocks = (n / 4 + 255) / 256;
+  blocks = blocks < 1 ? 1 : (blocks > kNormBlocks ? kNormBlocks : blocks);
+  sqnorm_partial_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(g, n, static_cast<float*>(workspace));
+  sqnorm_final_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(workspace), static_cast<int>(blocks), norm2);
+  if (step_inc != nullptr) step_inc_kernel<<<1, 1, 0, st>>>(step_inc);
+  return launch_status("ax2d_sqnorm");
+}
+
+extern "C" int ax2d_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* norm2,
+                              float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
+                              const int64_t* step, ax2d_stream_t stream) {
+  AX2D_CHECK_ARG(n >= 0 && step != nullptr && (max_norm <= 0.f || norm2 != nullptr), "ax2d_clip_adam: bad arguments");
+  if (n == 0) return AX2D_OK;
+  int64_t blocks = (n + 255) / 256;
+  blocks = blocks > kNumSMs * 8 ? kNumSMs * 8 : blocks;
+  clip_adam_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, n, norm2, grad_scale, max_norm, lr, beta1, beta2, eps, step);
+  return launch_status("ax2d_clip_adam");
+}
+
+extern "C" int ax2d_weighted_loss(const float* pred, const float* target, const float* weights, int64_t B, int T,
+                                  int kind, float* loss, float* g_pred, ax2d_stream_t stream) {
+  AX2D_CHECK_ARG(B > 0 && T > 0 && (kind == 0 || kind == 1), "ax2d_weighted_loss: bad arguments");
+  weighted_loss_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, target, weights, B, T, kind, loss,
+                                                                               g_pred);
+  return launch_status("ax2d_weighted_loss");
+}
