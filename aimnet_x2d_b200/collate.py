@@ -78,7 +78,9 @@ class GraphIndex:
             seg[1:] = np.cumsum(np.bincount(bi, minlength=B)).astype(np.int32)
         gi.max_seg = int(np.max(np.diff(seg))) if B else 0
 
-        if isinstance(edges, torch.Tensor):
+        if edges is None:
+            e_np = np.empty((0, 2), dtype=np.int64)
+        elif isinstance(edges, torch.Tensor):
             e_np = edges.detach().cpu().numpy()          # keeps the (possibly transposed) strides
         else:
             e_np = np.asarray(edges)

@@ -37,7 +37,7 @@ struct GemmArgs {
   int act, act_cols;
   const float* mask; int64_t ld_mask;
   float drop_p; uint64_t drop_seed; const uint64_t* drop_tick;
-  const float* resid[AX2D_MAX_SEG]; int64_t ld_resid[AX2D_MAX_SEG]; int n_resid;
+  const float* resid[AX2D_MAX_SEG]; int64_t ld_resid[AX2D_MAX_SEG]; int resid_cols[AX2D_MAX_SEG]; int n_resid;
   const float* dact_pre; int64_t ld_dact; int dact; int dact_cols;
   int accumulate;
 };
@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const GemmArgs g) {
       for (int j = 0; j < 4; ++j) v[j] *= drop[j];
     }
     for (int r = 0; r < g.n_resid; ++r) {
+      if (n >= g.resid_cols[r]) continue;
       const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid[r] + m * g.ld_resid[r] + n));
       v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
     }
@@ -390,6 +391,8 @@ extern "C" int ax2d_gemm(const ax2d_cmat* a, int trans_a, const ax2d_cmat* b, in
       AX2D_CHECK_ARG(ep->resid.ld[r] % 4 == 0, "ax2d_gemm: residual ld %% 4");
       g.resid[r] = ep->resid.ptr[r];
       g.ld_resid[r] = ep->resid.ld[r];
+      g.resid_cols[r] = ep->resid.width[r] > 0 ? ep->resid.width[r] : static_cast<int>(N);
+      AX2D_CHECK_ARG(g.resid_cols[r] % 4 == 0, "ax2d_gemm: residual width %% 4");
     }
     g.dact_pre = ep->dact_pre; g.ld_dact = ep->ld_dact; g.dact = ep->dact_pre != nullptr ? ep->dact : AX2D_ACT_NONE;
     g.dact_cols = ep->dact_cols > 0 ? ep->dact_cols : static_cast<int>(N);

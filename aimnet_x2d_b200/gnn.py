@@ -1,0 +1,214 @@
+"""B200-native ``GNN`` -- drop-in for the reference ``src/models/gnn.py`` (19-779).
+
+Identical constructor arguments, ``forward`` signature and return tuple, attribute names used by the
+reference's callers (``pooling``, ``concat_self_other``, ``message_passing_layers``, ``output_layer``,
+``loss_function``, ``task_type``, ``hidden_dim``, ``num_shells``, ``embedding_dim``, ``init_weights``,
+``get_model_info``) and ``state_dict`` keys/shapes, so reference checkpoints load unchanged.
+
+The forward wiring keeps node features in a padded layout (x_other: D -> multiple of 32 columns) between
+the fused kernels; ``torch.cat`` calls of the reference become multi-segment GEMM operands.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .activation import get_activation_function
+from .collate import GraphIndex
+from .layers import (FEATURE_PAD, INDEX_CACHE, MultiLayerPerceptron, ShellConvolutionLayer, _FusedLinear, pad1d,
+                     pad2d)
+from .pooling import create_pooling_layer
+
+FEATURE_ORDER = ("atom_type", "hydrogen_count", "degree", "hybridization")      # gnn.py:262-274
+
+
+class GNN(nn.Module):
+    def __init__(self, feature_sizes: Dict[str, int], hidden_dim: int, output_dim: int, num_shells: int = 3,
+                 num_message_passing_layers: int = 3, dropout: float = 0.05, ffn_hidden_dim: Optional[int] = None,
+                 ffn_num_layers: int = 3, pooling_type: str = "attention", task_type: str = "regression",
+                 embedding_dim: int = 64, use_partial_charges: bool = False, use_stereochemistry: bool = False,
+                 ffn_dropout: float = 0.05, activation_type: str = "silu", shell_conv_num_mlp_layers: int = 2,
+                 shell_conv_dropout: float = 0.05, attention_num_heads: int = 4, attention_temperature: float = 1.0,
+                 loss_function: str = "l1", verbose: bool = False):
+        super().__init__()
+        self.hidden_dim = hidden_dim
+        self.num_shells = num_shells
+        self.task_type = task_type
+        self.embedding_dim = embedding_dim
+        self.use_partial_charges = use_partial_charges
+        self.use_stereochemistry = use_stereochemistry
+        self.loss_function = loss_function
+        self.activation_type = activation_type
+        self._verbose = verbose
+        if ffn_hidden_dim is None:
+            ffn_hidden_dim = hidden_dim
+
+        # gnn.py:151-171
+        self.atom_type_embedding = nn.Embedding(feature_sizes["atom_type"], embedding_dim)
+        self.hydrogen_count_embedding = nn.Embedding(feature_sizes["hydrogen_count"], embedding_dim)
+        self.degree_embedding = nn.Embedding(feature_sizes["degree"], embedding_dim)
+        self.hybridization_embedding = nn.Embedding(feature_sizes["hybridization"], embedding_dim)
+
+        self.embedding_projection = nn.Linear(embedding_dim * len(feature_sizes), hidden_dim)   # gnn.py:95-96
+        self.activation = get_activation_function(activation_type)
+        self.x_other_dim = int(0.3 * hidden_dim)                                               # gnn.py:100-101
+        self.x_self_dim = hidden_dim - self.x_other_dim
+
+        self.message_passing_layers = nn.ModuleList([                                           # gnn.py:173-186
+            ShellConvolutionLayer(atom_input_dim=self.x_other_dim, output_dim=self.x_other_dim, num_hops=num_shells,
+                                  activation_type=activation_type, dropout=shell_conv_dropout,
+                                  num_mlp_layers=shell_conv_num_mlp_layers)
+            for _ in range(num_message_passing_layers)])
+
+        self.pooling = create_pooling_layer(pooling_type, hidden_dim, num_heads=attention_num_heads,
+                                            initial_temperature=attention_temperature)          # gnn.py:110-115
+
+        self.concat_self_other = _FusedLinear(hidden_dim, hidden_dim)                           # gnn.py:190
+        if self.use_stereochemistry:                                                            # gnn.py:192-195
+            self.stereochemical_embedding = nn.Linear(hidden_dim * 3, hidden_dim)               # dead parameter (Q6)
+            self.stereochemical_embedding_2 = _FusedLinear(self.x_other_dim * 3, self.x_other_dim)
+
+        self.post_pooling_projection = _FusedLinear(hidden_dim, ffn_hidden_dim)                 # gnn.py:121
+        self.ffn = MultiLayerPerceptron(input_dim=ffn_hidden_dim, hidden_dim=ffn_hidden_dim, output_dim=ffn_hidden_dim,
+                                        num_layers=ffn_num_layers, activation_type=activation_type,
+                                        dropout=ffn_dropout, use_skip=True)
+        self.skip_transform = _FusedLinear(ffn_hidden_dim, ffn_hidden_dim)                      # gnn.py:133
+        final_output_dim = output_dim * 4 if loss_function == "evidential" else output_dim      # gnn.py:136-141
+        self.output_layer = _FusedLinear(ffn_hidden_dim * 2, final_output_dim)                  # gnn.py:143
+        self.long_range_projection = nn.Linear(hidden_dim, ffn_hidden_dim)                      # dead parameter (Q6)
+        self.init_weights()
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _index_for(self, atom_features, edges, batch_indices, total_charges, tetra, cis, trans) -> GraphIndex:
+        dev = batch_indices.device
+        key = INDEX_CACHE.key(edges, batch_indices, tetra, cis, trans, *[atom_features[k] for k in FEATURE_ORDER],
+                              extra=(self.num_shells,))
+
+        def build():
+            sizes = {"atom_type": self.atom_type_embedding.num_embeddings,
+                     "hydrogen_count": self.hydrogen_count_embedding.num_embeddings,
+                     "degree": self.degree_embedding.num_embeddings,
+                     "hybridization": self.hybridization_embedding.num_embeddings}
+            return GraphIndex.build(edges, batch_indices, int(total_charges.shape[0]), self.num_shells,
+                                    {k: atom_features[k] for k in FEATURE_ORDER}, sizes, tetra, cis, trans).to(dev)
+
+        return INDEX_CACHE.get(key, build)
+
+    def forward(self, atom_features: Dict[str, torch.Tensor], multi_hop_edge_indices: torch.Tensor,
+                batch_indices: torch.Tensor, total_charges: torch.Tensor, tetrahedral_indices: torch.Tensor,
+                cis_indices: torch.Tensor, trans_indices: torch.Tensor, graph_index: Optional[GraphIndex] = None
+                ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """Reference ``gnn.py:197-260``.  ``graph_index`` (optional, from ``MolBatch``) carries the CSR / segment
+        offsets emitted at collation; when absent it is rebuilt from the index tensors (and cached)."""
+        gi = graph_index
+        if gi is None:
+            gi = self._index_for(atom_features, multi_hop_edge_indices, batch_indices, total_charges,
+                                 tetrahedral_indices, cis_indices, trans_indices)
+        D, S = self.x_other_dim, self.x_self_dim
+        Dp, Sp = ops.pad_to(D, FEATURE_PAD), ops.pad_to(S, FEATURE_PAD)
+        E = self.embedding_dim
+        Ep = ops.pad_to(E, 4)
+        tables = [getattr(self, f"{k}_embedding").weight for k in FEATURE_ORDER]
+        if Ep != E:
+            tables = [pad2d(t, t.shape[0], Ep) for t in tables]
+        nt = len(FEATURE_ORDER)
+        Wp = self.embedding_projection.weight
+        if Ep != E:
+            Wp = torch.cat([pad2d(Wp[:, i * E:(i + 1) * E], Wp.shape[0], Ep) for i in range(nt)], dim=1)
+        W_ep = torch.cat([pad2d(Wp[:S], Sp, nt * Ep), pad2d(Wp[S:], Dp, nt * Ep)], dim=0)
+        bp = self.embedding_projection.bias
+        b_ep = torch.cat([pad1d(bp[:S], Sp), pad1d(bp[S:], Dp)], dim=0)
+        opts = ops._Opts(act=self.activation_type, names=FEATURE_ORDER, emb_dim=Ep, s_pad=Sp, d_pad=Dp, gi=gi)
+        x_self, x = ops.EmbedProjFn.apply(opts, W_ep, b_ep, *tables,
+                                          *[atom_features[k].contiguous() for k in FEATURE_ORDER])   # gnn.py:220-231
+
+        if multi_hop_edge_indices.numel() > 0:                                                     # gnn.py:287
+            for layer in self.message_passing_layers:
+                if self.use_partial_charges:                                                       # gnn.py:290-293
+                    x = ops.ChargeEqFn.apply(x, total_charges, gi)
+                if self.use_stereochemistry:                                                       # gnn.py:296-299
+                    x = self._apply_stereochemistry(x, gi, D, Dp)
+                x = layer.forward_padded(x, gi, add_input=True)                                    # gnn.py:302-306
+
+        partial_charges = None
+        if self.use_partial_charges and D >= 2:                                                    # gnn.py:240-242
+            partial_charges = x[:, 0].clone()
+
+        atom_emb = self.concat_self_other(([x_self, x], [S, D]))                                   # gnn.py:245-246
+        x_pooled, attention_weights = self.pooling(atom_emb, batch_indices, graph_index=gi)        # gnn.py:249
+        v = self.post_pooling_projection(x_pooled)                                                 # gnn.py:252
+        v = self.ffn(v)                                                                            # gnn.py:253
+        skip = self.skip_transform(v)                                                              # gnn.py:256
+        Fh = v.shape[1]
+        output = self.output_layer(([v, skip], [Fh, Fh]))                                          # gnn.py:257-258
+        return output, attention_weights, partial_charges
+
+    def _apply_stereochemistry(self, x: torch.Tensor, gi: GraphIndex, D: int, Dp: int) -> torch.Tensor:
+        """Reference ``gnn.py:310-327``: Linear([x | cis_trans(x) | tetra(x)])."""
+        ct = ops.CisTransFn.apply(x, gi) if gi.cistrans is not None else x          # identity when empty (gnn.py:475-476)
+        tt = ops.TetraFn.apply(x, D, gi) if gi.tetra is not None else x             # identity when empty (gnn.py:402-403)
+        return self.stereochemical_embedding_2(([x, ct, tt], [D, D, D], Dp))       # padded [N, Dp], pad columns = 0
+
+    # ------------------------------------------------------------------------------------------ misc API
+    def init_weights(self) -> None:
+        """Reference ``gnn.py:660-703`` (xavier-uniform on the listed layers and embeddings, zero biases)."""
+        linear_layers = [self.embedding_projection, self.concat_self_other, self.post_pooling_projection,
+                         self.skip_transform, self.output_layer, self.long_range_projection]
+        if hasattr(self, "stereochemical_embedding"):
+            linear_layers += [self.stereochemical_embedding, self.stereochemical_embedding_2]
+        for layer in linear_layers:
+            nn.init.xavier_uniform_(layer.weight)
+            if layer.bias is not None:
+                nn.init.zeros_(layer.bias)
+        for emb in (self.atom_type_embedding, self.degree_embedding, self.hybridization_embedding,
+                    self.hydrogen_count_embedding):
+            nn.init.xavier_uniform_(emb.weight)
+        if hasattr(self.pooling, "attention_weights"):
+            for aw in self.pooling.attention_weights:
+                nn.init.xavier_uniform_(aw.weight)
+                if aw.bias is not None:
+                    nn.init.zeros_(aw.bias)
+        if self._verbose:
+            print("[GNN] Model weights initialized")
+
+    def get_model_info(self) -> Dict[str, object]:
+        total = sum(p.numel() for p in self.parameters())
+        trainable = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        return {"total_parameters": total, "trainable_parameters": trainable, "hidden_dim": self.hidden_dim,
+                "num_shells": self.num_shells, "embedding_dim": self.embedding_dim, "task_type": self.task_type,
+                "use_partial_charges": self.use_partial_charges, "use_stereochemistry": self.use_stereochemistry,
+                "loss_function": self.loss_function,
+                "num_message_passing_layers": len(self.message_passing_layers),
+                "pooling_type": type(self.pooling).__name__}
+
+    def __repr__(self) -> str:
+        info = self.get_model_info()
+        return (f"GNN(\n  parameters={info['total_parameters']:,}\n  hidden_dim={info['hidden_dim']}\n"
+                f"  num_shells={info['num_shells']}\n  task_type='{info['task_type']}'\n"
+                f"  loss_function='{info['loss_function']}'\n"
+                f"  features=[partial_charges={info['use_partial_charges']}, "
+                f"stereochemistry={info['use_stereochemistry']}]\n)")
+
+
+class GNNConfig:
+    """Reference ``gnn.py:738-779``."""
+
+    @staticmethod
+    def from_args(args) -> Dict[str, object]:
+        feature_sizes = {"atom_type": 119, "hydrogen_count": 9, "degree": 7, "hybridization": 7}
+        return {"feature_sizes": feature_sizes, "hidden_dim": args.hidden_dim,
+                "output_dim": getattr(args, "output_dim", 1), "num_shells": args.num_shells,
+                "num_message_passing_layers": args.num_message_passing_layers, "ffn_hidden_dim": args.ffn_hidden_dim,
+                "ffn_num_layers": args.ffn_num_layers, "pooling_type": args.pooling_type, "task_type": args.task_type,
+                "embedding_dim": args.embedding_dim, "use_partial_charges": args.use_partial_charges,
+                "use_stereochemistry": args.use_stereochemistry, "ffn_dropout": args.ffn_dropout,
+                "activation_type": args.activation_type, "shell_conv_num_mlp_layers": args.shell_conv_num_mlp_layers,
+                "shell_conv_dropout": args.shell_conv_dropout, "attention_num_heads": args.attention_num_heads,
+                "attention_temperature": args.attention_temperature, "loss_function": args.loss_function}
+
+    @staticmethod
+    def create_model_from_args(args) -> GNN:
+        return GNN(**GNNConfig.from_args(args))

@@ -1,0 +1,535 @@
+"""Python host side of the C ABI: thin launch wrappers + the autograd Functions of the hot path.
+
+torch is used here for device memory (caching allocator), the current CUDA stream and autograd
+bookkeeping only -- every computation on atom / molecule tensors is a libax2d kernel.  There is no
+CPU path: calling any op with a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_CODES, CMat, Epilogue, MAX_SEG, SEG_MODES
+
+
+def pad_to(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("aimnet_x2d_b200 ops run on CUDA tensors only (there is no CPU fallback); got a "
+                               f"{t.device} tensor")
+
+
+def _mat(segs: Sequence, allow_none: bool = False) -> CMat:
+    """segs: sequence of (tensor | None, width) -- 2-D fp32 tensors with unit column stride."""
+    m = CMat()
+    if len(segs) > MAX_SEG:
+        raise RuntimeError(f"at most {MAX_SEG} segments are supported, got {len(segs)}")
+    m.n_seg = len(segs)
+    for i, (t, w) in enumerate(segs):
+        if t is None:
+            if not allow_none:
+                raise RuntimeError("segment tensor is None")
+            m.ptr[i], m.ld[i] = None, 4
+        else:
+            _need_cuda(t)
+            if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+                raise RuntimeError(f"segment must be a 2-D fp32 tensor with unit column stride, got {t.dtype} "
+                                   f"{tuple(t.shape)} strides {t.stride()}")
+            m.ptr[i], m.ld[i] = t.data_ptr(), t.stride(0)
+        m.width[i] = int(w)
+    return m
+
+
+# ----------------------------------------------------------------------------------------------- raw launches
+def gemm(a_segs, b_segs, c_segs, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = True, *,
+         bias=None, pre_segs=None, act=None, act_cols=None, mask=None, drop_p: float = 0.0, drop_seed: int = 0,
+         drop_tick=None, resid=(), dact_pre=None, dact=None, dact_cols=None, accumulate: bool = False,
+         split_k: int = 1) -> None:
+    lib = _lib.load()
+    a, b, c = _mat(a_segs), _mat(b_segs), _mat(c_segs)
+    ep = Epilogue()
+    ep.bias = None if bias is None else bias.data_ptr()
+    if pre_segs:
+        ep.pre = _mat(pre_segs, allow_none=True)
+    ep.act = ACT_CODES[act]
+    ep.act_cols = int(N if act_cols is None else act_cols)
+    if mask is not None:
+        ep.mask, ep.ld_mask = mask.data_ptr(), mask.stride(0)
+    ep.drop_p, ep.drop_seed = float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF
+    ep.drop_tick = None if drop_tick is None else drop_tick.data_ptr()
+    if resid:
+        ep.resid = _mat([(r, w) for r, w in resid])
+    if dact_pre is not None:
+        ep.dact_pre, ep.ld_dact, ep.dact = dact_pre.data_ptr(), dact_pre.stride(0), ACT_CODES[dact]
+        ep.dact_cols = int(N if dact_cols is None else dact_cols)
+    ep.accumulate = int(accumulate)
+    ws = None
+    if split_k > 1:
+        nbytes = lib.ax2d_gemm_workspace(M, N, K, int(trans_a), split_k)
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=c_segs[0][0].device)
+    _lib.check(lib.ax2d_gemm(C.byref(a), int(trans_a), C.byref(b), int(trans_b), C.byref(c), M, N, K, C.byref(ep),
+                             split_k, _p(ws), _stream()), "ax2d_gemm")
+
+
+def colsum(segs, M: int, N: int, out: torch.Tensor, accumulate: bool = False) -> None:
+    lib = _lib.load()
+    ws = torch.empty(max(lib.ax2d_colsum_workspace(M, N) // 4, 1), dtype=torch.float32, device=out.device)
+    a = _mat(segs)
+    _lib.check(lib.ax2d_colsum(C.byref(a), M, N, _p(out), int(accumulate), _p(ws), _stream()), "ax2d_colsum")
+
+
+def act_bwd(g: torch.Tensor, pre: torch.Tensor, act: str) -> torch.Tensor:
+    out = torch.empty_like(pre)
+    _lib.check(_lib.load().ax2d_act_bwd(_p(g), g.stride(0), _p(pre), pre.stride(0), _p(out), out.stride(0),
+                                        pre.shape[0], pre.shape[1], ACT_CODES[act], _stream()), "ax2d_act_bwd")
+    return out
+
+
+def split_k_for(M: int, N: int, K: int) -> int:
+    tiles = ((M + 127) // 128) * ((N + 63) // 64)
+    s = max(1, min((148 * 3 + tiles - 1) // tiles, K // 256))
+    return int(s)
+
+
+def agg(x: torch.Tensor, gi, transpose: bool = False, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Forward (transpose=False): out[r] = sum x[col]; rows = gi.num_rows.  Backward: rows = N."""
+    lib = _lib.load()
+    _need_cuda(x)
+    N, width = gi.num_atoms, x.shape[1]
+    rows = N if transpose else gi.num_rows
+    out = torch.empty((rows, width), dtype=x.dtype, device=x.device)
+    rowptr, col = (gi.rowptr_t, gi.col_t) if transpose else (gi.rowptr, gi.col)
+    tiled = (gi.tile_local and gi.collapsed and x.stride(0) == width and width % 32 == 0
+             and gi.max_tile_rows * width * 4 <= 200 * 1024 and gi.n_tiles > 0)
+    _lib.check(lib.ax2d_agg(_p(x), x.stride(0), x.shape[0], _p(out), out.stride(0), rows, _p(rowptr), _p(col),
+                            _p(addend), 0 if addend is None else addend.stride(0), width,
+                            _p(gi.tile_ptr) if tiled else None, gi.n_tiles if tiled else 0,
+                            gi.max_tile_rows if tiled else 0, 0, _stream()), "ax2d_agg")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- dense helpers
+def _bias_grad(segs, M, N, device):
+    out = torch.empty(N, dtype=torch.float32, device=device)
+    colsum(segs, M, N, out)
+    return out
+
+
+def _weight_grad(g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device) -> torch.Tensor:
+    """dW[o, i] = sum_r G[r, o] X[r, i]  (G, X column-segmented) -- split over the rows, fixed-order reduce."""
+    dW = torch.empty((Nout, Kin), dtype=torch.float32, device=device)
+    gemm(g_segs, x_segs, [(dW, Kin)], Nout, Kin, M_rows, trans_a=True, trans_b=False,
+         split_k=split_k_for(Nout, Kin, M_rows))
+    return dW
+
+
+class _Opts:
+    """Non-tensor options handed to the autograd Functions."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = [a_0 | a_1 | ...] W^T + b without materialising the concatenation (gnn.py:245-246, 252, 256-258, 327).
+
+    args: opts(widths=[w_i], n_out=Np), W [Np, sum w_i], b [Np] | None, *a_segs"""
+
+    @staticmethod
+    def forward(ctx, opts, W, b, *a):
+        _need_cuda(W, *a)
+        M = a[0].shape[0]
+        K = sum(opts.widths)
+        out = torch.empty((M, opts.n_out), dtype=torch.float32, device=W.device)
+        gemm(list(zip(a, opts.widths)), [(W, K)], [(out, opts.n_out)], M, opts.n_out, K, bias=b)
+        ctx.opts = opts
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(W, *a)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        W, *a = ctx.saved_tensors
+        opts = ctx.opts
+        g = g.contiguous()
+        M, Np, K = g.shape[0], opts.n_out, sum(opts.widths)
+        gs = [(g, Np)]
+        d_a = [torch.empty((M, w), dtype=torch.float32, device=g.device) for w in opts.widths]
+        gemm(gs, [(W, K)], list(zip(d_a, opts.widths)), M, K, Np, trans_a=False, trans_b=False)
+        dW = _weight_grad(gs, list(zip(a, opts.widths)), M, Np, K, g.device)
+        db = _bias_grad(gs, M, Np, g.device) if ctx.has_bias else None
+        return (None, dW, db, *d_a)
+
+
+class MLPBlockFn(torch.autograd.Function):
+    """out = W2 drop(act(W1 h + b1)) + b2 (+ h)   (LinearBlock, layers.py:203-219).
+
+    args: opts(act, p, seed, tick, skip, w_in, w_out), h [M, w_in], W1 [w_out, w_in], b1, W2 [w_out, w_out], b2"""
+
+    @staticmethod
+    def forward(ctx, opts, h, W1, b1, W2, b2):
+        _need_cuda(h, W1, W2)
+        M, Wi, Wo = h.shape[0], opts.w_in, opts.w_out
+        u = torch.empty((M, Wo), dtype=torch.float32, device=h.device)
+        t = torch.empty_like(u)
+        out = torch.empty_like(u)
+        gemm([(h, Wi)], [(W1, Wi)], [(t, Wo)], M, Wo, Wi, bias=b1, pre_segs=[(u, Wo)], act=opts.act,
+             drop_p=opts.p, drop_seed=opts.seed, drop_tick=opts.tick)
+        gemm([(t, Wo)], [(W2, Wo)], [(out, Wo)], M, Wo, Wo, bias=b2, resid=[(h, Wo)] if opts.skip else [])
+        ctx.opts = opts
+        ctx.save_for_backward(h, W1, W2, u, t)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, W1, W2, u, t = ctx.saved_tensors
+        opts = ctx.opts
+        g = g.contiguous()
+        M, Wi, Wo = g.shape[0], opts.w_in, opts.w_out
+        dev = g.device
+        gs = [(g, Wo)]
+        dW2 = _weight_grad(gs, [(t, Wo)], M, Wo, Wo, dev)
+        db2 = _bias_grad(gs, M, Wo, dev)
+        du = torch.empty_like(u)
+        gemm(gs, [(W2, Wo)], [(du, Wo)], M, Wo, Wo, trans_b=False, dact_pre=u, dact=opts.act,
+             drop_p=opts.p, drop_seed=opts.seed, drop_tick=opts.tick)
+        dus = [(du, Wo)]
+        dW1 = _weight_grad(dus, [(h, Wi)], M, Wo, Wi, dev)
+        db1 = _bias_grad(dus, M, Wo, dev)
+        dh = torch.empty_like(h)
+        gemm(dus, [(W1, Wi)], [(dh, Wi)], M, Wi, Wo, trans_b=False, resid=[(g, Wi)] if opts.skip else [])
+        return None, dh, dW1, db1, dW2, db2
+
+
+class ShellConvFn(torch.autograd.Function):
+    """One ShellConvolutionLayer (layers.py:63-108) on padded features, optionally with the caller's
+    ``+ x`` residual (gnn.py:302-306) folded into the last epilogue.
+
+    args: opts(act, ps, seeds, tick, w_in, w_out, n_mlp, add_input, gi), x, W_io, b_io, (W1, b1, W2, b2) * n_mlp
+    W_io = [W_in ; W_skip] stacked over rows, columns = the non-zero hop chunks of the padded input."""
+
+    @staticmethod
+    def _segments(x, ag, Di):
+        N = x.shape[0]
+        return [(x, Di)] + [(ag[h * N:(h + 1) * N], Di) for h in range(ag.shape[0] // max(N, 1))]
+
+    @staticmethod
+    def forward(ctx, opts, x, W_io, b_io, *mlp):
+        _need_cuda(x, W_io)
+        gi, Di, Do, N = opts.gi, opts.w_in, opts.w_out, x.shape[0]
+        dev = x.device
+        ag = agg(x, gi)                                                     # layers.py:133-167
+        a_segs = ShellConvFn._segments(x, ag, Di)
+        K = Di * len(a_segs)
+        z0 = torch.empty((N, Do), dtype=torch.float32, device=dev)
+        h = torch.empty_like(z0)
+        gskip = torch.empty_like(z0)
+        gemm(a_segs, [(W_io, K)], [(h, Do), (gskip, Do)], N, 2 * Do, K, bias=b_io,
+             pre_segs=[(z0, Do), (None, Do)], act=opts.act, act_cols=Do)    # layers.py:82-87
+        saved = [x, ag, z0, W_io]
+        for k in range(opts.n_mlp):
+            W1, b1, W2, b2 = mlp[4 * k:4 * k + 4]
+            u = torch.empty_like(z0)
+            t = torch.empty_like(z0)
+            hn = torch.empty_like(z0)
+            gemm([(h, Do)], [(W1, Do)], [(t, Do)], N, Do, Do, bias=b1, pre_segs=[(u, Do)], act=opts.act,
+                 drop_p=opts.ps[k], drop_seed=opts.seeds[k], drop_tick=opts.tick)
+            resid = [(h, Do)]
+            if k == opts.n_mlp - 1:                                         # layers.py:106 (+ gnn.py:306)
+                resid.append((gskip, Do))
+                if opts.add_input:
+                    resid.append((x, Do))
+            gemm([(t, Do)], [(W2, Do)], [(hn, Do)], N, Do, Do, bias=b2, resid=resid)
+            saved += [h, u, t, W1, W2]
+            h = hn
+        if opts.n_mlp == 0:
+            h = h + gskip + (x if opts.add_input else 0)
+        ctx.opts = opts
+        ctx.save_for_backward(*saved)
+        return h
+
+    @staticmethod
+    def backward(ctx, g):
+        opts = ctx.opts
+        gi, Di, Do = opts.gi, opts.w_in, opts.w_out
+        saved = ctx.saved_tensors
+        x, ag, z0, W_io = saved[:4]
+        g = g.contiguous()
+        N, dev = g.shape[0], g.device
+        dh = g
+        grads_mlp: List[torch.Tensor] = []
+        if opts.n_mlp == 0:
+            dz0 = act_bwd(g, z0, opts.act)
+        for k in reversed(range(opts.n_mlp)):
+            h, u, t, W1, W2 = saved[4 + 5 * k:9 + 5 * k]
+            dhs = [(dh, Do)]
+            dW2 = _weight_grad(dhs, [(t, Do)], N, Do, Do, dev)
+            db2 = _bias_grad(dhs, N, Do, dev)
+            du = torch.empty_like(z0)
+            gemm(dhs, [(W2, Do)], [(du, Do)], N, Do, Do, trans_b=False, dact_pre=u, dact=opts.act,
+                 drop_p=opts.ps[k], drop_seed=opts.seeds[k], drop_tick=opts.tick)
+            dus = [(du, Do)]
+            dW1 = _weight_grad(dus, [(h, Do)], N, Do, Do, dev)
+            db1 = _bias_grad(dus, N, Do, dev)
+            dprev = torch.empty_like(z0)
+            if k == 0:      # d z0 = (dh + du W1) * act'(z0) in one epilogue
+                gemm(dus, [(W1, Do)], [(dprev, Do)], N, Do, Do, trans_b=False, resid=dhs, dact_pre=z0, dact=opts.act)
+                dz0 = dprev
+            else:
+                gemm(dus, [(W1, Do)], [(dprev, Do)], N, Do, Do, trans_b=False, resid=dhs)
+                dh = dprev
+            grads_mlp = [dW1, db1, dW2, db2] + grads_mlp
+        # input / skip projections: [dz0 | g] against [x | agg_1 .. agg_H]
+        a_segs = ShellConvFn._segments(x, ag, Di)
+        K = Di * len(a_segs)
+        gz = [(dz0, Do), (g, Do)]
+        dW_io = _weight_grad(gz, a_segs, N, 2 * Do, K, dev)
+        db_io = _bias_grad(gz, N, 2 * Do, dev)
+        dx1 = torch.empty((N, Di), dtype=torch.float32, device=dev)
+        dag = torch.empty_like(ag)
+        c_segs = ShellConvFn._segments(dx1, dag, Di)
+        gemm(gz, [(W_io, K)], c_segs, N, K, 2 * Do, trans_b=False,
+             resid=[(g, Di)] if opts.add_input else [])                   # + g only on the x columns
+        dx = agg(dag, gi, transpose=True, addend=dx1)                       # gather backward, CSR of src
+        return (None, dx, dW_io, db_io, *grads_mlp)
+
+
+class EmbedProjFn(torch.autograd.Function):
+    """Embedding lookups + cat + Linear + activation + split into (x_self, x_other)  (gnn.py:220-231, 262-274).
+
+    args: opts(act, names, emb_dim, s_pad, d_pad, gi, vocabs), W [s_pad+d_pad, T*E], b, *tables, then *indices"""
+
+    @staticmethod
+    def forward(ctx, opts, W, b, *rest):
+        nt = len(opts.names)
+        tables, indices = rest[:nt], rest[nt:]
+        _need_cuda(W, *tables, *indices)
+        lib = _lib.load()
+        N, E = indices[0].shape[0], opts.emb_dim
+        dev = W.device
+        e0 = torch.empty((N, nt * E), dtype=torch.float32, device=dev)
+        tp = (C.c_void_p * nt)(*[t.data_ptr() for t in tables])
+        ip = (C.c_void_p * nt)(*[i.data_ptr() for i in indices])
+        for i in indices:
+            if i.dtype != torch.int64 or not i.is_contiguous():
+                raise RuntimeError("atom feature indices must be contiguous int64 tensors")
+        _lib.check(lib.ax2d_embed_fwd(tp, ip, nt, E, N, _p(e0), e0.stride(0), _stream()), "ax2d_embed_fwd")
+        Sp, Dp = opts.s_pad, opts.d_pad
+        xs = torch.empty((N, Sp), dtype=torch.float32, device=dev)
+        xo = torch.empty((N, Dp), dtype=torch.float32, device=dev)
+        zs, zo = torch.empty_like(xs), torch.empty_like(xo)
+        gemm([(e0, nt * E)], [(W, nt * E)], [(xs, Sp), (xo, Dp)], N, Sp + Dp, nt * E, bias=b,
+             pre_segs=[(zs, Sp), (zo, Dp)], act=opts.act)
+        ctx.opts = opts
+        ctx.save_for_backward(W, e0, zs, zo, *tables)
+        return xs, xo
+
+    @staticmethod
+    def backward(ctx, gxs, gxo):
+        opts = ctx.opts
+        W, e0, zs, zo, *tables = ctx.saved_tensors
+        lib = _lib.load()
+        nt, E, Sp, Dp = len(opts.names), opts.emb_dim, opts.s_pad, opts.d_pad
+        N, dev = e0.shape[0], e0.device
+        dzs = act_bwd(gxs.contiguous(), zs, opts.act)
+        dzo = act_bwd(gxo.contiguous(), zo, opts.act)
+        gz = [(dzs, Sp), (dzo, Dp)]
+        dW = _weight_grad(gz, [(e0, nt * E)], N, Sp + Dp, nt * E, dev)
+        db = _bias_grad(gz, N, Sp + Dp, dev)
+        de0 = torch.empty_like(e0)
+        gemm(gz, [(W, nt * E)], [(de0, nt * E)], N, nt * E, Sp + Dp, trans_b=False)
+        g_tables = []
+        for ti, name in enumerate(opts.names):
+            order, ptr, vocab = opts.gi.embed[name]
+            if vocab != tables[ti].shape[0]:
+                raise RuntimeError(f"embedding index for '{name}' was built for vocab {vocab}, table has "
+                                   f"{tables[ti].shape[0]} rows")
+            gt = torch.empty_like(tables[ti])
+            ws = torch.empty(lib.ax2d_embed_bwd_workspace(vocab, E) // 4, dtype=torch.float32, device=dev)
+            _lib.check(lib.ax2d_embed_bwd(_p(de0), de0.stride(0), ti, E, vocab, _p(order), _p(ptr), _p(gt), _p(ws),
+                                          _stream()), "ax2d_embed_bwd")
+            g_tables.append(gt)
+        return (None, dW, db, *g_tables, *([None] * nt))
+
+
+# ----------------------------------------------------------------------------------------------- segment ops
+class AttnPoolFn(torch.autograd.Function):
+    """MultiHeadAttentionPoolingLayer.forward (pooling.py:122-172) as one fused kernel per direction."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, temperature, gi):
+        _need_cuda(x, w, b, temperature)
+        lib = _lib.load()
+        x = x.contiguous()
+        N, F = x.shape
+        heads, B = w.shape[0], gi.num_graphs
+        pooled = torch.empty((B, F), dtype=torch.float32, device=x.device)
+        attn = torch.empty((heads, N), dtype=torch.float32, device=x.device)
+        z = torch.empty_like(attn)
+        _lib.check(lib.ax2d_attn_pool_fwd(_p(x), F, _p(gi.seg_ptr), B, N, F, heads, _p(w), _p(b), _p(temperature),
+                                          _p(pooled), _p(attn), _p(z), gi.max_seg, _stream()), "ax2d_attn_pool_fwd")
+        ctx.gi = gi
+        ctx.save_for_backward(x, w, temperature, attn, z)
+        return pooled, attn
+
+    @staticmethod
+    def backward(ctx, g_pooled, g_attn):
+        x, w, temperature, attn, z = ctx.saved_tensors
+        gi = ctx.gi
+        lib = _lib.load()
+        N, F = x.shape
+        heads, B = w.shape[0], gi.num_graphs
+        dev = x.device
+        gx = torch.empty_like(x)
+        gw = torch.empty_like(w)
+        gb = torch.empty(heads, dtype=torch.float32, device=dev)
+        gT = torch.empty((), dtype=torch.float32, device=dev)
+        ws = torch.empty(lib.ax2d_attn_pool_bwd_workspace(B, F, heads) // 4, dtype=torch.float32, device=dev)
+        if g_pooled is None:
+            g_pooled = torch.zeros((B, F), dtype=torch.float32, device=dev)
+        g_attn = None if g_attn is None else g_attn.contiguous()
+        _lib.check(lib.ax2d_attn_pool_bwd(_p(x), F, _p(gi.seg_ptr), B, N, F, heads, _p(w), _p(temperature), _p(attn),
+                                          _p(z), _p(g_pooled.contiguous()), _p(g_attn), _p(gx), F, _p(gw), _p(gb),
+                                          _p(gT), _p(ws), gi.max_seg, _stream()), "ax2d_attn_pool_bwd")
+        return gx, gw, gb, gT, None
+
+
+class SegPoolFn(torch.autograd.Function):
+    """Mean / Max / Sum pooling (pooling.py:15-80) with torch_scatter semantics."""
+
+    @staticmethod
+    def forward(ctx, x, mode, gi):
+        _need_cuda(x)
+        lib = _lib.load()
+        N, F = x.shape
+        B = gi.num_graphs
+        out = torch.empty((B, F), dtype=torch.float32, device=x.device)
+        arg = torch.empty((B, F), dtype=torch.int32, device=x.device) if mode == "max" else None
+        _lib.check(lib.ax2d_seg_reduce_fwd(_p(x), x.stride(0), _p(gi.seg_ptr), B, F, SEG_MODES[mode], _p(out), _p(arg),
+                                           _stream()), "ax2d_seg_reduce_fwd")
+        ctx.gi, ctx.mode, ctx.shape = gi, mode, (N, F)
+        ctx.save_for_backward(arg if arg is not None else out.new_empty(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        gi, mode = ctx.gi, ctx.mode
+        N, F = ctx.shape
+        gx = torch.empty((N, F), dtype=torch.float32, device=g.device)
+        _lib.check(_lib.load().ax2d_seg_reduce_bwd(_p(g.contiguous()), _p(gi.seg_ptr), gi.num_graphs, F, SEG_MODES[mode],
+                                                   _p(arg) if mode == "max" else None, _p(gx), F, _stream()),
+                   "ax2d_seg_reduce_bwd")
+        return gx, None, None
+
+
+class ChargeEqFn(torch.autograd.Function):
+    """GNN._partial_charge_calculation (gnn.py:622-658) on padded features (columns 0 and 1 change)."""
+
+    @staticmethod
+    def forward(ctx, x, total_charges, gi):
+        _need_cuda(x, total_charges)
+        out = torch.empty_like(x)
+        stats = torch.empty((gi.num_graphs, 2), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().ax2d_charge_eq_fwd(_p(x), x.stride(0), _p(gi.seg_ptr), gi.num_graphs, x.shape[1],
+                                                  _p(total_charges.contiguous()), _p(out), out.stride(0), _p(stats),
+                                                  _stream()), "ax2d_charge_eq_fwd")
+        ctx.gi = gi
+        ctx.save_for_backward(x, out, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, out, stats = ctx.saved_tensors
+        gi = ctx.gi
+        g = g.contiguous()
+        gx = torch.empty_like(x)
+        _lib.check(_lib.load().ax2d_charge_eq_bwd(_p(x), x.stride(0), _p(out), out.stride(0), _p(gi.seg_ptr),
+                                                  gi.num_graphs, x.shape[1], _p(stats), _p(g), g.stride(0), _p(gx),
+                                                  gx.stride(0), _stream()), "ax2d_charge_eq_bwd")
+        return gx, None, None
+
+
+class TetraFn(torch.autograd.Function):
+    """GNN._tetrahedral_feature_calculation_physics_inspired (gnn.py:387-462), quirk Q4."""
+
+    @staticmethod
+    def forward(ctx, x, true_width, gi):
+        idx, slot_ptr, slot_idx, M = gi.tetra
+        out = torch.empty_like(x)
+        contrib = torch.empty((4 * M, x.shape[1]), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().ax2d_tetra_fwd(_p(x), x.stride(0), x.shape[0], x.shape[1], true_width, _p(idx), M,
+                                              _p(slot_ptr), _p(slot_idx), _p(contrib), _p(out), out.stride(0),
+                                              _stream()), "ax2d_tetra_fwd")
+        ctx.gi, ctx.true_width = gi, true_width
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        idx, slot_ptr, slot_idx, M = ctx.gi.tetra
+        g = g.contiguous()
+        gx = torch.empty_like(x)
+        rows = torch.empty((4 * M, x.shape[1]), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().ax2d_tetra_bwd(_p(x), x.stride(0), x.shape[0], x.shape[1], ctx.true_width, _p(idx), M,
+                                              _p(slot_ptr), _p(slot_idx), _p(g), g.stride(0), _p(rows), _p(gx),
+                                              gx.stride(0), _stream()), "ax2d_tetra_bwd")
+        return gx, None, None
+
+
+class CisTransFn(torch.autograd.Function):
+    """GNN._cis_trans_calculation (gnn.py:465-509), quirk Q3."""
+
+    @staticmethod
+    def forward(ctx, x, gi):
+        ctx.gi = gi
+        return CisTransFn._run(x, gi, 0)
+
+    @staticmethod
+    def _run(x, gi, transpose):
+        src, tgt, sign, n = gi.cistrans
+        out = torch.empty_like(x)
+        _lib.check(_lib.load().ax2d_cistrans(_p(x), x.stride(0), x.shape[0], x.shape[1], _p(src), _p(tgt), _p(sign), n,
+                                             transpose, _p(out), out.stride(0), _stream()), "ax2d_cistrans")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return CisTransFn._run(g.contiguous(), ctx.gi, 1), None
+
+
+class WeightedLossFn(torch.autograd.Function):
+    """WeightedL1Loss / WeightedMSELoss (losses.py:14-87) forward + gradient in one launch."""
+
+    @staticmethod
+    def forward(ctx, pred, target, weights, kind):
+        _need_cuda(pred, target, weights)
+        pred, target = pred.contiguous(), target.contiguous()
+        B, T = pred.shape
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        gp = torch.empty_like(pred)
+        _lib.check(_lib.load().ax2d_weighted_loss(_p(pred), _p(target), _p(weights.contiguous()), B, T, kind, _p(loss),
+                                                  _p(gp), _stream()), "ax2d_weighted_loss")
+        ctx.save_for_backward(gp)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (gp,) = ctx.saved_tensors
+        return gp * g, None, None, None

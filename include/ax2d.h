@@ -184,7 +184,7 @@ typedef struct {
   const float* mask;  int64_t ld_mask;      /* explicit dropout mask (already scaled) or NULL */
   float        drop_p; uint64_t drop_seed;  /* hash dropout if drop_p > 0 and mask == NULL */
   const uint64_t* drop_tick;    /* optional DEVICE counter added to drop_seed (CUDA-graph friendly; ax2d_tick) */
-  ax2d_cmat    resid;           /* up to AX2D_MAX_SEG residual matrices, each full width (n_seg = count) */
+  ax2d_cmat    resid;           /* n_seg residual matrices; matrix r is added to columns [0, width[r]) (0 = all) */
   const float* dact_pre; int64_t ld_dact; int32_t dact; /* columns < dact_cols: multiply by act'(dact_pre) (and the dropout above) */
   int32_t      dact_cols;
   int32_t      accumulate;      /* c += v instead of c = v */

