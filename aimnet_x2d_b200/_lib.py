@@ -35,6 +35,7 @@ _SIGNATURES = {
     "ax2d_abi_version": (c_int, []),
     "ax2d_error_string": (C.c_char_p, [c_int]),
     "ax2d_last_error": (C.c_char_p, []),
+    "ax2d_launch_count": (C.c_uint64, []),
     "ax2d_host_csr_build": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
                                     c_void_p, c_void_p, c_void_p]),
     "ax2d_host_tile_plan": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
@@ -91,7 +92,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f"{LIB_PATH} is missing: the CUDA extension is the only implementation of the hot path. "
-            "Build it with `python -m aimnet_x2d_b200.build` (or __graft_entry__.build()).")
+            "Build it with `python aimnet_x2d_b200/build.py` (or __graft_entry__.build()).")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol

@@ -1,7 +1,7 @@
 """In-tree build of libax2d.so (sm_100a only) with plain nvcc -- no torch headers involved.
 
-    python -m aimnet_x2d_b200.build            # incremental
-    python -m aimnet_x2d_b200.build --force
+    python aimnet_x2d_b200/build.py            # incremental (run as a script: importing the package needs the .so)
+    python aimnet_x2d_b200/build.py --force
 """
 from __future__ import annotations
 

@@ -9,6 +9,7 @@
 namespace ax2d {
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // host-side tally of kernels enqueued by this library (ax2d_launch_count)
 
 #define AX2D_CHECK_ARG(cond, ...)                    \
   do {                                               \
@@ -26,7 +27,8 @@ void set_error(const char* fmt, ...);
     }                                                                      \
   } while (0)
 
-inline int launch_status(const char* what) {
+inline int launch_status(const char* what, int n_kernels = 1) {
+  count_launches(n_kernels);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));

@@ -220,7 +220,7 @@ extern "C" int ax2d_sqnorm(const float* g, int64_t n, float* norm2, int64_t* ste
   sqnorm_partial_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(g, n, static_cast<float*>(workspace));
   sqnorm_final_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(workspace), static_cast<int>(blocks), norm2);
   if (step_inc != nullptr) step_inc_kernel<<<1, 1, 0, st>>>(step_inc);
-  return launch_status("ax2d_sqnorm");
+  return launch_status("ax2d_sqnorm", step_inc != nullptr ? 3 : 2);
 }
 
 extern "C" int ax2d_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* norm2,

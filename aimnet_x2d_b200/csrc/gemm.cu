@@ -449,7 +449,7 @@ extern "C" int ax2d_colsum(const ax2d_cmat* a, int64_t M, int64_t N, float* out,
   }
   colsum_final_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, st>>>(static_cast<const float*>(workspace), n_part,
                                                                                static_cast<int>(N), out, accumulate);
-  return launch_status("ax2d_colsum");
+  return launch_status("ax2d_colsum", n_part > 0 ? 2 : 1);
 }
 
 extern "C" int ax2d_act_bwd(const float* gr, int64_t ldg, const float* pre, int64_t ldp, float* out, int64_t ldo,

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
@@ -16,9 +17,12 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static std::atomic<uint64_t> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
 }  // namespace ax2d
 
 extern "C" int ax2d_abi_version(void) { return 1; }
+extern "C" uint64_t ax2d_launch_count(void) { return ax2d::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* ax2d_last_error(void) { return ax2d::g_err; }
 

@@ -12,6 +12,8 @@ namespace ax2d {
 
 constexpr int kPoolThreads = 128;
 constexpr int kMaxHeads = 8;
+// per-CTA partial record of the backward: [heads*F] gw, [heads] gb, [1] gT, padded to whole float4s
+__host__ __device__ constexpr int pool_partial_stride(int heads, int F) { return (heads * F + heads + 1 + 3) & ~3; }
 
 struct ChunkLoader {
   uint64_t* bar;
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_bwd_kernel(
     }
   }
   // ---- per-CTA partials: [NH*F] gw, [NH] gb, [1] gT
-  float* my = partials + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(NH) * F + NH + 1);
+  float* my = partials + static_cast<size_t>(blockIdx.x) * pool_partial_stride(NH, F);
 #pragma unroll
   for (int h = 0; h < NH; ++h)
 #pragma unroll
@@ -354,9 +356,9 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_bwd_kernel(
 __global__ void attn_pool_bwd_reduce_kernel(const float* __restrict__ partials, int n_part, int F, int heads,
                                             const float* __restrict__ temperature, float* __restrict__ gw,
                                             float* __restrict__ gb, float* __restrict__ gT) {
-  const int stride = heads * F + heads + 1;
+  const int stride = pool_partial_stride(heads, F);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= stride) return;
+  if (i >= heads * F + heads + 1) return;
   float s = 0.f;
   for (int p = 0; p < n_part; ++p) s += partials[static_cast<size_t>(p) * stride + i];
   const float invT = 1.f / __ldg(temperature);
@@ -462,7 +464,7 @@ extern "C" int ax2d_attn_pool_fwd(const float* x, int64_t ldx, const int32_t* se
 
 extern "C" int64_t ax2d_attn_pool_bwd_workspace(int64_t B, int F, int heads) {
   (void)B;
-  return static_cast<int64_t>(kPoolBwdMaxGrid) * (static_cast<int64_t>(heads) * F + heads + 1) * 4;
+  return static_cast<int64_t>(kPoolBwdMaxGrid) * pool_partial_stride(heads, F) * 4;
 }
 
 template <int NH>

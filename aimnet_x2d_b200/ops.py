@@ -15,6 +15,41 @@ from . import _lib
 from ._lib import ACT_CODES, CMat, Epilogue, MAX_SEG, SEG_MODES
 
 
+class KernelTimer:
+    """CUDA-event timing of individual C-ABI launches on the launching (= torch current) stream.
+
+    ``bench.py`` installs one over the timed region to obtain the live per-launch durations that the
+    roofline fractions are computed from.  Inactive (``TIMER is None``) it costs one attribute test."""
+
+    def __init__(self):
+        self.events = {}          # name -> list of (start, stop, algorithmic_bytes, flops)
+
+    def launch(self, name, fn, nbytes=0, flops=0):
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        self.events.setdefault(name, []).append((a, b, nbytes, flops))
+
+    def summary(self):
+        """name -> dict(launches, ms_total, ms_avg, bytes_avg, flops_avg); call after a device synchronize."""
+        out = {}
+        for name, evs in self.events.items():
+            ms = [a.elapsed_time(b) for a, b, _, _ in evs]
+            out[name] = dict(launches=len(evs), ms_total=sum(ms), ms_avg=sum(ms) / len(ms),
+                             bytes_avg=sum(e[2] for e in evs) / len(evs), flops_avg=sum(e[3] for e in evs) / len(evs))
+        return out
+
+
+TIMER: Optional[KernelTimer] = None
+
+
+def launch_count() -> int:
+    """Kernels enqueued by libax2d.so in this process so far."""
+    return int(_lib.load().ax2d_launch_count())
+
+
 def pad_to(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
@@ -82,8 +117,12 @@ def gemm(a_segs, b_segs, c_segs, M: int, N: int, K: int, trans_a: bool = False, 
     if split_k > 1:
         nbytes = lib.ax2d_gemm_workspace(M, N, K, int(trans_a), split_k)
         ws = torch.empty(nbytes // 4, dtype=torch.float32, device=c_segs[0][0].device)
-    _lib.check(lib.ax2d_gemm(C.byref(a), int(trans_a), C.byref(b), int(trans_b), C.byref(c), M, N, K, C.byref(ep),
-                             split_k, _p(ws), _stream()), "ax2d_gemm")
+    call = lambda: _lib.check(lib.ax2d_gemm(C.byref(a), int(trans_a), C.byref(b), int(trans_b), C.byref(c), M, N, K,
+                                            C.byref(ep), split_k, _p(ws), _stream()), "ax2d_gemm")
+    if TIMER is None:
+        call()
+    else:
+        TIMER.launch("gemm", call, nbytes=4 * (M * K + K * N + M * N), flops=2 * M * N * K)
 
 
 def colsum(segs, M: int, N: int, out: torch.Tensor, accumulate: bool = False) -> None:
@@ -116,11 +155,21 @@ def agg(x: torch.Tensor, gi, transpose: bool = False, addend: Optional[torch.Ten
     rowptr, col = (gi.rowptr_t, gi.col_t) if transpose else (gi.rowptr, gi.col)
     tiled = (gi.tile_local and gi.collapsed and x.stride(0) == width and width % 32 == 0
              and gi.max_tile_rows * width * 4 <= 200 * 1024 and gi.n_tiles > 0)
-    _lib.check(lib.ax2d_agg(_p(x), x.stride(0), x.shape[0], _p(out), out.stride(0), rows, _p(rowptr), _p(col),
-                            _p(addend), 0 if addend is None else addend.stride(0), width,
-                            _p(gi.tile_ptr) if tiled else None, gi.n_tiles if tiled else 0,
-                            gi.max_tile_rows if tiled else 0, 0, _stream()), "ax2d_agg")
+    call = lambda: _lib.check(lib.ax2d_agg(_p(x), x.stride(0), x.shape[0], _p(out), out.stride(0), rows, _p(rowptr),
+                                           _p(col), _p(addend), 0 if addend is None else addend.stride(0), width,
+                                           _p(gi.tile_ptr) if tiled else None, gi.n_tiles if tiled else 0,
+                                           gi.max_tile_rows if tiled else 0, 0, _stream()), "ax2d_agg")
+    if TIMER is None:
+        call()
+    else:
+        TIMER.launch("agg", call, nbytes=agg_bytes(x.shape[0], rows, gi.num_edges, width, addend is not None))
     return out
+
+
+def agg_bytes(n_src: int, n_rows: int, n_edges: int, width: int, with_addend: bool = False, elem: int = 4) -> int:
+    """ALGORITHMIC HBM bytes of one aggregation launch:
+    read x once + col indices + rowptr + write the result (+ read the addend in the fused backward)."""
+    return elem * n_src * width + 4 * n_edges + 4 * (n_rows + 1) + elem * n_rows * width * (2 if with_addend else 1)
 
 
 # ----------------------------------------------------------------------------------------------- dense helpers

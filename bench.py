@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- train molecules/s of the AIMNet-X2D hot path on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
+
+A "step" is one optimisation step of the reference's training loop (training/trainer.py:116-170:
+zero_grad -> GNN.forward -> WeightedL1Loss -> backward -> gradient all-reduce -> clip_grad_norm_(1.0) -> Adam)
+over one batch of synthetic molecules.  Default workload = BASELINE.json configs[1] ("c2"): QM9-shaped graphs
+(<= 29 atoms), 2048 graphs per GPU, hidden 512, 3 hops, 3 message-passing layers, 4-head attention pooling,
+12 targets, fp32, dropout active (p = 0.05, the reference defaults).  Weak scaling: every rank has its own
+ring of 2048-graph batches.
+
+value : whole-job molecules/s, batches resident in HBM, CUDA events, max over ranks.
+e2e   : same metric through the public call (TrainStep.__call__) with pinned HOST batches: H2D copies of the
+        batch and the D2H loss read are inside the timed region every step.
+roofline     : the aggregation kernel (ax2d_agg, the kernel BASELINE's metric names): algorithmic bytes per
+               launch / live CUDA-event duration inside the timed region, against MEASURED_PEAKS.json hbm_gbs.
+roofline_dense: same for the dense projections (ax2d_gemm), flops against the fp32 FFMA peak (SIMT fp32 path).
+cpu_baseline : the oracle port of the reference step on this box's host cores (bounded sample).
+
+--impl reference times that CPU path alone (rank 0 only under torchrun).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (kind, graphs per GPU, hops, layers, hidden, stereo, charges, description)
+    "c2": dict(kind="qm9", graphs=2048, hops=3, layers=3, hidden=512, stereo=False, charges=False,
+               desc="BASELINE configs[1]: synthetic QM9-shaped graphs (<=29 atoms), 2048-graph batches, 3-hop x 3 layers + "
+                    "attention pooling, fp32"),
+    "c3": dict(kind="drug", graphs=1024, hops=3, layers=3, hidden=512, stereo=True, charges=True,
+               desc="BASELINE configs[2]: synthetic drug-like graphs (20-70 heavy atoms), stereo + charges, 1024/GPU, fp32"),
+}
+T_TARGETS = 12
+RING = 4            # distinct batches per rank, rotated every step (per-step working set >> 126 MB L2)
+
+
+def env_rank():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [t.strip() for t in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = max(int(s[1]) for s in self.samples if s[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def make_batches(wl, rank, n):
+    from aimnet_x2d_b200 import synthetic as S
+    cfg_id = {"c2": 2, "c3": 3}[wl["name"]]
+    return [S.make_batch(1234 + cfg_id * 1000 + rank * 97 + i, wl["graphs"], wl["hops"], wl["kind"], T_TARGETS,
+                         stereo=wl["stereo"]) for i in range(n)]
+
+
+def model_cfg(wl):
+    return dict(hidden_dim=wl["hidden"], num_shells=wl["hops"], num_message_passing_layers=wl["layers"],
+                use_partial_charges=wl["charges"], use_stereochemistry=wl["stereo"])
+
+
+def build_model(wl, device):
+    import aimnet_x2d_b200 as ax
+    from aimnet_x2d_b200.synthetic import FEATURE_SIZES
+    torch.manual_seed(0)
+    model = ax.GNN(FEATURE_SIZES, wl["hidden"], T_TARGETS, num_shells=wl["hops"], num_message_passing_layers=wl["layers"],
+                   task_type="multitask", use_partial_charges=wl["charges"], use_stereochemistry=wl["stereo"])
+    model.init_weights()                                   # trainer.py:206-209
+    return model.to(device).train()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_fn(wl, batch):
+    """One reference training step on the CPU through the oracle port (test infrastructure used as the baseline
+    checker leg only): returns a closure that runs zero_grad/forward/L1/backward/clip/Adam once."""
+    from oracle import model_port as MP
+    from oracle.fixtures import det_state
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import gnn_shapes
+    cfg = model_cfg(wl)
+    P = det_state(gnn_shapes(cfg, T_TARGETS), 0)
+    keys = list(P)
+    for v in P.values():
+        v.requires_grad_(True)
+    state = dict(m=[torch.zeros_like(P[k]) for k in keys], v=[torch.zeros_like(P[k]) for k in keys])
+    ob = dict(atom_features_map=batch.atom_features_map, multi_hop_edge_indices=batch.multi_hop_edge_indices,
+              batch_indices=batch.batch_indices, total_charges=batch.total_charges,
+              final_tetrahedral_chiral_tensor=batch.final_tetrahedral_chiral_tensor,
+              final_cis_tensor=batch.final_cis_tensor, final_trans_tensor=batch.final_trans_tensor)
+    w = torch.ones(T_TARGETS)
+    N = int(batch.batch_indices.shape[0])
+    D = int(0.3 * wl["hidden"])
+    step_no = [0]
+
+    def masks():
+        # dropout is part of the reference step (p = 0.05 in the conv MLPs and the FFN); Bernoulli masks drawn per
+        # step like nn.Dropout does
+        keep = 0.95
+        conv = [[(torch.rand(N, D) < keep).float() / keep for _ in range(2)] for _ in range(wl["layers"])]
+        ffn = [(torch.rand(wl["graphs_sample"], wl["hidden"]) < keep).float() / keep for _ in range(3)]
+        return dict(conv=conv, ffn=ffn)
+
+    def step():
+        for v in P.values():
+            v.grad = None
+        out, _, _, _ = MP.gnn_forward(P, cfg, ob, dropout=masks())
+        loss = MP.weighted_l1(out, batch.targets, w)
+        loss.backward()
+        ks = [k for k in keys if P[k].grad is not None]
+        step_no[0] += 1
+        with torch.no_grad():
+            MP.clip_and_adam([P[k] for k in ks], [P[k].grad for k in ks],
+                             dict(m=[state["m"][keys.index(k)] for k in ks], v=[state["v"][keys.index(k)] for k in ks]),
+                             step=step_no[0])
+        return float(loss.detach())
+    return step
+
+
+def run_cpu(wl, steps, warmup, budget_s):
+    """Time the CPU path on a bounded sample: the sample size (molecules per step) is chosen from a probe step so
+    that warmup + steps fit in ``budget_s`` seconds; capped at the workload's own batch."""
+    from aimnet_x2d_b200 import synthetic as S
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wl = dict(wl)
+    probe_n = min(128, wl["graphs"])
+    wl["graphs_sample"] = probe_n
+    b = S.make_batch(99, probe_n, wl["hops"], wl["kind"], T_TARGETS, stereo=wl["stereo"])
+    fn = cpu_step_fn(wl, b)
+    fn()
+    t0 = time.perf_counter(); fn(); t_probe = time.perf_counter() - t0
+    per_mol = t_probe / probe_n
+    n = int(min(wl["graphs"], max(probe_n, budget_s / max(steps + warmup, 1) / per_mol)))
+    n = max(64, (n // 64) * 64)
+    wl["graphs_sample"] = n
+    b = S.make_batch(1234 + 2000, n, wl["hops"], wl["kind"], T_TARGETS, stereo=wl["stereo"])
+    fn = cpu_step_fn(wl, b)
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    return dict(value=n / t, unit="molecules/s", cores=cores, kind="port",
+                sample=f"{n}-molecule batch of the same workload (full batch {wl['graphs']}), {steps} timed steps after "
+                       f"{warmup} warm-up, mean {t * 1e3:.1f} ms/step, torch CPU threads={cores}; oracle/model_port.py "
+                       f"restatement of the reference step"), t * 1e3, n
+
+
+def reference_arm(args, wl):
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    base, ms, n = run_cpu(wl, args.steps, max(args.warmup, 1), budget_s=150.0)
+    line = {"impl": "reference", "metric": "train molecules/sec", "value": base["value"], "unit": "molecules/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "sample_molecules_per_step": n},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def ours_arm(args, wl):
+    import torch.distributed as dist
+
+    import aimnet_x2d_b200 as ax
+    from aimnet_x2d_b200 import ops
+    from aimnet_x2d_b200.trainer import TrainStep
+    rank, local_rank, world = env_rank()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    host = [b.pin_memory() for b in make_batches(wl, rank, RING)]
+    dev_batches = [b.to(device) for b in host]
+    model = build_model(wl, device)
+    weights = torch.ones(T_TARGETS)
+    crit = ax.WeightedL1Loss(weights).to(device)
+    opt = ax.FlatAdam(model.parameters(), lr=2.5e-4, max_grad_norm=1.0)
+    if world > 1:                                          # DDP broadcasts rank 0's parameters at wrap time
+        dist.broadcast(opt.flat_param, src=0)
+    stepper = TrainStep(model, crit, opt, device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident: `value`
+    for i in range(args.warmup):
+        stepper.device_step(dev_batches[i % RING])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    timer = ops.KernelTimer()
+    ops.TIMER = timer
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = stepper.device_step(dev_batches[i % RING])
+    e1.record()
+    barrier()
+    ops.TIMER = None
+    launches = ops.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag.set()
+    sampler.join()
+    final_loss = float(loss)
+
+    # ---- end to end through the public call: host batches, H2D inside, loss read back every step
+    for i in range(max(args.warmup, 1)):
+        stepper(host[i % RING])
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        stepper(host[i % RING])
+    f1.record()
+    barrier()
+    ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    mols = wl["graphs"] * world * args.steps
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ks = timer.summary()
+        step_ms = ms / args.steps
+        roof = roof_dense = None
+        if "agg" in ks:
+            a = ks["agg"]
+            ach = a["bytes_avg"] / (a["ms_avg"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "ax2d_agg (agg_kernel: CSR gather-reduce, fwd + bwd launches)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "launches_per_step": a["launches"] / args.steps,
+                    "avg_launch_us": a["ms_avg"] * 1e3, "algorithmic_bytes_per_launch": a["bytes_avg"],
+                    "share_of_step": a["ms_total"] / ms}
+        if "gemm" in ks:
+            g = ks["gemm"]
+            tf = g["flops_avg"] / (g["ms_avg"] * 1e-3) / 1e12
+            fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FFMA lanes x 2 flop x max clock
+            roof_dense = {"bound": "fp32-ffma", "kernel": "ax2d_gemm (gemm_kernel: exact-fp32 SIMT, fused epilogues)",
+                          "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
+                          "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (no measured fp32 peak on file)",
+                          "launches_per_step": g["launches"] / args.steps, "avg_launch_us": g["ms_avg"] * 1e3,
+                          "share_of_step": g["ms_total"] / ms}
+        h2d = host[0].nbytes()
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _, _ = run_cpu(wl, 2, 1, budget_s=20.0)
+        gi = host[0].graph_index
+        line = {"metric": "train molecules/sec", "value": mols / (ms * 1e-3), "unit": "molecules/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["desc"], "graphs_per_gpu": wl["graphs"], "global_batch": wl["graphs"] * world,
+                           "atoms_per_batch": gi.num_atoms, "edges_per_batch": gi.num_edges, "targets": T_TARGETS,
+                           "dropout": 0.05, "parallelism": f"dp{world}",
+                           "l2": f"ring of {RING} distinct batches per rank; per-step activations + saved tensors "
+                                 f"(> 1 GB) exceed the 126 MB L2, no explicit flush"},
+                "e2e": {"value": mols / (ms_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "roofline": roof, "roofline_dense": roof_dense, "cpu_baseline": cpu,
+                "clocks": sampler.summary(), "final_loss": final_loss}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload], name=args.workload)
+    if args.impl == "reference":
+        reference_arm(args, wl)
+    else:
+        ours_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,8 @@ enum { AX2D_SEG_SUM = 0, AX2D_SEG_MEAN = 1, AX2D_SEG_MAX = 2 };
 int         ax2d_abi_version(void);
 const char* ax2d_error_string(int code);
 const char* ax2d_last_error(void);
+/* number of CUDA kernels this library has enqueued in this process so far (bench.py's gpu_launches). */
+uint64_t    ax2d_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Collation-time integer work (HOST).  Replaces the Python loops of
