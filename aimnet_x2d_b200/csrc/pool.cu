@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_bwd_kernel(
   float* coef = dzs + static_cast<size_t>(NH) * CH;               // [CH]  sum_h a / H
   float* ds = coef + CH;                                          // [CH]
   float* sdot = ds + CH;                                          // [NH]
+  float* zmax = sdot + NH;                                        // [NH]  per-(head, molecule) max score
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int F4 = F >> 2;
@@ -248,14 +249,19 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_bwd_kernel(
     __syncthreads();
     // ---- sdot_h = sum_i a[h,i] da[h,i]
     for (int h = warp; h < NH; h += kPoolThreads / 32) {
-      float s = 0.f;
+      float s = 0.f, zm = -INFINITY;
       for (int i = lane; i < n; i += 32) {
         float da = single ? ds[i] : gx[static_cast<int64_t>(n0 + i) * ldgx];
         if (g_attn != nullptr) da += g_attn[static_cast<int64_t>(h) * N + n0 + i];
         s += attn[static_cast<int64_t>(h) * N + n0 + i] * da;
+        zm = fmaxf(zm, zbuf[static_cast<int64_t>(h) * N + n0 + i]);
       }
       s = warp_sum(s);
-      if (lane == 0) sdot[h] = s;
+      zm = warp_max(zm);
+      if (lane == 0) {
+        sdot[h] = s;
+        zmax[h] = zm;
+      }
     }
     __syncthreads();
     // ---- pass B: dz, gx, parameter-gradient partials
@@ -283,7 +289,10 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_bwd_kernel(
           dzs[h * CH + i] = dz;
           asum += a;
           gb_loc[h] += dz;
-          gT_loc += dz * zbuf[o];
+          // sum_i dz[h,i] == 0 per (head, molecule), so z may be shifted by its maximum: the terms shrink from
+          // |dz| * |z| to |dz| * (max - z) and the rounding noise of the cancelling sum is no longer multiplied
+          // by the common offset of the scores
+          gT_loc += dz * (zbuf[o] - zmax[h]);
         }
         coef[i] = asum * inv_h;
       }
@@ -370,7 +379,7 @@ __global__ void attn_pool_bwd_reduce_kernel(const float* __restrict__ partials, 
 static int pool_chunk_rows(int F, int heads, int max_rows_hint, bool bwd) {
   // shared-memory budget ~96 KB per CTA so that two CTAs fit on an SM
   const int budget = 96 * 1024;
-  const int fixed = bwd ? (F * 4 + heads * 4 + 64) : (heads * F * 4 + 64);
+  const int fixed = bwd ? (F * 4 + heads * 8 + 64) : (heads * F * 4 + 64);
   const int per_row = F * 4 + heads * 4 + 8;
   int ch = (budget - fixed) / per_row;
   if (ch < 1) ch = 1;
@@ -473,7 +482,7 @@ static int launch_pool_bwd(const float* x, const int32_t* seg_ptr, int64_t B, in
                            const float* g_attn, float* gx, int64_t ldgx, float* gw, float* gb, float* gT, void* ws,
                            int max_rows_hint, cudaStream_t st) {
   const int CH = pool_chunk_rows(F, NH, max_rows_hint, true);
-  const size_t smem = (static_cast<size_t>(CH) * F + F + static_cast<size_t>(NH) * CH + 2 * CH + NH) * 4;
+  const size_t smem = (static_cast<size_t>(CH) * F + F + static_cast<size_t>(NH) * CH + 2 * CH + 2 * NH) * 4;
   auto kern = attn_pool_bwd_kernel<NH>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   const int grid = B < kPoolBwdMaxGrid ? static_cast<int>(B) : kPoolBwdMaxGrid;
