@@ -69,6 +69,10 @@ _SIGNATURES = {
     "ax2d_gemm_workspace": (c_int64, [c_int64, c_int64, c_int64, c_int, c_int]),
     "ax2d_gemm": (c_int, [C.POINTER(CMat), c_int, C.POINTER(CMat), c_int, C.POINTER(CMat), c_int64, c_int64, c_int64,
                           C.POINTER(Epilogue), c_int, c_void_p, c_void_p]),
+    "ax2d_split_tf32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "ax2d_gemm_tc_supported": (c_int, [C.POINTER(CMat), c_int64, c_int64, c_int64]),
+    "ax2d_gemm_tc": (c_int, [C.POINTER(CMat), c_void_p, c_void_p, c_int64, C.POINTER(CMat), c_int64, c_int64, c_int64,
+                             C.POINTER(Epilogue), c_void_p]),
     "ax2d_act_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     "ax2d_tick": (c_int, [c_void_p, c_void_p]),
     "ax2d_colsum_workspace": (c_int64, [c_int64, c_int64]),

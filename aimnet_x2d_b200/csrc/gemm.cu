@@ -7,48 +7,20 @@
 //
 // Tiling: CTA 128x64, BK = 16, 256 threads, 8x4 register tile per thread, shared-memory double buffer
 // with register prefetch of the next k-tile.
-#include "common.cuh"
+#include "gemm_common.cuh"
 
 namespace ax2d {
 
 constexpr int BM = 128, BN = 64, BK = 16, GEMM_THREADS = 256;
 constexpr int AS_LD = BM + 4, BS_LD = BN + 4;
 
-struct SegView {          // column-segmented read-only matrix
-  const float* ptr[AX2D_MAX_SEG];
-  int64_t ld[AX2D_MAX_SEG];
-  int start[AX2D_MAX_SEG + 1];
-  int n_seg;
-};
-struct SegOut {
-  float* ptr[AX2D_MAX_SEG];
-  int64_t ld[AX2D_MAX_SEG];
-  int start[AX2D_MAX_SEG + 1];
-  int n_seg;
-};
-
 struct GemmArgs {
   SegView a, b;
-  SegOut c, pre;
+  EpiArgs e;
   int64_t M, N, K;
   int64_t k_begin_stride;     // split-k: k range per blockIdx.z (multiple of BK); 0 if no split
   float* ws;                  // split-k partial output [split][M][N]
-  const float* bias;
-  int act, act_cols;
-  const float* mask; int64_t ld_mask;
-  float drop_p; uint64_t drop_seed; const uint64_t* drop_tick;
-  const float* resid[AX2D_MAX_SEG]; int64_t ld_resid[AX2D_MAX_SEG]; int resid_cols[AX2D_MAX_SEG]; int n_resid;
-  const float* dact_pre; int64_t ld_dact; int dact; int dact_cols;
-  int accumulate;
 };
-
-__device__ __forceinline__ int find_seg(const int* start, int n_seg, int col) {
-  int s = 0;
-#pragma unroll
-  for (int i = 1; i < AX2D_MAX_SEG; ++i)
-    if (i < n_seg && col >= start[i]) s = i;
-  return s;
-}
 
 // Loads one float4 of a logical operand element block.
 //  REDUCE_COLS: operand is [rows = m or n][cols = k]  (k contiguous);  float4 spans k..k+3 of row `r`.
@@ -62,7 +34,7 @@ __device__ __forceinline__ float4 load_op(const SegView& v, int64_t r, int64_t r
 }
 
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constant__ GemmArgs g) {
   __shared__ __align__(16) float As[2][BK][AS_LD];
   __shared__ __align__(16) float Bs[2][BK][BS_LD];
   const int tid = threadIdx.x;
@@ -166,60 +138,30 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const GemmArgs g) {
     }
     return;
   }
-  const int cs = find_seg(g.c.start, g.c.n_seg, n);
-  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (g.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-  const bool dropping = g.mask != nullptr || g.drop_p > 0.f;
-  const float inv_keep = g.drop_p > 0.f ? 1.f / (1.f - g.drop_p) : 1.f;
-  const uint64_t seed = g.drop_seed + (g.drop_tick != nullptr ? __ldg(reinterpret_cast<const unsigned long long*>(g.drop_tick)) * 0xD1B54A32D192ED03ull : 0ull);
+  const EpiCtx cx = epi_ctx(g.e);
+  const EpiCol col = epi_col(g.e, n);
+  if constexpr (TA) {      // weight gradients: plain store / accumulate only (checked on the host)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int64_t m = m0 + ty * 4 + (i & 3) + 64 * (i >> 2);
-    if (m >= g.M) continue;
-    float v[4] = {acc[i][0] + bias4.x, acc[i][1] + bias4.y, acc[i][2] + bias4.z, acc[i][3] + bias4.w};
-    if (g.pre.n_seg > 0) {
-      const int ps = find_seg(g.pre.start, g.pre.n_seg, n);
-      if (g.pre.ptr[ps] != nullptr)
-        *reinterpret_cast<float4*>(g.pre.ptr[ps] + m * g.pre.ld[ps] + (n - g.pre.start[ps])) = make_float4(v[0], v[1], v[2], v[3]);
+    for (int i = 0; i < 8; ++i) {
+      const int64_t m = m0 + ty * 4 + (i & 3) + 64 * (i >> 2);
+      if (m >= g.M) continue;
+      EpiOperands o;
+      epi_prefetch(g.e, col, m, o);
+      epi_finish<AX2D_ACT_NONE, AX2D_ACT_NONE, false>(g.e, cx, col, m, o, acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
-    float drop[4] = {1.f, 1.f, 1.f, 1.f};
-    if (dropping) {
-      if (g.mask != nullptr) {
-        const float4 mk = __ldg(reinterpret_cast<const float4*>(g.mask + m * g.ld_mask + n));
-        drop[0] = mk.x; drop[1] = mk.y; drop[2] = mk.z; drop[3] = mk.w;
-      } else {
+  } else {
+    const bool dropping = cx.dropping;
+    AX2D_EPI_DISPATCH(g.e.act, g.e.dact, dropping, {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          drop[j] = drop_scale(seed, static_cast<uint64_t>(m) * static_cast<uint64_t>(g.N) + (n + j), g.drop_p, inv_keep);
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + ty * 4 + (i & 3) + 64 * (i >> 2);
+        if (m < g.M) {
+          EpiOperands o;
+          epi_prefetch(g.e, col, m, o);
+          epi_finish<ACT, DACT, DROP>(g.e, cx, col, m, o, acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
       }
-    }
-    if (g.act != AX2D_ACT_NONE) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (n + j < g.act_cols) v[j] = act_fwd(g.act, v[j]);
-    }
-    if (dropping && g.dact == AX2D_ACT_NONE) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] *= drop[j];
-    }
-    for (int r = 0; r < g.n_resid; ++r) {
-      if (n >= g.resid_cols[r]) continue;
-      const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid[r] + m * g.ld_resid[r] + n));
-      v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
-    }
-    if (g.dact != AX2D_ACT_NONE && n < g.dact_cols) {
-      const float4 pv = __ldg(reinterpret_cast<const float4*>(g.dact_pre + m * g.ld_dact + n));
-      v[0] *= act_bwd(g.dact, pv.x) * drop[0];
-      v[1] *= act_bwd(g.dact, pv.y) * drop[1];
-      v[2] *= act_bwd(g.dact, pv.z) * drop[2];
-      v[3] *= act_bwd(g.dact, pv.w) * drop[3];
-    }
-    float4* dst = reinterpret_cast<float4*>(g.c.ptr[cs] + m * g.c.ld[cs] + (n - g.c.start[cs]));
-    if (g.accumulate) {
-      const float4 o = *dst;
-      v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
-    }
-    *dst = make_float4(v[0], v[1], v[2], v[3]);
+    });
   }
 }
 
@@ -244,21 +186,38 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   *dst = s;
 }
 
-// column sums, two passes with a fixed order
-constexpr int kColsumRows = 512;
-__global__ void __launch_bounds__(128) colsum_partial_kernel(SegView a, int64_t M, int N4, float* __restrict__ partial) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N4) return;
+// column sums, two passes with a fixed order.  Pass 1: a CTA covers 128 columns x kColsumRows rows; a warp reads
+// 512 contiguous bytes of one row (lane = float4 column), the 8 warps take rows r, r+8, ...; their partial sums
+// are combined through shared memory in warp order.
+constexpr int kColsumRows = 256;
+__global__ void __launch_bounds__(256) colsum_partial_kernel(SegView a, int64_t M, int N4, float* __restrict__ partial) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * kColsumRows;
   const int64_t r1 = r0 + kColsumRows < M ? r0 + kColsumRows : M;
-  const int s = find_seg(a.start, a.n_seg, c * 4);
-  const float* base = a.ptr[s] + (c * 4 - a.start[s]);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t r = r0; r < r1; ++r) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(base + r * a.ld[s]));
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  if (c < N4) {
+    const int s = find_seg(a.start, a.n_seg, c * 4);
+    const float* base = a.ptr[s] + (c * 4 - a.start[s]);
+    const int64_t ld = a.ld[s];
+#pragma unroll 4
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + r * ld));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
   }
-  reinterpret_cast<float4*>(partial + static_cast<int64_t>(blockIdx.y) * N4 * 4)[c] = acc;
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < N4) {
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 v = red[w][lane];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    reinterpret_cast<float4*>(partial + static_cast<int64_t>(blockIdx.y) * N4 * 4)[c] = t;
+  }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int n_part, int N, float* __restrict__ out,
                                     int accumulate) {
@@ -283,7 +242,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
 }
 __global__ void tick_kernel(unsigned long long* c) { c[0] += 1ull; }
 
-static int to_view(const ax2d_cmat* m, SegView* v, int64_t total, const char* what) {
+int to_view(const ax2d_cmat* m, SegView* v, int64_t total, const char* what) {
   int acc = 0;
   if (m->n_seg < 1 || m->n_seg > AX2D_MAX_SEG) {
     set_error("ax2d_gemm: %s has %d segments", what, m->n_seg);
@@ -311,7 +270,7 @@ static int to_view(const ax2d_cmat* m, SegView* v, int64_t total, const char* wh
   }
   return AX2D_OK;
 }
-static int to_out(const ax2d_mat* m, SegOut* v, int64_t total, const char* what, bool allow_null) {
+int to_out(const ax2d_mat* m, SegOut* v, int64_t total, const char* what, bool allow_null) {
   int acc = 0;
   if (m->n_seg < 1 || m->n_seg > AX2D_MAX_SEG) {
     set_error("ax2d_gemm: %s has %d segments", what, m->n_seg);
@@ -344,6 +303,47 @@ static int to_out(const ax2d_mat* m, SegOut* v, int64_t total, const char* what,
   return AX2D_OK;
 }
 
+int fill_epilogue(const ax2d_epilogue* ep, int64_t M, int64_t N, EpiArgs* e) {
+  // e->c has been set by the caller; everything else starts from zero
+  SegOut keep = e->c;
+  memset(e, 0, sizeof(*e));
+  e->c = keep;
+  e->M = M;
+  e->N = N;
+  e->dact_cols = static_cast<int>(N);
+  e->act_cols = static_cast<int>(N);
+  if (ep == nullptr) return AX2D_OK;
+  int rc;
+  e->bias = ep->bias;
+  if (ep->pre.n_seg > 0 && (rc = to_out(&ep->pre, &e->pre, N, "pre", true)) != AX2D_OK) return rc;
+  e->act = ep->act; e->act_cols = ep->act_cols;
+  e->mask = ep->mask; e->ld_mask = ep->ld_mask;
+  e->drop_p = ep->drop_p; e->drop_seed = ep->drop_seed; e->drop_tick = ep->drop_tick;
+  AX2D_CHECK_ARG(ep->resid.n_seg >= 0 && ep->resid.n_seg <= AX2D_MAX_SEG, "ax2d_gemm: too many residuals");
+  e->n_resid = ep->resid.n_seg;
+  for (int r = 0; r < e->n_resid; ++r) {
+    AX2D_CHECK_ALIGN(ep->resid.ptr[r]);
+    AX2D_CHECK_ARG(ep->resid.ld[r] % 4 == 0, "ax2d_gemm: residual ld %% 4");
+    e->resid[r] = ep->resid.ptr[r];
+    e->ld_resid[r] = ep->resid.ld[r];
+    e->resid_cols[r] = ep->resid.width[r] > 0 ? ep->resid.width[r] : static_cast<int>(N);
+    AX2D_CHECK_ARG(e->resid_cols[r] % 4 == 0, "ax2d_gemm: residual width %% 4");
+  }
+  e->dact_pre = ep->dact_pre; e->ld_dact = ep->ld_dact; e->dact = ep->dact_pre != nullptr ? ep->dact : AX2D_ACT_NONE;
+  e->dact_cols = ep->dact_cols > 0 ? ep->dact_cols : static_cast<int>(N);
+  e->accumulate = ep->accumulate;
+  AX2D_CHECK_ALIGN(ep->bias);
+  AX2D_CHECK_ALIGN(ep->mask);
+  AX2D_CHECK_ALIGN(ep->dact_pre);
+  AX2D_CHECK_ARG(ep->drop_p >= 0.f && ep->drop_p < 1.f, "ax2d_gemm: dropout p=%f", ep->drop_p);
+  AX2D_CHECK_ARG(ep->mask == nullptr || ep->ld_mask % 4 == 0, "ax2d_gemm: mask ld %% 4");
+  AX2D_CHECK_ARG(e->act == AX2D_ACT_NONE || e->dact == AX2D_ACT_NONE, "ax2d_gemm: act and dact cannot be combined");
+  AX2D_CHECK_ARG(e->act >= AX2D_ACT_NONE && e->act <= AX2D_ACT_SILU && e->dact >= AX2D_ACT_NONE && e->dact <= AX2D_ACT_SILU,
+                 "ax2d_gemm: unknown activation code");
+  AX2D_CHECK_ARG(e->act_cols % 4 == 0 && e->dact_cols % 4 == 0, "ax2d_gemm: act_cols / dact_cols must be multiples of 4");
+  return AX2D_OK;
+}
+
 }  // namespace ax2d
 
 using namespace ax2d;
@@ -367,7 +367,7 @@ extern "C" int ax2d_gemm(const ax2d_cmat* a, int trans_a, const ax2d_cmat* b, in
   // A: segments run along K (trans_a == 0) or along M (trans_a == 1)
   if ((rc = to_view(a, &g.a, trans_a ? M : K, "A")) != AX2D_OK) return rc;
   if ((rc = to_view(b, &g.b, trans_b ? K : N, "B")) != AX2D_OK) return rc;
-  if ((rc = to_out(c, &g.c, N, "C", false)) != AX2D_OK) return rc;
+  if ((rc = to_out(c, &g.e.c, N, "C", false)) != AX2D_OK) return rc;
   if (!trans_a && g.a.n_seg > 1)
     for (int s = 0; s < g.a.n_seg; ++s)
       AX2D_CHECK_ARG(a->width[s] % BK == 0, "ax2d_gemm: K-segments of A must be multiples of %d", BK);
@@ -378,30 +378,7 @@ extern "C" int ax2d_gemm(const ax2d_cmat* a, int trans_a, const ax2d_cmat* b, in
   AX2D_CHECK_ARG(K % 4 == 0 || (trans_a && !trans_b), "ax2d_gemm: K must be a multiple of 4 for k-contiguous operands");
   g.M = M; g.N = N; g.K = K;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (ep != nullptr) {
-    g.bias = ep->bias;
-    if (ep->pre.n_seg > 0 && (rc = to_out(&ep->pre, &g.pre, N, "pre", true)) != AX2D_OK) return rc;
-    g.act = ep->act; g.act_cols = ep->act_cols;
-    g.mask = ep->mask; g.ld_mask = ep->ld_mask;
-    g.drop_p = ep->drop_p; g.drop_seed = ep->drop_seed; g.drop_tick = ep->drop_tick;
-    AX2D_CHECK_ARG(ep->resid.n_seg >= 0 && ep->resid.n_seg <= AX2D_MAX_SEG, "ax2d_gemm: too many residuals");
-    g.n_resid = ep->resid.n_seg;
-    for (int r = 0; r < g.n_resid; ++r) {
-      AX2D_CHECK_ALIGN(ep->resid.ptr[r]);
-      AX2D_CHECK_ARG(ep->resid.ld[r] % 4 == 0, "ax2d_gemm: residual ld %% 4");
-      g.resid[r] = ep->resid.ptr[r];
-      g.ld_resid[r] = ep->resid.ld[r];
-      g.resid_cols[r] = ep->resid.width[r] > 0 ? ep->resid.width[r] : static_cast<int>(N);
-      AX2D_CHECK_ARG(g.resid_cols[r] % 4 == 0, "ax2d_gemm: residual width %% 4");
-    }
-    g.dact_pre = ep->dact_pre; g.ld_dact = ep->ld_dact; g.dact = ep->dact_pre != nullptr ? ep->dact : AX2D_ACT_NONE;
-    g.dact_cols = ep->dact_cols > 0 ? ep->dact_cols : static_cast<int>(N);
-    g.accumulate = ep->accumulate;
-    AX2D_CHECK_ALIGN(ep->bias);
-    AX2D_CHECK_ALIGN(ep->mask);
-    AX2D_CHECK_ALIGN(ep->dact_pre);
-    AX2D_CHECK_ARG(ep->drop_p >= 0.f && ep->drop_p < 1.f, "ax2d_gemm: dropout p=%f", ep->drop_p);
-  }
+  if ((rc = fill_epilogue(ep, M, N, &g.e)) != AX2D_OK) return rc;
   dim3 grid(static_cast<unsigned>((N + BN - 1) / BN), static_cast<unsigned>((M + BM - 1) / BM), 1);
   if (split_k > 1) {
     AX2D_CHECK_ARG(workspace != nullptr, "ax2d_gemm: split_k needs a workspace");
@@ -416,6 +393,9 @@ extern "C" int ax2d_gemm(const ax2d_cmat* a, int trans_a, const ax2d_cmat* b, in
     g.ws = static_cast<float*>(workspace);
     grid.z = static_cast<unsigned>((K + per - 1) / per);
   }
+  AX2D_CHECK_ARG(!trans_a || (g.e.act == AX2D_ACT_NONE && g.e.dact == AX2D_ACT_NONE && g.e.mask == nullptr &&
+                              g.e.drop_p == 0.f),
+                 "ax2d_gemm: trans_a (weight-gradient) products support only bias / residual / accumulate epilogues");
   if (trans_a && trans_b) gemm_kernel<true, true><<<grid, GEMM_THREADS, 0, st>>>(g);
   else if (trans_a) gemm_kernel<true, false><<<grid, GEMM_THREADS, 0, st>>>(g);
   else if (trans_b) gemm_kernel<false, true><<<grid, GEMM_THREADS, 0, st>>>(g);
@@ -425,7 +405,7 @@ extern "C" int ax2d_gemm(const ax2d_cmat* a, int trans_a, const ax2d_cmat* b, in
   if (split_k > 1) {
     const int64_t total = M * (N / 4);
     splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-        g.ws, static_cast<int>(grid.z), M, N, g.c, g.accumulate);
+        g.ws, static_cast<int>(grid.z), M, N, g.e.c, g.e.accumulate);
     rc = launch_status("ax2d_gemm(split-k reduce)");
   }
   return rc;
@@ -444,8 +424,8 @@ extern "C" int ax2d_colsum(const ax2d_cmat* a, int64_t M, int64_t N, float* out,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int n_part = static_cast<int>((M + kColsumRows - 1) / kColsumRows);
   if (n_part > 0) {
-    dim3 grid(static_cast<unsigned>((N / 4 + 127) / 128), static_cast<unsigned>(n_part));
-    colsum_partial_kernel<<<grid, 128, 0, st>>>(v, M, static_cast<int>(N / 4), static_cast<float*>(workspace));
+    dim3 grid(static_cast<unsigned>((N / 4 + 31) / 32), static_cast<unsigned>(n_part));
+    colsum_partial_kernel<<<grid, 256, 0, st>>>(v, M, static_cast<int>(N / 4), static_cast<float*>(workspace));
   }
   colsum_final_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, st>>>(static_cast<const float*>(workspace), n_part,
                                                                                static_cast<int>(N), out, accumulate);

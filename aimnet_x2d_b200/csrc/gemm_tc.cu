@@ -1,0 +1,446 @@
+// Dense projections on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), fp32-faithful.
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )       A: activations (column-segmented, K-major, fp32)
+//                                                 B: weights, K-major, pre-split into (hi, lo) fp32 arrays
+//
+// The fp32 configuration must match the reference within 1e-5 (BASELINE.json), which rules out plain TF32
+// (2^-11 operand rounding).  Every operand is therefore split into two TF32-representable terms,
+//   a = a_hi + a_lo,  a_hi = a rounded to 10 explicit mantissa bits,  a_lo = a - a_hi (exact in fp32),
+// and the product is accumulated in fp32 TMEM as  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (the dropped a_lo*b_lo term
+// is <= 2^-22 relative): three kind::tf32 MMAs per k-step ("3xTF32").
+//
+// One CTA computes a 128 x BN output tile (BN <= 256, all of N when it fits):
+//   warp 0      : TMA producer -- per k-block (32 fp32 = one 128-byte swizzle row) one tensor-map load of the raw
+//                 A tile [128 x 32] and of B_hi / B_lo [BN x 32] into a ring of shared-memory stages (SWIZZLE_128B),
+//                 completion on an mbarrier (complete_tx).
+//   warps 2..5  : splitters -- rewrite the raw A tile in place as a_hi and emit a_lo into a second buffer at the
+//                 SAME byte offsets (the split is element-wise, so the swizzled layout is preserved for free), then
+//                 fence.proxy.async + mbarrier arrive.  After the main loop the same warps run the epilogue.
+//   warp 1      : one thread issues the tcgen05.mma instructions (A and B from shared-memory descriptors, the
+//                 accumulator in TMEM), tcgen05.commit releases each stage back to the producer and finally
+//                 signals the epilogue.  The warp also owns the TMEM allocation.
+//   epilogue    : tcgen05.ld (32 lanes x 32 columns per warp) -> shared-memory transpose -> the fused epilogue of
+//                 gemm_common.cuh with row-contiguous 128-bit global accesses (bias, pre-activation copy,
+//                 activation, counter-based dropout, residuals, activation backward, segmented outputs).
+#include <cuda.h>
+
+#include "gemm_common.cuh"
+
+namespace ax2d {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 16;                        // fp32 per 64-byte swizzle row
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;     // 8 KB
+
+struct TcMaps {
+  CUtensorMap a[AX2D_MAX_SEG];
+  CUtensorMap b_hi;
+  CUtensorMap b_lo;
+};
+
+struct TcArgs {
+  EpiArgs e;
+  int seg_kb_start[AX2D_MAX_SEG + 1];   // first k-block of every A segment
+  int n_seg;
+  int num_kb;
+  int BN;
+  int stages;
+  int tmem_cols;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, 64-byte swizzle (cute::UMMA::SmemDescriptor; canonical layout
+// Swizzle<2,4,3> o ((8,n),(4,2)):((16,SBO),(1,4)) in fp32 elements: rows of 64 bytes, 8-row groups of 512 bytes):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |
+//   [32,46) stride byte offset >> 4 = 512 B between 8-row groups | [46,48) version = 1 (sm_100) | [61,64) layout = 4
+__device__ __forceinline__ uint64_t smem_desc_k_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = bn.
+__device__ __forceinline__ uint32_t idesc_tf32(int bn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | (static_cast<uint32_t>(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float round_tf32(float v) {
+  // round-to-nearest (half away from zero) onto 10 explicit mantissa bits
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  // v - hi is exact in fp32; lo is rounded to TF32 as well so that the tensor core sees exactly representable
+  // inputs whatever its own fp32 -> tf32 conversion does (dropped: <= 2^-23 |v|)
+  hi = round_tf32(v);
+  lo = round_tf32(v - hi);
+}
+
+// Epilogue of one warp: its 32 accumulator rows (TMEM lanes 32 q .. 32 q + 31), 32 columns at a time:
+// tcgen05.ld (lane = row, registers = columns) -> shared-memory transpose -> 8 lanes per row, float4 per lane, so
+// every global access of the fused epilogue is a row-contiguous 128-byte segment.
+template <int ACT, int DACT, bool DROP>
+__device__ __noinline__ void tc_epilogue(const TcArgs& g, const EpiCtx& cx, uint32_t tmem_base, float* stg, int m0, int n0,
+                                         int q, int lane) {
+  const int64_t M = g.e.M;
+  const int N = static_cast<int>(g.e.N);
+  const int cg = lane & 7;
+  for (int c0 = 0; c0 < g.BN; c0 += 32) {
+    if (n0 + c0 >= N) break;
+    uint32_t r[32];
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+    __syncwarp();
+    const int n = n0 + c0 + cg * 4;
+    if (n < N) {
+      const EpiCol col = epi_col(g.e, n);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        // issue the global loads of four rows before consuming any (only 8 epilogue warps are resident per SM)
+        EpiOperands o[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const int rl = (half * 4 + ii) * 4 + (lane >> 3);
+          const int64_t m = static_cast<int64_t>(m0) + q * 32 + rl;
+          if (m < M) epi_prefetch(g.e, col, m, o[ii]);
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const int rl = (half * 4 + ii) * 4 + (lane >> 3);
+          const int64_t m = static_cast<int64_t>(m0) + q * 32 + rl;
+          const float* sp = stg + rl * 33 + cg * 4;
+          if (m < M) epi_finish<ACT, DACT, DROP>(g.e, cx, col, m, o[ii], sp[0], sp[1], sp[2], sp[3]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], split_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = g.BN, S = g.stages;
+  const uint32_t b_bytes = static_cast<uint32_t>(BN) * TC_BK * 4;
+  const uint32_t stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+  // align the dynamic region to 1024 B (SWIZZLE_128B atoms)
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  auto stage_a = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };
+  auto stage_alo = [&](int s) { return stage_a(s) + TC_A_BYTES; };
+  auto stage_bhi = [&](int s) { return stage_a(s) + 2 * TC_A_BYTES; };
+  auto stage_blo = [&](int s) { return stage_a(s) + 2 * TC_A_BYTES + b_bytes; };
+
+  const int m0 = blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, static_cast<uint32_t>(g.tmem_cols));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int seg = 0;
+      for (int kb = 0; kb < g.num_kb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = static_cast<uint32_t>(kb / S) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        while (seg + 1 < g.n_seg && kb >= g.seg_kb_start[seg + 1]) ++seg;
+        mbar_expect_tx(&full_bar[s], TC_A_BYTES + 2 * b_bytes);
+        tma_load_2d(stage_a(s), &maps.a[seg], &full_bar[s], (kb - g.seg_kb_start[seg]) * TC_BK, m0);
+        tma_load_2d(stage_bhi(s), &maps.b_hi, &full_bar[s], kb * TC_BK, n0);
+        tma_load_2d(stage_blo(s), &maps.b_lo, &full_bar[s], kb * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(BN);
+      for (int kb = 0; kb < g.num_kb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = static_cast<uint32_t>(kb / S) & 1u;
+        mbar_wait(&full_bar[s], ph);     // B_hi / B_lo (and raw A) have landed
+        mbar_wait(&split_bar[s], ph);    // A has been rewritten as (hi, lo)
+        tc_fence_after();
+        const uint64_t da_hi = smem_desc_k_sw64(smem_u32(stage_a(s)));
+        const uint64_t da_lo = smem_desc_k_sw64(smem_u32(stage_alo(s)));
+        const uint64_t db_hi = smem_desc_k_sw64(smem_u32(stage_bhi(s)));
+        const uint64_t db_lo = smem_desc_k_sw64(smem_u32(stage_blo(s)));
+#pragma unroll
+        for (int j = 0; j < TC_BK / 8; ++j) {
+          const uint64_t adv = static_cast<uint64_t>((j * 8 * 4) >> 4);     // 32 bytes per k-step inside the swizzle row
+          umma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, (kb | j) != 0 ? 1u : 0u);
+          umma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
+          umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);      // stage free once these MMAs have read it
+      }
+      umma_commit(&acc_bar);             // accumulator complete
+    }
+  } else {
+    // ===================================================================== splitters, then epilogue (128 threads)
+    const int t = threadIdx.x - 64;
+    for (int kb = 0; kb < g.num_kb; ++kb) {
+      const int s = kb % S;
+      const uint32_t ph = static_cast<uint32_t>(kb / S) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      float4* a = reinterpret_cast<float4*>(stage_a(s));
+      float4* l = reinterpret_cast<float4*>(stage_alo(s));
+#pragma unroll
+      for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
+        const float4 v = a[t + 128 * i];
+        float4 h, o;
+        split_tf32(v.x, h.x, o.x);
+        split_tf32(v.y, h.y, o.y);
+        split_tf32(v.z, h.z, o.z);
+        split_tf32(v.w, h.w, o.w);
+        a[t + 128 * i] = h;
+        l[t + 128 * i] = o;
+      }
+      fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&split_bar[s]);
+    }
+
+    // ---- epilogue: TMEM lanes [32 q, 32 q + 32) belong to warp (warp_id % 4) == q
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);   // stage memory is free now
+    const EpiCtx cx = epi_ctx(g.e);
+    const bool dropping = cx.dropping;
+    AX2D_EPI_DISPATCH(g.e.act, g.e.dact, dropping, {
+      tc_epilogue<ACT, DACT, DROP>(g, cx, tmem_base, stg, m0, n0, warp & 3, lane);
+    });
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(g.tmem_cols));
+  }
+}
+
+// elementwise (hi, lo) split of a weight matrix, optionally transposed: out[r, c] = split(w[c, r]) if transpose.
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, int64_t ldw, int rows, int cols,
+                                                         int transpose, float* __restrict__ hi, float* __restrict__ lo,
+                                                         int64_t ldo) {
+  // out is [rows, cols]; source is w[rows, cols] or, transposed, w[cols, rows]
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (!transpose) {
+    for (int r = by + ty; r < by + 32 && r < rows; r += 8) {
+      const int c = bx + tx;
+      if (c < cols) {
+        float h, l;
+        split_tf32(w[static_cast<int64_t>(r) * ldw + c], h, l);
+        hi[static_cast<int64_t>(r) * ldo + c] = h;
+        lo[static_cast<int64_t>(r) * ldo + c] = l;
+      }
+    }
+    return;
+  }
+  // transposed: read w[c, r] coalesced along r (source columns), write out[r, c] coalesced along c
+  for (int c = bx + ty; c < bx + 32; c += 8) {
+    const int r = by + tx;
+    tile[c - bx][tx] = (c < cols && r < rows) ? w[static_cast<int64_t>(c) * ldw + r] : 0.f;
+  }
+  __syncthreads();
+  for (int r = by + ty; r < by + 32 && r < rows; r += 8) {
+    const int c = bx + tx;
+    if (c < cols) {
+      float h, l;
+      split_tf32(tile[tx][r - by], h, l);
+      hi[static_cast<int64_t>(r) * ldo + c] = h;
+      lo[static_cast<int64_t>(r) * ldo + c] = l;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major matrix [outer rows, inner cols] with leading dimension ld; box = [box_outer x 16], 64 B swizzle,
+// out-of-bounds elements read as zero.
+static int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("ax2d_gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+    return AX2D_ERR_UNSUPPORTED;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {TC_BK, static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("ax2d_gemm_tc: cuTensorMapEncodeTiled failed (%d) for a [%lld x %lld] matrix, ld %lld, box %d", (int)r,
+              (long long)outer, (long long)inner, (long long)ld, box_outer);
+    return AX2D_ERR_ARG;
+  }
+  return AX2D_OK;
+}
+
+}  // namespace ax2d
+
+using namespace ax2d;
+
+extern "C" int ax2d_split_tf32(const float* w, int64_t ldw, int rows, int cols, int transpose, float* hi, float* lo,
+                               int64_t ldo, ax2d_stream_t stream) {
+  AX2D_CHECK_ARG(w != nullptr && hi != nullptr && lo != nullptr && rows > 0 && cols > 0 && ldo >= cols,
+                 "ax2d_split_tf32: bad arguments");
+  dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
+  split_tf32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, ldw, rows, cols, transpose, hi, lo, ldo);
+  return launch_status("ax2d_split_tf32");
+}
+
+extern "C" int ax2d_gemm_tc_supported(const ax2d_cmat* a, int64_t M, int64_t N, int64_t K) {
+  if (a == nullptr || M < 1 || N < 32 || N % 4 != 0 || K < TC_BK || K % TC_BK != 0) return 0;
+  if (a->n_seg < 1 || a->n_seg > AX2D_MAX_SEG) return 0;
+  for (int s = 0; s < a->n_seg; ++s)
+    if (a->width[s] <= 0 || a->width[s] % TC_BK != 0 || a->ld[s] % 4 != 0 || (reinterpret_cast<uintptr_t>(a->ptr[s]) & 15u)) return 0;
+  return 1;
+}
+
+extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* b_lo, int64_t ldb, const ax2d_mat* c,
+                            int64_t M, int64_t N, int64_t K, const ax2d_epilogue* ep, ax2d_stream_t stream) {
+  AX2D_CHECK_ARG(a != nullptr && b_hi != nullptr && b_lo != nullptr && c != nullptr, "ax2d_gemm_tc: null operand");
+  AX2D_CHECK_ARG(ax2d_gemm_tc_supported(a, M, N, K), "ax2d_gemm_tc: unsupported shape M=%lld N=%lld K=%lld (see ax2d.h)",
+                 (long long)M, (long long)N, (long long)K);
+  AX2D_CHECK_ARG(ldb % 4 == 0 && ldb >= K, "ax2d_gemm_tc: bad ldb");
+  AX2D_CHECK_ALIGN(b_hi);
+  AX2D_CHECK_ALIGN(b_lo);
+  TcArgs g;
+  memset(&g, 0, sizeof(g));
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  if ((rc = to_out(c, &g.e.c, N, "C", false)) != AX2D_OK) return rc;
+  if ((rc = fill_epilogue(ep, M, N, &g.e)) != AX2D_OK) return rc;
+  // tile shape: all of N in one tile when it fits 256 columns, otherwise equal tiles rounded up to 32
+  const int n_tiles = static_cast<int>((N + 255) / 256);
+  int BN = static_cast<int>((N + n_tiles - 1) / n_tiles);
+  BN = (BN + 31) / 32 * 32;
+  g.BN = BN;
+  g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  int acc = 0, kb = 0;
+  g.n_seg = a->n_seg;
+  for (int s = 0; s < a->n_seg; ++s) {
+    g.seg_kb_start[s] = kb;
+    if ((rc = make_map(&maps.a[s], a->ptr[s], a->width[s], M, a->ld[s], TC_BM)) != AX2D_OK) return rc;
+    kb += a->width[s] / TC_BK;
+    acc += a->width[s];
+  }
+  for (int s = a->n_seg; s <= AX2D_MAX_SEG; ++s) g.seg_kb_start[s] = kb;
+  AX2D_CHECK_ARG(acc == K, "ax2d_gemm_tc: A segments cover %d columns, expected %lld", acc, (long long)K);
+  g.num_kb = kb;
+  if ((rc = make_map(&maps.b_hi, b_hi, K, N, ldb, BN)) != AX2D_OK) return rc;
+  if ((rc = make_map(&maps.b_lo, b_lo, K, N, ldb, BN)) != AX2D_OK) return rc;
+  const size_t stage_bytes = 2 * static_cast<size_t>(TC_A_BYTES) + 2 * static_cast<size_t>(BN) * TC_BK * 4;
+  // two CTAs per SM (one's epilogue overlaps the other's main loop; 2 x 256 TMEM columns): <= 110 KB of stages each
+  int stages = static_cast<int>((110 * 1024) / stage_bytes);
+  stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages;
+  stages = stages > g.num_kb ? g.num_kb : stages;
+  if (stages < 1) stages = 1;
+  g.stages = stages;
+  size_t smem = stages * stage_bytes;
+  if (smem < 4 * 32 * 33 * 4) smem = 4 * 32 * 33 * 4;     // epilogue transpose staging
+  smem += 1024;                                          // alignment slack
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      set_error("ax2d_gemm_tc: cannot raise the dynamic shared memory limit to %zu: %s", smem, cudaGetErrorString(e));
+      return AX2D_ERR_LAUNCH;
+    }
+    configured = smem;
+  }
+  dim3 grid(static_cast<unsigned>((M + TC_BM - 1) / TC_BM), static_cast<unsigned>(n_tiles));
+  gemm_tc_kernel<<<grid, TC_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, g);
+  return launch_status("ax2d_gemm_tc");
+}

@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_bwd_kernel(
   float* ds = coef + CH;                                          // [CH]
   float* sdot = ds + CH;                                          // [NH]
   float* zmax = sdot + NH;                                        // [NH]  per-(head, molecule) max score
+  float* resid = zmax + NH;                                       // [NH]  sum_i dz[h,i] (rounding residual)
+  int* amax = reinterpret_cast<int*>(resid + NH);                 // [NH]  first arg-max atom (molecule-local)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int F4 = F >> 2;
@@ -247,20 +249,41 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_bwd_kernel(
       }
     }
     __syncthreads();
-    // ---- sdot_h = sum_i a[h,i] da[h,i]
+    // ---- per head: sdot_h = sum_i a[h,i] da[h,i], the score maximum / its first position, and the residual
+    //      r_h = sum_i dz[h,i].  In exact arithmetic r_h == 0; the reference's scatter_softmax is the composite
+    //      exp(z - max) / sum, whose autograd routes -sum_i dz[h,i] to the arg-max atom (gradient of the
+    //      gathered maximum, torch_scatter softmax.py), i.e. the reference's dz sums to zero up to ONE rounding.
+    //      The same correction is applied here: it is what keeps the shift-sensitive sums (gw, gb, gT) at the
+    //      reference's accuracy when scores / features carry a large common offset.
     for (int h = warp; h < NH; h += kPoolThreads / 32) {
       float s = 0.f, zm = -INFINITY;
+      int am = 0x7fffffff;
       for (int i = lane; i < n; i += 32) {
         float da = single ? ds[i] : gx[static_cast<int64_t>(n0 + i) * ldgx];
         if (g_attn != nullptr) da += g_attn[static_cast<int64_t>(h) * N + n0 + i];
         s += attn[static_cast<int64_t>(h) * N + n0 + i] * da;
-        zm = fmaxf(zm, zbuf[static_cast<int64_t>(h) * N + n0 + i]);
+        const float zv = zbuf[static_cast<int64_t>(h) * N + n0 + i];
+        if (zv > zm) { zm = zv; am = i; }
       }
       s = warp_sum(s);
-      zm = warp_max(zm);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float oz = __shfl_xor_sync(0xffffffffu, zm, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+        if (oz > zm || (oz == zm && oa < am)) { zm = oz; am = oa; }
+      }
+      float r = 0.f;
+      for (int i = lane; i < n; i += 32) {
+        float da = single ? ds[i] : gx[static_cast<int64_t>(n0 + i) * ldgx];
+        if (g_attn != nullptr) da += g_attn[static_cast<int64_t>(h) * N + n0 + i];
+        r += attn[static_cast<int64_t>(h) * N + n0 + i] * (da - s);
+      }
+      r = warp_sum(r);
       if (lane == 0) {
         sdot[h] = s;
         zmax[h] = zm;
+        resid[h] = r;
+        amax[h] = am;
       }
     }
     __syncthreads();
@@ -285,7 +308,8 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_bwd_kernel(
           const float a = attn[o];
           float da = d;
           if (g_attn != nullptr) da += g_attn[o];
-          const float dz = a * (da - sdot[h]);
+          float dz = a * (da - sdot[h]);
+          if (c0 + i == amax[h]) dz -= resid[h];
           dzs[h * CH + i] = dz;
           asum += a;
           gb_loc[h] += dz;
@@ -362,14 +386,27 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_bwd_kernel(
   }
 }
 
-__global__ void attn_pool_bwd_reduce_kernel(const float* __restrict__ partials, int n_part, int F, int heads,
-                                            const float* __restrict__ temperature, float* __restrict__ gw,
-                                            float* __restrict__ gb, float* __restrict__ gT) {
+// fixed-order reduction of the per-CTA partial records: lane = entry, the 8 warps take partials p, p+8, ...
+__global__ void __launch_bounds__(256) attn_pool_bwd_reduce_kernel(const float* __restrict__ partials, int n_part, int F,
+                                                                   int heads, const float* __restrict__ temperature,
+                                                                   float* __restrict__ gw, float* __restrict__ gb,
+                                                                   float* __restrict__ gT) {
+  __shared__ float red[8][32];
   const int stride = pool_partial_stride(heads, F);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= heads * F + heads + 1) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const int total = heads * F + heads + 1;
   float s = 0.f;
-  for (int p = 0; p < n_part; ++p) s += partials[static_cast<size_t>(p) * stride + i];
+  if (i < total) {
+#pragma unroll 4
+    for (int p = warp; p < n_part; p += 8) s += __ldg(partials + static_cast<size_t>(p) * stride + i);
+  }
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp != 0 || i >= total) return;
+  s = red[0][lane];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) s += red[w][lane];
   const float invT = 1.f / __ldg(temperature);
   if (i < heads * F) gw[i] = s * invT;
   else if (i < heads * F + heads) gb[i - heads * F] = s * invT;
@@ -379,7 +416,7 @@ __global__ void attn_pool_bwd_reduce_kernel(const float* __restrict__ partials, 
 static int pool_chunk_rows(int F, int heads, int max_rows_hint, bool bwd) {
   // shared-memory budget ~96 KB per CTA so that two CTAs fit on an SM
   const int budget = 96 * 1024;
-  const int fixed = bwd ? (F * 4 + heads * 8 + 64) : (heads * F * 4 + 64);
+  const int fixed = bwd ? (F * 4 + heads * 16 + 64) : (heads * F * 4 + 64);
   const int per_row = F * 4 + heads * 4 + 8;
   int ch = (budget - fixed) / per_row;
   if (ch < 1) ch = 1;
@@ -482,7 +519,7 @@ static int launch_pool_bwd(const float* x, const int32_t* seg_ptr, int64_t B, in
                            const float* g_attn, float* gx, int64_t ldgx, float* gw, float* gb, float* gT, void* ws,
                            int max_rows_hint, cudaStream_t st) {
   const int CH = pool_chunk_rows(F, NH, max_rows_hint, true);
-  const size_t smem = (static_cast<size_t>(CH) * F + F + static_cast<size_t>(NH) * CH + 2 * CH + 2 * NH) * 4;
+  const size_t smem = (static_cast<size_t>(CH) * F + F + static_cast<size_t>(NH) * CH + 2 * CH + 4 * NH) * 4;
   auto kern = attn_pool_bwd_kernel<NH>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   const int grid = B < kPoolBwdMaxGrid ? static_cast<int>(B) : kPoolBwdMaxGrid;
@@ -491,7 +528,7 @@ static int launch_pool_bwd(const float* x, const int32_t* seg_ptr, int64_t B, in
   int rc = launch_status("ax2d_attn_pool_bwd");
   if (rc != AX2D_OK) return rc;
   const int total = NH * F + NH + 1;
-  attn_pool_bwd_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ws), grid, F, NH,
+  attn_pool_bwd_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(static_cast<const float*>(ws), grid, F, NH,
                                                                     temperature, gw, gb, gT);
   return launch_status("ax2d_attn_pool_bwd(reduce)");
 }

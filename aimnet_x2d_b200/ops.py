@@ -91,6 +91,21 @@ def _mat(segs: Sequence, allow_none: bool = False) -> CMat:
 
 
 # ----------------------------------------------------------------------------------------------- raw launches
+USE_TENSOR_CORES = True     # dense contractions with M >= TC_MIN_ROWS run on tcgen05 (3xTF32 split); SIMT fp32 otherwise
+TC_MIN_ROWS = 256
+
+
+def split_tf32(w: torch.Tensor, transpose: bool = False):
+    """(hi, lo) fp32 pair with hi + lo == w (or w^T), hi representable in TF32 -- the weight operand of ax2d_gemm_tc."""
+    lib = _lib.load()
+    rows, cols = (w.shape[1], w.shape[0]) if transpose else (w.shape[0], w.shape[1])
+    hi = torch.empty((rows, cols), dtype=torch.float32, device=w.device)
+    lo = torch.empty_like(hi)
+    _lib.check(lib.ax2d_split_tf32(_p(w), w.stride(0), rows, cols, int(transpose), _p(hi), _p(lo), cols, _stream()),
+               "ax2d_split_tf32")
+    return hi, lo
+
+
 def gemm(a_segs, b_segs, c_segs, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = True, *,
          bias=None, pre_segs=None, act=None, act_cols=None, mask=None, drop_p: float = 0.0, drop_seed: int = 0,
          drop_tick=None, resid=(), dact_pre=None, dact=None, dact_cols=None, accumulate: bool = False,
@@ -113,6 +128,18 @@ def gemm(a_segs, b_segs, c_segs, M: int, N: int, K: int, trans_a: bool = False, 
         ep.dact_pre, ep.ld_dact, ep.dact = dact_pre.data_ptr(), dact_pre.stride(0), ACT_CODES[dact]
         ep.dact_cols = int(N if dact_cols is None else dact_cols)
     ep.accumulate = int(accumulate)
+    if (USE_TENSOR_CORES and not trans_a and split_k == 1 and M >= TC_MIN_ROWS and len(b_segs) == 1
+            and lib.ax2d_gemm_tc_supported(C.byref(a), M, N, K)):
+        # y = x W^T (trans_b) takes W [N, K] as it is; dx = dy W (not trans_b) needs W^T, produced by the split kernel
+        w = b_segs[0][0]
+        hi, lo = split_tf32(w[:N, :K] if trans_b else w[:K, :N], transpose=not trans_b)
+        call = lambda: _lib.check(lib.ax2d_gemm_tc(C.byref(a), _p(hi), _p(lo), hi.stride(0), C.byref(c), M, N, K,
+                                                   C.byref(ep), _stream()), "ax2d_gemm_tc")
+        if TIMER is None:
+            call()
+        else:
+            TIMER.launch("gemm_tc", call, nbytes=4 * (M * K + K * N + M * N), flops=2 * M * N * K)
+        return
     ws = None
     if split_k > 1:
         nbytes = lib.ax2d_gemm_workspace(M, N, K, int(trans_a), split_k)

@@ -316,7 +316,9 @@ def ours_arm(args, wl):
                 "e2e": {"value": mols / (ms_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "roofline": roof, "roofline_dense": roof_dense, "cpu_baseline": cpu,
-                "clocks": sampler.summary(), "final_loss": final_loss}
+                "clocks": sampler.summary(), "final_loss": final_loss,
+                "timed_launch_groups": {k: {"launches_per_step": v["launches"] / args.steps, "avg_us": v["ms_avg"] * 1e3,
+                                            "share_of_step": v["ms_total"] / ms} for k, v in ks.items()}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

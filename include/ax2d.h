@@ -196,6 +196,16 @@ int64_t ax2d_gemm_workspace(int64_t M, int64_t N, int64_t K, int trans_a, int sp
 int ax2d_gemm(const ax2d_cmat* a, int trans_a, const ax2d_cmat* b, int trans_b,
               const ax2d_mat* c, int64_t M, int64_t N, int64_t K,
               const ax2d_epilogue* ep, int split_k, void* workspace, ax2d_stream_t stream);
+/* Tensor-core path (tcgen05 / TMEM / TMA) for the same contraction, fp32-faithful by a 3xTF32 operand split:
+ *   C[M,N] = epilogue( A[M,K] * B[N,K]^T ),  A column-segmented activations, B = weights given as two fp32 arrays
+ *   b_hi + b_lo == B produced by ax2d_split_tf32 (transpose = 1 turns a [K,N] row-major operand -- the weight of a
+ *   data-gradient product dX = dY W -- into the [N,K] K-major form).  Same epilogue semantics as ax2d_gemm.
+ * Supported when every A segment width and K are multiples of 16, N >= 32, N % 4 == 0 (ax2d_gemm_tc_supported). */
+int ax2d_split_tf32(const float* w, int64_t ldw, int rows, int cols, int transpose, float* hi, float* lo, int64_t ldo,
+                    ax2d_stream_t stream);
+int ax2d_gemm_tc_supported(const ax2d_cmat* a, int64_t M, int64_t N, int64_t K);
+int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* b_lo, int64_t ldb, const ax2d_mat* c,
+                 int64_t M, int64_t N, int64_t K, const ax2d_epilogue* ep, ax2d_stream_t stream);
 /* elementwise g_pre[m,n] = g[m,n] * act'(pre[m,n]) for n < width (width % 4 == 0). */
 int ax2d_act_bwd(const float* g, int64_t ldg, const float* pre, int64_t ldp, float* out, int64_t ldo,
                  int64_t M, int width, int act, ax2d_stream_t stream);
