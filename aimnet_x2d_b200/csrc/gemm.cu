@@ -303,6 +303,12 @@ int to_out(const ax2d_mat* m, SegOut* v, int64_t total, const char* what, bool a
   return AX2D_OK;
 }
 
+int splitk_reduce(const float* ws, int split, int64_t M, int64_t N, const SegOut& c, int accumulate, cudaStream_t st) {
+  const int64_t total = M * (N / 4);
+  splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(ws, split, M, N, c, accumulate);
+  return launch_status("split-k reduce");
+}
+
 int fill_epilogue(const ax2d_epilogue* ep, int64_t M, int64_t N, EpiArgs* e) {
   // e->c has been set by the caller; everything else starts from zero
   SegOut keep = e->c;

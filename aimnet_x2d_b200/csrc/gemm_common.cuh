@@ -108,7 +108,7 @@ __device__ __forceinline__ void drop_scale4(const EpiCtx& cx, uint64_t idx, floa
   d[3] = (h1 >> 16) >= cx.thresh ? cx.inv_keep : 0.f;
 }
 
-constexpr int kEpiPrefetchResid = 3;
+constexpr int kEpiPrefetchResid = 2;
 struct EpiCol {      // per-thread constants of one float4 column group n..n+3
   float* c; int64_t ldc;
   float* pre; int64_t ldpre;                                          // nullptr: no pre-activation copy here
@@ -117,7 +117,10 @@ struct EpiCol {      // per-thread constants of one float4 column group n..n+3
   const float* mask; int64_t ldm;
   float4 bias;
   bool act_on;
+  bool accumulate;
+  bool more_resid;     // residuals beyond the prefetched ones exist (rare; read through g)
   int n;
+  uint32_t ncols;      // N: row pitch of the dropout counter
 };
 __device__ __forceinline__ EpiCol epi_col(const EpiArgs& g, int n) {
   EpiCol k;
@@ -142,12 +145,15 @@ __device__ __forceinline__ EpiCol epi_col(const EpiArgs& g, int n) {
   k.ldm = g.ld_mask;
   k.bias = g.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(g.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
   k.act_on = n < g.act_cols;
+  k.accumulate = g.accumulate != 0;
+  k.more_resid = g.n_resid > kEpiPrefetchResid;
   k.n = n;
+  k.ncols = static_cast<uint32_t>(g.N);
   return k;
 }
-struct EpiOperands {
+struct EpiOperands {       // the operands worth issuing early: the first two residuals and the saved pre-activation
   float4 resid[kEpiPrefetchResid];
-  float4 dpre, mask, cold;
+  float4 dpre;
 };
 __device__ __forceinline__ void epi_prefetch(const EpiArgs& g, const EpiCol& k, int64_t m, EpiOperands& o) {
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -155,8 +161,6 @@ __device__ __forceinline__ void epi_prefetch(const EpiArgs& g, const EpiCol& k, 
   for (int r = 0; r < kEpiPrefetchResid; ++r)
     o.resid[r] = k.resid[r] != nullptr ? __ldg(reinterpret_cast<const float4*>(k.resid[r] + m * k.ldr[r])) : z;
   o.dpre = k.dpre != nullptr ? __ldg(reinterpret_cast<const float4*>(k.dpre + m * k.lddp)) : z;
-  o.mask = k.mask != nullptr ? __ldg(reinterpret_cast<const float4*>(k.mask + m * k.ldm)) : z;
-  o.cold = g.accumulate ? *reinterpret_cast<const float4*>(k.c + m * k.ldc) : z;
 }
 template <int ACT, int DACT, bool DROP>
 __device__ __forceinline__ void epi_finish(const EpiArgs& g, const EpiCtx& cx, const EpiCol& k, int64_t m,
@@ -166,9 +170,10 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& g, const EpiCtx& cx, c
   float drop[4] = {1.f, 1.f, 1.f, 1.f};
   if constexpr (DROP) {
     if (k.mask != nullptr) {
-      drop[0] = o.mask.x; drop[1] = o.mask.y; drop[2] = o.mask.z; drop[3] = o.mask.w;
+      const float4 mk = __ldg(reinterpret_cast<const float4*>(k.mask + m * k.ldm));
+      drop[0] = mk.x; drop[1] = mk.y; drop[2] = mk.z; drop[3] = mk.w;
     } else {
-      drop_scale4(cx, static_cast<uint64_t>(m) * static_cast<uint64_t>(g.N) + static_cast<uint64_t>(k.n), drop);
+      drop_scale4(cx, static_cast<uint64_t>(m) * k.ncols + static_cast<uint64_t>(k.n), drop);
     }
   }
   if constexpr (ACT != AX2D_ACT_NONE) {
@@ -185,10 +190,12 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& g, const EpiCtx& cx, c
   for (int r = 0; r < kEpiPrefetchResid; ++r) {     // zeros where the residual does not apply
     v[0] += o.resid[r].x; v[1] += o.resid[r].y; v[2] += o.resid[r].z; v[3] += o.resid[r].w;
   }
-  for (int r = kEpiPrefetchResid; r < g.n_resid; ++r) {
-    if (k.n >= g.resid_cols[r]) continue;
-    const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid[r] + m * g.ld_resid[r] + k.n));
-    v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
+  if (k.more_resid) {
+    for (int r = kEpiPrefetchResid; r < g.n_resid; ++r) {
+      if (k.n >= g.resid_cols[r]) continue;
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid[r] + m * g.ld_resid[r] + k.n));
+      v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
+    }
   }
   if constexpr (DACT != AX2D_ACT_NONE) {
     if (k.dpre != nullptr) {
@@ -198,10 +205,12 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& g, const EpiCtx& cx, c
       v[3] *= act_bwd_t<DACT>(o.dpre.w) * drop[3];
     }
   }
-  if (g.accumulate) {
-    v[0] += o.cold.x; v[1] += o.cold.y; v[2] += o.cold.z; v[3] += o.cold.w;
+  float4* dst = reinterpret_cast<float4*>(k.c + m * k.ldc);
+  if (k.accumulate) {
+    const float4 cold = *dst;
+    v[0] += cold.x; v[1] += cold.y; v[2] += cold.z; v[3] += cold.w;
   }
-  *reinterpret_cast<float4*>(k.c + m * k.ldc) = make_float4(v[0], v[1], v[2], v[3]);
+  *dst = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // Calls f(std::integral_constant<int, ACT>, std::integral_constant<int, DACT>, std::bool_constant<DROP>) for the
@@ -234,6 +243,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& g, const EpiCtx& cx, c
 // host helpers (gemm.cu)
 int to_view(const ax2d_cmat* m, SegView* v, int64_t total, const char* what);
 int to_out(const ax2d_mat* m, SegOut* v, int64_t total, const char* what, bool allow_null);
-int fill_epilogue(const ax2d_epilogue* ep, int64_t M, int64_t N, EpiArgs* e);   // validates + copies; c is set by the caller
+int fill_epilogue(const ax2d_epilogue* ep, int64_t M, int64_t N, EpiArgs* e);
+int splitk_reduce(const float* ws, int split, int64_t M, int64_t N, const SegOut& c, int accumulate, cudaStream_t st);   // validates + copies; c is set by the caller
 
 }  // namespace ax2d

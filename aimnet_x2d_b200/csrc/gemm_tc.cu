@@ -6,8 +6,10 @@
 // The fp32 configuration must match the reference within 1e-5 (BASELINE.json), which rules out plain TF32
 // (2^-11 operand rounding).  Every operand is therefore split into two TF32-representable terms,
 //   a = a_hi + a_lo,  a_hi = a rounded to 10 explicit mantissa bits,  a_lo = a - a_hi (exact in fp32),
-// and the product is accumulated in fp32 TMEM as  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (the dropped a_lo*b_lo term
-// is <= 2^-22 relative): three kind::tf32 MMAs per k-step ("3xTF32").
+// (a_lo additionally rounded to TF32: <= 2^-23 |a| dropped), and the product is accumulated in fp32 TMEM as
+//   a_lo*b_lo + a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
+// four kind::tf32 MMAs per k-step.  Every partial product is exact in fp32 (11 x 11 significant bits); what is
+// lost is 2 x 2^-23 relative per product (the rounding of the two lo terms), the same order as an fp32 FMA chain.
 //
 // One CTA computes a 128 x BN output tile (BN <= 256, all of N when it fits):
 //   warp 0      : TMA producer -- per k-block (32 fp32 = one 128-byte swizzle row) one tensor-map load of the raw
@@ -30,7 +32,8 @@ namespace ax2d {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 16;                        // fp32 per 64-byte swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;                  // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 split + epilogue
+constexpr int TC_WORKERS = TC_THREADS - 64;       // splitter / epilogue threads
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;     // 8 KB
 
@@ -41,6 +44,7 @@ struct TcMaps {
 };
 
 struct TcArgs {
+  unsigned long long* dbg;             // development aid: phase timestamps of CTA (0,0) (ax2d_debug_timing); normally null
   EpiArgs e;
   int seg_kb_start[AX2D_MAX_SEG + 1];   // first k-block of every A segment
   int n_seg;
@@ -51,6 +55,15 @@ struct TcArgs {
 };
 
 // ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(slot)                                                                             \
+  do {                                                                                             \
+    if (g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0) g.dbg[slot] = gtime();             \
+  } while (0)
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -131,41 +144,52 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
 // Epilogue of one warp: its 32 accumulator rows (TMEM lanes 32 q .. 32 q + 31), 32 columns at a time:
 // tcgen05.ld (lane = row, registers = columns) -> shared-memory transpose -> 8 lanes per row, float4 per lane, so
 // every global access of the fused epilogue is a row-contiguous 128-byte segment.
+// ws != nullptr: raw partial sums go to the split-K workspace slice [M, N] at ws instead of the output segments.
+// Inlined into the kernel on purpose: `e` is then known to live in the (immutable, constant-cached) kernel parameter
+// space; behind a real call it degrades to generic loads that must be re-issued after every global store.
 template <int ACT, int DACT, bool DROP>
-__device__ __noinline__ void tc_epilogue(const TcArgs& g, const EpiCtx& cx, uint32_t tmem_base, float* stg, int m0, int n0,
-                                         int q, int lane) {
-  const int64_t M = g.e.M;
-  const int N = static_cast<int>(g.e.N);
+__device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws, const EpiCtx& cx, uint32_t tmem_base,
+                                         float* stg, int m0, int n0, int q, int lane, int first_chunk,
+                                         unsigned long long* dbg = nullptr) {
+  const int64_t M = e.M;
+  const int N = static_cast<int>(e.N);
   const int cg = lane & 7;
-  for (int c0 = 0; c0 < g.BN; c0 += 32) {
+  // two warps share each TMEM lane quarter and take alternate 32-column chunks
+  for (int c0 = 32 * first_chunk; c0 < BN; c0 += 64) {
     if (n0 + c0 >= N) break;
     uint32_t r[32];
+    if (dbg != nullptr && c0 == 0) dbg[8] = gtime();
     tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
+    if (dbg != nullptr && c0 == 0) dbg[9] = gtime();
 #pragma unroll
     for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
     __syncwarp();
+    if (dbg != nullptr && c0 == 0) dbg[10] = gtime();
     const int n = n0 + c0 + cg * 4;
     if (n < N) {
-      const EpiCol col = epi_col(g.e, n);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        // issue the global loads of four rows before consuming any (only 8 epilogue warps are resident per SM)
-        EpiOperands o[4];
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-          const int rl = (half * 4 + ii) * 4 + (lane >> 3);
-          const int64_t m = static_cast<int64_t>(m0) + q * 32 + rl;
-          if (m < M) epi_prefetch(g.e, col, m, o[ii]);
-        }
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-          const int rl = (half * 4 + ii) * 4 + (lane >> 3);
-          const int64_t m = static_cast<int64_t>(m0) + q * 32 + rl;
-          const float* sp = stg + rl * 33 + cg * 4;
-          if (m < M) epi_finish<ACT, DACT, DROP>(g.e, cx, col, m, o[ii], sp[0], sp[1], sp[2], sp[3]);
-        }
+      EpiCol col = epi_col(e, n);
+      if (ws != nullptr) {
+        col.c = ws + n;
+        col.ldc = N;
+      }
+      if (dbg != nullptr && c0 == 0) dbg[11] = gtime();
+      // rolled on purpose: two rows per iteration (their loads are issued before either is consumed); a fully
+      // unrolled body is ~2.7 k instructions per template instance and thrashes the 32 KB instruction cache
+#pragma unroll 1
+      for (int i = 0; i < 8; i += 2) {
+        const int rl0 = i * 4 + (lane >> 3), rl1 = rl0 + 4;
+        const int64_t ma = static_cast<int64_t>(m0) + q * 32 + rl0, mb = ma + 4;
+        EpiOperands oa, ob;
+        if (ma < M) epi_prefetch(e, col, ma, oa);
+        if (mb < M) epi_prefetch(e, col, mb, ob);
+        const float* sa = stg + rl0 * 33 + cg * 4;
+        const float* sb = stg + rl1 * 33 + cg * 4;
+        if (ma < M) epi_finish<ACT, DACT, DROP>(e, cx, col, ma, oa, sa[0], sa[1], sa[2], sa[3]);
+        if (mb < M) epi_finish<ACT, DACT, DROP>(e, cx, col, mb, ob, sb[0], sb[1], sb[2], sb[3]);
+        if (dbg != nullptr && c0 == 0 && i == 0) dbg[12] = gtime();
       }
     }
+    if (dbg != nullptr && c0 == 0) dbg[13] = gtime();
     __syncwarp();
   }
 }
@@ -189,11 +213,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
 
   const int m0 = blockIdx.x * TC_BM;
   const int n0 = blockIdx.y * BN;
+  if (threadIdx.x == 0) TC_STAMP(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], 128);
+      mbar_init(&split_bar[s], TC_WORKERS / 32);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&acc_bar, 1);
@@ -204,6 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -228,7 +254,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         const int s = kb % S;
         const uint32_t ph = static_cast<uint32_t>(kb / S) & 1u;
         mbar_wait(&full_bar[s], ph);     // B_hi / B_lo (and raw A) have landed
+        if (kb == 0) TC_STAMP(2);
         mbar_wait(&split_bar[s], ph);    // A has been rewritten as (hi, lo)
+        if (kb == 0) TC_STAMP(3);
         tc_fence_after();
         const uint64_t da_hi = smem_desc_k_sw64(smem_u32(stage_a(s)));
         const uint64_t da_lo = smem_desc_k_sw64(smem_u32(stage_alo(s)));
@@ -237,13 +265,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < TC_BK / 8; ++j) {
           const uint64_t adv = static_cast<uint64_t>((j * 8 * 4) >> 4);     // 32 bytes per k-step inside the swizzle row
-          umma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, (kb | j) != 0 ? 1u : 0u);
+          // smallest terms first; the lo*lo term (2^-22 relative) is kept so that the result is at fp32 level
+          umma_tf32(tmem_base, da_lo + adv, db_lo + adv, idesc, (kb | j) != 0 ? 1u : 0u);
+          umma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, 1u);
           umma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
           umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, 1u);
         }
         umma_commit(&empty_bar[s]);      // stage free once these MMAs have read it
       }
       umma_commit(&acc_bar);             // accumulator complete
+      TC_STAMP(4);
     }
   } else {
     // ===================================================================== splitters, then epilogue (128 threads)
@@ -255,29 +286,195 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
       float4* a = reinterpret_cast<float4*>(stage_a(s));
       float4* l = reinterpret_cast<float4*>(stage_alo(s));
 #pragma unroll
-      for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
-        const float4 v = a[t + 128 * i];
+      for (int i = 0; i < TC_A_BYTES / 16 / TC_WORKERS; ++i) {
+        const float4 v = a[t + TC_WORKERS * i];
         float4 h, o;
         split_tf32(v.x, h.x, o.x);
         split_tf32(v.y, h.y, o.y);
         split_tf32(v.z, h.z, o.z);
         split_tf32(v.w, h.w, o.w);
-        a[t + 128 * i] = h;
-        l[t + 128 * i] = o;
+        a[t + TC_WORKERS * i] = h;
+        l[t + TC_WORKERS * i] = o;
       }
       fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&split_bar[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split_bar[s]);
     }
 
     // ---- epilogue: TMEM lanes [32 q, 32 q + 32) belong to warp (warp_id % 4) == q
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
-    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);   // stage memory is free now
+    if (threadIdx.x == 64) TC_STAMP(5);
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);   // stage memory is free now (8 x 4224 B)
     const EpiCtx cx = epi_ctx(g.e);
     const bool dropping = cx.dropping;
     AX2D_EPI_DISPATCH(g.e.act, g.e.dact, dropping, {
-      tc_epilogue<ACT, DACT, DROP>(g, cx, tmem_base, stg, m0, n0, warp & 3, lane);
+      tc_epilogue<ACT, DACT, DROP>(g.e, g.BN, nullptr, cx, tmem_base, stg, m0, n0, warp & 3, lane, (warp - 2) >> 2,
+                                   (threadIdx.x == 64 && blockIdx.x == 0 && blockIdx.y == 0) ? g.dbg : nullptr);
     });
+    if (threadIdx.x == 64) TC_STAMP(6);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(7);
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(g.tmem_cols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- weight gradients
+//   dW[No, Ki] = sum_m G[m, o] * X[m, i]        (G, X column-segmented activations, contraction over the rows m)
+// Both operands are "MN-major" for the tensor core: the contraction index is the ROW of a row-major matrix.  For
+// 32-bit MN-major operands the only shared-memory layout the tensor core accepts is the 128-byte swizzle with a
+// 32-byte base (cute: Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> o [32 elements x 4 rows], descriptor layout type 1;
+// TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  A TMA box [32 rows x 32 columns] (128-byte rows) lands as one column
+// chunk of that canonical layout: 4-row groups of 512 B (SBO), column chunks of 32 elements 4096 B apart (LBO).  One k-block = 32 rows of G and X; the CTA's output tile is 128 (o) x BN (i); the
+// row range is split over blockIdx.z and the partial tiles are reduced in a fixed order by splitk_reduce_kernel.
+constexpr int WG_KB = 32;
+// The tensor core accumulates in fp32 with truncation (measured: a systematic ~3e-8 relative loss per accumulation
+// step on same-sign sums), so one TMEM accumulator covers at most 32 k-blocks = 1024 rows = 128 accumulation steps;
+// longer contractions are cut into more splits, which are then summed by splitk_reduce_kernel in round-to-nearest.
+constexpr int WG_MAX_KB_PER_SPLIT = 32;
+constexpr int WG_CHUNK_BYTES = WG_KB * 128;      // one [32 x 32] fp32 box
+struct WgMaps {
+  CUtensorMap a[AX2D_MAX_SEG];
+  CUtensorMap b[AX2D_MAX_SEG];
+};
+struct WgArgs {
+  EpiArgs e;                       // M = No, N = Ki; used directly when there is a single split
+  int a_start[AX2D_MAX_SEG + 1], a_nseg;
+  int b_start[AX2D_MAX_SEG + 1], b_nseg;
+  int num_kb, kb_per_split;
+  int BN, stages, tmem_cols;
+  float* ws;                       // [splits][No][Ki] or nullptr
+};
+
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(WG_CHUNK_BYTES >> 4) << 16;   // LBO: next 32-element chunk along M / N
+  d |= static_cast<uint64_t>(512 >> 4) << 32;              // SBO: next group of 4 contraction rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;                     // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_wgrad_kernel(const __grid_constant__ WgMaps maps,
+                                                                      const __grid_constant__ WgArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], split_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = g.BN, S = g.stages;
+  const int a_chunks = TC_BM / 32, b_chunks = BN / 32;
+  const uint32_t raw_bytes = static_cast<uint32_t>(a_chunks + b_chunks) * WG_CHUNK_BYTES;
+  const uint32_t stage_bytes = 2 * raw_bytes;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  auto stage_raw = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };   // A chunks then B chunks (hi after split)
+  auto stage_lo = [&](int s) { return stage_raw(s) + raw_bytes; };
+
+  const int m0 = blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * BN;
+  const int kb0 = blockIdx.z * g.kb_per_split;
+  int kb1 = kb0 + g.kb_per_split;
+  kb1 = kb1 < g.num_kb ? kb1 : g.num_kb;
+  const int nkb = kb1 - kb0;       // >= 1 by construction of the grid
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], TC_WORKERS / 32);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, static_cast<uint32_t>(g.tmem_cols));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % S;
+        const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], raw_bytes);
+        const int row = (kb0 + it) * WG_KB;
+        unsigned char* dst = stage_raw(s);
+        for (int c = 0; c < a_chunks; ++c) {          // columns beyond the last segment: fully out-of-bounds box -> zeros
+          const int o = m0 + 32 * c;
+          const int sg = find_seg(g.a_start, g.a_nseg, o);
+          tma_load_2d(dst + c * WG_CHUNK_BYTES, &maps.a[sg], &full_bar[s], o - g.a_start[sg], row);
+        }
+        dst += a_chunks * WG_CHUNK_BYTES;
+        for (int c = 0; c < b_chunks; ++c) {
+          const int i = n0 + 32 * c;
+          const int sg = find_seg(g.b_start, g.b_nseg, i);
+          tma_load_2d(dst + c * WG_CHUNK_BYTES, &maps.b[sg], &full_bar[s], i - g.b_start[sg], row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D = F32, A = B = TF32, both MN-major (bits 15, 16), M = 128, N = BN
+      const uint32_t idesc = idesc_tf32(BN) | (1u << 15) | (1u << 16);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % S;
+        const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        mbar_wait(&split_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(stage_raw(s)), b_hi = a_hi + a_chunks * WG_CHUNK_BYTES;
+        const uint32_t a_lo = smem_u32(stage_lo(s)), b_lo = a_lo + a_chunks * WG_CHUNK_BYTES;
+#pragma unroll
+        for (int j = 0; j < WG_KB / 8; ++j) {
+          const uint32_t adv = j * 1024;                   // 8 contraction rows = two 4-row swizzle atoms
+          const uint64_t dah = smem_desc_mn_sw128_32b(a_hi + adv), dal = smem_desc_mn_sw128_32b(a_lo + adv);
+          const uint64_t dbh = smem_desc_mn_sw128_32b(b_hi + adv), dbl = smem_desc_mn_sw128_32b(b_lo + adv);
+          umma_tf32(tmem_base, dal, dbl, idesc, (it | j) != 0 ? 1u : 0u);
+          umma_tf32(tmem_base, dal, dbh, idesc, 1u);
+          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&acc_bar);
+    }
+  } else {
+    const int t = threadIdx.x - 64;
+    const int n4 = static_cast<int>(raw_bytes / 16);
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % S;
+      const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      float4* a = reinterpret_cast<float4*>(stage_raw(s));
+      float4* l = reinterpret_cast<float4*>(stage_lo(s));
+#pragma unroll 4
+      for (int i = t; i < n4; i += TC_WORKERS) {
+        const float4 v = a[i];
+        float4 h, o;
+        split_tf32(v.x, h.x, o.x);
+        split_tf32(v.y, h.y, o.y);
+        split_tf32(v.z, h.z, o.z);
+        split_tf32(v.w, h.w, o.w);
+        a[i] = h;
+        l[i] = o;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split_bar[s]);
+    }
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+    const EpiCtx cx = epi_ctx(g.e);
+    float* ws = g.ws != nullptr ? g.ws + static_cast<int64_t>(blockIdx.z) * g.e.M * g.e.N : nullptr;
+    tc_epilogue<AX2D_ACT_NONE, AX2D_ACT_NONE, false>(g.e, BN, ws, cx, tmem_base, stg, m0, n0, warp & 3, lane, (warp - 2) >> 2);
   }
   tc_fence_before();
   __syncthreads();
@@ -345,7 +542,8 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D fp32 row-major matrix [outer rows, inner cols] with leading dimension ld; box = [box_outer x 16], 64 B swizzle,
 // out-of-bounds elements read as zero.
-static int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+static int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer,
+                    int box_inner = TC_BK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_64B) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("ax2d_gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
@@ -353,10 +551,10 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t o
   }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  cuuint32_t box[2] = {TC_BK, static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("ax2d_gemm_tc: cuTensorMapEncodeTiled failed (%d) for a [%lld x %lld] matrix, ld %lld, box %d", (int)r,
@@ -369,6 +567,12 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t inner, int64_t o
 }  // namespace ax2d
 
 using namespace ax2d;
+
+static unsigned long long* g_tc_dbg = nullptr;
+// development aid (not part of include/ax2d.h): 8 x u64 device buffer receiving %globaltimer stamps of CTA (0,0) of
+// every following ax2d_gemm_tc launch: start, setup done, first tile landed, first tile split, MMAs issued,
+// accumulator ready, epilogue done, CTA done.  nullptr switches it off.
+extern "C" void ax2d_debug_timing(unsigned long long* buf) { g_tc_dbg = buf; }
 
 extern "C" int ax2d_split_tf32(const float* w, int64_t ldw, int rows, int cols, int transpose, float* hi, float* lo,
                                int64_t ldo, ax2d_stream_t stream) {
@@ -397,6 +601,7 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
   AX2D_CHECK_ALIGN(b_lo);
   TcArgs g;
   memset(&g, 0, sizeof(g));
+  g.dbg = g_tc_dbg;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
@@ -429,7 +634,7 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
   if (stages < 1) stages = 1;
   g.stages = stages;
   size_t smem = stages * stage_bytes;
-  if (smem < 4 * 32 * 33 * 4) smem = 4 * 32 * 33 * 4;     // epilogue transpose staging
+  if (smem < 8 * 32 * 33 * 4) smem = 8 * 32 * 33 * 4;     // epilogue transpose staging
   smem += 1024;                                          // alignment slack
   static size_t configured = 0;
   if (smem > configured) {
@@ -443,4 +648,105 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
   dim3 grid(static_cast<unsigned>((M + TC_BM - 1) / TC_BM), static_cast<unsigned>(n_tiles));
   gemm_tc_kernel<<<grid, TC_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, g);
   return launch_status("ax2d_gemm_tc");
+}
+
+extern "C" int ax2d_gemm_tc_wgrad_supported(const ax2d_cmat* a, const ax2d_cmat* b, int64_t M, int64_t N, int64_t K) {
+  // a: G [K rows, M columns (segmented)], b: X [K rows, N columns (segmented)]
+  if (a == nullptr || b == nullptr || M < 32 || N < 32 || M % 4 != 0 || N % 4 != 0 || K < 1) return 0;
+  const ax2d_cmat* ops_[2] = {a, b};
+  for (const ax2d_cmat* m : ops_) {
+    if (m->n_seg < 1 || m->n_seg > AX2D_MAX_SEG) return 0;
+    for (int s = 0; s < m->n_seg; ++s)
+      if (m->width[s] <= 0 || m->width[s] % 32 != 0 || m->ld[s] % 4 != 0 || (reinterpret_cast<uintptr_t>(m->ptr[s]) & 15u)) return 0;
+  }
+  return 1;
+}
+
+extern "C" int64_t ax2d_gemm_tc_wgrad_workspace(int64_t M, int64_t N, int64_t K) {
+  const int64_t n_tiles = (N + 255) / 256;
+  const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * n_tiles;
+  const int64_t num_kb = (K + WG_KB - 1) / WG_KB;
+  int64_t split = (kNumSMs + tiles - 1) / tiles;
+  const int64_t by_chain = (num_kb + WG_MAX_KB_PER_SPLIT - 1) / WG_MAX_KB_PER_SPLIT;
+  split = split < by_chain ? by_chain : split;
+  split = split > num_kb ? num_kb : split;
+  return split > 1 ? split * M * N * 4 : 0;
+}
+
+// C[M,N] (+)= A^T B with A = a [K, M], B = b [K, N] (both column-segmented, contraction over the K rows).
+extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const ax2d_mat* c, int64_t M, int64_t N, int64_t K,
+                                  int accumulate, void* workspace, ax2d_stream_t stream) {
+  AX2D_CHECK_ARG(c != nullptr && ax2d_gemm_tc_wgrad_supported(a, b, M, N, K),
+                 "ax2d_gemm_tc_wgrad: unsupported operands M=%lld N=%lld K=%lld (segment widths must be multiples of 32)",
+                 (long long)M, (long long)N, (long long)K);
+  WgArgs g;
+  memset(&g, 0, sizeof(g));
+  WgMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  if ((rc = to_out(c, &g.e.c, N, "C", false)) != AX2D_OK) return rc;
+  ax2d_epilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.accumulate = accumulate;
+  if ((rc = fill_epilogue(&ep, M, N, &g.e)) != AX2D_OK) return rc;
+  int acc = 0;
+  g.a_nseg = a->n_seg;
+  for (int s = 0; s < a->n_seg; ++s) {
+    g.a_start[s] = acc;
+    if ((rc = make_map(&maps.a[s], a->ptr[s], a->width[s], K, a->ld[s], WG_KB, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != AX2D_OK) return rc;
+    acc += a->width[s];
+  }
+  for (int s = a->n_seg; s <= AX2D_MAX_SEG; ++s) g.a_start[s] = acc;
+  AX2D_CHECK_ARG(acc == M, "ax2d_gemm_tc_wgrad: A segments cover %d columns, expected %lld", acc, (long long)M);
+  acc = 0;
+  g.b_nseg = b->n_seg;
+  for (int s = 0; s < b->n_seg; ++s) {
+    g.b_start[s] = acc;
+    if ((rc = make_map(&maps.b[s], b->ptr[s], b->width[s], K, b->ld[s], WG_KB, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != AX2D_OK) return rc;
+    acc += b->width[s];
+  }
+  for (int s = b->n_seg; s <= AX2D_MAX_SEG; ++s) g.b_start[s] = acc;
+  AX2D_CHECK_ARG(acc == N, "ax2d_gemm_tc_wgrad: B segments cover %d columns, expected %lld", acc, (long long)N);
+  const int n_tiles = static_cast<int>((N + 255) / 256);
+  int BN = static_cast<int>((N + n_tiles - 1) / n_tiles);
+  BN = (BN + 31) / 32 * 32;
+  g.BN = BN;
+  g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  const int m_tiles = static_cast<int>((M + TC_BM - 1) / TC_BM);
+  g.num_kb = static_cast<int>((K + WG_KB - 1) / WG_KB);
+  int split = (kNumSMs + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
+  const int by_chain = (g.num_kb + WG_MAX_KB_PER_SPLIT - 1) / WG_MAX_KB_PER_SPLIT;
+  split = split < by_chain ? by_chain : split;
+  split = split > g.num_kb ? g.num_kb : split;
+  g.kb_per_split = (g.num_kb + split - 1) / split;
+  split = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;      // no empty split
+  if (split > 1) {
+    AX2D_CHECK_ARG(workspace != nullptr, "ax2d_gemm_tc_wgrad: workspace required (ax2d_gemm_tc_wgrad_workspace)");
+    AX2D_CHECK_ALIGN(workspace);
+    g.ws = static_cast<float*>(workspace);
+  }
+  const size_t stage_bytes = 2 * static_cast<size_t>(TC_BM / 32 + BN / 32) * WG_CHUNK_BYTES;
+  int stages = static_cast<int>((224 * 1024) / stage_bytes);
+  stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages;
+  stages = stages > g.kb_per_split ? g.kb_per_split : stages;
+  if (stages < 1) stages = 1;
+  g.stages = stages;
+  size_t smem = stages * stage_bytes;
+  if (smem < 8 * 32 * 33 * 4) smem = 8 * 32 * 33 * 4;
+  smem += 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      set_error("ax2d_gemm_tc_wgrad: cannot raise the dynamic shared memory limit to %zu: %s", smem, cudaGetErrorString(e));
+      return AX2D_ERR_LAUNCH;
+    }
+    configured = smem;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), static_cast<unsigned>(split));
+  gemm_tc_wgrad_kernel<<<grid, TC_THREADS, smem, st>>>(maps, g);
+  rc = launch_status("ax2d_gemm_tc_wgrad");
+  if (rc != AX2D_OK || split == 1) return rc;
+  return splitk_reduce(g.ws, split, M, N, g.e.c, accumulate, st);
 }

@@ -209,6 +209,19 @@ def _bias_grad(segs, M, N, device):
 def _weight_grad(g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device) -> torch.Tensor:
     """dW[o, i] = sum_r G[r, o] X[r, i]  (G, X column-segmented) -- split over the rows, fixed-order reduce."""
     dW = torch.empty((Nout, Kin), dtype=torch.float32, device=device)
+    lib = _lib.load()
+    if USE_TENSOR_CORES and M_rows >= TC_MIN_ROWS:
+        a, b, c = _mat(g_segs), _mat(x_segs), _mat([(dW, Kin)])
+        if lib.ax2d_gemm_tc_wgrad_supported(C.byref(a), C.byref(b), Nout, Kin, M_rows):
+            nbytes = lib.ax2d_gemm_tc_wgrad_workspace(Nout, Kin, M_rows)
+            ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=device)
+            call = lambda: _lib.check(lib.ax2d_gemm_tc_wgrad(C.byref(a), C.byref(b), C.byref(c), Nout, Kin, M_rows, 0, _p(ws),
+                                                             _stream()), "ax2d_gemm_tc_wgrad")
+            if TIMER is None:
+                call()
+            else:
+                TIMER.launch("gemm_tc_wgrad", call, nbytes=4 * M_rows * (Nout + Kin), flops=2 * M_rows * Nout * Kin)
+            return dW
     gemm(g_segs, x_segs, [(dW, Kin)], Nout, Kin, M_rows, trans_a=True, trans_b=False,
          split_k=split_k_for(Nout, Kin, M_rows))
     return dW
