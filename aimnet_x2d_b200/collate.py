@@ -347,6 +347,68 @@ class MolBatch:
         return n
 
 
+def pad_batch(batch: MolBatch, num_atoms: int, num_edges: int, num_dummy: int = 64, num_tiles: Optional[int] = None,
+              tile_rows: int = DEFAULT_TILE_ROWS, feature_sizes: Optional[Dict[str, int]] = None) -> MolBatch:
+    """Static-shape version of a collated batch (what a CUDA-graph-captured training step needs: every launch
+    configuration and scalar kernel argument must be the same from batch to batch).
+
+    ``num_dummy`` edge-less dummy molecules are appended; together they hold the ``num_atoms - N`` padding atoms
+    (at most 29 each, like a QM9 molecule, so that they pack into the same whole-molecule row tiles).  Their feature
+    indices are 0, their targets are never read: the loss is taken over the first ``B`` (real) rows only, so no
+    gradient flows through them.  ``col`` arrays are padded to ``num_edges`` entries and the tile list to
+    ``num_tiles`` (trailing tiles are empty).  Real molecules keep their rows, CSR rows and results bit-for-bit."""
+    gi0 = batch.graph_index
+    N, B = gi0.num_atoms, gi0.num_graphs
+    pad = num_atoms - N
+    if pad < 0 or pad > 29 * num_dummy:
+        raise ValueError(f"cannot pad {N} atoms to {num_atoms} with {num_dummy} dummy molecules of <= 29 atoms")
+    if gi0.num_edges > num_edges:
+        raise ValueError(f"batch has {gi0.num_edges} edges, capacity {num_edges}")
+    sizes = np.full(num_dummy, pad // num_dummy, dtype=np.int64)
+    sizes[: pad % num_dummy] += 1
+    out = MolBatch()
+    out.__dict__.update(batch.__dict__)
+    zl = lambda n: torch.zeros(n, dtype=torch.long)
+    out.atom_features_map = {k: torch.cat([v, zl(pad)]) for k, v in batch.atom_features_map.items()}
+    out.batch_indices = torch.cat([batch.batch_indices, torch.from_numpy(np.repeat(np.arange(B, B + num_dummy), sizes))])
+    out.batch = out.batch_indices
+    out.x = torch.cat([batch.x, torch.zeros((pad,) + tuple(batch.x.shape[1:]), dtype=batch.x.dtype)], 0)
+    if isinstance(batch.targets, torch.Tensor):
+        out.targets = torch.cat([batch.targets, torch.zeros((num_dummy,) + tuple(batch.targets.shape[1:]))], 0)
+    out.total_charges = torch.cat([batch.total_charges, torch.zeros(num_dummy)])
+    if batch.atomic_numbers is not None:
+        out.atomic_numbers = torch.cat([batch.atomic_numbers, zl(pad)])
+    out.smiles_list = list(batch.smiles_list) + [""] * num_dummy
+    gi = GraphIndex.build(batch.multi_hop_edge_indices, out.batch_indices, B + num_dummy, gi0.num_hops,
+                          out.atom_features_map, feature_sizes or {k: v[2] for k, v in gi0.embed.items()},
+                          batch.final_tetrahedral_chiral_tensor, batch.final_cis_tensor, batch.final_trans_tensor, tile_rows)
+    if not (gi.collapsed and gi.tile_local):
+        raise ValueError("static padding supports the shipped collation only (no edge leaves its molecule)")
+
+    def grow(t: torch.Tensor, n: int, fill: int) -> torch.Tensor:
+        return t if t.numel() >= n else torch.cat([t, torch.full((n - t.numel(),), fill, dtype=t.dtype)])
+
+    gi.col, gi.col_t = grow(gi.col, num_edges, 0), grow(gi.col_t, num_edges, 0)
+    nt = gi.n_tiles if num_tiles is None else int(num_tiles)
+    if gi.n_tiles > nt:
+        raise ValueError(f"batch needs {gi.n_tiles} row tiles, capacity {nt}")
+    gi.tile_ptr = grow(gi.tile_ptr, nt + 1, num_atoms)
+    gi.n_tiles = nt
+    gi.max_tile_rows = max(int(tile_rows), 29)
+    gi.max_seg = max(int(tile_rows), 29)
+    out.graph_index = gi
+    out.num_real_graphs = B
+    return out
+
+
+def static_signature(batch: MolBatch) -> tuple:
+    """Everything a captured step bakes in: two padded batches are interchangeable iff their signatures are equal."""
+    gi = batch.graph_index
+    return (gi.num_atoms, gi.num_graphs, gi.num_rows, gi.n_tiles, gi.max_tile_rows, gi.max_seg, int(gi.col.numel()),
+            gi.collapsed, gi.tile_local, gi.tetra is None, gi.cistrans is None, getattr(batch, "num_real_graphs", gi.num_graphs),
+            tuple(sorted((k, v[2]) for k, v in gi.embed.items())))
+
+
 def collate_fn(data_list):
     """Drop-in for ``iterable_collate_fn`` (datasets/loaders.py:10-15)."""
     kept = [d for d in data_list if d is not None]

@@ -52,6 +52,7 @@ struct TcArgs {
   int BN;
   int stages;
   int tmem_cols;
+  int acc2;                            // column offset of the small-term accumulator (0: single accumulator)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX
@@ -112,6 +113,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // Shared-memory matrix descriptor, K-major operand, 64-byte swizzle (cute::UMMA::SmemDescriptor; canonical layout
 // Swizzle<2,4,3> o ((8,n),(4,2)):((16,SBO),(1,4)) in fp32 elements: rows of 64 bytes, 8-row groups of 512 bytes):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |
@@ -149,7 +161,7 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
 // space; behind a real call it degrades to generic loads that must be re-issued after every global store.
 template <int ACT, int DACT, bool DROP>
 __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws, const EpiCtx& cx, uint32_t tmem_base,
-                                         float* stg, int m0, int n0, int q, int lane, int first_chunk,
+                                         float* stg, int m0, int n0, int q, int lane, int first_chunk, uint32_t acc2,
                                          unsigned long long* dbg = nullptr) {
   const int64_t M = e.M;
   const int N = static_cast<int>(e.N);
@@ -161,6 +173,16 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
     if (dbg != nullptr && c0 == 0) dbg[8] = gtime();
     tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
     if (dbg != nullptr && c0 == 0) dbg[9] = gtime();
+    if (acc2 != 0) {      // main (hi*hi) + small-term accumulator, summed here in round-to-nearest
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r2[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc2 + static_cast<uint32_t>(c0 + 16 * hh), r2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          r[16 * hh + j] = __float_as_uint(__uint_as_float(r[16 * hh + j]) + __uint_as_float(r2[j]));
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
     __syncwarp();
@@ -265,11 +287,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < TC_BK / 8; ++j) {
           const uint64_t adv = static_cast<uint64_t>((j * 8 * 4) >> 4);     // 32 bytes per k-step inside the swizzle row
-          // smallest terms first; the lo*lo term (2^-22 relative) is kept so that the result is at fp32 level
-          umma_tf32(tmem_base, da_lo + adv, db_lo + adv, idesc, (kb | j) != 0 ? 1u : 0u);
-          umma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, 1u);
-          umma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
-          umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, 1u);
+          // The tensor core's fp32 accumulation truncates, so every MMA into a large accumulator costs up to one
+          // ulp of it.  When TMEM allows (acc2 != 0) the three small terms go to their own accumulator (2^-11 of the
+          // magnitude, so their truncation is negligible) and only hi*hi touches the main one.
+          const uint32_t first = (kb | j) != 0 ? 1u : 0u;
+          const uint32_t t_small = tmem_base + static_cast<uint32_t>(g.acc2);
+          umma_tf32(t_small, da_lo + adv, db_lo + adv, idesc, first);
+          umma_tf32(t_small, da_lo + adv, db_hi + adv, idesc, 1u);
+          umma_tf32(t_small, da_hi + adv, db_lo + adv, idesc, 1u);
+          umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, g.acc2 != 0 ? first : 1u);
         }
         umma_commit(&empty_bar[s]);      // stage free once these MMAs have read it
       }
@@ -310,7 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     const bool dropping = cx.dropping;
     AX2D_EPI_DISPATCH(g.e.act, g.e.dact, dropping, {
       tc_epilogue<ACT, DACT, DROP>(g.e, g.BN, nullptr, cx, tmem_base, stg, m0, n0, warp & 3, lane, (warp - 2) >> 2,
-                                   (threadIdx.x == 64 && blockIdx.x == 0 && blockIdx.y == 0) ? g.dbg : nullptr);
+                                   static_cast<uint32_t>(g.acc2), (threadIdx.x == 64 && blockIdx.x == 0 && blockIdx.y == 0) ? g.dbg : nullptr);
     });
     if (threadIdx.x == 64) TC_STAMP(6);
   }
@@ -347,6 +373,7 @@ struct WgArgs {
   int b_start[AX2D_MAX_SEG + 1], b_nseg;
   int num_kb, kb_per_split;
   int BN, stages, tmem_cols;
+  int acc2;                        // column offset of the small-term accumulator
   float* ws;                       // [splits][No][Ki] or nullptr
 };
 
@@ -436,10 +463,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_wgrad_kernel(const __gr
           const uint32_t adv = j * 1024;                   // 8 contraction rows = two 4-row swizzle atoms
           const uint64_t dah = smem_desc_mn_sw128_32b(a_hi + adv), dal = smem_desc_mn_sw128_32b(a_lo + adv);
           const uint64_t dbh = smem_desc_mn_sw128_32b(b_hi + adv), dbl = smem_desc_mn_sw128_32b(b_lo + adv);
-          umma_tf32(tmem_base, dal, dbl, idesc, (it | j) != 0 ? 1u : 0u);
-          umma_tf32(tmem_base, dal, dbh, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          const uint32_t first = (it | j) != 0 ? 1u : 0u;
+          const uint32_t t_small = tmem_base + static_cast<uint32_t>(g.acc2);    // see gemm_tc_kernel
+          umma_tf32(t_small, dal, dbl, idesc, first);
+          umma_tf32(t_small, dal, dbh, idesc, 1u);
+          umma_tf32(t_small, dah, dbl, idesc, 1u);
+          umma_tf32(tmem_base, dah, dbh, idesc, first);
         }
         umma_commit(&empty_bar[s]);
       }
@@ -474,7 +503,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_wgrad_kernel(const __gr
     float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
     const EpiCtx cx = epi_ctx(g.e);
     float* ws = g.ws != nullptr ? g.ws + static_cast<int64_t>(blockIdx.z) * g.e.M * g.e.N : nullptr;
-    tc_epilogue<AX2D_ACT_NONE, AX2D_ACT_NONE, false>(g.e, BN, ws, cx, tmem_base, stg, m0, n0, warp & 3, lane, (warp - 2) >> 2);
+    tc_epilogue<AX2D_ACT_NONE, AX2D_ACT_NONE, false>(g.e, BN, ws, cx, tmem_base, stg, m0, n0, warp & 3, lane, (warp - 2) >> 2,
+                                                     static_cast<uint32_t>(g.acc2));
   }
   tc_fence_before();
   __syncthreads();
@@ -613,6 +643,10 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
   BN = (BN + 31) / 32 * 32;
   g.BN = BN;
   g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  if (BN <= 128) {          // two CTAs per SM share 512 TMEM columns: a second accumulator fits only for narrow tiles
+    g.acc2 = g.tmem_cols;
+    g.tmem_cols *= 2;
+  }
   int acc = 0, kb = 0;
   g.n_seg = a->n_seg;
   for (int s = 0; s < a->n_seg; ++s) {
@@ -712,6 +746,8 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
   BN = (BN + 31) / 32 * 32;
   g.BN = BN;
   g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  g.acc2 = g.tmem_cols;     // one CTA per SM: main + small-term accumulator (<= 512 columns)
+  g.tmem_cols *= 2;
   const int m_tiles = static_cast<int>((M + TC_BM - 1) / TC_BM);
   g.num_kb = static_cast<int>((K + WG_KB - 1) / WG_KB);
   int split = (kNumSMs + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);

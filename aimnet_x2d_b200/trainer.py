@@ -11,7 +11,9 @@ from typing import Optional
 
 import torch
 
-from .collate import MolBatch
+import torch.distributed as dist
+
+from .collate import MolBatch, static_signature
 from .optim import FlatAdam
 
 
@@ -44,4 +46,99 @@ class TrainStep:
         """Host batch in, loss out: includes the H2D copies and (``return_float``) the ``loss.item()``
         device->host read the reference does every step (trainer.py:169)."""
         loss = self.device_step(self.to_device(batch))
+        return float(loss.item()) if return_float else loss
+
+
+def _batch_tensors(b: MolBatch):
+    """Every tensor of a (padded) batch that the step reads on the device, in a fixed order."""
+    gi = b.graph_index
+    ts = [b.batch_indices, b.targets, b.total_charges, b.final_tetrahedral_chiral_tensor, b.final_cis_tensor,
+          b.final_trans_tensor]
+    ts += [b.atom_features_map[k] for k in sorted(b.atom_features_map)]
+    ts += [gi.rowptr, gi.col, gi.rowptr_t, gi.col_t, gi.seg_ptr, gi.tile_ptr]
+    for k in sorted(gi.embed):
+        ts += [gi.embed[k][0], gi.embed[k][1]]
+    return ts
+
+
+class GraphedTrainStep:
+    """The same training step captured ONCE as CUDA graphs and replayed for every batch of the same static
+    signature (``collate.pad_batch``): no per-kernel host work is left in the loop, which is what lets a ~3 ms GPU
+    step run at GPU speed (the eager path needs ~10 ms of Python / launch time for its ~250 launches).
+
+    Per step: H2D copies of the batch into the static device slot -> graph A (zero_grad, forward, loss, backward)
+    -> [world > 1: ONE NCCL all-reduce of the flat gradient arena] -> graph B (clip + Adam).  The loss is a static
+    device scalar; ``__call__`` reads it back like ``trainer.py:169`` does.
+    """
+
+    def __init__(self, model: torch.nn.Module, criterion: torch.nn.Module, optimizer: FlatAdam, device=None):
+        self.eager = TrainStep(model, criterion, optimizer, device)
+        self.model, self.criterion, self.optimizer = model, criterion, optimizer
+        self.device = self.eager.device
+        self.slot: Optional[MolBatch] = None
+        self.signature = None
+        self.graph_fb = self.graph_opt = None
+        self.loss = None
+
+    def _fwd_bwd(self) -> torch.Tensor:
+        bd, opt = self.slot, self.optimizer
+        opt.zero_grad()
+        out, _, _ = self.model(bd.atom_features_map, bd.multi_hop_edge_indices, bd.batch_indices, bd.total_charges,
+                               bd.final_tetrahedral_chiral_tensor, bd.final_cis_tensor, bd.final_trans_tensor,
+                               graph_index=bd.graph_index)
+        n = getattr(bd, "num_real_graphs", out.shape[0])          # dummy (padding) molecules carry no loss
+        loss = self.criterion(out[:n], bd.targets[:n])
+        loss.backward()
+        return loss.detach()
+
+    def capture(self, padded: MolBatch, warmup: int = 3) -> None:
+        """Allocate the static slot from ``padded`` (a host batch from ``pad_batch``), run ``warmup`` eager steps on a
+        side stream (their effect on parameters / optimiser state is rolled back), then capture."""
+        opt = self.optimizer
+        self.slot = padded.to(self.device)
+        self.signature = static_signature(padded)
+        saved = [t.clone() for t in (opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.step_count)]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._fwd_bwd()
+                opt.all_reduce_grads()
+                opt.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fb):
+            self.loss = self._fwd_bwd()
+        self.graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_opt):
+            opt.step()
+        with torch.no_grad():
+            for dst, src in zip((opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.step_count), saved):
+                dst.copy_(src)
+        torch.cuda.synchronize()
+
+    def load(self, padded: MolBatch) -> None:
+        """H2D copies of a padded host batch into the static slot (pinned source => asynchronous)."""
+        if static_signature(padded) != self.signature:
+            raise RuntimeError("batch does not match the static signature the step was captured for; pad it with the "
+                               "same capacities (collate.pad_batch) or capture a new GraphedTrainStep")
+        for dst, src in zip(_batch_tensors(self.slot), _batch_tensors(padded)):
+            if dst.shape != src.shape:
+                raise RuntimeError(f"static slot tensor {tuple(dst.shape)} vs batch tensor {tuple(src.shape)}")
+            if dst.numel():
+                dst.copy_(src, non_blocking=True)
+
+    def replay(self) -> torch.Tensor:
+        self.graph_fb.replay()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.optimizer.all_reduce_grads()
+        self.graph_opt.replay()
+        return self.loss
+
+    def __call__(self, padded: MolBatch, return_float: bool = True):
+        if self.graph_fb is None:
+            self.capture(padded)
+        self.load(padded)
+        loss = self.replay()
         return float(loss.item()) if return_float else loss

@@ -209,12 +209,24 @@ def reference_arm(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def pad_ring(batches, n_dummy=64):
+    """Static-shape versions of the ring's batches (one CUDA-graph capture serves all of them)."""
+    from aimnet_x2d_b200.collate import pad_batch
+    n_max = max(b.graph_index.num_atoms for b in batches)
+    e_max = max(b.graph_index.num_edges for b in batches)
+    n_pad = (n_max + n_dummy + 127) // 128 * 128
+    e_cap = (int(e_max * 1.02) + 1023) // 1024 * 1024
+    first = [pad_batch(b, n_pad, e_cap, n_dummy) for b in batches]
+    t_cap = max(p.graph_index.n_tiles for p in first) + 8
+    return [pad_batch(b, n_pad, e_cap, n_dummy, t_cap) for b in batches]
+
+
 def ours_arm(args, wl):
     import torch.distributed as dist
 
     import aimnet_x2d_b200 as ax
     from aimnet_x2d_b200 import ops
-    from aimnet_x2d_b200.trainer import TrainStep
+    from aimnet_x2d_b200.trainer import GraphedTrainStep, TrainStep, _batch_tensors
     rank, local_rank, world = env_rank()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
@@ -222,7 +234,9 @@ def ours_arm(args, wl):
     device = torch.device(f"cuda:{local_rank}")
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    host = [b.pin_memory() for b in make_batches(wl, rank, RING)]
+    raw = make_batches(wl, rank, RING)
+    graphs = not args.eager and not wl["stereo"]
+    host = [b.pin_memory() for b in (pad_ring(raw) if graphs else raw)]
     dev_batches = [b.to(device) for b in host]
     model = build_model(wl, device)
     weights = torch.ones(T_TARGETS)
@@ -230,7 +244,24 @@ def ours_arm(args, wl):
     opt = ax.FlatAdam(model.parameters(), lr=2.5e-4, max_grad_norm=1.0)
     if world > 1:                                          # DDP broadcasts rank 0's parameters at wrap time
         dist.broadcast(opt.flat_param, src=0)
-    stepper = TrainStep(model, crit, opt, device)
+    eager = TrainStep(model, crit, opt, device)
+    launches_per_step = None
+    if graphs:
+        stepper = GraphedTrainStep(model, crit, opt, device)
+        l0 = ops.launch_count()
+        stepper.capture(host[0], warmup=2)
+        launches_per_step = (ops.launch_count() - l0) // 3      # 2 eager warm-ups + 1 capture pass
+
+        def dev_step(i):                                   # batch i is already in HBM: D2D into the static slot
+            stepper.load(dev_batches[i % RING])
+            return stepper.replay()
+
+        def host_step(i):                                  # public call: pinned host batch -> H2D -> replay -> loss
+            return stepper(host[i % RING])
+    else:
+        stepper = eager
+        dev_step = lambda i: eager.device_step(dev_batches[i % RING])
+        host_step = lambda i: eager(host[i % RING])
 
     def barrier():
         if world > 1:
@@ -239,21 +270,18 @@ def ours_arm(args, wl):
 
     # ---- device-resident: `value`
     for i in range(args.warmup):
-        stepper.device_step(dev_batches[i % RING])
+        dev_step(i)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    timer = ops.KernelTimer()
-    ops.TIMER = timer
     l0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        loss = stepper.device_step(dev_batches[i % RING])
+        loss = dev_step(i)
     e1.record()
     barrier()
-    ops.TIMER = None
-    launches = ops.launch_count() - l0
+    launches = (ops.launch_count() - l0) if launches_per_step is None else launches_per_step * args.steps
     ms = e0.elapsed_time(e1)
     sampler.stop_flag.set()
     sampler.join()
@@ -261,17 +289,30 @@ def ours_arm(args, wl):
 
     # ---- end to end through the public call: host batches, H2D inside, loss read back every step
     for i in range(max(args.warmup, 1)):
-        stepper(host[i % RING])
+        host_step(i)
     barrier()
-    t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
-        stepper(host[i % RING])
+        host_step(i)
     f1.record()
     barrier()
-    ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3 * 0.0)
     ms_e2e = f0.elapsed_time(f1)
+
+    # ---- per-kernel CUDA-event timing: the same steps replayed eagerly (events cannot be recorded inside a graph)
+    timer = ops.KernelTimer()
+    n_prof = min(args.steps, 5)
+    eager.device_step(dev_batches[0])
+    barrier()
+    ops.TIMER = timer
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for i in range(n_prof):
+        eager.device_step(dev_batches[i % RING])
+    p1.record()
+    barrier()
+    ops.TIMER = None
+    ms_prof = p0.elapsed_time(p1)
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
     if world > 1:
@@ -283,42 +324,52 @@ def ours_arm(args, wl):
         ks = timer.summary()
         step_ms = ms / args.steps
         roof = roof_dense = None
+        kernel_ms = sum(v["ms_total"] for v in ks.values()) / n_prof     # per step, timed launch groups only
         if "agg" in ks:
             a = ks["agg"]
             ach = a["bytes_avg"] / (a["ms_avg"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": "ax2d_agg (agg_kernel: CSR gather-reduce, fwd + bwd launches)",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                    "peak_source": peak_src, "launches_per_step": a["launches"] / args.steps,
+                    "peak_source": peak_src, "launches_per_step": a["launches"] / n_prof,
                     "avg_launch_us": a["ms_avg"] * 1e3, "algorithmic_bytes_per_launch": a["bytes_avg"],
-                    "share_of_step": a["ms_total"] / ms}
-        if "gemm" in ks:
-            g = ks["gemm"]
-            tf = g["flops_avg"] / (g["ms_avg"] * 1e-3) / 1e12
-            fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FFMA lanes x 2 flop x max clock
-            roof_dense = {"bound": "fp32-ffma", "kernel": "ax2d_gemm (gemm_kernel: exact-fp32 SIMT, fused epilogues)",
-                          "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
-                          "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (no measured fp32 peak on file)",
-                          "launches_per_step": g["launches"] / args.steps, "avg_launch_us": g["ms_avg"] * 1e3,
-                          "share_of_step": g["ms_total"] / ms}
-        h2d = host[0].nbytes()
+                    "share_of_step": a["ms_total"] / n_prof / step_ms,
+                    "timing": "CUDA events around each launch, eager replay of the timed steps (not recordable inside a graph)"}
+        dense = [k for k in ("gemm_tc", "gemm_tc_wgrad", "gemm") if k in ks]
+        if dense:
+            fl = sum(ks[k]["flops_avg"] * ks[k]["launches"] for k in dense)
+            tm = sum(ks[k]["ms_total"] for k in dense) * 1e-3
+            tf = fl / tm / 1e12
+            tf32_peak = 0.5 * 1393.4            # dense TF32 = half the measured sustained bf16 rate (MEASURED_PEAKS.json)
+            roof_dense = {"bound": "tensor", "kernel": "ax2d_gemm_tc / ax2d_gemm_tc_wgrad (tcgen05 kind::tf32, 4 MMAs per "
+                                                         "k-step: fp32-faithful split) + SIMT remainder",
+                          "achieved": tf, "peak": tf32_peak, "unit": "TFLOP/s (useful fp32 flops)", "frac": tf / tf32_peak,
+                          "peak_source": "0.5 x measured sustained bf16 (MEASURED_PEAKS.json); the split issues 4 tf32 "
+                                         "MMAs per useful product, so frac <= 0.25 by construction",
+                          "launches_per_step": sum(ks[k]["launches"] for k in dense) / n_prof,
+                          "share_of_step": tm * 1e3 / n_prof / step_ms}
+        h2d = sum(t_.numel() * t_.element_size() for t_ in _batch_tensors(host[0])) if graphs else host[0].nbytes()
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _, _ = run_cpu(wl, 2, 1, budget_s=20.0)
-        gi = host[0].graph_index
+        gi = raw[0].graph_index
         line = {"metric": "train molecules/sec", "value": mols / (ms * 1e-3), "unit": "molecules/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["desc"], "graphs_per_gpu": wl["graphs"], "global_batch": wl["graphs"] * world,
                            "atoms_per_batch": gi.num_atoms, "edges_per_batch": gi.num_edges, "targets": T_TARGETS,
                            "dropout": 0.05, "parallelism": f"dp{world}",
+                           "execution": ("CUDA graphs over static-shape (padded) batches: "
+                                         f"{host[0].graph_index.num_atoms} atom rows incl. 64 dummy molecules") if graphs
+                           else "eager launches",
                            "l2": f"ring of {RING} distinct batches per rank; per-step activations + saved tensors "
                                  f"(> 1 GB) exceed the 126 MB L2, no explicit flush"},
-                "e2e": {"value": mols / (ms_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
+                "e2e": {"value": mols / (ms_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "roofline": roof, "roofline_dense": roof_dense, "cpu_baseline": cpu,
                 "clocks": sampler.summary(), "final_loss": final_loss,
-                "timed_launch_groups": {k: {"launches_per_step": v["launches"] / args.steps, "avg_us": v["ms_avg"] * 1e3,
-                                            "share_of_step": v["ms_total"] / ms} for k, v in ks.items()}}
+                "eager_ms_per_step": ms_prof / n_prof, "timed_kernel_ms_per_step": kernel_ms,
+                "timed_launch_groups": {k: {"launches_per_step": v["launches"] / n_prof, "avg_us": v["ms_avg"] * 1e3}
+                                        for k, v in ks.items()}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -332,6 +383,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="per-kernel launches instead of CUDA graphs")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload], name=args.workload)
     if args.impl == "reference":

@@ -1,0 +1,93 @@
+"""GPU: static-shape padding (collate.pad_batch) and the CUDA-graph captured training step (trainer.GraphedTrainStep)
+against the eager step on the same batches."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import RTOL_F32, assert_close, gnn_shapes
+from oracle.fixtures import FEATURE_SIZES, det_state
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+CFG = dict(hidden_dim=64, num_shells=3, num_message_passing_layers=2)
+
+
+def _model(seed=9):
+    import aimnet_x2d_b200 as ax
+    m = ax.GNN(FEATURE_SIZES, 64, 3, num_shells=3, num_message_passing_layers=2, task_type="multitask",
+               shell_conv_dropout=0.0, ffn_dropout=0.0)
+    m.load_state_dict(det_state(gnn_shapes(CFG, 3), seed))
+    return m.to(DEV).train()
+
+
+def _fwd(model, b):
+    return model(b.atom_features_map, b.multi_hop_edge_indices, b.batch_indices, b.total_charges,
+                 b.final_tetrahedral_chiral_tensor, b.final_cis_tensor, b.final_trans_tensor, graph_index=b.graph_index)
+
+
+def test_padding_leaves_real_molecules_untouched():
+    import aimnet_x2d_b200 as ax
+    from aimnet_x2d_b200 import synthetic as S
+    from aimnet_x2d_b200.collate import pad_batch
+    raw = S.make_batch(31, 24, 3, "qm9", num_targets=3)
+    N = raw.graph_index.num_atoms
+    pad = pad_batch(raw, N + 100, raw.graph_index.num_edges + 500, num_dummy=8)
+    assert pad.graph_index.num_atoms == N + 100 and pad.graph_index.num_graphs == 32 and pad.num_real_graphs == 24
+    assert np.array_equal(pad.graph_index.rowptr.numpy()[: N + 1], raw.graph_index.rowptr.numpy())
+    assert np.all(pad.graph_index.rowptr.numpy()[N:] == raw.graph_index.num_edges)        # dummy atoms have no edges
+    crit = ax.WeightedL1Loss(torch.ones(3)).to(DEV)
+    outs, grads = [], []
+    for b, n in ((raw.to(DEV), 24), (pad.to(DEV), 24)):
+        model = _model()
+        out, attn, _ = _fwd(model, b)
+        crit(out[:n], b.targets[:n]).backward()
+        outs.append((out[:n].detach().cpu().numpy(), attn[:, :N].detach().cpu().numpy()))
+        grads.append({k: p.grad.detach().cpu().numpy() for k, p in model.named_parameters() if p.grad is not None})
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for k in grads[0]:
+        if "attention_weights" in k and k.endswith(".bias"):
+            continue                                           # rounding noise of an exactly cancelling sum
+        assert_close(grads[1][k], grads[0][k], RTOL_F32, "padded vs unpadded grad " + k)
+
+
+def test_graph_replay_equals_eager_step():
+    import aimnet_x2d_b200 as ax
+    from aimnet_x2d_b200 import synthetic as S
+    from aimnet_x2d_b200.collate import pad_batch
+    from aimnet_x2d_b200.trainer import GraphedTrainStep, TrainStep
+    raws = [S.make_batch(40 + i, 24, 3, "qm9", num_targets=3) for i in range(3)]
+    n_pad = max(b.graph_index.num_atoms for b in raws) + 64
+    e_cap = max(b.graph_index.num_edges for b in raws) + 64
+    first = [pad_batch(b, n_pad, e_cap, 8) for b in raws]
+    t_cap = max(p.graph_index.n_tiles for p in first) + 2
+    padded = [pad_batch(b, n_pad, e_cap, 8, t_cap).pin_memory() for b in raws]
+    crit = ax.WeightedL1Loss(torch.linspace(0.5, 1.5, 3)).to(DEV)
+    m_e, m_g = _model(), _model()
+    o_e = ax.FlatAdam(m_e.parameters(), lr=1e-3)
+    o_g = ax.FlatAdam(m_g.parameters(), lr=1e-3)
+
+    class PaddedEager(TrainStep):                              # eager step with the same "real rows only" loss
+        def device_step(self, bd):
+            self.optimizer.zero_grad()
+            out, _, _ = _fwd(self.model, bd)
+            loss = self.criterion(out[: bd.num_real_graphs], bd.targets[: bd.num_real_graphs])
+            loss.backward()
+            self.optimizer.step()
+            return loss.detach()
+
+    eager = PaddedEager(m_e, crit, o_e, DEV)
+    graphed = GraphedTrainStep(m_g, crit, o_g, DEV)
+    graphed.capture(padded[0], warmup=2)
+    assert torch.equal(o_g.flat_param, o_e.flat_param)         # warm-up steps were rolled back
+    assert int(o_g.step_count) == 0
+    for it in range(5):
+        b = padded[it % 3]
+        le = eager(b)
+        lg = graphed(b)
+        assert le == lg, (it, le, lg)
+    torch.cuda.synchronize()
+    assert torch.equal(o_g.flat_param, o_e.flat_param) and int(o_g.step_count) == 5
+    # a batch padded to other capacities is refused instead of silently replaying the wrong launch configuration
+    other = pad_batch(raws[0], n_pad + 128, e_cap, 8, t_cap + 4)
+    with pytest.raises(RuntimeError):
+        graphed(other)
