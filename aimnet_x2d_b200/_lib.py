@@ -42,7 +42,7 @@ _SIGNATURES = {
                                     C.POINTER(c_int64), C.POINTER(c_int64), C.POINTER(C.c_int32)]),
     "ax2d_host_shell_edges": (c_int64, [c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64]),
     "ax2d_agg": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
-                         c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_void_p]),
+                         c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "ax2d_attn_pool_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ax2d_attn_pool_bwd_workspace": (c_int64, [c_int64, c_int, c_int]),

@@ -41,7 +41,8 @@ class GraphIndex:
     ``tile_local``      True when no edge leaves its tile (no edge leaves its molecule, molecular.py:429-433)
     """
 
-    _TENSORS = ("rowptr", "col", "rowptr_t", "col_t", "seg_ptr", "tile_ptr")
+    _TENSORS = ("rowptr", "col", "rowptr_t", "col_t", "seg_ptr", "tile_ptr", "tile_info", "tile_info_t")
+    INDEX_SLACK = 8     # readable entries past the logical end of rowptr / col (16-byte copy windows of the tiled kernel)
 
     def __init__(self):
         self.num_atoms = 0
@@ -53,8 +54,10 @@ class GraphIndex:
         self.tile_local = False
         self.n_tiles = 0
         self.max_tile_rows = 0
+        self.max_tile_edges = 0
         self.max_seg = 0
         self.rowptr = self.col = self.rowptr_t = self.col_t = self.seg_ptr = self.tile_ptr = None
+        self.tile_info = self.tile_info_t = None     # [n_tiles, 4] int32: row0, row1, rowptr[row0], rowptr[row1]
         self.embed: Dict[str, tuple] = {}      # name -> (order int32 [N], ptr int32 [vocab+1], vocab)
         self.tetra = None                      # (idx int32 [M,4], slot_ptr int32 [N+1], slot_idx int32 [4M], M)
         self.cistrans = None                   # (src int32, tgt int32, sign f32, n_upd)
@@ -95,10 +98,11 @@ class GraphIndex:
             gi.collapsed = tmax < N
         R = N if gi.collapsed else num_hops * N
         gi.num_rows = R
-        rowptr = np.zeros(R + 1, dtype=np.int32)
-        col = np.zeros(max(E, 1), dtype=np.int32)
-        rowptr_t = np.zeros(N + 1, dtype=np.int32)
-        col_t = np.zeros(max(E, 1), dtype=np.int32)
+        slack = GraphIndex.INDEX_SLACK
+        rowptr = np.zeros(R + 1 + slack, dtype=np.int32)
+        col = np.zeros(max(E, 1) + slack, dtype=np.int32)
+        rowptr_t = np.zeros(N + 1 + slack, dtype=np.int32)
+        col_t = np.zeros(max(E, 1) + slack, dtype=np.int32)
         if E:
             se, sc = (s // 8 for s in e_np.strides)
             _lib.check(lib.ax2d_host_csr_build(_ptr(e_np), E, se, sc, N, R, 0, _ptr(rowptr), _ptr(col), None),
@@ -121,10 +125,13 @@ class GraphIndex:
             _lib.check(lib.ax2d_host_tile_plan(_ptr(seg), B, cap, _ptr(rowptr_t), _ptr(col_t), _ptr(tp2),
                                                C.byref(t2), C.byref(m2), C.byref(l2)), "ax2d_host_tile_plan")
             gi.tile_local = bool(l2.value)
+        rowptr[R + 1:] = E                       # slack entries: harmless values
+        rowptr_t[N + 1:] = E
         gi.rowptr, gi.col = torch.from_numpy(rowptr), torch.from_numpy(col)
         gi.rowptr_t, gi.col_t = torch.from_numpy(rowptr_t), torch.from_numpy(col_t)
         gi.seg_ptr = torch.from_numpy(seg)
         gi.tile_ptr = torch.from_numpy(tile_ptr[: gi.n_tiles + 1].copy())
+        gi.refresh_tile_info()
 
         if atom_features is not None:
             sizes = feature_sizes or {}
@@ -132,6 +139,22 @@ class GraphIndex:
                 gi.add_embedding_index(name, idx, sizes.get(name))
         gi.set_stereo(tetra, cis, trans)
         return gi
+
+    def refresh_tile_info(self) -> None:
+        """Per-tile descriptors of the persistent aggregation kernel, for the forward and the transposed CSR."""
+        tp = self.tile_ptr.numpy().astype(np.int64)
+        nt = self.n_tiles
+        if nt == 0 or not self.collapsed:
+            self.tile_info = self.tile_info_t = None
+            self.max_tile_edges = 0
+            return
+        mx = 0
+        for name, rp in (("tile_info", self.rowptr), ("tile_info_t", self.rowptr_t)):
+            r = rp.numpy()
+            info = np.stack([tp[:nt], tp[1:nt + 1], r[tp[:nt]], r[tp[1:nt + 1]]], axis=1).astype(np.int32)
+            mx = max(mx, int((info[:, 3] - info[:, 2]).max()))
+            setattr(self, name, torch.from_numpy(np.ascontiguousarray(info)))
+        self.max_tile_edges = mx
 
     def add_embedding_index(self, name: str, idx, vocab: Optional[int] = None) -> None:
         """Atoms sorted (stably) by table row: the CPU ``index_add`` order of the embedding backward."""
@@ -183,7 +206,7 @@ class GraphIndex:
         out.__dict__.update(self.__dict__)
         mv = lambda t: t.to(device, non_blocking=non_blocking)
         for k in self._TENSORS:
-            setattr(out, k, mv(getattr(self, k)))
+            setattr(out, k, None if getattr(self, k) is None else mv(getattr(self, k)))
         out.embed = {k: (mv(o), mv(p), v) for k, (o, p, v) in self.embed.items()}
         if self.tetra is not None:
             i, sp, si, M = self.tetra
@@ -197,7 +220,7 @@ class GraphIndex:
         out = GraphIndex()
         out.__dict__.update(self.__dict__)
         for k in self._TENSORS:
-            setattr(out, k, getattr(self, k).pin_memory())
+            setattr(out, k, None if getattr(self, k) is None else getattr(self, k).pin_memory())
         out.embed = {k: (o.pin_memory(), p.pin_memory(), v) for k, (o, p, v) in self.embed.items()}
         if self.tetra is not None:
             i, sp, si, M = self.tetra
@@ -208,7 +231,7 @@ class GraphIndex:
         return out
 
     def nbytes(self) -> int:
-        n = sum(getattr(self, k).numel() * 4 for k in self._TENSORS)
+        n = sum(getattr(self, k).numel() * 4 for k in self._TENSORS if getattr(self, k) is not None)
         n += sum((o.numel() + p.numel()) * 4 for o, p, _ in self.embed.values())
         if self.tetra is not None:
             n += sum(t.numel() * 4 for t in self.tetra[:3])
@@ -348,7 +371,8 @@ class MolBatch:
 
 
 def pad_batch(batch: MolBatch, num_atoms: int, num_edges: int, num_dummy: int = 64, num_tiles: Optional[int] = None,
-              tile_rows: int = DEFAULT_TILE_ROWS, feature_sizes: Optional[Dict[str, int]] = None) -> MolBatch:
+              tile_rows: int = DEFAULT_TILE_ROWS, feature_sizes: Optional[Dict[str, int]] = None,
+              max_tile_edges: int = 0) -> MolBatch:
     """Static-shape version of a collated batch (what a CUDA-graph-captured training step needs: every launch
     configuration and scalar kernel argument must be the same from batch to batch).
 
@@ -388,13 +412,16 @@ def pad_batch(batch: MolBatch, num_atoms: int, num_edges: int, num_dummy: int = 
     def grow(t: torch.Tensor, n: int, fill: int) -> torch.Tensor:
         return t if t.numel() >= n else torch.cat([t, torch.full((n - t.numel(),), fill, dtype=t.dtype)])
 
-    gi.col, gi.col_t = grow(gi.col, num_edges, 0), grow(gi.col_t, num_edges, 0)
+    gi.col = grow(gi.col, num_edges + GraphIndex.INDEX_SLACK, 0)
+    gi.col_t = grow(gi.col_t, num_edges + GraphIndex.INDEX_SLACK, 0)
     nt = gi.n_tiles if num_tiles is None else int(num_tiles)
     if gi.n_tiles > nt:
         raise ValueError(f"batch needs {gi.n_tiles} row tiles, capacity {nt}")
     gi.tile_ptr = grow(gi.tile_ptr, nt + 1, num_atoms)
     gi.n_tiles = nt
+    gi.refresh_tile_info()                      # trailing tiles are empty: {N, N, E, E}
     gi.max_tile_rows = max(int(tile_rows), 29)
+    gi.max_tile_edges = max(gi.max_tile_edges, int(max_tile_edges))
     gi.max_seg = max(int(tile_rows), 29)
     out.graph_index = gi
     out.num_real_graphs = B
@@ -404,7 +431,8 @@ def pad_batch(batch: MolBatch, num_atoms: int, num_edges: int, num_dummy: int = 
 def static_signature(batch: MolBatch) -> tuple:
     """Everything a captured step bakes in: two padded batches are interchangeable iff their signatures are equal."""
     gi = batch.graph_index
-    return (gi.num_atoms, gi.num_graphs, gi.num_rows, gi.n_tiles, gi.max_tile_rows, gi.max_seg, int(gi.col.numel()),
+    return (gi.num_atoms, gi.num_graphs, gi.num_rows, gi.n_tiles, gi.max_tile_rows, gi.max_tile_edges, gi.max_seg,
+            int(gi.col.numel()),
             gi.collapsed, gi.tile_local, gi.tetra is None, gi.cistrans is None, getattr(batch, "num_real_graphs", gi.num_graphs),
             tuple(sorted((k, v[2]) for k, v in gi.embed.items())))
 

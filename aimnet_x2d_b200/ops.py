@@ -179,13 +179,14 @@ def agg(x: torch.Tensor, gi, transpose: bool = False, addend: Optional[torch.Ten
     N, width = gi.num_atoms, x.shape[1]
     rows = N if transpose else gi.num_rows
     out = torch.empty((rows, width), dtype=x.dtype, device=x.device)
-    rowptr, col = (gi.rowptr_t, gi.col_t) if transpose else (gi.rowptr, gi.col)
-    tiled = (gi.tile_local and gi.collapsed and x.stride(0) == width and width % 32 == 0
-             and gi.max_tile_rows * width * 4 <= 200 * 1024 and gi.n_tiles > 0)
+    rowptr, col, info = (gi.rowptr_t, gi.col_t, gi.tile_info_t) if transpose else (gi.rowptr, gi.col, gi.tile_info)
+    tiled = (gi.tile_local and gi.collapsed and x.stride(0) == width and width % 32 == 0 and info is not None
+             and gi.max_tile_rows * width * 4 + gi.max_tile_edges * 4 <= 200 * 1024 and gi.n_tiles > 0)
     call = lambda: _lib.check(lib.ax2d_agg(_p(x), x.stride(0), x.shape[0], _p(out), out.stride(0), rows, _p(rowptr),
                                            _p(col), _p(addend), 0 if addend is None else addend.stride(0), width,
-                                           _p(gi.tile_ptr) if tiled else None, gi.n_tiles if tiled else 0,
-                                           gi.max_tile_rows if tiled else 0, 0, _stream()), "ax2d_agg")
+                                           _p(info) if tiled else None, gi.n_tiles if tiled else 0,
+                                           gi.max_tile_rows if tiled else 0, gi.max_tile_edges if tiled else 0, 0,
+                                           _stream()), "ax2d_agg")
     if TIMER is None:
         call()
     else:

@@ -55,7 +55,7 @@ def _batch_tensors(b: MolBatch):
     ts = [b.batch_indices, b.targets, b.total_charges, b.final_tetrahedral_chiral_tensor, b.final_cis_tensor,
           b.final_trans_tensor]
     ts += [b.atom_features_map[k] for k in sorted(b.atom_features_map)]
-    ts += [gi.rowptr, gi.col, gi.rowptr_t, gi.col_t, gi.seg_ptr, gi.tile_ptr]
+    ts += [gi.rowptr, gi.col, gi.rowptr_t, gi.col_t, gi.seg_ptr, gi.tile_ptr, gi.tile_info, gi.tile_info_t]
     for k in sorted(gi.embed):
         ts += [gi.embed[k][0], gi.embed[k][1]]
     return ts

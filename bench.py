@@ -218,7 +218,8 @@ def pad_ring(batches, n_dummy=64):
     e_cap = (int(e_max * 1.02) + 1023) // 1024 * 1024
     first = [pad_batch(b, n_pad, e_cap, n_dummy) for b in batches]
     t_cap = max(p.graph_index.n_tiles for p in first) + 8
-    return [pad_batch(b, n_pad, e_cap, n_dummy, t_cap) for b in batches]
+    me_cap = (max(p.graph_index.max_tile_edges for p in first) + 63) // 64 * 64
+    return [pad_batch(b, n_pad, e_cap, n_dummy, t_cap, max_tile_edges=me_cap) for b in batches]
 
 
 def ours_arm(args, wl):

@@ -81,15 +81,18 @@ int64_t ax2d_host_shell_edges(int64_t B, const int64_t* atom_ptr, const int64_t*
  *   out[r,:] = (addend ? addend[r,:] : 0) + sum_{k in [rowptr[r], rowptr[r+1])} x[col[k],:]
  * summed sequentially in CSR order (bit-identical to the reference CPU scatter_add).  Backward is the
  * same call with the transposed CSR.  width % 4 == 0.
- * Tiled mode (tile_ptr != NULL): requires n_out_rows == n_src_rows, ldx == width, width % 32 == 0 and
- * tile-local columns (ax2d_host_tile_plan); each CTA stages its tile of x in shared memory with one
- * bulk async copy and gathers from there.  Otherwise a global-gather kernel is used.
+ * Tiled mode (tile_info != NULL): requires n_out_rows == n_src_rows, ldx == width, width % 32 == 0 and tile-local
+ * columns (ax2d_host_tile_plan).  tile_info is [n_tiles][4] int32 = {row0, row1, rowptr[row0], rowptr[row1]} per tile
+ * (16-byte aligned); max_tile_rows / max_tile_edges bound row1 - row0 and the edge count of a tile.  A persistent
+ * kernel stages each tile's rows of x AND its rowptr / col windows in shared memory with bulk async copies issued by
+ * a producer warp several tiles ahead and gathers from there; rowptr and col must be readable up to 3 entries past
+ * their logical end (16-byte windows).  Otherwise a global-gather kernel is used.
  * ---------------------------------------------------------------------------------------------- */
 int ax2d_agg(const void* x, int64_t ldx, int64_t n_src_rows,
              void* out, int64_t ldo, int64_t n_out_rows,
              const int32_t* rowptr, const int32_t* col,
              const void* addend, int64_t ld_addend, int width,
-             const int32_t* tile_ptr, int64_t n_tiles, int max_tile_rows,
+             const int32_t* tile_info, int64_t n_tiles, int max_tile_rows, int max_tile_edges,
              int dtype, ax2d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ def test_padding_leaves_real_molecules_untouched():
     N = raw.graph_index.num_atoms
     pad = pad_batch(raw, N + 100, raw.graph_index.num_edges + 500, num_dummy=8)
     assert pad.graph_index.num_atoms == N + 100 and pad.graph_index.num_graphs == 32 and pad.num_real_graphs == 24
-    assert np.array_equal(pad.graph_index.rowptr.numpy()[: N + 1], raw.graph_index.rowptr.numpy())
+    assert np.array_equal(pad.graph_index.rowptr.numpy()[: N + 1], raw.graph_index.rowptr.numpy()[: N + 1])
     assert np.all(pad.graph_index.rowptr.numpy()[N:] == raw.graph_index.num_edges)        # dummy atoms have no edges
     crit = ax.WeightedL1Loss(torch.ones(3)).to(DEV)
     outs, grads = [], []
@@ -60,7 +60,8 @@ def test_graph_replay_equals_eager_step():
     e_cap = max(b.graph_index.num_edges for b in raws) + 64
     first = [pad_batch(b, n_pad, e_cap, 8) for b in raws]
     t_cap = max(p.graph_index.n_tiles for p in first) + 2
-    padded = [pad_batch(b, n_pad, e_cap, 8, t_cap).pin_memory() for b in raws]
+    me_cap = max(p.graph_index.max_tile_edges for p in first)
+    padded = [pad_batch(b, n_pad, e_cap, 8, t_cap, max_tile_edges=me_cap).pin_memory() for b in raws]
     crit = ax.WeightedL1Loss(torch.linspace(0.5, 1.5, 3)).to(DEV)
     m_e, m_g = _model(), _model()
     o_e = ax.FlatAdam(m_e.parameters(), lr=1e-3)
@@ -88,6 +89,6 @@ def test_graph_replay_equals_eager_step():
     torch.cuda.synchronize()
     assert torch.equal(o_g.flat_param, o_e.flat_param) and int(o_g.step_count) == 5
     # a batch padded to other capacities is refused instead of silently replaying the wrong launch configuration
-    other = pad_batch(raws[0], n_pad + 128, e_cap, 8, t_cap + 4)
+    other = pad_batch(raws[0], n_pad + 128, e_cap, 8, t_cap + 4, max_tile_edges=me_cap)
     with pytest.raises(RuntimeError):
         graphed(other)
