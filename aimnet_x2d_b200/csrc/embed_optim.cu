@@ -23,24 +23,43 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedArgs a, int n_table
 }
 
 // Two-level fixed-order segment sum over atoms sorted (stably) by table row.
-// grid = (vocab, splits): CTA (v, s) sums its slice of the segment; 16 lanes x float4 cover emb_dim <= 64*...
-__global__ void __launch_bounds__(128) embed_bwd_partial_kernel(const float* __restrict__ g_out, int64_t ldg,
+// grid = (vocab, splits): CTA (v, s) sums its slice of row v's atoms.  256 threads = 16 float4 column lanes x 16 row
+// lanes: row lane y takes atoms lo + y, lo + y + 16, ... (each a coalesced 16 x 16 B read), the 16 partial sums are
+// combined through shared memory in row-lane order.  emb_dim <= 64 per pass (wider tables loop over column blocks).
+__global__ void __launch_bounds__(256) embed_bwd_partial_kernel(const float* __restrict__ g_out, int64_t ldg,
                                                                 int col0, int E4, const int32_t* __restrict__ order,
                                                                 const int32_t* __restrict__ ptr, int splits,
                                                                 float* __restrict__ partial) {
+  __shared__ float4 red[16][16];
   const int v = blockIdx.x, s = blockIdx.y;
   const int beg = ptr[v], end = ptr[v + 1];
   const int len = end - beg;
   const int chunk = (len + splits - 1) / splits;
   const int lo = beg + s * chunk;
   const int hi = lo + chunk < end ? lo + chunk : end;
-  for (int c = threadIdx.x; c < E4; c += blockDim.x) {
+  const int cx = threadIdx.x & 15, ry = threadIdx.x >> 4;
+  for (int c0 = 0; c0 < E4; c0 += 16) {
+    const int c = c0 + cx;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = lo; k < hi; ++k) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(g_out + static_cast<int64_t>(order[k]) * ldg + col0) + c);
-      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    if (c < E4) {
+#pragma unroll 4
+      for (int k = lo + ry; k < hi; k += 16) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(g_out + static_cast<int64_t>(__ldg(order + k)) * ldg + col0) + c);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
     }
-    reinterpret_cast<float4*>(partial + (static_cast<int64_t>(v) * splits + s) * E4 * 4)[c] = acc;
+    red[ry][cx] = acc;
+    __syncthreads();
+    if (ry == 0 && c < E4) {
+      float4 t = red[0][cx];
+#pragma unroll
+      for (int y = 1; y < 16; ++y) {
+        const float4 u = red[y][cx];
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      reinterpret_cast<float4*>(partial + (static_cast<int64_t>(v) * splits + s) * E4 * 4)[c] = t;
+    }
+    __syncthreads();
   }
 }
 __global__ void embed_bwd_final_kernel(const float* __restrict__ partial, int splits, int E, int64_t vocab,
@@ -196,7 +215,7 @@ extern "C" int ax2d_embed_bwd(const float* g_out, int64_t ldg, int table, int em
   AX2D_CHECK_ALIGN(workspace);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(static_cast<unsigned>(vocab), kEmbedSplits);
-  embed_bwd_partial_kernel<<<grid, 32, 0, st>>>(g_out, ldg, table * emb_dim, emb_dim / 4, order, ptr, kEmbedSplits,
+  embed_bwd_partial_kernel<<<grid, 256, 0, st>>>(g_out, ldg, table * emb_dim, emb_dim / 4, order, ptr, kEmbedSplits,
                                                 static_cast<float*>(workspace));
   int rc = launch_status("ax2d_embed_bwd(partial)");
   if (rc != AX2D_OK) return rc;

@@ -165,11 +165,21 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constan
   }
 }
 
+// vec_ws / vec_out (optional): `split` partial vectors of length M reduced the same way (fused bias gradient)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int split, int64_t M,
-                                                            int64_t N, SegOut c, int accumulate) {
+                                                            int64_t N, SegOut c, int accumulate,
+                                                            const float* __restrict__ vec_ws, float* __restrict__ vec_out) {
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t N4 = N >> 2;
-  if (t >= M * N4) return;
+  if (t >= M * N4) {
+    const int64_t i = t - M * N4;
+    if (vec_ws != nullptr && i < M) {
+      float sv = 0.f;
+      for (int z = 0; z < split; ++z) sv += __ldg(vec_ws + static_cast<int64_t>(z) * M + i);
+      vec_out[i] = sv;
+    }
+    return;
+  }
   const int64_t m = t / N4;
   const int n = static_cast<int>(t % N4) * 4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -303,9 +313,11 @@ int to_out(const ax2d_mat* m, SegOut* v, int64_t total, const char* what, bool a
   return AX2D_OK;
 }
 
-int splitk_reduce(const float* ws, int split, int64_t M, int64_t N, const SegOut& c, int accumulate, cudaStream_t st) {
-  const int64_t total = M * (N / 4);
-  splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(ws, split, M, N, c, accumulate);
+int splitk_reduce(const float* ws, int split, int64_t M, int64_t N, const SegOut& c, int accumulate, const float* vec_ws,
+                  float* vec_out, cudaStream_t st) {
+  const int64_t total = M * (N / 4) + (vec_ws != nullptr ? M : 0);
+  splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(ws, split, M, N, c, accumulate, vec_ws,
+                                                                                  vec_out);
   return launch_status("split-k reduce");
 }
 
@@ -411,7 +423,7 @@ extern "C" int ax2d_gemm(const ax2d_cmat* a, int trans_a, const ax2d_cmat* b, in
   if (split_k > 1) {
     const int64_t total = M * (N / 4);
     splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-        g.ws, static_cast<int>(grid.z), M, N, g.e.c, g.e.accumulate);
+        g.ws, static_cast<int>(grid.z), M, N, g.e.c, g.e.accumulate, nullptr, nullptr);
     rc = launch_status("ax2d_gemm(split-k reduce)");
   }
   return rc;

@@ -54,8 +54,8 @@ __device__ __forceinline__ float act_fwd_t(float v) {
   else if constexpr (ACT == AX2D_ACT_LEAKYRELU) return v > 0.f ? v : 0.01f * v;
   else if constexpr (ACT == AX2D_ACT_ELU) return v > 0.f ? v : expm1f(v);
   else if constexpr (ACT == AX2D_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-  else if constexpr (ACT == AX2D_ACT_SILU) return v / (1.f + expf(-v));
-  else return v;
+  else if constexpr (ACT == AX2D_ACT_SILU) return v * __frcp_rn(1.f + expf(-v));   // correctly rounded reciprocal: no
+  else return v;                                                                  // division slow path (FCHK + fix-up)
 }
 template <int ACT>
 __device__ __forceinline__ float act_bwd_t(float v) {
@@ -67,7 +67,7 @@ __device__ __forceinline__ float act_bwd_t(float v) {
     const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
     return cdf + v * pdf;
   } else if constexpr (ACT == AX2D_ACT_SILU) {
-    const float sg = 1.f / (1.f + expf(-v));
+    const float sg = __frcp_rn(1.f + expf(-v));
     return sg * (1.f + v * (1.f - sg));
   } else return 1.f;
 }
@@ -162,9 +162,13 @@ __device__ __forceinline__ void epi_prefetch(const EpiArgs& g, const EpiCol& k, 
     o.resid[r] = k.resid[r] != nullptr ? __ldg(reinterpret_cast<const float4*>(k.resid[r] + m * k.ldr[r])) : z;
   o.dpre = k.dpre != nullptr ? __ldg(reinterpret_cast<const float4*>(k.dpre + m * k.lddp)) : z;
 }
+// `m` addresses rows relative to the pointers in `k`; `row` (default m) is the absolute row, used for the dropout
+// counter and the rarely used operands that are read through `g`.
 template <int ACT, int DACT, bool DROP>
 __device__ __forceinline__ void epi_finish(const EpiArgs& g, const EpiCtx& cx, const EpiCol& k, int64_t m,
-                                           const EpiOperands& o, float a0, float a1, float a2, float a3) {
+                                           const EpiOperands& o, float a0, float a1, float a2, float a3,
+                                           int64_t row = -1) {
+  if (row < 0) row = m;
   float v[4] = {a0 + k.bias.x, a1 + k.bias.y, a2 + k.bias.z, a3 + k.bias.w};
   if (k.pre != nullptr) *reinterpret_cast<float4*>(k.pre + m * k.ldpre) = make_float4(v[0], v[1], v[2], v[3]);
   float drop[4] = {1.f, 1.f, 1.f, 1.f};
@@ -173,7 +177,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& g, const EpiCtx& cx, c
       const float4 mk = __ldg(reinterpret_cast<const float4*>(k.mask + m * k.ldm));
       drop[0] = mk.x; drop[1] = mk.y; drop[2] = mk.z; drop[3] = mk.w;
     } else {
-      drop_scale4(cx, static_cast<uint64_t>(m) * k.ncols + static_cast<uint64_t>(k.n), drop);
+      drop_scale4(cx, static_cast<uint64_t>(row) * k.ncols + static_cast<uint64_t>(k.n), drop);
     }
   }
   if constexpr (ACT != AX2D_ACT_NONE) {
@@ -193,7 +197,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& g, const EpiCtx& cx, c
   if (k.more_resid) {
     for (int r = kEpiPrefetchResid; r < g.n_resid; ++r) {
       if (k.n >= g.resid_cols[r]) continue;
-      const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid[r] + m * g.ld_resid[r] + k.n));
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid[r] + row * g.ld_resid[r] + k.n));
       v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
     }
   }
@@ -244,6 +248,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& g, const EpiCtx& cx, c
 int to_view(const ax2d_cmat* m, SegView* v, int64_t total, const char* what);
 int to_out(const ax2d_mat* m, SegOut* v, int64_t total, const char* what, bool allow_null);
 int fill_epilogue(const ax2d_epilogue* ep, int64_t M, int64_t N, EpiArgs* e);
-int splitk_reduce(const float* ws, int split, int64_t M, int64_t N, const SegOut& c, int accumulate, cudaStream_t st);   // validates + copies; c is set by the caller
+int splitk_reduce(const float* ws, int split, int64_t M, int64_t N, const SegOut& c, int accumulate, const float* vec_ws,
+                  float* vec_out, cudaStream_t st);   // validates + copies; c is set by the caller
 
 }  // namespace ax2d

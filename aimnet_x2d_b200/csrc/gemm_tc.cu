@@ -195,20 +195,36 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
         col.ldc = N;
       }
       if (dbg != nullptr && c0 == 0) dbg[11] = gtime();
-      // rolled on purpose: two rows per iteration (their loads are issued before either is consumed); a fully
-      // unrolled body is ~2.7 k instructions per template instance and thrashes the 32 KB instruction cache
+      // rolled on purpose (a fully unrolled body is ~2.7 k instructions per template instance and thrashes the 32 KB
+      // instruction cache); two rows per iteration, their loads issued before either is consumed.  All row pointers
+      // advance by 8 rows per iteration instead of being recomputed from 64-bit products.
+      EpiCol ca = col;
+      const int64_t mfirst = static_cast<int64_t>(m0) + q * 32 + (lane >> 3);
+      ca.c += mfirst * col.ldc;
+      if (ca.pre != nullptr) ca.pre += mfirst * col.ldpre;
+#pragma unroll
+      for (int rr = 0; rr < kEpiPrefetchResid; ++rr)
+        if (ca.resid[rr] != nullptr) ca.resid[rr] += mfirst * col.ldr[rr];
+      if (ca.dpre != nullptr) ca.dpre += mfirst * col.lddp;
+      if (ca.mask != nullptr) ca.mask += mfirst * col.ldm;
+      const float* sp = stg + (lane >> 3) * 33 + cg * 4;
 #pragma unroll 1
       for (int i = 0; i < 8; i += 2) {
-        const int rl0 = i * 4 + (lane >> 3), rl1 = rl0 + 4;
-        const int64_t ma = static_cast<int64_t>(m0) + q * 32 + rl0, mb = ma + 4;
+        const int64_t ma = mfirst + 4 * i, mb = ma + 4;
         EpiOperands oa, ob;
-        if (ma < M) epi_prefetch(e, col, ma, oa);
-        if (mb < M) epi_prefetch(e, col, mb, ob);
-        const float* sa = stg + rl0 * 33 + cg * 4;
-        const float* sb = stg + rl1 * 33 + cg * 4;
-        if (ma < M) epi_finish<ACT, DACT, DROP>(e, cx, col, ma, oa, sa[0], sa[1], sa[2], sa[3]);
-        if (mb < M) epi_finish<ACT, DACT, DROP>(e, cx, col, mb, ob, sb[0], sb[1], sb[2], sb[3]);
+        if (ma < M) epi_prefetch(e, ca, 0, oa);
+        if (mb < M) epi_prefetch(e, ca, 4, ob);
+        if (ma < M) epi_finish<ACT, DACT, DROP>(e, cx, ca, 0, oa, sp[0], sp[1], sp[2], sp[3], ma);
+        if (mb < M) epi_finish<ACT, DACT, DROP>(e, cx, ca, 4, ob, sp[4 * 33], sp[4 * 33 + 1], sp[4 * 33 + 2], sp[4 * 33 + 3], mb);
         if (dbg != nullptr && c0 == 0 && i == 0) dbg[12] = gtime();
+        sp += 8 * 33;
+        ca.c += 8 * col.ldc;
+        if (ca.pre != nullptr) ca.pre += 8 * col.ldpre;
+#pragma unroll
+        for (int rr = 0; rr < kEpiPrefetchResid; ++rr)
+          if (ca.resid[rr] != nullptr) ca.resid[rr] += 8 * col.ldr[rr];
+        if (ca.dpre != nullptr) ca.dpre += 8 * col.lddp;
+        if (ca.mask != nullptr) ca.mask += 8 * col.ldm;
       }
     }
     if (dbg != nullptr && c0 == 0) dbg[13] = gtime();
@@ -375,6 +391,8 @@ struct WgArgs {
   int BN, stages, tmem_cols;
   int acc2;                        // column offset of the small-term accumulator
   float* ws;                       // [splits][No][Ki] or nullptr
+  float* db;                       // optional fused bias gradient: column sums of G, [splits][No] partials (or the
+                                   // final [No] vector when there is a single split); nullptr = not requested
 };
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t smem_addr) {
@@ -477,12 +495,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_wgrad_kernel(const __gr
   } else {
     const int t = threadIdx.x - 64;
     const int n4 = static_cast<int>(raw_bytes / 16);
+    // Fused bias gradient (db[o] = sum_m G[m, o]): the splitters already hold every element of the G tile in
+    // registers.  Float4 #t of every [32 x 32] chunk is always (row t / 8, 16-byte slot t % 8) of that chunk, so
+    // thread t keeps one running float4 per A chunk; only the CTAs of the first column tile do it.
+    const bool want_db = g.db != nullptr && blockIdx.y == 0;
+    float4 colsum[TC_BM / 32];
+#pragma unroll
+    for (int c = 0; c < TC_BM / 32; ++c) colsum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int it = 0; it < nkb; ++it) {
       const int s = it % S;
       const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
       mbar_wait(&full_bar[s], ph);
       float4* a = reinterpret_cast<float4*>(stage_raw(s));
       float4* l = reinterpret_cast<float4*>(stage_lo(s));
+      if (want_db) {
+#pragma unroll
+        for (int c = 0; c < TC_BM / 32; ++c) {
+          const float4 v = a[t + TC_WORKERS * c];
+          colsum[c].x += v.x; colsum[c].y += v.y; colsum[c].z += v.z; colsum[c].w += v.w;
+        }
+      }
 #pragma unroll 4
       for (int i = t; i < n4; i += TC_WORKERS) {
         const float4 v = a[i];
@@ -502,6 +534,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_wgrad_kernel(const __gr
     tc_fence_after();
     float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
     const EpiCtx cx = epi_ctx(g.e);
+    if (want_db) {
+      // shared memory is free now (all MMAs retired); 256 x 4 float4 behind the epilogue staging area
+      float4* red = reinterpret_cast<float4*>(smem + 8 * 32 * 33 * 4);
+#pragma unroll
+      for (int c = 0; c < TC_BM / 32; ++c) red[c * TC_WORKERS + t] = colsum[c];
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory");      // the 8 worker warps only
+      if (t < TC_BM) {
+        // logical column n of chunk c, row r lives in 32-byte unit (n / 8) ^ (r & 3) of the row (Swizzle<2,5,2>)
+        const int c = t >> 5, n = t & 31;
+        const float* base = reinterpret_cast<const float*>(red + c * TC_WORKERS);
+        float sum = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int slot = 2 * ((n >> 3) ^ (r & 3)) + ((n >> 2) & 1);
+          sum += base[(r * 8 + slot) * 4 + (n & 3)];
+        }
+        const int64_t o = static_cast<int64_t>(m0) + t;
+        if (o < g.e.M) g.db[static_cast<int64_t>(blockIdx.z) * g.e.M + o] = sum;
+      }
+    }
     float* ws = g.ws != nullptr ? g.ws + static_cast<int64_t>(blockIdx.z) * g.e.M * g.e.N : nullptr;
     tc_epilogue<AX2D_ACT_NONE, AX2D_ACT_NONE, false>(g.e, BN, ws, cx, tmem_base, stg, m0, n0, warp & 3, lane, (warp - 2) >> 2,
                                                      static_cast<uint32_t>(g.acc2));
@@ -637,10 +689,19 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
   int rc;
   if ((rc = to_out(c, &g.e.c, N, "C", false)) != AX2D_OK) return rc;
   if ((rc = fill_epilogue(ep, M, N, &g.e)) != AX2D_OK) return rc;
-  // tile shape: all of N in one tile when it fits 256 columns, otherwise equal tiles rounded up to 32
-  const int n_tiles = static_cast<int>((N + 255) / 256);
+  // tile shape: as few column tiles as fit 256 accumulator columns -- unless the row tiles alone cannot fill the
+  // machine (the [B, 512] head products: 16 row tiles), in which case N is cut into narrower tiles until there is
+  // about one CTA per SM (narrow tiles also get deeper stage rings and the second accumulator)
+  const int64_t m_tiles = (M + TC_BM - 1) / TC_BM;
+  int n_tiles = static_cast<int>((N + 255) / 256);
+  if (m_tiles * n_tiles < kNumSMs) {
+    const int want = static_cast<int>((kNumSMs + m_tiles - 1) / m_tiles);
+    const int most = static_cast<int>((N + 31) / 32);
+    n_tiles = want < most ? want : most;
+  }
   int BN = static_cast<int>((N + n_tiles - 1) / n_tiles);
   BN = (BN + 31) / 32 * 32;
+  n_tiles = static_cast<int>((N + BN - 1) / BN);
   g.BN = BN;
   g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   if (BN <= 128) {          // two CTAs per SM share 512 TMEM columns: a second accumulator fits only for narrow tiles
@@ -679,7 +740,7 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
     }
     configured = smem;
   }
-  dim3 grid(static_cast<unsigned>((M + TC_BM - 1) / TC_BM), static_cast<unsigned>(n_tiles));
+  dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles));
   gemm_tc_kernel<<<grid, TC_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, g);
   return launch_status("ax2d_gemm_tc");
 }
@@ -704,12 +765,12 @@ extern "C" int64_t ax2d_gemm_tc_wgrad_workspace(int64_t M, int64_t N, int64_t K)
   const int64_t by_chain = (num_kb + WG_MAX_KB_PER_SPLIT - 1) / WG_MAX_KB_PER_SPLIT;
   split = split < by_chain ? by_chain : split;
   split = split > num_kb ? num_kb : split;
-  return split > 1 ? split * M * N * 4 : 0;
+  return split > 1 ? split * (M * N + M) * 4 : 0;       // partial tiles + partial bias-gradient vectors
 }
 
 // C[M,N] (+)= A^T B with A = a [K, M], B = b [K, N] (both column-segmented, contraction over the K rows).
 extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const ax2d_mat* c, int64_t M, int64_t N, int64_t K,
-                                  int accumulate, void* workspace, ax2d_stream_t stream) {
+                                  int accumulate, float* bias_grad, void* workspace, ax2d_stream_t stream) {
   AX2D_CHECK_ARG(c != nullptr && ax2d_gemm_tc_wgrad_supported(a, b, M, N, K),
                  "ax2d_gemm_tc_wgrad: unsupported operands M=%lld N=%lld K=%lld (segment widths must be multiples of 32)",
                  (long long)M, (long long)N, (long long)K);
@@ -760,6 +821,9 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
     AX2D_CHECK_ARG(workspace != nullptr, "ax2d_gemm_tc_wgrad: workspace required (ax2d_gemm_tc_wgrad_workspace)");
     AX2D_CHECK_ALIGN(workspace);
     g.ws = static_cast<float*>(workspace);
+    g.db = bias_grad != nullptr ? g.ws + static_cast<int64_t>(split) * M * N : nullptr;
+  } else {
+    g.db = bias_grad;
   }
   const size_t stage_bytes = 2 * static_cast<size_t>(TC_BM / 32 + BN / 32) * WG_CHUNK_BYTES;
   int stages = static_cast<int>((224 * 1024) / stage_bytes);
@@ -768,7 +832,8 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
   if (stages < 1) stages = 1;
   g.stages = stages;
   size_t smem = stages * stage_bytes;
-  if (smem < 8 * 32 * 33 * 4) smem = 8 * 32 * 33 * 4;
+  const size_t epi_bytes = 8 * 32 * 33 * 4 + (TC_BM / 32) * TC_WORKERS * 16;   // transpose staging + bias-gradient reduce
+  if (smem < epi_bytes) smem = epi_bytes;
   smem += 1024;
   static size_t configured = 0;
   if (smem > configured) {
@@ -784,5 +849,5 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
   gemm_tc_wgrad_kernel<<<grid, TC_THREADS, smem, st>>>(maps, g);
   rc = launch_status("ax2d_gemm_tc_wgrad");
   if (rc != AX2D_OK || split == 1) return rc;
-  return splitk_reduce(g.ws, split, M, N, g.e.c, accumulate, st);
+  return splitk_reduce(g.ws, split, M, N, g.e.c, accumulate, g.db, bias_grad, st);
 }

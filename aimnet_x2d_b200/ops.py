@@ -207,8 +207,10 @@ def _bias_grad(segs, M, N, device):
     return out
 
 
-def _weight_grad(g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device) -> torch.Tensor:
-    """dW[o, i] = sum_r G[r, o] X[r, i]  (G, X column-segmented) -- split over the rows, fixed-order reduce."""
+def _weight_grad(g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device, bias: bool = False):
+    """dW[o, i] = sum_r G[r, o] X[r, i]  (G, X column-segmented) and, with ``bias``, db[o] = sum_r G[r, o].
+    Returns dW or (dW, db).  Tensor-core kernel (split over the rows, fixed-order reduce, bias gradient fused)
+    when the operands qualify; exact-fp32 SIMT GEMM + column-sum kernels otherwise."""
     dW = torch.empty((Nout, Kin), dtype=torch.float32, device=device)
     lib = _lib.load()
     if USE_TENSOR_CORES and M_rows >= TC_MIN_ROWS:
@@ -216,16 +218,17 @@ def _weight_grad(g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device) -> to
         if lib.ax2d_gemm_tc_wgrad_supported(C.byref(a), C.byref(b), Nout, Kin, M_rows):
             nbytes = lib.ax2d_gemm_tc_wgrad_workspace(Nout, Kin, M_rows)
             ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=device)
-            call = lambda: _lib.check(lib.ax2d_gemm_tc_wgrad(C.byref(a), C.byref(b), C.byref(c), Nout, Kin, M_rows, 0, _p(ws),
-                                                             _stream()), "ax2d_gemm_tc_wgrad")
+            db = torch.empty(Nout, dtype=torch.float32, device=device) if bias else None
+            call = lambda: _lib.check(lib.ax2d_gemm_tc_wgrad(C.byref(a), C.byref(b), C.byref(c), Nout, Kin, M_rows, 0, _p(db),
+                                                             _p(ws), _stream()), "ax2d_gemm_tc_wgrad")
             if TIMER is None:
                 call()
             else:
                 TIMER.launch("gemm_tc_wgrad", call, nbytes=4 * M_rows * (Nout + Kin), flops=2 * M_rows * Nout * Kin)
-            return dW
+            return (dW, db) if bias else dW
     gemm(g_segs, x_segs, [(dW, Kin)], Nout, Kin, M_rows, trans_a=True, trans_b=False,
          split_k=split_k_for(Nout, Kin, M_rows))
-    return dW
+    return (dW, _bias_grad(g_segs, M_rows, Nout, device)) if bias else dW
 
 
 class _Opts:
@@ -261,8 +264,10 @@ class LinearFn(torch.autograd.Function):
         gs = [(g, Np)]
         d_a = [torch.empty((M, w), dtype=torch.float32, device=g.device) for w in opts.widths]
         gemm(gs, [(W, K)], list(zip(d_a, opts.widths)), M, K, Np, trans_a=False, trans_b=False)
-        dW = _weight_grad(gs, list(zip(a, opts.widths)), M, Np, K, g.device)
-        db = _bias_grad(gs, M, Np, g.device) if ctx.has_bias else None
+        if ctx.has_bias:
+            dW, db = _weight_grad(gs, list(zip(a, opts.widths)), M, Np, K, g.device, bias=True)
+        else:
+            dW, db = _weight_grad(gs, list(zip(a, opts.widths)), M, Np, K, g.device), None
         return (None, dW, db, *d_a)
 
 
@@ -293,14 +298,12 @@ class MLPBlockFn(torch.autograd.Function):
         M, Wi, Wo = g.shape[0], opts.w_in, opts.w_out
         dev = g.device
         gs = [(g, Wo)]
-        dW2 = _weight_grad(gs, [(t, Wo)], M, Wo, Wo, dev)
-        db2 = _bias_grad(gs, M, Wo, dev)
+        dW2, db2 = _weight_grad(gs, [(t, Wo)], M, Wo, Wo, dev, bias=True)
         du = torch.empty_like(u)
         gemm(gs, [(W2, Wo)], [(du, Wo)], M, Wo, Wo, trans_b=False, dact_pre=u, dact=opts.act,
              drop_p=opts.p, drop_seed=opts.seed, drop_tick=opts.tick)
         dus = [(du, Wo)]
-        dW1 = _weight_grad(dus, [(h, Wi)], M, Wo, Wi, dev)
-        db1 = _bias_grad(dus, M, Wo, dev)
+        dW1, db1 = _weight_grad(dus, [(h, Wi)], M, Wo, Wi, dev, bias=True)
         dh = torch.empty_like(h)
         gemm(dus, [(W1, Wi)], [(dh, Wi)], M, Wi, Wo, trans_b=False, resid=[(g, Wi)] if opts.skip else [])
         return None, dh, dW1, db1, dW2, db2
@@ -368,14 +371,12 @@ class ShellConvFn(torch.autograd.Function):
         for k in reversed(range(opts.n_mlp)):
             h, u, t, W1, W2 = saved[4 + 5 * k:9 + 5 * k]
             dhs = [(dh, Do)]
-            dW2 = _weight_grad(dhs, [(t, Do)], N, Do, Do, dev)
-            db2 = _bias_grad(dhs, N, Do, dev)
+            dW2, db2 = _weight_grad(dhs, [(t, Do)], N, Do, Do, dev, bias=True)
             du = torch.empty_like(z0)
             gemm(dhs, [(W2, Do)], [(du, Do)], N, Do, Do, trans_b=False, dact_pre=u, dact=opts.act,
                  drop_p=opts.ps[k], drop_seed=opts.seeds[k], drop_tick=opts.tick)
             dus = [(du, Do)]
-            dW1 = _weight_grad(dus, [(h, Do)], N, Do, Do, dev)
-            db1 = _bias_grad(dus, N, Do, dev)
+            dW1, db1 = _weight_grad(dus, [(h, Do)], N, Do, Do, dev, bias=True)
             dprev = torch.empty_like(z0)
             if k == 0:      # d z0 = (dh + du W1) * act'(z0) in one epilogue
                 gemm(dus, [(W1, Do)], [(dprev, Do)], N, Do, Do, trans_b=False, resid=dhs, dact_pre=z0, dact=opts.act)
@@ -388,8 +389,7 @@ class ShellConvFn(torch.autograd.Function):
         a_segs = ShellConvFn._segments(x, ag, Di)
         K = Di * len(a_segs)
         gz = [(dz0, Do), (g, Do)]
-        dW_io = _weight_grad(gz, a_segs, N, 2 * Do, K, dev)
-        db_io = _bias_grad(gz, N, 2 * Do, dev)
+        dW_io, db_io = _weight_grad(gz, a_segs, N, 2 * Do, K, dev, bias=True)
         dx1 = torch.empty((N, Di), dtype=torch.float32, device=dev)
         dag = torch.empty_like(ag)
         c_segs = ShellConvFn._segments(dx1, dag, Di)
@@ -439,8 +439,7 @@ class EmbedProjFn(torch.autograd.Function):
         dzs = act_bwd(gxs.contiguous(), zs, opts.act)
         dzo = act_bwd(gxo.contiguous(), zo, opts.act)
         gz = [(dzs, Sp), (dzo, Dp)]
-        dW = _weight_grad(gz, [(e0, nt * E)], N, Sp + Dp, nt * E, dev)
-        db = _bias_grad(gz, N, Sp + Dp, dev)
+        dW, db = _weight_grad(gz, [(e0, nt * E)], N, Sp + Dp, nt * E, dev, bias=True)
         de0 = torch.empty_like(e0)
         gemm(gz, [(W, nt * E)], [(de0, nt * E)], N, nt * E, Sp + Dp, trans_b=False)
         g_tables = []

@@ -211,11 +211,13 @@ int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* b_lo, int64
                  int64_t M, int64_t N, int64_t K, const ax2d_epilogue* ep, ax2d_stream_t stream);
 /* Weight gradients on the tensor cores: C[M,N] (+)= A^T B, A = a [K rows, M columns], B = b [K rows, N columns], both
  * column-segmented activations (dW = dY^T X of every nn.Linear; contraction over the K atom / molecule rows, split
- * over CTAs and reduced in a fixed order).  Segment widths must be multiples of 32, M, N >= 32. */
+ * over CTAs and reduced in a fixed order).  Segment widths must be multiples of 32, M, N >= 32.
+ * bias_grad (optional, [M]): receives the column sums of A (db = sum_rows dY) computed from the tiles the kernel
+ * already stages -- replaces a separate ax2d_colsum pass. */
 int     ax2d_gemm_tc_wgrad_supported(const ax2d_cmat* a, const ax2d_cmat* b, int64_t M, int64_t N, int64_t K);
 int64_t ax2d_gemm_tc_wgrad_workspace(int64_t M, int64_t N, int64_t K);
 int     ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const ax2d_mat* c, int64_t M, int64_t N, int64_t K,
-                           int accumulate, void* workspace, ax2d_stream_t stream);
+                           int accumulate, float* bias_grad, void* workspace, ax2d_stream_t stream);
 /* elementwise g_pre[m,n] = g[m,n] * act'(pre[m,n]) for n < width (width % 4 == 0). */
 int ax2d_act_bwd(const float* g, int64_t ldg, const float* pre, int64_t ldp, float* out, int64_t ldo,
                  int64_t M, int width, int act, ax2d_stream_t stream);

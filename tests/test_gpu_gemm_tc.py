@@ -159,7 +159,7 @@ def test_gemm_tc_wgrad_matches_float64(rows, gw, xw):
     try:
         t = ops.KernelTimer()
         ops.TIMER = t
-        dW = ops._weight_grad(list(zip(G, gw)), list(zip(X, xw)), rows, No, Ki, DEV)
+        dW, db = ops._weight_grad(list(zip(G, gw)), list(zip(X, xw)), rows, No, Ki, DEV, bias=True)
         ops.TIMER = None
         assert "gemm_tc_wgrad" in t.events
     finally:
@@ -172,6 +172,9 @@ def test_gemm_tc_wgrad_matches_float64(rows, gw, xw):
     cond = float((Gd.abs().t() @ Xd.abs()).max())
     err = float((dW.double() - ref).abs().max())
     assert err <= max(4e-7 * cond, 1e-5 * float(ref.abs().max())) , f"abs error {err:.3e}, cond {cond:.3e}"
+    # fused bias gradient = column sums of G
+    db_ref = Gd.sum(0)
+    assert float((db.double() - db_ref).abs().max()) <= max(4e-7 * float(Gd.abs().sum(0).max()), 1e-5 * float(db_ref.abs().max()))
     # deterministic: fixed-order split-K reduction
     dW2 = ops._weight_grad(list(zip(G, gw)), list(zip(X, xw)), rows, No, Ki, DEV)
     assert torch.equal(dW, dW2)

@@ -56,23 +56,27 @@ def main():
             kw = dict(bias=bias, pre_segs=[(z, n // 2), (None, n // 2)], act="silu", act_cols=n // 2)
         elif kind == "bias":
             kw = dict(bias=bias)
-        # L2 flush buffer between iterations (inputs of the big shapes exceed L2 anyway)
-        flush = torch.empty(64 * 1024 * 1024, device=dev)
         hi, lo = ops.split_tf32(W)
         for _ in range(3):
             ops.gemm(list(zip(a, widths)), [(W, k)], c, m, n, k, **kw)
         torch.cuda.synchronize()
-        ts = []
-        for _ in range(args.iters):
-            flush.zero_()
-            t = ops.KernelTimer()
-            ops.TIMER = t
-            ops.gemm(list(zip(a, widths)), [(W, k)], c, m, n, k, **kw)
-            ops.TIMER = None
-            torch.cuda.synchronize()
-            ts.append(list(t.summary().values())[0]["ms_avg"] * 1e3)
-        ts.sort()
-        us = ts[len(ts) // 2]
+        # pure device time: `reps` launches captured in a CUDA graph, replayed between two events.  Inputs rotate over
+        # several buffers so that they do not stay in L2 between launches.
+        nbuf = 4 if m > 10000 else 1
+        As = [[torch.randn(m, w, device=dev) for w in widths] for _ in range(nbuf)]
+        reps = 16
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(reps):
+                ops.gemm(list(zip(As[i % nbuf], widths)), [(W, k)], c, m, n, k, **kw)
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps      # includes the tiny split_tf32 launch of the weight (~3 us)
         flops = 2.0 * m * n * k
         bytes_ = 4.0 * (m * k + n * k + m * n)
         print(f"{name:36s} M={m:6d} K={k:4d} N={n:4d}  {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  "
