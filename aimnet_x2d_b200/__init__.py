@@ -17,6 +17,7 @@ from .collate import GraphIndex, MolBatch, MolData, collate_fn  # noqa: E402
 from .gnn import GNN, GNNConfig  # noqa: E402
 from .layers import LinearBlock, MultiLayerPerceptron, ShellConvolutionLayer  # noqa: E402
 from .losses import WeightedL1Loss, WeightedMSELoss  # noqa: E402
+from .inference import GraphedInferenceStep, InferenceStep  # noqa: E402
 from .optim import FlatAdam  # noqa: E402
 from .pooling import (MaxPoolingLayer, MeanPoolingLayer, MultiHeadAttentionPoolingLayer, SumPoolingLayer,  # noqa: E402
                       create_pooling_layer)
@@ -24,4 +25,4 @@ from .pooling import (MaxPoolingLayer, MeanPoolingLayer, MultiHeadAttentionPooli
 __all__ = ["GNN", "GNNConfig", "ShellConvolutionLayer", "LinearBlock", "MultiLayerPerceptron", "MeanPoolingLayer",
            "MaxPoolingLayer", "SumPoolingLayer", "MultiHeadAttentionPoolingLayer", "create_pooling_layer",
            "WeightedL1Loss", "WeightedMSELoss", "GraphIndex", "MolBatch", "MolData", "collate_fn", "FlatAdam",
-           "get_activation_function"]
+           "get_activation_function", "InferenceStep", "GraphedInferenceStep"]

@@ -420,9 +420,10 @@ def pad_batch(batch: MolBatch, num_atoms: int, num_edges: int, num_dummy: int = 
     gi.tile_ptr = grow(gi.tile_ptr, nt + 1, num_atoms)
     gi.n_tiles = nt
     gi.refresh_tile_info()                      # trailing tiles are empty: {N, N, E, E}
-    gi.max_tile_rows = max(int(tile_rows), 29)
+    # capacities, not the batch's own maxima (pass tile_rows >= the largest molecule for a batch-independent signature)
+    gi.max_tile_rows = max(int(tile_rows), 29, gi.max_tile_rows)
     gi.max_tile_edges = max(gi.max_tile_edges, int(max_tile_edges))
-    gi.max_seg = max(int(tile_rows), 29)
+    gi.max_seg = max(int(tile_rows), 29, gi.max_seg)
     out.graph_index = gi
     out.num_real_graphs = B
     return out

@@ -35,6 +35,9 @@ constexpr int TC_BK = 16;                        // fp32 per 64-byte swizzle row
 constexpr int TC_THREADS = 320;                  // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 split + epilogue
 constexpr int TC_WORKERS = TC_THREADS - 64;       // splitter / epilogue threads
 constexpr int TC_MAX_STAGES = 6;
+#ifndef AX2D_TC_TERMS
+#define AX2D_TC_TERMS 4     // 4: lo*lo kept (fp32-level); 3: classic 3xTF32 (drops a 2^-22 relative term)
+#endif
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;     // 8 KB
 
 struct TcMaps {
@@ -308,8 +311,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
           // magnitude, so their truncation is negligible) and only hi*hi touches the main one.
           const uint32_t first = (kb | j) != 0 ? 1u : 0u;
           const uint32_t t_small = tmem_base + static_cast<uint32_t>(g.acc2);
+#if AX2D_TC_TERMS == 4
           umma_tf32(t_small, da_lo + adv, db_lo + adv, idesc, first);
           umma_tf32(t_small, da_lo + adv, db_hi + adv, idesc, 1u);
+#else
+          umma_tf32(t_small, da_lo + adv, db_hi + adv, idesc, first);
+#endif
           umma_tf32(t_small, da_hi + adv, db_lo + adv, idesc, 1u);
           umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, g.acc2 != 0 ? first : 1u);
         }
@@ -483,8 +490,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_wgrad_kernel(const __gr
           const uint64_t dbh = smem_desc_mn_sw128_32b(b_hi + adv), dbl = smem_desc_mn_sw128_32b(b_lo + adv);
           const uint32_t first = (it | j) != 0 ? 1u : 0u;
           const uint32_t t_small = tmem_base + static_cast<uint32_t>(g.acc2);    // see gemm_tc_kernel
+#if AX2D_TC_TERMS == 4
           umma_tf32(t_small, dal, dbl, idesc, first);
           umma_tf32(t_small, dal, dbh, idesc, 1u);
+#else
+          umma_tf32(t_small, dal, dbh, idesc, first);
+#endif
           umma_tf32(t_small, dah, dbl, idesc, 1u);
           umma_tf32(tmem_base, dah, dbh, idesc, first);
         }

@@ -42,6 +42,9 @@ WORKLOADS = {
     "c2": dict(kind="qm9", graphs=2048, hops=3, layers=3, hidden=512, stereo=False, charges=False,
                desc="BASELINE configs[1]: synthetic QM9-shaped graphs (<=29 atoms), 2048-graph batches, 3-hop x 3 layers + "
                     "attention pooling, fp32"),
+    "c5": dict(kind="qm9", graphs=4096, hops=3, layers=3, hidden=512, stereo=False, charges=True, mode="inference",
+               desc="BASELINE configs[4]: inference / embedding extraction + partial charges, 4096 QM9-shaped molecules per "
+                    "iteration per GPU, batch-sharded, no collectives, fp32"),
     "c3": dict(kind="drug", graphs=1024, hops=3, layers=3, hidden=512, stereo=True, charges=True,
                desc="BASELINE configs[2]: synthetic drug-like graphs (20-70 heavy atoms), stereo + charges, 1024/GPU, fp32"),
 }
@@ -126,7 +129,7 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------ workloads
 def make_batches(wl, rank, n):
     from aimnet_x2d_b200 import synthetic as S
-    cfg_id = {"c2": 2, "c3": 3}[wl["name"]]
+    cfg_id = {"c2": 2, "c3": 3, "c5": 5}[wl["name"]]
     return [S.make_batch(1234 + cfg_id * 1000 + rank * 97 + i, wl["graphs"], wl["hops"], wl["kind"], T_TARGETS,
                          stereo=wl["stereo"]) for i in range(n)]
 
@@ -447,6 +450,75 @@ def ours_arm(args, wl):
         dist.destroy_process_group()
 
 
+def infer_arm(args, wl):
+    """Forward-only workload (configs[4]): outputs + pooled embeddings + partial charges per batch; ranks are
+    independent replicas over their own shard of the molecules (no process group is created)."""
+    import aimnet_x2d_b200 as ax
+    from aimnet_x2d_b200 import ops
+    from aimnet_x2d_b200.trainer import _batch_tensors
+    rank, local_rank, world = env_rank()
+    torch.cuda.set_device(local_rank)
+    device = torch.device(f"cuda:{local_rank}")
+    raw = make_batches(wl, rank, RING)
+    host = [b.pin_memory() for b in pad_ring(raw)]
+    dev_batches = [b.to(device) for b in host]
+    model = build_model(wl, device).eval()
+    step = ax.GraphedInferenceStep(model, device)
+    l0 = ops.launch_count()
+    step.capture(host[0], warmup=2)
+    launches_per_step = (ops.launch_count() - l0) // 3
+    res = step.replay()
+    out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in res.items()
+                if k in ("outputs", "embeddings", "partial_charges") and v is not None}
+
+    def dev_step(i):
+        step.load(dev_batches[i % RING])
+        return step.replay()
+
+    def host_step(i):
+        r = step(host[i % RING])
+        for k, dst in out_host.items():
+            dst.copy_(r[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return r
+    for i in range(args.warmup):
+        dev_step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        dev_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    for i in range(max(args.warmup, 1)):
+        host_step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        host_step(i)
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    sampler.stop_flag.set()
+    sampler.join()
+    # ranks are independent: every rank prints its own line to stderr, rank 0 the JSON line scaled by the world size
+    mols = wl["graphs"] * args.steps
+    if rank == 0:
+        gi = raw[0].graph_index
+        d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+        line = {"metric": "inference molecules/sec", "value": world * mols / (ms * 1e-3), "unit": "molecules/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["desc"], "graphs_per_gpu": wl["graphs"], "atoms_per_batch": gi.num_atoms,
+                           "edges_per_batch": gi.num_edges, "parallelism": f"replicas x{world} (value = rank 0 x world size)",
+                           "execution": "CUDA graph, forward only (eval)"},
+                "e2e": {"value": world * mols / (ms_e2e * 1e-3), "unit": "molecules/s",
+                        "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in _batch_tensors(host[0]))),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches_per_step * args.steps), "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -460,6 +532,8 @@ def main():
     wl = dict(WORKLOADS[args.workload], name=args.workload)
     if args.impl == "reference":
         reference_arm(args, wl)
+    elif wl.get("mode") == "inference":
+        infer_arm(args, wl)
     else:
         ours_arm(args, wl)
 

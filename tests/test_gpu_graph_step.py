@@ -92,3 +92,48 @@ def test_graph_replay_equals_eager_step():
     other = pad_batch(raws[0], n_pad + 128, e_cap, 8, t_cap + 4, max_tile_edges=me_cap)
     with pytest.raises(RuntimeError):
         graphed(other)
+
+
+def test_inference_step_matches_oracle_and_graph_replay():
+    """Forward-only path (predictor.py / extractors.py): outputs, pooled embeddings (pooling hook) and partial charges."""
+    import aimnet_x2d_b200 as ax
+    from aimnet_x2d_b200 import synthetic as S
+    from aimnet_x2d_b200.collate import pad_batch
+    from oracle import model_port as MP
+    cfg = dict(CFG, use_partial_charges=True)
+    P = det_state(gnn_shapes(cfg, 3), 13)
+    model = ax.GNN(FEATURE_SIZES, 64, 3, num_shells=3, num_message_passing_layers=2, task_type="multitask",
+                   use_partial_charges=True)
+    model.load_state_dict(P)
+    model.to(DEV).train()                                       # the step switches to eval itself and restores the mode
+    raw = S.make_batch(61, 20, 3, "drug", num_targets=3)
+    r = ax.InferenceStep(model, DEV, atom_embeddings=True)(raw)
+    assert model.training
+    ob = dict(atom_features_map=raw.atom_features_map, multi_hop_edge_indices=raw.multi_hop_edge_indices,
+              batch_indices=raw.batch_indices, total_charges=raw.total_charges,
+              final_tetrahedral_chiral_tensor=raw.final_tetrahedral_chiral_tensor,
+              final_cis_tensor=raw.final_cis_tensor, final_trans_tensor=raw.final_trans_tensor)
+    ro, _, rq, extras = MP.gnn_forward(P, cfg, ob)
+    assert_close(r["outputs"].cpu().numpy(), ro.numpy(), RTOL_F32, "inference outputs")
+    assert_close(r["embeddings"].cpu().numpy(), extras["pooled"].numpy(), RTOL_F32, "pooled embeddings")
+    assert_close(r["partial_charges"].cpu().numpy(), rq.numpy(), RTOL_F32, "partial charges")
+    assert_close(r["atom_embeddings"].cpu().numpy()[:, :64], extras["atom_embeddings"].numpy(), RTOL_F32, "atom embeddings")
+    # graph replay over padded batches == eager on the same padded batch, for a batch other than the captured one
+    raws = [raw, S.make_batch(62, 20, 3, "drug", num_targets=3)]
+    n_pad = max(b.graph_index.num_atoms for b in raws) + 64
+    e_cap = max(b.graph_index.num_edges for b in raws) + 64
+    first = [pad_batch(b, n_pad, e_cap, 32, tile_rows=192) for b in raws]
+    caps = dict(num_tiles=max(p.graph_index.n_tiles for p in first) + 2,
+                max_tile_edges=max(p.graph_index.max_tile_edges for p in first))
+    padded = [pad_batch(b, n_pad, e_cap, 32, tile_rows=192, **caps) for b in raws]
+    g = ax.GraphedInferenceStep(model, DEV)
+    g.capture(padded[0])
+    rg = g(padded[1])
+    re_ = ax.InferenceStep(model, DEV)(padded[1])
+    for k in ("outputs", "embeddings", "partial_charges"):
+        assert torch.equal(rg[k], re_[k]), k
+    assert_close(rg["outputs"].cpu().numpy(), MP.gnn_forward(P, cfg, dict(
+        atom_features_map=raws[1].atom_features_map, multi_hop_edge_indices=raws[1].multi_hop_edge_indices,
+        batch_indices=raws[1].batch_indices, total_charges=raws[1].total_charges,
+        final_tetrahedral_chiral_tensor=raws[1].final_tetrahedral_chiral_tensor, final_cis_tensor=raws[1].final_cis_tensor,
+        final_trans_tensor=raws[1].final_trans_tensor))[0].numpy(), RTOL_F32, "graphed inference outputs")
