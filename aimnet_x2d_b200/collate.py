@@ -372,7 +372,7 @@ class MolBatch:
 
 def pad_batch(batch: MolBatch, num_atoms: int, num_edges: int, num_dummy: int = 64, num_tiles: Optional[int] = None,
               tile_rows: int = DEFAULT_TILE_ROWS, feature_sizes: Optional[Dict[str, int]] = None,
-              max_tile_edges: int = 0) -> MolBatch:
+              max_tile_edges: int = 0, num_tetra: Optional[int] = None, pad_cistrans: bool = False) -> MolBatch:
     """Static-shape version of a collated batch (what a CUDA-graph-captured training step needs: every launch
     configuration and scalar kernel argument must be the same from batch to batch).
 
@@ -380,7 +380,12 @@ def pad_batch(batch: MolBatch, num_atoms: int, num_edges: int, num_dummy: int = 
     (at most 29 each, like a QM9 molecule, so that they pack into the same whole-molecule row tiles).  Their feature
     indices are 0, their targets are never read: the loss is taken over the first ``B`` (real) rows only, so no
     gradient flows through them.  ``col`` arrays are padded to ``num_edges`` entries and the tile list to
-    ``num_tiles`` (trailing tiles are empty).  Real molecules keep their rows, CSR rows and results bit-for-bit."""
+    ``num_tiles`` (trailing tiles are empty).  Real molecules keep their rows, CSR rows and results bit-for-bit.
+
+    Stereo batches: ``num_tetra`` pads the list of tetrahedral centres with dummy centres whose four "neighbours" are
+    dummy atoms (real atoms are listed / zeroed exactly as before, gnn.py:456-460; a batch WITHOUT real centres stays
+    un-padded because the reference then skips the term altogether, gnn.py:402-403).  ``pad_cistrans`` fills the cis /
+    trans update list (at most four rows, quirk Q3) up to four with zero-weight updates on a dummy atom."""
     gi0 = batch.graph_index
     N, B = gi0.num_atoms, gi0.num_graphs
     pad = num_atoms - N
@@ -403,9 +408,27 @@ def pad_batch(batch: MolBatch, num_atoms: int, num_edges: int, num_dummy: int = 
     if batch.atomic_numbers is not None:
         out.atomic_numbers = torch.cat([batch.atomic_numbers, zl(pad)])
     out.smiles_list = list(batch.smiles_list) + [""] * num_dummy
+    tetra = batch.final_tetrahedral_chiral_tensor
+    if num_tetra is not None and tetra is not None and tetra.numel() > 0:
+        M = int(tetra.shape[0])
+        if M > num_tetra:
+            raise ValueError(f"batch has {M} tetrahedral centres, capacity {num_tetra}")
+        if pad < 4:
+            raise ValueError("padding tetrahedral centres needs at least 4 padding atoms")
+        dummy = torch.arange(N, N + 4, dtype=torch.long).repeat(num_tetra - M, 1)
+        tetra = torch.cat([tetra.reshape(-1, 4), dummy], 0)
     gi = GraphIndex.build(batch.multi_hop_edge_indices, out.batch_indices, B + num_dummy, gi0.num_hops,
                           out.atom_features_map, feature_sizes or {k: v[2] for k, v in gi0.embed.items()},
-                          batch.final_tetrahedral_chiral_tensor, batch.final_cis_tensor, batch.final_trans_tensor, tile_rows)
+                          tetra, batch.final_cis_tensor, batch.final_trans_tensor, tile_rows)
+    if pad_cistrans:
+        if pad < 1:
+            raise ValueError("padding the cis/trans updates needs at least one padding atom")
+        src, tgt, sign, n = gi.cistrans if gi.cistrans is not None else (torch.zeros(0, dtype=torch.int32),) * 2 + (
+            torch.zeros(0), 0)
+        fill = 4 - n
+        gi.cistrans = (torch.cat([src, torch.full((fill,), N, dtype=torch.int32)]),
+                       torch.cat([tgt, torch.full((fill,), N, dtype=torch.int32)]),
+                       torch.cat([sign.float(), torch.zeros(fill)]), 4)
     if not (gi.collapsed and gi.tile_local):
         raise ValueError("static padding supports the shipped collation only (no edge leaves its molecule)")
 
@@ -434,7 +457,8 @@ def static_signature(batch: MolBatch) -> tuple:
     gi = batch.graph_index
     return (gi.num_atoms, gi.num_graphs, gi.num_rows, gi.n_tiles, gi.max_tile_rows, gi.max_tile_edges, gi.max_seg,
             int(gi.col.numel()),
-            gi.collapsed, gi.tile_local, gi.tetra is None, gi.cistrans is None, getattr(batch, "num_real_graphs", gi.num_graphs),
+            gi.collapsed, gi.tile_local, None if gi.tetra is None else gi.tetra[3],
+            None if gi.cistrans is None else gi.cistrans[3], getattr(batch, "num_real_graphs", gi.num_graphs),
             tuple(sorted((k, v[2]) for k, v in gi.embed.items())))
 
 

@@ -52,12 +52,16 @@ class TrainStep:
 def _batch_tensors(b: MolBatch):
     """Every tensor of a (padded) batch that the step reads on the device, in a fixed order."""
     gi = b.graph_index
-    ts = [b.batch_indices, b.targets, b.total_charges, b.final_tetrahedral_chiral_tensor, b.final_cis_tensor,
-          b.final_trans_tensor]
+    ts = [b.batch_indices, b.targets, b.total_charges]
     ts += [b.atom_features_map[k] for k in sorted(b.atom_features_map)]
     ts += [gi.rowptr, gi.col, gi.rowptr_t, gi.col_t, gi.seg_ptr, gi.tile_ptr, gi.tile_info, gi.tile_info_t]
     for k in sorted(gi.embed):
         ts += [gi.embed[k][0], gi.embed[k][1]]
+    # stereo: the kernels read the int32 artefacts of the GraphIndex, not the reference's index tensors
+    if gi.tetra is not None:
+        ts += list(gi.tetra[:3])
+    if gi.cistrans is not None:
+        ts += list(gi.cistrans[:3])
     return ts
 
 

@@ -286,10 +286,17 @@ def pad_ring(batches, n_dummy=64):
     e_max = max(b.graph_index.num_edges for b in batches)
     n_pad = (n_max + n_dummy + 127) // 128 * 128
     e_cap = (int(e_max * 1.02) + 1023) // 1024 * 1024
-    first = [pad_batch(b, n_pad, e_cap, n_dummy) for b in batches]
+    seg_max = max(b.graph_index.max_seg for b in batches)
+    rows = 32 if seg_max <= 32 else (seg_max + 31) // 32 * 32          # tile capacity: the largest molecule
+    first = [pad_batch(b, n_pad, e_cap, n_dummy, tile_rows=rows) for b in batches]
     t_cap = max(p.graph_index.n_tiles for p in first) + 8
     me_cap = (max(p.graph_index.max_tile_edges for p in first) + 63) // 64 * 64
-    return [pad_batch(b, n_pad, e_cap, n_dummy, t_cap, max_tile_edges=me_cap) for b in batches]
+    stereo = any(b.graph_index.tetra is not None or b.graph_index.cistrans is not None for b in batches)
+    m_cap = None
+    if stereo:
+        m_cap = (max(0 if b.graph_index.tetra is None else b.graph_index.tetra[3] for b in batches) + 63) // 64 * 64
+    return [pad_batch(b, n_pad, e_cap, n_dummy, t_cap, tile_rows=rows, max_tile_edges=me_cap, num_tetra=m_cap,
+                      pad_cistrans=stereo) for b in batches]
 
 
 def ours_arm(args, wl):
@@ -306,7 +313,7 @@ def ours_arm(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     raw = make_batches(wl, rank, RING)
-    graphs = not args.eager and not wl["stereo"]
+    graphs = not args.eager
     host = [b.pin_memory() for b in (pad_ring(raw) if graphs else raw)]
     dev_batches = [b.to(device) for b in host]
     model = build_model(wl, device)

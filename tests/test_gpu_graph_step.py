@@ -137,3 +137,54 @@ def test_inference_step_matches_oracle_and_graph_replay():
         batch_indices=raws[1].batch_indices, total_charges=raws[1].total_charges,
         final_tetrahedral_chiral_tensor=raws[1].final_tetrahedral_chiral_tensor, final_cis_tensor=raws[1].final_cis_tensor,
         final_trans_tensor=raws[1].final_trans_tensor))[0].numpy(), RTOL_F32, "graphed inference outputs")
+
+
+def test_stereo_batches_pad_to_a_static_shape_and_replay():
+    """Drug-like batches with tetrahedral centres, cis/trans updates and partial charges: padding with dummy centres /
+    zero-weight updates leaves the real molecules untouched, and the captured step replays batch after batch."""
+    import aimnet_x2d_b200 as ax
+    from aimnet_x2d_b200 import synthetic as S
+    from aimnet_x2d_b200.collate import pad_batch, static_signature
+    from aimnet_x2d_b200.trainer import GraphedTrainStep
+    cfg = dict(CFG, use_partial_charges=True, use_stereochemistry=True)
+    P = det_state(gnn_shapes(cfg, 3), 17)
+
+    def model():
+        m = ax.GNN(FEATURE_SIZES, 64, 3, num_shells=3, num_message_passing_layers=2, task_type="multitask",
+                   use_partial_charges=True, use_stereochemistry=True, shell_conv_dropout=0.0, ffn_dropout=0.0)
+        m.load_state_dict(P)
+        return m.to(DEV).train()
+
+    raws = [S.make_batch(80 + i, 24, 3, "drug", num_targets=3, stereo=True) for i in range(3)]
+    assert all(b.graph_index.tetra is not None for b in raws)
+    n_pad = max(b.graph_index.num_atoms for b in raws) + 96
+    e_cap = max(b.graph_index.num_edges for b in raws) + 64
+    kw = dict(tile_rows=192, num_tetra=max(b.graph_index.tetra[3] for b in raws) + 3, pad_cistrans=True)
+    first = [pad_batch(b, n_pad, e_cap, 32, **kw) for b in raws]
+    kw.update(num_tiles=max(p.graph_index.n_tiles for p in first) + 1,
+              max_tile_edges=max(p.graph_index.max_tile_edges for p in first))
+    padded = [pad_batch(b, n_pad, e_cap, 32, **kw).pin_memory() for b in raws]
+    assert len({static_signature(p) for p in padded}) == 1
+    # real molecules: identical outputs / charges with and without the padding
+    m0 = model()
+    o_raw, _, q_raw = _fwd(m0, raws[1].to(DEV))
+    o_pad, _, q_pad = _fwd(m0, padded[1].to(DEV))
+    n_real = raws[1].graph_index.num_atoms
+    assert torch.equal(o_raw, o_pad[:24]) and torch.equal(q_raw, q_pad[:n_real])
+    # graph replay == eager on the same padded batches
+    crit = ax.WeightedL1Loss(torch.ones(3)).to(DEV)
+    m_e, m_g = model(), model()
+    o_e, o_g = ax.FlatAdam(m_e.parameters(), lr=1e-3), ax.FlatAdam(m_g.parameters(), lr=1e-3)
+    graphed = GraphedTrainStep(m_g, crit, o_g, DEV)
+    graphed.capture(padded[0], warmup=2)
+    for it in range(4):
+        b = padded[it % 3]
+        bd = b.to(DEV)
+        o_e.zero_grad()
+        out, _, _ = _fwd(m_e, bd)
+        le = crit(out[:24], bd.targets[:24])
+        le.backward()
+        o_e.step()
+        assert float(le) == graphed(b), it
+    torch.cuda.synchronize()
+    assert torch.equal(o_g.flat_param, o_e.flat_param)
