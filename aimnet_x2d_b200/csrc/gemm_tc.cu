@@ -780,7 +780,7 @@ extern "C" int ax2d_split_tf32(const float* w, int64_t ldw, int rows, int cols, 
 }
 
 extern "C" int ax2d_gemm_tc_supported(const ax2d_cmat* a, int64_t M, int64_t N, int64_t K) {
-  if (a == nullptr || M < 1 || N < 32 || N % 4 != 0 || K < TC_BK || K % TC_BK != 0) return 0;
+  if (a == nullptr || M < 1 || N < 4 || N % 4 != 0 || K < TC_BK || K % TC_BK != 0) return 0;
   if (a->n_seg < 1 || a->n_seg > AX2D_MAX_SEG) return 0;
   for (int s = 0; s < a->n_seg; ++s)
     if (a->width[s] <= 0 || a->width[s] % TC_BK != 0 || a->ld[s] % 4 != 0 || (reinterpret_cast<uintptr_t>(a->ptr[s]) & 15u)) return 0;

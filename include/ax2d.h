@@ -203,7 +203,7 @@ int ax2d_gemm(const ax2d_cmat* a, int trans_a, const ax2d_cmat* b, int trans_b,
  *   C[M,N] = epilogue( A[M,K] * B[N,K]^T ),  A column-segmented activations, B = weights given as two fp32 arrays
  *   b_hi + b_lo == B produced by ax2d_split_tf32 (transpose = 1 turns a [K,N] row-major operand -- the weight of a
  *   data-gradient product dX = dY W -- into the [N,K] K-major form).  Same epilogue semantics as ax2d_gemm.
- * Supported when every A segment width and K are multiples of 16, N >= 32, N % 4 == 0 (ax2d_gemm_tc_supported). */
+ * Supported when every A segment width and K are multiples of 16 and N % 4 == 0 (ax2d_gemm_tc_supported). */
 int ax2d_split_tf32(const float* w, int64_t ldw, int rows, int cols, int transpose, float* hi, float* lo, int64_t ldo,
                     ax2d_stream_t stream);
 int ax2d_gemm_tc_supported(const ax2d_cmat* a, int64_t M, int64_t N, int64_t K);

@@ -31,6 +31,7 @@ SHAPES = [
     (2048, [512], 512),          # head
     (513, [64, 32], 36),         # N not a multiple of 32
     (128, [32], 32),             # single k-block, single tile
+    (2112, [512, 512], 12),      # output layer: N far below the 32-column tile (TMA box larger than the weight)
 ]
 
 
