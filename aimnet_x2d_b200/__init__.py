@@ -19,10 +19,12 @@ from .layers import LinearBlock, MultiLayerPerceptron, ShellConvolutionLayer  # 
 from .losses import WeightedL1Loss, WeightedMSELoss  # noqa: E402
 from .inference import GraphedInferenceStep, InferenceStep  # noqa: E402
 from .optim import FlatAdam  # noqa: E402
+from .trainer import GraphedTrainStep, TrainStep  # noqa: E402
 from .pooling import (MaxPoolingLayer, MeanPoolingLayer, MultiHeadAttentionPoolingLayer, SumPoolingLayer,  # noqa: E402
                       create_pooling_layer)
 
 __all__ = ["GNN", "GNNConfig", "ShellConvolutionLayer", "LinearBlock", "MultiLayerPerceptron", "MeanPoolingLayer",
            "MaxPoolingLayer", "SumPoolingLayer", "MultiHeadAttentionPoolingLayer", "create_pooling_layer",
            "WeightedL1Loss", "WeightedMSELoss", "GraphIndex", "MolBatch", "MolData", "collate_fn", "FlatAdam",
-           "get_activation_function", "InferenceStep", "GraphedInferenceStep"]
+           "get_activation_function", "InferenceStep", "GraphedInferenceStep", "TrainStep",
+           "GraphedTrainStep"]

@@ -261,3 +261,68 @@ extern "C" int ax2d_weighted_loss(const float* pred, const float* target, const 
                                                                                g_pred);
   return launch_status("ax2d_weighted_loss");
 }
+
+// ---------------------------------------------------------------------------------------------- packed weights
+// One launch per step instead of ~190 tiny ones: every projection weight of the model is gathered from its
+// reference-shaped parameter into the padded / packed layout the kernels consume (zero padding lives in the
+// destination and is never written), split into the two TF32 terms of the tensor-core path (plain and transposed:
+// forward / data-gradient operands), and -- the other way round -- the packed weight gradients are accumulated
+// into the parameters' .grad storage.
+struct PackDesc {           // one rectangular block; 88 bytes (packed.py mirrors the layout)
+  const float* src;         // parameter block [rows, cols], leading dimension src_ld
+  float* grad_dst;          // same block inside the parameter's .grad (may be null: frozen parameter)
+  float* w;                 // packed fp32 copy              [.., dst_ld]
+  float* hi; float* lo;     // TF32 split of it (may be null: bias vectors)
+  float* hiT; float* loT;   // transposed split              [.., dstT_ld] (may be null)
+  const float* g;           // packed gradient block          [.., dst_ld]
+  int32_t rows, cols, src_ld, dst_ld, dstT_ld, pad;
+};
+__device__ __forceinline__ float pk_round_tf32(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+}
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackDesc* __restrict__ table) {
+  const PackDesc d = table[blockIdx.y];
+  const int total = d.rows * d.cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / d.cols, c = i - r * d.cols;
+    const float v = d.src[static_cast<int64_t>(r) * d.src_ld + c];
+    d.w[static_cast<int64_t>(r) * d.dst_ld + c] = v;
+    if (d.hi != nullptr) {
+      const float h = pk_round_tf32(v), l = pk_round_tf32(v - h);
+      d.hi[static_cast<int64_t>(r) * d.dst_ld + c] = h;
+      d.lo[static_cast<int64_t>(r) * d.dst_ld + c] = l;
+      if (d.hiT != nullptr) {
+        d.hiT[static_cast<int64_t>(c) * d.dstT_ld + r] = h;
+        d.loT[static_cast<int64_t>(c) * d.dstT_ld + r] = l;
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) unpack_grads_kernel(const PackDesc* __restrict__ table) {
+  const PackDesc d = table[blockIdx.y];
+  if (d.grad_dst == nullptr) return;
+  const int total = d.rows * d.cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / d.cols, c = i - r * d.cols;
+    d.grad_dst[static_cast<int64_t>(r) * d.src_ld + c] += d.g[static_cast<int64_t>(r) * d.dst_ld + c];
+  }
+}
+
+extern "C" int ax2d_pack_weights(const void* table, int n_blocks, int max_block_elems, ax2d_stream_t stream) {
+  using namespace ax2d;
+  AX2D_CHECK_ARG(table != nullptr && n_blocks > 0 && max_block_elems > 0, "ax2d_pack_weights: bad arguments");
+  int gx = (max_block_elems + 255) / 256;
+  gx = gx > 64 ? 64 : gx;
+  dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(n_blocks));
+  pack_weights_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<const PackDesc*>(table));
+  return launch_status("ax2d_pack_weights");
+}
+extern "C" int ax2d_unpack_grads(const void* table, int n_blocks, int max_block_elems, ax2d_stream_t stream) {
+  using namespace ax2d;
+  AX2D_CHECK_ARG(table != nullptr && n_blocks > 0 && max_block_elems > 0, "ax2d_unpack_grads: bad arguments");
+  int gx = (max_block_elems + 255) / 256;
+  gx = gx > 64 ? 64 : gx;
+  dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(n_blocks));
+  unpack_grads_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<const PackDesc*>(table));
+  return launch_status("ax2d_unpack_grads");
+}

@@ -20,6 +20,7 @@ from .activation import get_activation_function
 from .collate import GraphIndex
 from .layers import (FEATURE_PAD, INDEX_CACHE, MultiLayerPerceptron, ShellConvolutionLayer, _FusedLinear, pad1d,
                      pad2d)
+from .packed import PackAnchorFn, PackedWeights
 from .pooling import create_pooling_layer
 
 FEATURE_ORDER = ("atom_type", "hydrogen_count", "degree", "hybridization")      # gnn.py:262-274
@@ -79,6 +80,8 @@ class GNN(nn.Module):
         final_output_dim = output_dim * 4 if loss_function == "evidential" else output_dim      # gnn.py:136-141
         self.output_layer = _FusedLinear(ffn_hidden_dim * 2, final_output_dim)                  # gnn.py:143
         self.long_range_projection = nn.Linear(hidden_dim, ffn_hidden_dim)                      # dead parameter (Q6)
+        self.use_packed_weights = True      # one pack kernel per forward instead of per-call torch pad / cat / split
+        self._packed: Dict[tuple, PackedWeights] = {}
         self.init_weights()
 
     # ------------------------------------------------------------------------------------------ forward
@@ -96,6 +99,51 @@ class GNN(nn.Module):
                                     {k: atom_features[k] for k in FEATURE_ORDER}, sizes, tetra, cis, trans).to(dev)
 
         return INDEX_CACHE.get(key, build)
+
+    def _packed_weights(self, gi: GraphIndex) -> Optional[PackedWeights]:
+        """The packed operands of every projection of this model for the hop layout of ``gi`` (built once per device
+        and layout), or None when the per-call path has to be used: embedding widths that need padding, parameters
+        that are not all trainable fp32 CUDA tensors (the gradients are collected behind the first embedding table)."""
+        if not self.use_packed_weights or self.embedding_dim % 4 != 0:
+            return None
+        t0 = self.atom_type_embedding.weight
+        if not t0.is_cuda or t0.dtype != torch.float32 or (torch.is_grad_enabled() and not t0.requires_grad):
+            return None
+        key = (str(t0.device), bool(gi.collapsed))
+        pk = self._packed.get(key)
+        if pk is not None:
+            return pk
+        if any(p.dtype != torch.float32 or p.device != t0.device for p in self.parameters()):
+            return None
+        pk = self._declare_packed(t0.device, bool(gi.collapsed))
+        if pk is not None:
+            self._packed[key] = pk
+        return pk
+
+    def _declare_packed(self, device, collapsed: bool) -> Optional[PackedWeights]:
+        D, S = self.x_other_dim, self.x_self_dim
+        Dp, Sp = ops.pad_to(D, FEATURE_PAD), ops.pad_to(S, FEATURE_PAD)
+        ntE = self.embedding_dim * len(FEATURE_ORDER)
+        H4 = ops.pad_to(self.hidden_dim, 4)
+        pk = PackedWeights(device)
+        Wp, bp = self.embedding_projection.weight, self.embedding_projection.bias
+        pk.add("ep.W", Sp + Dp, ntE, [(Wp, 0, S, 0, ntE, 0, 0), (Wp, S, S + D, 0, ntE, Sp, 0)])
+        pk.add("ep.b", 1, Sp + Dp, [(bp, 0, 1, 0, S, 0, 0), (bp, 0, 1, S, S + D, 0, Sp)], vector=True)
+        for i, layer in enumerate(self.message_passing_layers):
+            if layer.global_skip_proj is None:
+                return None
+            layer.declare_packed(pk, f"mp.{i}", collapsed)
+        self.concat_self_other.declare_packed(pk, "cso", [S, D], [Sp, Dp])
+        if self.use_stereochemistry:
+            self.stereochemical_embedding_2.declare_packed(pk, "stereo2", [D, D, D], [Dp, Dp, Dp], n_out=Dp)
+        F4 = ops.pad_to(self.post_pooling_projection.out_features, 4)
+        self.post_pooling_projection.declare_packed(pk, "ppp", [self.hidden_dim], [H4])
+        self.ffn.declare_packed(pk, "ffn")
+        if F4 == self.post_pooling_projection.out_features:      # the segments of the output layer are unpadded
+            self.skip_transform.declare_packed(pk, "skip", [F4], [F4])
+            self.output_layer.declare_packed(pk, "out", [F4, F4], [F4, F4])
+        pk.finalize()
+        return pk
 
     def forward(self, atom_features: Dict[str, torch.Tensor], multi_hop_edge_indices: torch.Tensor,
                 batch_indices: torch.Tensor, total_charges: torch.Tensor, tetrahedral_indices: torch.Tensor,
@@ -115,42 +163,50 @@ class GNN(nn.Module):
         if Ep != E:
             tables = [pad2d(t, t.shape[0], Ep) for t in tables]
         nt = len(FEATURE_ORDER)
-        Wp = self.embedding_projection.weight
-        if Ep != E:
-            Wp = torch.cat([pad2d(Wp[:, i * E:(i + 1) * E], Wp.shape[0], Ep) for i in range(nt)], dim=1)
-        W_ep = torch.cat([pad2d(Wp[:S], Sp, nt * Ep), pad2d(Wp[S:], Dp, nt * Ep)], dim=0)
-        bp = self.embedding_projection.bias
-        b_ep = torch.cat([pad1d(bp[:S], Sp), pad1d(bp[S:], Dp)], dim=0)
+        pk = self._packed_weights(gi)
+        use = (lambda name: (pk, name) if f"{name}.W" in pk or f"{name}.W_io" in pk or f"{name}.0.W1" in pk else None) \
+            if pk is not None else (lambda name: None)
+        if pk is not None:
+            # refreshes the packed operands now; its backward (the last node of the graph) collects their gradients
+            tables[0] = PackAnchorFn.apply(pk, tables[0])
+            W_ep, b_ep = pk["ep.W"], pk["ep.b"]
+        else:
+            Wp = self.embedding_projection.weight
+            if Ep != E:
+                Wp = torch.cat([pad2d(Wp[:, i * E:(i + 1) * E], Wp.shape[0], Ep) for i in range(nt)], dim=1)
+            W_ep = torch.cat([pad2d(Wp[:S], Sp, nt * Ep), pad2d(Wp[S:], Dp, nt * Ep)], dim=0)
+            bp = self.embedding_projection.bias
+            b_ep = torch.cat([pad1d(bp[:S], Sp), pad1d(bp[S:], Dp)], dim=0)
         opts = ops._Opts(act=self.activation_type, names=FEATURE_ORDER, emb_dim=Ep, s_pad=Sp, d_pad=Dp, gi=gi)
         x_self, x = ops.EmbedProjFn.apply(opts, W_ep, b_ep, *tables,
                                           *[atom_features[k].contiguous() for k in FEATURE_ORDER])   # gnn.py:220-231
 
         if multi_hop_edge_indices.numel() > 0:                                                     # gnn.py:287
-            for layer in self.message_passing_layers:
+            for i, layer in enumerate(self.message_passing_layers):
                 if self.use_partial_charges:                                                       # gnn.py:290-293
                     x = ops.ChargeEqFn.apply(x, total_charges, gi)
                 if self.use_stereochemistry:                                                       # gnn.py:296-299
-                    x = self._apply_stereochemistry(x, gi, D, Dp)
-                x = layer.forward_padded(x, gi, add_input=True)                                    # gnn.py:302-306
+                    x = self._apply_stereochemistry(x, gi, D, Dp, use("stereo2"))
+                x = layer.forward_padded(x, gi, add_input=True, packed=use(f"mp.{i}"))             # gnn.py:302-306
 
         partial_charges = None
         if self.use_partial_charges and D >= 2:                                                    # gnn.py:240-242
             partial_charges = x[:, 0].clone()
 
-        atom_emb = self.concat_self_other(([x_self, x], [S, D]))                                   # gnn.py:245-246
+        atom_emb = self.concat_self_other(([x_self, x], [S, D]), packed=use("cso"))                # gnn.py:245-246
         x_pooled, attention_weights = self.pooling(atom_emb, batch_indices, graph_index=gi)        # gnn.py:249
-        v = self.post_pooling_projection(x_pooled)                                                 # gnn.py:252
-        v = self.ffn(v)                                                                            # gnn.py:253
-        skip = self.skip_transform(v)                                                              # gnn.py:256
+        v = self.post_pooling_projection(x_pooled, packed=use("ppp"))                              # gnn.py:252
+        v = self.ffn(v, packed=use("ffn"))                                                         # gnn.py:253
+        skip = self.skip_transform(v, packed=use("skip"))                                          # gnn.py:256
         Fh = v.shape[1]
-        output = self.output_layer(([v, skip], [Fh, Fh]))                                          # gnn.py:257-258
+        output = self.output_layer(([v, skip], [Fh, Fh]), packed=use("out"))                       # gnn.py:257-258
         return output, attention_weights, partial_charges
 
-    def _apply_stereochemistry(self, x: torch.Tensor, gi: GraphIndex, D: int, Dp: int) -> torch.Tensor:
+    def _apply_stereochemistry(self, x: torch.Tensor, gi: GraphIndex, D: int, Dp: int, packed=None) -> torch.Tensor:
         """Reference ``gnn.py:310-327``: Linear([x | cis_trans(x) | tetra(x)])."""
         ct = ops.CisTransFn.apply(x, gi) if gi.cistrans is not None else x          # identity when empty (gnn.py:475-476)
         tt = ops.TetraFn.apply(x, D, gi) if gi.tetra is not None else x             # identity when empty (gnn.py:402-403)
-        return self.stereochemical_embedding_2(([x, ct, tt], [D, D, D], Dp))       # padded [N, Dp], pad columns = 0
+        return self.stereochemical_embedding_2(([x, ct, tt], [D, D, D], Dp), packed=packed)  # padded [N, Dp], pads = 0
 
     # ------------------------------------------------------------------------------------------ misc API
     def init_weights(self) -> None:

@@ -2,8 +2,9 @@
 
 Same constructor arguments, forward signatures, attribute names and ``state_dict`` keys/shapes as the
 reference ``src/models/layers.py`` (17-267); the computation is the fused CUDA path of ``ops.py``.
-Padded / packed weights are derived per call from the parameters (never stored), so checkpoints
-round-trip with the reference.
+Padded / packed weights are derived from the parameters -- per call with torch ops for stand-alone modules, by
+one kernel per forward inside ``GNN`` (``packed.PackedWeights``) -- and are never part of the ``state_dict``, so
+checkpoints round-trip with the reference.
 """
 from __future__ import annotations
 
@@ -144,21 +145,48 @@ class ShellConvolutionLayer(nn.Module):
         return chunks
 
     # ------------------------------------------------------------------ fused path on padded features
-    def forward_padded(self, xp: torch.Tensor, gi: GraphIndex, add_input: bool) -> torch.Tensor:
+    def declare_packed(self, pk, prefix: str, collapsed: bool) -> None:
+        """Declare this layer's packed operands in a ``packed.PackedWeights``: W_io = [W_in ; W_skip] over the column
+        chunks that meet non-zero data, b_io, and the padded MLP weights."""
+        Din, Dout, H = self.atom_input_dim, self.output_dim, self.num_hops
+        Di, Do = ops.pad_to(Din, FEATURE_PAD), ops.pad_to(Dout, FEATURE_PAD)
+        used = 1 + (1 if collapsed else H)
+        projs = (self.input_proj, self.global_skip_proj)
+        pk.add(f"{prefix}.W_io", 2 * Do, used * Di,
+               [(pr.weight, 0, Dout, c * Din, (c + 1) * Din, j * Do, c * Di) for j, pr in enumerate(projs) for c in range(used)])
+        pk.add(f"{prefix}.b_io", 1, 2 * Do, [(pr.bias, 0, 1, 0, Dout, 0, j * Do) for j, pr in enumerate(projs)], vector=True)
+        for k, blk in enumerate(self.mlp_blocks):
+            for name in ("linear_1", "linear_2"):
+                pk.add(f"{prefix}.{k}.{name}.W", Do, Do, [(blk[name].weight, 0, Dout, 0, Dout, 0, 0)])
+                pk.add(f"{prefix}.{k}.{name}.b", 1, Do, [(blk[name].bias, 0, 1, 0, Dout, 0, 0)], vector=True)
+
+    def forward_padded(self, xp: torch.Tensor, gi: GraphIndex, add_input: bool, packed=None) -> torch.Tensor:
+        """``packed = (PackedWeights, prefix)``: read the operands declared by ``declare_packed`` instead of deriving
+        them from the parameters with torch ops."""
         if self.global_skip_proj is None:
             raise NotImplementedError("ShellConvolutionLayer without global_skip_proj "
                                       "(atom_input_dim * (num_hops + 1) == output_dim) is not supported")
         Din, Dout, H = self.atom_input_dim, self.output_dim, self.num_hops
         Di, Do = ops.pad_to(Din, FEATURE_PAD), ops.pad_to(Dout, FEATURE_PAD)
         used = 1 + (1 if gi.collapsed else H)
-        w_io = torch.cat([pack_chunked(self.input_proj.weight, Do, H + 1, Din, Di, used),
-                          pack_chunked(self.global_skip_proj.weight, Do, H + 1, Din, Di, used)], dim=0)
-        b_io = torch.cat([pad1d(self.input_proj.bias, Do), pad1d(self.global_skip_proj.bias, Do)], dim=0)
+        if packed is not None:
+            pk, prefix = packed
+            w_io, b_io = pk[f"{prefix}.W_io"], pk[f"{prefix}.b_io"]
+            if w_io.shape[1] != used * Di:
+                raise RuntimeError("packed shell weights were declared for a different hop layout")
+        else:
+            w_io = torch.cat([pack_chunked(self.input_proj.weight, Do, H + 1, Din, Di, used),
+                              pack_chunked(self.global_skip_proj.weight, Do, H + 1, Din, Di, used)], dim=0)
+            b_io = torch.cat([pad1d(self.input_proj.bias, Do), pad1d(self.global_skip_proj.bias, Do)], dim=0)
         ps = []
         mlp = []
-        for blk in self.mlp_blocks:
+        for k, blk in enumerate(self.mlp_blocks):
             d = blk["dropout"]            # each nn.Dropout keeps its own .training flag (MC-dropout flips only those)
             ps.append(float(d.p) if (d.training and d.p > 0) else 0.0)
+            if packed is not None:
+                mlp += [pk[f"{prefix}.{k}.linear_1.W"], pk[f"{prefix}.{k}.linear_1.b"],
+                        pk[f"{prefix}.{k}.linear_2.W"], pk[f"{prefix}.{k}.linear_2.b"]]
+                continue
             mlp += [pad2d(blk["linear_1"].weight, Do, Do), pad1d(blk["linear_1"].bias, Do),
                     pad2d(blk["linear_2"].weight, Do, Do), pad1d(blk["linear_2"].bias, Do)]
         tick = self._clock.advance() if any(p > 0 for p in ps) else None
@@ -174,23 +202,44 @@ class _FusedLinear(nn.Linear):
     """``nn.Linear`` (same parameters / state_dict) whose forward is the libax2d GEMM.  It also accepts a
     list of already padded column segments so that the reference's ``torch.cat`` is never materialised."""
 
-    def forward(self, x):  # type: ignore[override]
+    def declare_packed(self, pk, prefix: str, true_widths, widths, n_out=None) -> None:
+        """Packed operand for a call with column segments of ``true_widths`` padded to ``widths``."""
+        n_out = ops.pad_to(self.out_features, 4) if n_out is None else n_out
+        blocks, off, dst = [], 0, 0
+        for tw, w in zip(true_widths, widths):
+            blocks.append((self.weight, 0, self.out_features, off, off + tw, 0, dst))
+            off += tw
+            dst += w
+        if off != self.in_features:
+            raise ValueError(f"{prefix}: segments cover {off} of {self.in_features} input features")
+        pk.add(f"{prefix}.W", n_out, dst, blocks)
+        if self.bias is not None:
+            pk.add(f"{prefix}.b", 1, n_out, [(self.bias, 0, 1, 0, self.out_features, 0, 0)], vector=True)
+
+    def forward(self, x, packed=None):  # type: ignore[override]
         if isinstance(x, (list, tuple)):
             segs, true_widths = x[0], x[1]   # ([tensors], [true widths][, padded out width]) -- internal convention
             widths = [s.shape[1] for s in segs]
             n_out = x[2] if len(x) > 2 else ops.pad_to(self.out_features, 4)
-            cols = []
-            off = 0
-            for tw, w in zip(true_widths, widths):
-                cols.append(pad2d(self.weight[:, off:off + tw], n_out, w))
-                off += tw
-            W = cols[0] if len(cols) == 1 else torch.cat(cols, dim=1)
-            out = ops.LinearFn.apply(ops._Opts(widths=widths, n_out=n_out), W, pad1d(self.bias, n_out), *segs)
+            if packed is not None:
+                pk, prefix = packed
+                W, b = pk[f"{prefix}.W"], (pk[f"{prefix}.b"] if self.bias is not None else None)
+                if tuple(W.shape) != (n_out, sum(widths)):
+                    raise RuntimeError(f"{prefix}: packed weight {tuple(W.shape)} vs call ({n_out}, {sum(widths)})")
+            else:
+                cols = []
+                off = 0
+                for tw, w in zip(true_widths, widths):
+                    cols.append(pad2d(self.weight[:, off:off + tw], n_out, w))
+                    off += tw
+                W = cols[0] if len(cols) == 1 else torch.cat(cols, dim=1)
+                b = pad1d(self.bias, n_out)
+            out = ops.LinearFn.apply(ops._Opts(widths=widths, n_out=n_out), W, b, *segs)
             return out if (n_out == self.out_features or len(x) > 2) else out[:, : self.out_features]
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
         k = ops.pad_to(self.in_features, 4)
-        out = self.forward(([pad_cols(x2, k).contiguous()], [self.in_features]))
+        out = self.forward(([pad_cols(x2, k).contiguous()], [self.in_features]), packed=packed)
         return out.reshape(*lead, self.out_features)
 
 
@@ -209,7 +258,15 @@ class LinearBlock(nn.Module):
         self.skip_proj = None                      # unreachable in the reference as well (layers.py:190,198)
         self._clock = DropClock()
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def declare_packed(self, pk, prefix: str) -> None:
+        din, dout = self.linear1.in_features, self.linear1.out_features
+        wi, wo = ops.pad_to(din, 4), ops.pad_to(dout, 4)
+        pk.add(f"{prefix}.W1", wo, wi, [(self.linear1.weight, 0, dout, 0, din, 0, 0)])
+        pk.add(f"{prefix}.b1", 1, wo, [(self.linear1.bias, 0, 1, 0, dout, 0, 0)], vector=True)
+        pk.add(f"{prefix}.W2", wo, wo, [(self.linear2.weight, 0, dout, 0, dout, 0, 0)])
+        pk.add(f"{prefix}.b2", 1, wo, [(self.linear2.bias, 0, 1, 0, dout, 0, 0)], vector=True)
+
+    def forward(self, x: torch.Tensor, packed=None) -> torch.Tensor:
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
         din, dout = self.linear1.in_features, self.linear1.out_features
@@ -218,9 +275,13 @@ class LinearBlock(nn.Module):
         tick = self._clock.advance() if p > 0 else None
         opts = ops._Opts(act=self.activation_type, p=p, seed=self._clock.seed, tick=tick, skip=self.use_skip,
                          w_in=wi, w_out=wo)
-        out = ops.MLPBlockFn.apply(opts, pad_cols(x2, wi).contiguous(), pad2d(self.linear1.weight, wo, wi),
-                                   pad1d(self.linear1.bias, wo), pad2d(self.linear2.weight, wo, wo),
-                                   pad1d(self.linear2.bias, wo))
+        if packed is not None:
+            pk, prefix = packed
+            ws = [pk[f"{prefix}.{n}"] for n in ("W1", "b1", "W2", "b2")]
+        else:
+            ws = [pad2d(self.linear1.weight, wo, wi), pad1d(self.linear1.bias, wo), pad2d(self.linear2.weight, wo, wo),
+                  pad1d(self.linear2.bias, wo)]
+        out = ops.MLPBlockFn.apply(opts, pad_cols(x2, wi).contiguous(), *ws)
         return out[:, :dout].reshape(*lead, dout) if wo != dout else out.reshape(*lead, dout)
 
 
@@ -240,7 +301,11 @@ class MultiLayerPerceptron(nn.Module):
             layers.append(LinearBlock(hidden_dim, output_dim, activation_type, dropout, False))
         self.layers = nn.ModuleList(layers)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        for layer in self.layers:
-            x = layer(x)
+    def declare_packed(self, pk, prefix: str) -> None:
+        for i, layer in enumerate(self.layers):
+            layer.declare_packed(pk, f"{prefix}.{i}")
+
+    def forward(self, x: torch.Tensor, packed=None) -> torch.Tensor:
+        for i, layer in enumerate(self.layers):
+            x = layer(x) if packed is None else layer(x, packed=(packed[0], f"{packed[1]}.{i}"))
         return x

@@ -12,6 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
+from .packed import packed_info
 from ._lib import ACT_CODES, CMat, Epilogue, MAX_SEG, SEG_MODES
 
 
@@ -132,7 +133,13 @@ def gemm(a_segs, b_segs, c_segs, M: int, N: int, K: int, trans_a: bool = False, 
             and lib.ax2d_gemm_tc_supported(C.byref(a), M, N, K)):
         # y = x W^T (trans_b) takes W [N, K] as it is; dx = dy W (not trans_b) needs W^T, produced by the split kernel
         w = b_segs[0][0]
-        hi, lo = split_tf32(w[:N, :K] if trans_b else w[:K, :N], transpose=not trans_b)
+        info = packed_info(w)
+        if info is not None and info.hi is not None:      # operands kept ready by packed.PackedWeights
+            hi, lo = (info.hi, info.lo) if trans_b else (info.hiT, info.loT)
+            if tuple(hi.shape) != (N, K):
+                raise RuntimeError(f"packed weight {tuple(hi.shape)} does not match the contraction ({N}, {K})")
+        else:
+            hi, lo = split_tf32(w[:N, :K] if trans_b else w[:K, :N], transpose=not trans_b)
         call = lambda: _lib.check(lib.ax2d_gemm_tc(C.byref(a), _p(hi), _p(lo), hi.stride(0), C.byref(c), M, N, K,
                                                    C.byref(ep), _stream()), "ax2d_gemm_tc")
         if TIMER is None:
@@ -207,18 +214,21 @@ def _bias_grad(segs, M, N, device):
     return out
 
 
-def _weight_grad(g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device, bias: bool = False):
+def _weight_grad(g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device, bias: bool = False, out=None, out_bias=None):
     """dW[o, i] = sum_r G[r, o] X[r, i]  (G, X column-segmented) and, with ``bias``, db[o] = sum_r G[r, o].
     Returns dW or (dW, db).  Tensor-core kernel (split over the rows, fixed-order reduce, bias gradient fused)
-    when the operands qualify; exact-fp32 SIMT GEMM + column-sum kernels otherwise."""
-    dW = torch.empty((Nout, Kin), dtype=torch.float32, device=device)
+    when the operands qualify; exact-fp32 SIMT GEMM + column-sum kernels otherwise.  ``out`` / ``out_bias``:
+    write into these (contiguous) buffers instead of fresh tensors."""
+    dW = torch.empty((Nout, Kin), dtype=torch.float32, device=device) if out is None else out
+    if tuple(dW.shape) != (Nout, Kin) or not dW.is_contiguous():
+        raise RuntimeError(f"weight-gradient buffer {tuple(dW.shape)} vs ({Nout}, {Kin})")
     lib = _lib.load()
     if USE_TENSOR_CORES and M_rows >= TC_MIN_ROWS:
         a, b, c = _mat(g_segs), _mat(x_segs), _mat([(dW, Kin)])
         if lib.ax2d_gemm_tc_wgrad_supported(C.byref(a), C.byref(b), Nout, Kin, M_rows):
             nbytes = lib.ax2d_gemm_tc_wgrad_workspace(Nout, Kin, M_rows)
             ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=device)
-            db = torch.empty(Nout, dtype=torch.float32, device=device) if bias else None
+            db = (torch.empty(Nout, dtype=torch.float32, device=device) if out_bias is None else out_bias) if bias else None
             call = lambda: _lib.check(lib.ax2d_gemm_tc_wgrad(C.byref(a), C.byref(b), C.byref(c), Nout, Kin, M_rows, 0, _p(db),
                                                              _p(ws), _stream()), "ax2d_gemm_tc_wgrad")
             if TIMER is None:
@@ -228,7 +238,36 @@ def _weight_grad(g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device, bias:
             return (dW, db) if bias else dW
     gemm(g_segs, x_segs, [(dW, Kin)], Nout, Kin, M_rows, trans_a=True, trans_b=False,
          split_k=split_k_for(Nout, Kin, M_rows))
-    return (dW, _bias_grad(g_segs, M_rows, Nout, device)) if bias else dW
+    if not bias:
+        return dW
+    if out_bias is None:
+        return dW, _bias_grad(g_segs, M_rows, Nout, device)
+    colsum(g_segs, M_rows, Nout, out_bias)
+    return dW, out_bias
+
+
+def _param_grads(W, b, g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device):
+    """(dW, db) for autograd.  For packed weights (``packed.PackedWeights``) the gradients go straight into the packed
+    gradient buffers -- collected into ``.grad`` by ONE kernel at the end of backward -- and autograd gets (None, None)."""
+    iw = packed_info(W)
+    if iw is None:
+        if b is None:
+            return _weight_grad(g_segs, x_segs, M_rows, Nout, Kin, device), None
+        return _weight_grad(g_segs, x_segs, M_rows, Nout, Kin, device, bias=True)
+    ib = packed_info(b)
+    if b is not None and ib is None:
+        raise RuntimeError("a packed weight needs a packed bias")
+    if not iw.written:
+        _weight_grad(g_segs, x_segs, M_rows, Nout, Kin, device, bias=b is not None, out=iw.grad,
+                     out_bias=None if b is None else ib.grad)
+    else:           # a weight shared by several calls (stereochemical_embedding_2 serves every layer): sum them
+        r = _weight_grad(g_segs, x_segs, M_rows, Nout, Kin, device, bias=b is not None)
+        iw.grad.add_(r[0] if b is not None else r)
+        if b is not None:
+            ib.grad.add_(r[1])
+    iw.written = True
+    iw.owner.dirty = True
+    return None, None
 
 
 class _Opts:
@@ -236,6 +275,16 @@ class _Opts:
 
     def __init__(self, **kw):
         self.__dict__.update(kw)
+
+
+def _keep_packed(ctx, *ws) -> None:
+    """Remember the packed weight tensors themselves: the objects autograd hands back from ``saved_tensors`` need not
+    carry the ``_ax2d`` attribute."""
+    ctx.packed_ws = [w if packed_info(w) is not None else None for w in ws]
+
+
+def _packed_or(ctx, *saved):
+    return [s if p is None else p for p, s in zip(ctx.packed_ws, saved)]
 
 
 class LinearFn(torch.autograd.Function):
@@ -251,23 +300,22 @@ class LinearFn(torch.autograd.Function):
         out = torch.empty((M, opts.n_out), dtype=torch.float32, device=W.device)
         gemm(list(zip(a, opts.widths)), [(W, K)], [(out, opts.n_out)], M, opts.n_out, K, bias=b)
         ctx.opts = opts
-        ctx.has_bias = b is not None
+        ctx.bias = b
+        _keep_packed(ctx, W)
         ctx.save_for_backward(W, *a)
         return out
 
     @staticmethod
     def backward(ctx, g):
         W, *a = ctx.saved_tensors
+        (W,) = _packed_or(ctx, W)
         opts = ctx.opts
         g = g.contiguous()
         M, Np, K = g.shape[0], opts.n_out, sum(opts.widths)
         gs = [(g, Np)]
         d_a = [torch.empty((M, w), dtype=torch.float32, device=g.device) for w in opts.widths]
         gemm(gs, [(W, K)], list(zip(d_a, opts.widths)), M, K, Np, trans_a=False, trans_b=False)
-        if ctx.has_bias:
-            dW, db = _weight_grad(gs, list(zip(a, opts.widths)), M, Np, K, g.device, bias=True)
-        else:
-            dW, db = _weight_grad(gs, list(zip(a, opts.widths)), M, Np, K, g.device), None
+        dW, db = _param_grads(W, ctx.bias, gs, list(zip(a, opts.widths)), M, Np, K, g.device)
         return (None, dW, db, *d_a)
 
 
@@ -287,23 +335,27 @@ class MLPBlockFn(torch.autograd.Function):
              drop_p=opts.p, drop_seed=opts.seed, drop_tick=opts.tick)
         gemm([(t, Wo)], [(W2, Wo)], [(out, Wo)], M, Wo, Wo, bias=b2, resid=[(h, Wo)] if opts.skip else [])
         ctx.opts = opts
+        ctx.biases = (b1, b2)
+        _keep_packed(ctx, W1, W2)
         ctx.save_for_backward(h, W1, W2, u, t)
         return out
 
     @staticmethod
     def backward(ctx, g):
         h, W1, W2, u, t = ctx.saved_tensors
+        W1, W2 = _packed_or(ctx, W1, W2)
+        b1, b2 = ctx.biases
         opts = ctx.opts
         g = g.contiguous()
         M, Wi, Wo = g.shape[0], opts.w_in, opts.w_out
         dev = g.device
         gs = [(g, Wo)]
-        dW2, db2 = _weight_grad(gs, [(t, Wo)], M, Wo, Wo, dev, bias=True)
+        dW2, db2 = _param_grads(W2, b2, gs, [(t, Wo)], M, Wo, Wo, dev)
         du = torch.empty_like(u)
         gemm(gs, [(W2, Wo)], [(du, Wo)], M, Wo, Wo, trans_b=False, dact_pre=u, dact=opts.act,
              drop_p=opts.p, drop_seed=opts.seed, drop_tick=opts.tick)
         dus = [(du, Wo)]
-        dW1, db1 = _weight_grad(dus, [(h, Wi)], M, Wo, Wi, dev, bias=True)
+        dW1, db1 = _param_grads(W1, b1, dus, [(h, Wi)], M, Wo, Wi, dev)
         dh = torch.empty_like(h)
         gemm(dus, [(W1, Wi)], [(dh, Wi)], M, Wi, Wo, trans_b=False, resid=[(g, Wi)] if opts.skip else [])
         return None, dh, dW1, db1, dW2, db2
@@ -353,6 +405,8 @@ class ShellConvFn(torch.autograd.Function):
         if opts.n_mlp == 0:
             h = h + gskip + (x if opts.add_input else 0)
         ctx.opts = opts
+        ctx.biases = (b_io, *[mlp[4 * k + j] for k in range(opts.n_mlp) for j in (1, 3)])
+        _keep_packed(ctx, *saved)
         ctx.save_for_backward(*saved)
         return h
 
@@ -360,8 +414,9 @@ class ShellConvFn(torch.autograd.Function):
     def backward(ctx, g):
         opts = ctx.opts
         gi, Di, Do = opts.gi, opts.w_in, opts.w_out
-        saved = ctx.saved_tensors
+        saved = _packed_or(ctx, *ctx.saved_tensors)
         x, ag, z0, W_io = saved[:4]
+        b_io, *b_mlp = ctx.biases
         g = g.contiguous()
         N, dev = g.shape[0], g.device
         dh = g
@@ -371,12 +426,12 @@ class ShellConvFn(torch.autograd.Function):
         for k in reversed(range(opts.n_mlp)):
             h, u, t, W1, W2 = saved[4 + 5 * k:9 + 5 * k]
             dhs = [(dh, Do)]
-            dW2, db2 = _weight_grad(dhs, [(t, Do)], N, Do, Do, dev, bias=True)
+            dW2, db2 = _param_grads(W2, b_mlp[2 * k + 1], dhs, [(t, Do)], N, Do, Do, dev)
             du = torch.empty_like(z0)
             gemm(dhs, [(W2, Do)], [(du, Do)], N, Do, Do, trans_b=False, dact_pre=u, dact=opts.act,
                  drop_p=opts.ps[k], drop_seed=opts.seeds[k], drop_tick=opts.tick)
             dus = [(du, Do)]
-            dW1, db1 = _weight_grad(dus, [(h, Do)], N, Do, Do, dev, bias=True)
+            dW1, db1 = _param_grads(W1, b_mlp[2 * k], dus, [(h, Do)], N, Do, Do, dev)
             dprev = torch.empty_like(z0)
             if k == 0:      # d z0 = (dh + du W1) * act'(z0) in one epilogue
                 gemm(dus, [(W1, Do)], [(dprev, Do)], N, Do, Do, trans_b=False, resid=dhs, dact_pre=z0, dact=opts.act)
@@ -389,7 +444,7 @@ class ShellConvFn(torch.autograd.Function):
         a_segs = ShellConvFn._segments(x, ag, Di)
         K = Di * len(a_segs)
         gz = [(dz0, Do), (g, Do)]
-        dW_io, db_io = _weight_grad(gz, a_segs, N, 2 * Do, K, dev, bias=True)
+        dW_io, db_io = _param_grads(W_io, b_io, gz, a_segs, N, 2 * Do, K, dev)
         dx1 = torch.empty((N, Di), dtype=torch.float32, device=dev)
         dag = torch.empty_like(ag)
         c_segs = ShellConvFn._segments(dx1, dag, Di)
@@ -426,6 +481,8 @@ class EmbedProjFn(torch.autograd.Function):
         gemm([(e0, nt * E)], [(W, nt * E)], [(xs, Sp), (xo, Dp)], N, Sp + Dp, nt * E, bias=b,
              pre_segs=[(zs, Sp), (zo, Dp)], act=opts.act)
         ctx.opts = opts
+        ctx.bias = b
+        _keep_packed(ctx, W)
         ctx.save_for_backward(W, e0, zs, zo, *tables)
         return xs, xo
 
@@ -433,13 +490,14 @@ class EmbedProjFn(torch.autograd.Function):
     def backward(ctx, gxs, gxo):
         opts = ctx.opts
         W, e0, zs, zo, *tables = ctx.saved_tensors
+        (W,) = _packed_or(ctx, W)
         lib = _lib.load()
         nt, E, Sp, Dp = len(opts.names), opts.emb_dim, opts.s_pad, opts.d_pad
         N, dev = e0.shape[0], e0.device
         dzs = act_bwd(gxs.contiguous(), zs, opts.act)
         dzo = act_bwd(gxo.contiguous(), zo, opts.act)
         gz = [(dzs, Sp), (dzo, Dp)]
-        dW, db = _weight_grad(gz, [(e0, nt * E)], N, Sp + Dp, nt * E, dev, bias=True)
+        dW, db = _param_grads(W, ctx.bias, gz, [(e0, nt * E)], N, Sp + Dp, nt * E, dev)
         de0 = torch.empty_like(e0)
         gemm(gz, [(W, nt * E)], [(de0, nt * E)], N, nt * E, Sp + Dp, trans_b=False)
         g_tables = []

@@ -1,0 +1,197 @@
+"""Packed projection weights: the padded / packed / TF32-split operands of every ``nn.Linear`` on the path, refreshed
+from the reference-shaped parameters by ONE kernel per forward (``ax2d_pack_weights``), and the weight gradients
+accumulated back into the parameters' ``.grad`` by ONE kernel per backward (``ax2d_unpack_grads``).
+
+The parameters stay what the reference defines (names, shapes, ``state_dict``); everything here is a derived cache.
+Without it every call pads / concatenates / splits its weights with ~190 small torch and split kernels per training
+step and autograd adds ~60 gradient-accumulation kernels; with it the projections read ready operands and write
+their weight gradients straight into the packed gradient buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DESC = np.dtype([("src", "u8"), ("grad", "u8"), ("w", "u8"), ("hi", "u8"), ("lo", "u8"), ("hiT", "u8"), ("loT", "u8"),
+                  ("g", "u8"), ("rows", "i4"), ("cols", "i4"), ("src_ld", "i4"), ("dst_ld", "i4"), ("dstT_ld", "i4"),
+                  ("pad", "i4")])
+assert _DESC.itemsize == 88
+
+
+class PackInfo:
+    """Attached to a packed weight tensor as ``t._ax2d``: its TF32 terms (plain and transposed) and the buffer its
+    gradient is written to."""
+    __slots__ = ("hi", "lo", "hiT", "loT", "grad", "owner", "written")
+
+    def __init__(self, hi, lo, hiT, loT, grad, owner):
+        self.hi, self.lo, self.hiT, self.loT, self.grad, self.owner = hi, lo, hiT, loT, grad, owner
+        self.written = False      # the gradient buffer already holds a contribution of the running backward pass
+
+
+def packed_info(t) -> Optional[PackInfo]:
+    return None if t is None else getattr(t, "_ax2d", None)
+
+
+class _Matrix:
+    def __init__(self, name, rows, cols, blocks, vector):
+        self.name, self.rows, self.cols, self.blocks, self.vector = name, rows, cols, blocks, vector
+        self.off = 0
+
+
+class PackedWeights:
+    """``add(name, rows, cols, blocks)`` declares a packed matrix built from rectangular blocks of parameters:
+    ``blocks = [(param, r0, r1, c0, c1, dst_r, dst_c), ...]`` (for a bias: rows = 1, r0 = 0, r1 = 1, columns = entries).
+    ``finalize()`` allocates the (zero) arenas; ``refresh()`` / ``unpack_grads()`` launch the two kernels."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.mats: Dict[str, _Matrix] = {}
+        self.tensors: Dict[str, torch.Tensor] = {}
+        self._table = None
+        self._table_key = None
+        self._n_blocks = 0
+        self._max_elems = 1
+        self.dirty = False
+
+    # a derived cache: copies / pickles of the owning module rebuild their own
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (type(None), ())
+
+    def add(self, name: str, rows: int, cols: int, blocks: Sequence[Tuple], vector: bool = False) -> None:
+        for (p, r0, r1, c0, c1, dr, dc) in blocks:
+            if p.dim() == 1:
+                if not (r0 == 0 and r1 == 1 and 0 <= c0 <= c1 <= p.shape[0]):
+                    raise ValueError(f"{name}: bad vector block")
+            elif not (0 <= r0 <= r1 <= p.shape[0] and 0 <= c0 <= c1 <= p.shape[1]):
+                raise ValueError(f"{name}: block outside its parameter")
+            if dr + (r1 - r0) > rows or dc + (c1 - c0) > cols:
+                raise ValueError(f"{name}: block outside the packed matrix")
+        self.mats[name] = _Matrix(name, int(rows), int(cols), list(blocks), vector)
+
+    def finalize(self) -> None:
+        n = 0
+        for m in self.mats.values():
+            m.off = n
+            n += (m.rows * m.cols + 3) // 4 * 4              # 16-byte aligned matrices
+        z = lambda: torch.zeros(max(n, 4), dtype=torch.float32, device=self.device)
+        self.w, self.hi, self.lo, self.hiT, self.loT, self.grad = z(), z(), z(), z(), z(), z()
+        for m in self.mats.values():
+            sl = slice(m.off, m.off + m.rows * m.cols)
+            shape = (m.cols,) if m.vector else (m.rows, m.cols)
+            t = self.w[sl].view(shape)
+            gr = self.grad[sl].view(shape)
+            if m.vector:
+                info = PackInfo(None, None, None, None, gr, self)
+            else:
+                info = PackInfo(self.hi[sl].view(shape), self.lo[sl].view(shape), self.hiT[sl].view(m.cols, m.rows),
+                                self.loT[sl].view(m.cols, m.rows), gr, self)
+            t._ax2d = info
+            self.tensors[m.name] = t
+        self._n_blocks = sum(len(m.blocks) for m in self.mats.values())
+        self._max_elems = max([1] + [(b[2] - b[1]) * (b[4] - b[3]) for m in self.mats.values() for b in m.blocks])
+
+    def __getitem__(self, name: str) -> torch.Tensor:
+        return self.tensors[name]
+
+    def __contains__(self, name: str) -> bool:
+        return name in self.tensors
+
+    # ------------------------------------------------------------------ descriptor table
+    def _params(self) -> List[torch.nn.Parameter]:
+        return [b[0] for m in self.mats.values() for b in m.blocks]
+
+    def _key(self, with_grads: bool):
+        ps = self._params()
+        return (tuple(p.data_ptr() for p in ps),
+                tuple((p.grad.data_ptr() if p.grad is not None else 0) for p in ps) if with_grads else None)
+
+    def _build(self, with_grads: bool) -> None:
+        rec = np.zeros(self._n_blocks, dtype=_DESC)
+        i = 0
+        for m in self.mats.values():
+            base = 4 * m.off
+            for (p, r0, r1, c0, c1, dr, dc) in m.blocks:
+                if p.dtype != torch.float32 or not p.is_contiguous() or p.device != self.device:
+                    raise RuntimeError(f"packed weights need contiguous fp32 parameters on {self.device} ({m.name})")
+                ld = 1 if p.dim() == 1 else p.shape[1]
+                src_off = 4 * (c0 if p.dim() == 1 else r0 * ld + c0)
+                dst_off = base + 4 * (dr * m.cols + dc)
+                dstT_off = base + 4 * (dc * m.rows + dr)
+                d = rec[i]
+                d["src"] = p.data_ptr() + src_off
+                d["grad"] = (p.grad.data_ptr() + src_off) if (with_grads and p.grad is not None and p.requires_grad) else 0
+                d["w"] = self.w.data_ptr() + dst_off
+                d["g"] = self.grad.data_ptr() + dst_off
+                if not m.vector:
+                    d["hi"], d["lo"] = self.hi.data_ptr() + dst_off, self.lo.data_ptr() + dst_off
+                    d["hiT"], d["loT"] = self.hiT.data_ptr() + dstT_off, self.loT.data_ptr() + dstT_off
+                d["rows"], d["cols"] = r1 - r0, c1 - c0
+                d["src_ld"] = (c1 - c0) if p.dim() == 1 else ld
+                d["dst_ld"], d["dstT_ld"] = m.cols, m.rows
+                i += 1
+        host = torch.from_numpy(rec.view(np.uint8).copy())
+        if self._table is None:
+            self._table = host.to(self.device)
+        else:                       # in place: a captured CUDA graph keeps reading this buffer
+            self._table.copy_(host)
+        self._table_key = self._key(with_grads)
+
+    def _ensure(self, with_grads: bool) -> None:
+        if with_grads:
+            for p in self._params():
+                if p.requires_grad and p.grad is None:
+                    p.grad = torch.zeros_like(p)
+        key = self._key(with_grads)
+        if self._table is None or self._table_key is None or key[0] != self._table_key[0] or (
+                with_grads and key[1] != self._table_key[1]):
+            self._build(with_grads)
+
+    # ------------------------------------------------------------------ the two launches
+    def _clear_grads(self) -> None:
+        self.grad.zero_()
+        for t in self.tensors.values():
+            t._ax2d.written = False
+        self.dirty = False
+
+    def refresh(self) -> None:
+        from .ops import _stream
+        self._ensure(False)
+        if self.dirty:                       # gradients of an earlier backward that nobody collected
+            self._clear_grads()
+        _lib.check(_lib.load().ax2d_pack_weights(C.c_void_p(self._table.data_ptr()), self._n_blocks, self._max_elems,
+                                                 _stream()), "ax2d_pack_weights")
+
+    def unpack_grads(self) -> None:
+        """p.grad += packed gradient, for every parameter block; the packed gradient buffers are cleared afterwards."""
+        from .ops import _stream
+        if not self.dirty:
+            return
+        self._ensure(True)
+        _lib.check(_lib.load().ax2d_unpack_grads(C.c_void_p(self._table.data_ptr()), self._n_blocks, self._max_elems,
+                                                 _stream()), "ax2d_unpack_grads")
+        self._clear_grads()
+
+
+class PackAnchorFn(torch.autograd.Function):
+    """Identity on a leaf that every other operation of the forward pass depends on (an embedding table): its forward
+    refreshes the packed weights, its backward -- the LAST node autograd executes -- adds the packed weight gradients
+    into the parameters' ``.grad``."""
+
+    @staticmethod
+    def forward(ctx, pk: PackedWeights, t: torch.Tensor):
+        pk.refresh()
+        ctx.pk = pk
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.pk.unpack_grads()
+        return None, g

@@ -244,6 +244,17 @@ int ax2d_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, cons
                    float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
                    const int64_t* step, ax2d_stream_t stream);
 
+/* Packed weights: ONE launch gathers every projection weight / bias from its reference-shaped parameter into the
+ * padded, packed layouts the kernels read (plus the two TF32 terms, plain and transposed), and one launch adds the
+ * packed weight gradients back into the parameters' gradients.  `table` is a DEVICE array of n_blocks 96-byte block
+ * descriptors (layout: struct PackDesc in csrc/embed_optim.cu, built by aimnet_x2d_b200/packed.py):
+ *   { const float* src; float* grad_dst; float* w; float* hi; float* lo; float* hiT; float* loT; const float* g;
+ *     int32 rows, cols, src_ld, dst_ld, dstT_ld, pad; }
+ * Replaces the per-call torch pad / cat / slice / accumulate kernels around every nn.Linear (layers.py:47-61,
+ * gnn.py:96-146). */
+int ax2d_pack_weights(const void* table, int n_blocks, int max_block_elems, ax2d_stream_t stream);
+int ax2d_unpack_grads(const void* table, int n_blocks, int max_block_elems, ax2d_stream_t stream);
+
 /* a12  WeightedL1Loss / WeightedMSELoss (models/losses.py:14-87): loss[0] = mean_b sum_t w_t |p-y|
  * (kind 0) or w_t (p-y)^2 (kind 1); g_pred = d loss / d pred * upstream (upstream = 1 if NULL). */
 int ax2d_weighted_loss(const float* pred, const float* target, const float* weights, int64_t B, int T,

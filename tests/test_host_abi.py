@@ -210,3 +210,74 @@ def test_state_dict_keys_and_shapes_match_reference():
         GNN({"atom_type": 119, "hydrogen_count": 9, "degree": 7, "hybridization": 7}, 64, 1, pooling_type="nope")
     with pytest.raises(ValueError):
         GNN({"atom_type": 119, "hydrogen_count": 9, "degree": 7, "hybridization": 7}, 64, 1, activation_type="tanh")
+
+
+def _emulate_pack(pk):
+    """numpy restatement of pack_weights_kernel over the descriptor table (host memory here)."""
+    import ctypes
+    import numpy as np
+    pk._ensure(False)
+    rec = np.frombuffer(pk._table.numpy().tobytes(), dtype=pk_desc())
+
+    def arr(ptr, n):
+        return np.ctypeslib.as_array(ctypes.cast(int(ptr), ctypes.POINTER(ctypes.c_float)), shape=(n,))
+
+    for d in rec:
+        R, Cc = int(d["rows"]), int(d["cols"])
+        src = arr(d["src"], (R - 1) * int(d["src_ld"]) + Cc)
+        w = arr(d["w"], (R - 1) * int(d["dst_ld"]) + Cc)
+        for r in range(R):
+            w[r * int(d["dst_ld"]): r * int(d["dst_ld"]) + Cc] = src[r * int(d["src_ld"]): r * int(d["src_ld"]) + Cc]
+        if d["hiT"]:
+            wT = arr(d["hiT"], (Cc - 1) * int(d["dstT_ld"]) + R)
+            for r in range(R):
+                wT[r: r + (Cc - 1) * int(d["dstT_ld"]) + 1: int(d["dstT_ld"])] = src[r * int(d["src_ld"]): r * int(d["src_ld"]) + Cc]
+
+
+def pk_desc():
+    from aimnet_x2d_b200.packed import _DESC
+    return _DESC
+
+
+@pytest.mark.parametrize("collapsed", [True, False])
+def test_packed_weight_table_matches_per_call_packing(collapsed):
+    """Host logic of packed.PackedWeights: the block table must lay the parameters out exactly as the per-call torch
+    packing (layers.pack_chunked / pad2d / cat) does.  The kernel is emulated with numpy over host memory."""
+    import torch
+    import aimnet_x2d_b200 as ax
+    from aimnet_x2d_b200 import ops
+    from aimnet_x2d_b200.layers import FEATURE_PAD, pack_chunked, pad1d, pad2d
+    sizes = {"atom_type": 119, "hydrogen_count": 9, "degree": 7, "hybridization": 7}
+    torch.manual_seed(0)
+    m = ax.GNN(sizes, 64, 3, num_shells=3, num_message_passing_layers=2, use_stereochemistry=True, ffn_hidden_dim=48)
+    for p in m.parameters():
+        torch.nn.init.normal_(p)
+    pk = m._declare_packed("cpu", collapsed)
+    _emulate_pack(pk)
+    D, S = m.x_other_dim, m.x_self_dim
+    Dp, Sp = ops.pad_to(D, FEATURE_PAD), ops.pad_to(S, FEATURE_PAD)
+    H = m.num_shells
+    used = 2 if collapsed else H + 1
+    for i, layer in enumerate(m.message_passing_layers):
+        want = torch.cat([pack_chunked(layer.input_proj.weight, Dp, H + 1, D, Dp, used),
+                          pack_chunked(layer.global_skip_proj.weight, Dp, H + 1, D, Dp, used)], dim=0)
+        assert torch.equal(pk[f"mp.{i}.W_io"], want.detach())
+        assert torch.equal(pk[f"mp.{i}.W_io"]._ax2d.hiT, want.detach().t())      # hiT arena emulated with the raw value
+        wb = torch.cat([pad1d(layer.input_proj.bias, Dp), pad1d(layer.global_skip_proj.bias, Dp)])
+        assert torch.equal(pk[f"mp.{i}.b_io"], wb.detach())
+        assert torch.equal(pk[f"mp.{i}.1.linear_2.W"], pad2d(layer.mlp_blocks[1]["linear_2"].weight, Dp, Dp).detach())
+    W = m.concat_self_other.weight
+    want = torch.cat([pad2d(W[:, :S], 64, Sp), pad2d(W[:, S:], 64, Dp)], dim=1)
+    assert torch.equal(pk["cso.W"], want.detach())
+    Wp = m.embedding_projection.weight
+    assert torch.equal(pk["ep.W"], torch.cat([pad2d(Wp[:S], Sp, 256), pad2d(Wp[S:], Dp, 256)], dim=0).detach())
+    W2 = m.stereochemical_embedding_2.weight
+    want = torch.cat([pad2d(W2[:, j * D:(j + 1) * D], Dp, Dp) for j in range(3)], dim=1)
+    assert torch.equal(pk["stereo2.W"], want.detach())
+    assert torch.equal(pk["out.W"], pad2d(m.output_layer.weight, 4, 96).detach())
+    assert torch.equal(pk["ffn.1.W2"], m.ffn.layers[1].linear2.weight.detach())
+    # a derived cache: never in the state_dict, dropped by deepcopy
+    import copy
+    assert not any("packed" in k for k in m.state_dict())
+    m._packed[("cpu", collapsed)] = pk
+    assert copy.deepcopy(m)._packed[("cpu", collapsed)] is None
