@@ -48,14 +48,23 @@ __device__ __forceinline__ int find_seg(const int* start, int n_seg, int col) {
 // per-column setup (EpiCol, once per thread and column group), a LOAD half and a COMPUTE/STORE half so that
 // callers with few resident warps can issue the loads of several rows before consuming any.
 
+// sigmoid through the two special-function approximations (ex2.approx: 2^-22 relative, rcp.approx: 1 ulp): ~1e-7
+// relative, two orders below the 1e-5 parity tolerance, and 5 instructions instead of the ~25 of expf + IEEE
+// reciprocal -- the fused epilogues are bound by their instruction count
+__device__ __forceinline__ float fast_sigmoid(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * v));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
 template <int ACT>
 __device__ __forceinline__ float act_fwd_t(float v) {
   if constexpr (ACT == AX2D_ACT_RELU) return v > 0.f ? v : 0.f;
   else if constexpr (ACT == AX2D_ACT_LEAKYRELU) return v > 0.f ? v : 0.01f * v;
   else if constexpr (ACT == AX2D_ACT_ELU) return v > 0.f ? v : expm1f(v);
   else if constexpr (ACT == AX2D_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-  else if constexpr (ACT == AX2D_ACT_SILU) return v * __frcp_rn(1.f + expf(-v));   // correctly rounded reciprocal: no
-  else return v;                                                                  // division slow path (FCHK + fix-up)
+  else if constexpr (ACT == AX2D_ACT_SILU) return v * fast_sigmoid(v);
+  else return v;
 }
 template <int ACT>
 __device__ __forceinline__ float act_bwd_t(float v) {
@@ -67,18 +76,19 @@ __device__ __forceinline__ float act_bwd_t(float v) {
     const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
     return cdf + v * pdf;
   } else if constexpr (ACT == AX2D_ACT_SILU) {
-    const float sg = __frcp_rn(1.f + expf(-v));
+    const float sg = fast_sigmoid(v);
     return sg * (1.f + v * (1.f - sg));
   } else return 1.f;
 }
 
 // Counter-based dropout: the keep decision of element (m, n) is a pure function of (seed, m * N + n), so the
 // backward pass regenerates the forward mask instead of storing it.  One 32-bit avalanche hash (murmur3 finaliser)
-// per PAIR of elements, 16 bits each: keep iff bits >= round(p * 65536).
+// per GROUP OF FOUR elements and one more odd multiply of it give 4 x 16 bits: keep iff bits >= round(p * 65536).
 struct EpiCtx {      // per-thread constants of the epilogue
   bool dropping;
   float inv_keep;
   uint32_t seed_lo, seed_hi, thresh;
+  uint32_t base0;    // seed mix for linear indices below 2^34 (every realistic matrix)
 };
 __device__ __forceinline__ EpiCtx epi_ctx(const EpiArgs& g) {
   EpiCtx c;
@@ -90,6 +100,9 @@ __device__ __forceinline__ EpiCtx epi_ctx(const EpiArgs& g) {
   c.seed_lo = static_cast<uint32_t>(seed);
   c.seed_hi = static_cast<uint32_t>(seed >> 32);
   c.thresh = static_cast<uint32_t>(g.drop_p * 65536.f + 0.5f);
+  uint32_t h = c.seed_hi;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  c.base0 = h ^ c.seed_lo;
   return c;
 }
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
@@ -98,10 +111,10 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
 }
 // keep-scales of the four elements starting at linear index idx (idx % 4 == 0)
 __device__ __forceinline__ void drop_scale4(const EpiCtx& cx, uint64_t idx, float d[4]) {
-  const uint32_t lo = static_cast<uint32_t>(idx >> 1), hi = static_cast<uint32_t>(idx >> 33);
-  const uint32_t base = mix32(hi ^ cx.seed_hi) ^ cx.seed_lo;
+  const uint32_t lo = static_cast<uint32_t>(idx >> 2), hi = static_cast<uint32_t>(idx >> 34);
+  const uint32_t base = hi == 0u ? cx.base0 : (mix32(hi ^ cx.seed_hi) ^ cx.seed_lo);
   const uint32_t h0 = mix32((lo * 0x9E3779B1u) ^ base);
-  const uint32_t h1 = mix32(((lo + 1u) * 0x9E3779B1u) ^ base);
+  const uint32_t h1 = h0 * 0x9E3779B1u + 0x7F4A7C15u;
   d[0] = (h0 & 0xFFFFu) >= cx.thresh ? cx.inv_keep : 0.f;
   d[1] = (h0 >> 16) >= cx.thresh ? cx.inv_keep : 0.f;
   d[2] = (h1 & 0xFFFFu) >= cx.thresh ? cx.inv_keep : 0.f;

@@ -32,8 +32,11 @@ namespace ax2d {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 16;                        // fp32 per 64-byte swizzle row
-constexpr int TC_THREADS = 320;                  // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 split + epilogue
-constexpr int TC_WORKERS = TC_THREADS - 64;       // splitter / epilogue threads
+constexpr int TC_SPLIT_WARPS = 4;                // warps 2..5
+constexpr int TC_EPI_WARPS = 12;                 // warps 6..17: three per TMEM lane quarter
+constexpr int TC_THREADS = 32 * (2 + TC_SPLIT_WARPS + TC_EPI_WARPS);   // warp 0 TMA, warp 1 MMA + TMEM
+constexpr int TC_WORKERS = 256;                  // weight-gradient kernel: splitter / epilogue threads
+constexpr int TC_WG_THREADS = 64 + TC_WORKERS;
 constexpr int TC_MAX_STAGES = 6;
 #ifndef AX2D_TC_TERMS
 #define AX2D_TC_TERMS 4     // 4: lo*lo kept (fp32-level); 3: classic 3xTF32 (drops a 2^-22 relative term)
@@ -56,6 +59,9 @@ struct TcArgs {
   int stages;
   int tmem_cols;
   int acc2;                            // column offset of the small-term accumulator (0: single accumulator)
+  int n_tiles, total_tiles;            // projection kernel: column tiles per row tile, all tiles
+  int acc_stride;                      // TMEM columns between the two accumulator buffers
+  int a_base;                          // first TMEM column of the A ring
 };
 
 // ---------------------------------------------------------------------------------------------- PTX
@@ -99,6 +105,82 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TMEM (lane = row, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-collective variants: called by ALL lanes of a converged warp, one elected lane issues.  Inside an
+// `if (lane == 0)` branch the compiler cannot use the uniform datapath these instructions need and wraps every
+// one of them in an ELECT / branch loop with R2UR moves (measured: ~75 cycles per MMA issued, more than the 80
+// cycles a 128 x 160 x 8 MMA occupies the tensor pipe); issued from converged code they cost a few cycles.
+__device__ __forceinline__ void umma_tf32_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_w(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_w(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -216,13 +298,13 @@ __device__ __forceinline__ TileEpi tile_epi(const EpiArgs& e, int64_t m0, int n0
 template <int ACT, int DACT, bool DROP>
 __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws, const EpiCtx& cx, uint32_t tmem_base,
                                          float* stg, int m0, int n0, int q, int lane, int first_chunk, uint32_t acc2,
-                                         unsigned long long* dbg = nullptr) {
+                                         unsigned long long* dbg = nullptr, int chunk_step = 64) {
   const int64_t M = e.M;
   const int N = static_cast<int>(e.N);
   const int cg = lane & 7;
   const TileEpi te = tile_epi(e, m0, n0, (n0 + BN < N ? n0 + BN : N), ws);
-  // two warps share each TMEM lane quarter and take alternate 32-column chunks
-  for (int c0 = 32 * first_chunk; c0 < BN; c0 += 64) {
+  // the warps that share a TMEM lane quarter take the 32-column chunks round-robin
+  for (int c0 = 32 * first_chunk; c0 < BN; c0 += chunk_step) {
     if (n0 + c0 >= N) break;
     uint32_t r[32];
     if (dbg != nullptr && c0 == 0) dbg[8] = gtime();
@@ -238,8 +320,14 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
           r[16 * hh + j] = __float_as_uint(__uint_as_float(r[16 * hh + j]) + __uint_as_float(r2[j]));
       }
     }
+    // transpose through shared memory with 128-bit accesses: row `lane` stores its eight float4 column groups at
+    // slots (group ^ (lane & 7)) of its 128-byte row -- conflict-free for the stores (a quarter-warp hits 8 different
+    // slots) and for the row-contiguous reads below (a quarter-warp reads one whole row)
+    float4* stg4 = reinterpret_cast<float4*>(stg);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+    for (int j = 0; j < 8; ++j)
+      stg4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
     __syncwarp();
     if (dbg != nullptr && c0 == 0) dbg[10] = gtime();
     const int n = n0 + c0 + cg * 4;
@@ -252,15 +340,16 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
         const float* pr0 = te.res0 + mrow * te.ldres0 + n;
         const float* pr1 = te.res1 + mrow * te.ldres1 + n;
         const float* pdp = te.dp + mrow * te.lddp + n;
-        const float* sp = stg + (lane >> 3) * 33 + cg * 4;
+        const int r0w = lane >> 3;               // this lane's rows: r0w + 4 i
         uint64_t didx = static_cast<uint64_t>(mrow) * static_cast<uint32_t>(N) + static_cast<uint32_t>(n);
-#pragma unroll 2
+#pragma unroll 4
         for (int i = 0; i < 8; ++i) {          // rows mrow + 4 i
           float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, dp = r0;
           if (te.nres > 0) r0 = __ldg(reinterpret_cast<const float4*>(pr0));
           if (te.nres > 1) r1 = __ldg(reinterpret_cast<const float4*>(pr1));
           if (te.has_dp) dp = __ldg(reinterpret_cast<const float4*>(pdp));
-          float v[4] = {sp[0] + b4.x, sp[1] + b4.y, sp[2] + b4.z, sp[3] + b4.w};
+          const float4 s4 = stg4[(r0w + 4 * i) * 8 + (cg ^ ((r0w + 4 * i) & 7))];
+          float v[4] = {s4.x + b4.x, s4.y + b4.y, s4.z + b4.z, s4.w + b4.w};
           if (te.has_pre) *reinterpret_cast<float4*>(ppre) = make_float4(v[0], v[1], v[2], v[3]);
           float drop[4] = {1.f, 1.f, 1.f, 1.f};
           if constexpr (DROP) drop_scale4(cx, didx, drop);
@@ -285,7 +374,6 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
             }
           }
           *reinterpret_cast<float4*>(pc) = make_float4(v[0], v[1], v[2], v[3]);
-          sp += 4 * 33;
           pc += 4 * te.ldc;
           ppre += 4 * te.ldpre;
           pr0 += 4 * te.ldres0;
@@ -313,17 +401,18 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
         if (ca.resid[rr] != nullptr) ca.resid[rr] += mfirst * col.ldr[rr];
       if (ca.dpre != nullptr) ca.dpre += mfirst * col.lddp;
       if (ca.mask != nullptr) ca.mask += mfirst * col.ldm;
-      const float* sp = stg + (lane >> 3) * 33 + cg * 4;
+      const int r0w = lane >> 3;
 #pragma unroll 1
       for (int i = 0; i < 8; i += 2) {
+        const int ra = r0w + 4 * i, rb = ra + 4;
+        const float4 sa = stg4[ra * 8 + (cg ^ (ra & 7))], sb = stg4[rb * 8 + (cg ^ (rb & 7))];
         const int64_t ma = mfirst + 4 * i, mb = ma + 4;
         EpiOperands oa, ob;
         if (ma < M) epi_prefetch(e, ca, 0, oa);
         if (mb < M) epi_prefetch(e, ca, 4, ob);
-        if (ma < M) epi_finish<ACT, DACT, DROP>(e, cx, ca, 0, oa, sp[0], sp[1], sp[2], sp[3], ma);
-        if (mb < M) epi_finish<ACT, DACT, DROP>(e, cx, ca, 4, ob, sp[4 * 33], sp[4 * 33 + 1], sp[4 * 33 + 2], sp[4 * 33 + 3], mb);
+        if (ma < M) epi_finish<ACT, DACT, DROP>(e, cx, ca, 0, oa, sa.x, sa.y, sa.z, sa.w, ma);
+        if (mb < M) epi_finish<ACT, DACT, DROP>(e, cx, ca, 4, ob, sb.x, sb.y, sb.z, sb.w, mb);
         if (dbg != nullptr && c0 == 0 && i == 0) dbg[12] = gtime();
-        sp += 8 * 33;
         ca.c += 8 * col.ldc;
         if (ca.pre != nullptr) ca.pre += 8 * col.ldpre;
 #pragma unroll
@@ -339,139 +428,227 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcArgs g) {
+// Persistent: one CTA per SM walks the output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (column tiles of one
+// row tile are adjacent in that order, so the CTAs that share an A tile run at the same time and it is read from HBM
+// once).
+//
+// Two things bound the first version of this kernel (one tile per CTA, two CTAs per SM, both operands from shared
+// memory), both measured with per-CTA %globaltimer stamps:
+//  * all CTAs moved through "main loop" (tensor-bound) and "epilogue" (HBM-bound) in lockstep, so neither resource
+//    was busy for more than half of the time.  Here the accumulator is double-buffered in TMEM and the epilogue warps
+//    drain tile i while the producer / splitter / MMA warps run the main loop of tile i + 1;
+//  * shared-memory bandwidth: four MMAs per k-step, each re-reading its A and B tiles from shared memory, plus the
+//    splitters' read-modify-write of A came to ~124 KB per k-block = ~970 cycles at 128 B/cycle, against 640 cycles
+//    of tensor time.  Here the split A operand goes to TENSOR MEMORY (tcgen05.st, lane = row, column = k) and the
+//    MMAs take it from there (tcgen05.mma with a TMEM A operand); shared memory only carries the raw A tile once
+//    and the B tiles: ~76 KB per k-block.
+//
+// TMEM columns (W = acc_stride >= BN, at most 192): [0, W) accumulator 0, [W, 2 W) accumulator 1 (small-term
+// accumulators at +96 when BN <= 96), [2 W, 512) the A ring: 32 columns (hi 16 | lo 16) per pipeline stage.
+constexpr int TC_MAX_BN = 192;
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcArgs g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], split_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_bar;
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], split_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = g.BN, S = g.stages;
   const uint32_t b_bytes = static_cast<uint32_t>(BN) * TC_BK * 4;
-  const uint32_t stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
-  // align the dynamic region to 1024 B (SWIZZLE_128B atoms)
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t stage_bytes = TC_A_BYTES + 2 * b_bytes;
+  // align the dynamic region to 1024 B (swizzle atoms)
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the address space and
+  // emits LDS / STS instead of generic loads and stores for everything derived from it)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   auto stage_a = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };
-  auto stage_alo = [&](int s) { return stage_a(s) + TC_A_BYTES; };
-  auto stage_bhi = [&](int s) { return stage_a(s) + 2 * TC_A_BYTES; };
-  auto stage_blo = [&](int s) { return stage_a(s) + 2 * TC_A_BYTES + b_bytes; };
+  auto stage_bhi = [&](int s) { return stage_a(s) + TC_A_BYTES; };
+  auto stage_blo = [&](int s) { return stage_a(s) + TC_A_BYTES + b_bytes; };
+  float* stg_base = reinterpret_cast<float*>(smem + static_cast<size_t>(S) * stage_bytes);     // epilogue transposes
 
-  const int m0 = blockIdx.x * TC_BM;
-  const int n0 = blockIdx.y * BN;
-  if (threadIdx.x == 0) TC_STAMP(0);
+  // development aid, all CTAs: dbg[16 + 8 cta + {0..5}] = start, end, SM id, main loops issued, first accumulator
+  // ready, last epilogue done
+  unsigned long long* cta_dbg = g.dbg != nullptr ? g.dbg + 16 + 32 * blockIdx.x : nullptr;
+  if (cta_dbg != nullptr && threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    cta_dbg[0] = gtime();
+    cta_dbg[2] = smid;
+    cta_dbg[11] = clock64();
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], TC_WORKERS / 32);
+      mbar_init(&split_bar[s], TC_SPLIT_WARPS);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&acc_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], TC_EPI_WARPS);
+    }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_smem, static_cast<uint32_t>(g.tmem_cols));
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 512u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  if (threadIdx.x == 0) TC_STAMP(1);
+  const int n_tiles = g.n_tiles, total = g.total_tiles, num_kb = g.num_kb;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (whole warp, elected issue)
+    int s = 0;              // stage and phase advance by increments: an integer division by the runtime stage count
+    uint32_t ph = 0;        // costs this single, latency-exposed warp ~200 cycles per k-block
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
       int seg = 0;
-      for (int kb = 0; kb < g.num_kb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = static_cast<uint32_t>(kb / S) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
+      for (int kb = 0; kb < num_kb; ++kb, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
+        mbar_wait(&empty_bar[s], ph ^ 1u);      // the MMAs that read this stage (smem B and TMEM A slot) are done
+        __syncwarp();
         while (seg + 1 < g.n_seg && kb >= g.seg_kb_start[seg + 1]) ++seg;
-        mbar_expect_tx(&full_bar[s], TC_A_BYTES + 2 * b_bytes);
-        tma_load_2d(stage_a(s), &maps.a[seg], &full_bar[s], (kb - g.seg_kb_start[seg]) * TC_BK, m0);
-        tma_load_2d(stage_bhi(s), &maps.b_hi, &full_bar[s], kb * TC_BK, n0);
-        tma_load_2d(stage_blo(s), &maps.b_lo, &full_bar[s], kb * TC_BK, n0);
+        mbar_expect_tx_w(&full_bar[s], TC_A_BYTES + 2 * b_bytes);
+        tma_load_2d_w(stage_a(s), &maps.a[seg], &full_bar[s], (kb - g.seg_kb_start[seg]) * TC_BK, m0);
+        tma_load_2d_w(stage_bhi(s), &maps.b_hi, &full_bar[s], kb * TC_BK, n0);
+        tma_load_2d_w(stage_blo(s), &maps.b_lo, &full_bar[s], kb * TC_BK, n0);
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(BN);
-      for (int kb = 0; kb < g.num_kb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = static_cast<uint32_t>(kb / S) & 1u;
-        mbar_wait(&full_bar[s], ph);     // B_hi / B_lo (and raw A) have landed
-        if (kb == 0) TC_STAMP(2);
-        mbar_wait(&split_bar[s], ph);    // A has been rewritten as (hi, lo)
-        if (kb == 0) TC_STAMP(3);
+    // ===================================================================== MMA issuer (whole warp, elected issue)
+    const uint32_t idesc = idesc_tf32(BN);
+    int s = 0, j = 0;
+    uint32_t ph = 0;
+    long long t_issue = 0, t_wait = 0, t_acc = 0;
+    const long long t_loop0 = clock64();
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++j) {
+      const int buf = j & 1;
+      const long long ca = clock64();
+      mbar_wait(&acc_empty[buf], (static_cast<uint32_t>(j >> 1) & 1u) ^ 1u);   // epilogue of tile j - 2 has drained it
+      tc_fence_after();
+      t_acc += clock64() - ca;
+      const uint32_t t_main = tmem_base + static_cast<uint32_t>(buf * g.acc_stride);
+      const uint32_t t_small = t_main + static_cast<uint32_t>(g.acc2);
+      for (int kb = 0; kb < num_kb; ++kb, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
+        const long long c0 = clock64();
+        mbar_wait(&full_bar[s], ph);     // B_hi / B_lo have landed
+        mbar_wait(&split_bar[s], ph);    // (a_hi, a_lo) are in TMEM
         tc_fence_after();
-        const uint64_t da_hi = smem_desc_k_sw64(smem_u32(stage_a(s)));
-        const uint64_t da_lo = smem_desc_k_sw64(smem_u32(stage_alo(s)));
+        __syncwarp();
+        const long long c1 = clock64();
+        t_wait += c1 - c0;
+        const uint32_t a_hi = tmem_base + static_cast<uint32_t>(g.a_base + s * 2 * TC_BK);
+        const uint32_t a_lo = a_hi + TC_BK;
         const uint64_t db_hi = smem_desc_k_sw64(smem_u32(stage_bhi(s)));
         const uint64_t db_lo = smem_desc_k_sw64(smem_u32(stage_blo(s)));
 #pragma unroll
-        for (int j = 0; j < TC_BK / 8; ++j) {
-          const uint64_t adv = static_cast<uint64_t>((j * 8 * 4) >> 4);     // 32 bytes per k-step inside the swizzle row
+        for (int jj = 0; jj < TC_BK / 8; ++jj) {
+          const uint64_t adv = static_cast<uint64_t>((jj * 8 * 4) >> 4);     // 32 bytes per k-step inside the swizzle row
+          const uint32_t ak = static_cast<uint32_t>(jj * 8);                 // 8 TMEM columns per k-step
           // The tensor core's fp32 accumulation truncates, so every MMA into a large accumulator costs up to one
           // ulp of it.  When TMEM allows (acc2 != 0) the three small terms go to their own accumulator (2^-11 of the
           // magnitude, so their truncation is negligible) and only hi*hi touches the main one.
-          const uint32_t first = (kb | j) != 0 ? 1u : 0u;
-          const uint32_t t_small = tmem_base + static_cast<uint32_t>(g.acc2);
+          const uint32_t first = (kb | jj) != 0 ? 1u : 0u;
 #if AX2D_TC_TERMS == 4
-          umma_tf32(t_small, da_lo + adv, db_lo + adv, idesc, first);
-          umma_tf32(t_small, da_lo + adv, db_hi + adv, idesc, 1u);
+          umma_tf32_ts_w(t_small, a_lo + ak, db_lo + adv, idesc, first);
+          umma_tf32_ts_w(t_small, a_lo + ak, db_hi + adv, idesc, 1u);
 #else
-          umma_tf32(t_small, da_lo + adv, db_hi + adv, idesc, first);
+          umma_tf32_ts_w(t_small, a_lo + ak, db_hi + adv, idesc, first);
 #endif
-          umma_tf32(t_small, da_hi + adv, db_lo + adv, idesc, 1u);
-          umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, g.acc2 != 0 ? first : 1u);
+          umma_tf32_ts_w(t_small, a_hi + ak, db_lo + adv, idesc, 1u);
+          umma_tf32_ts_w(t_main, a_hi + ak, db_hi + adv, idesc, g.acc2 != 0 ? first : 1u);
         }
-        umma_commit(&empty_bar[s]);      // stage free once these MMAs have read it
+        umma_commit_w(&empty_bar[s]);      // stage free once these MMAs have read it
+        t_issue += clock64() - c1;
       }
-      umma_commit(&acc_bar);             // accumulator complete
-      TC_STAMP(4);
+      umma_commit_w(&acc_full[buf]);       // accumulator of this tile complete
+    }
+    if (cta_dbg != nullptr && lane == 0) { cta_dbg[3] = gtime(); cta_dbg[6] = t_issue; cta_dbg[7] = t_wait; cta_dbg[8] = t_acc; cta_dbg[13] = clock64() - t_loop0; }
+  } else if (warp < 2 + TC_SPLIT_WARPS) {
+    // ===================================================================== splitters: thread = row of the A tile
+    // raw row (64 bytes in the 64-byte-swizzled stage: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3), which
+    // also makes the 8 rows of a quarter-warp hit 8 different bank groups) -> (hi, lo) -> TMEM lane r, 16 columns each
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int sw = (row >> 1) & 3;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
+        mbar_wait(&full_bar[s], ph);
+        const float4* a = reinterpret_cast<const float4*>(stage_a(s)) + row * (TC_BK / 4);
+        uint32_t hi[TC_BK], lo[TC_BK];
+#pragma unroll
+        for (int c = 0; c < TC_BK / 4; ++c) {
+          const float4 v = a[c ^ sw];
+          float h, o;
+          split_tf32(v.x, h, o); hi[4 * c + 0] = __float_as_uint(h); lo[4 * c + 0] = __float_as_uint(o);
+          split_tf32(v.y, h, o); hi[4 * c + 1] = __float_as_uint(h); lo[4 * c + 1] = __float_as_uint(o);
+          split_tf32(v.z, h, o); hi[4 * c + 2] = __float_as_uint(h); lo[4 * c + 2] = __float_as_uint(o);
+          split_tf32(v.w, h, o); hi[4 * c + 3] = __float_as_uint(h); lo[4 * c + 3] = __float_as_uint(o);
+        }
+        const uint32_t slot = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g.a_base + s * 2 * TC_BK);
+        tmem_st16(slot, hi);
+        tmem_st16(slot + TC_BK, lo);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);
+      }
     }
   } else {
-    // ===================================================================== splitters, then epilogue (128 threads)
-    const int t = threadIdx.x - 64;
-    for (int kb = 0; kb < g.num_kb; ++kb) {
-      const int s = kb % S;
-      const uint32_t ph = static_cast<uint32_t>(kb / S) & 1u;
-      mbar_wait(&full_bar[s], ph);
-      float4* a = reinterpret_cast<float4*>(stage_a(s));
-      float4* l = reinterpret_cast<float4*>(stage_alo(s));
-#pragma unroll
-      for (int i = 0; i < TC_A_BYTES / 16 / TC_WORKERS; ++i) {
-        const float4 v = a[t + TC_WORKERS * i];
-        float4 h, o;
-        split_tf32(v.x, h.x, o.x);
-        split_tf32(v.y, h.y, o.y);
-        split_tf32(v.z, h.z, o.z);
-        split_tf32(v.w, h.w, o.w);
-        a[t + TC_WORKERS * i] = h;
-        l[t + TC_WORKERS * i] = o;
-      }
-      fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&split_bar[s]);
-    }
-
-    // ---- epilogue: TMEM lanes [32 q, 32 q + 32) belong to warp (warp_id % 4) == q
-    mbar_wait(&acc_bar, 0);
-    tc_fence_after();
-    if (threadIdx.x == 64) TC_STAMP(5);
-    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);   // stage memory is free now (8 x 4224 B)
+    // ===================================================================== epilogue warps
+    // TMEM lanes [32 q, 32 q + 32) can be read by the warps with (warp id % 4) == q; two warps per quarter take
+    // alternate 32-column chunks.
+    const int ew = warp - (2 + TC_SPLIT_WARPS);
+    float* stg = stg_base + ew * (32 * 32);
     const EpiCtx cx = epi_ctx(g.e);
     const bool dropping = cx.dropping;
-    AX2D_EPI_DISPATCH(g.e.act, g.e.dact, dropping, {
-      tc_epilogue<ACT, DACT, DROP>(g.e, g.BN, nullptr, cx, tmem_base, stg, m0, n0, warp & 3, lane, (warp - 2) >> 2,
-                                   static_cast<uint32_t>(g.acc2), (threadIdx.x == 64 && blockIdx.x == 0 && blockIdx.y == 0) ? g.dbg : nullptr);
-    });
-    if (threadIdx.x == 64) TC_STAMP(6);
+    int j = 0;
+    long long e_wait = 0, e_work = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++j) {
+      const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
+      const int buf = j & 1;
+      {
+        // while this tile's main loop runs: pull the rows the epilogue will read (residuals, activation-backward
+        // operand) into L2, so that its loads do not each pay an HBM round trip with only two warps per scheduler
+        const int n1 = n0 + BN < static_cast<int>(g.e.N) ? n0 + BN : static_cast<int>(g.e.N);
+        const TileEpi te = tile_epi(g.e, m0, n0, n1, nullptr);
+        if (te.ok) {
+          const int lines = ((n1 - n0) * 4 + 127) / 128;            // 128-byte lines per row of the tile
+          const int et = threadIdx.x - 32 * (2 + TC_SPLIT_WARPS);
+          for (int i = et; i < TC_BM * lines; i += 32 * TC_EPI_WARPS) {
+            const int64_t row = m0 + i / lines;
+            const int col = n0 + (i % lines) * 32;
+            if (te.nres > 0) prefetch_l2(te.res0 + row * te.ldres0 + col);
+            if (te.nres > 1) prefetch_l2(te.res1 + row * te.ldres1 + col);
+            if (te.has_dp) prefetch_l2(te.dp + row * te.lddp + col);
+          }
+        }
+      }
+      const long long ce0 = clock64();
+      mbar_wait(&acc_full[buf], static_cast<uint32_t>(j >> 1) & 1u);
+      tc_fence_after();
+      const long long ce1 = clock64();
+      e_wait += ce1 - ce0;
+      if (cta_dbg != nullptr && j == 0 && ew == 0 && lane == 0) cta_dbg[4] = gtime();
+      AX2D_EPI_DISPATCH(g.e.act, g.e.dact, dropping, {
+        tc_epilogue<ACT, DACT, DROP>(g.e, BN, nullptr, cx, tmem_base + static_cast<uint32_t>(buf * g.acc_stride), stg, m0, n0,
+                                     warp & 3, lane, ew >> 2, static_cast<uint32_t>(g.acc2),
+                                     (cta_dbg != nullptr && ew == 0 && lane == 0 && j == 0) ? cta_dbg + 8 : nullptr,
+                                     32 * (TC_EPI_WARPS / 4));
+      });
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      e_work += clock64() - ce1;
+    }
+    if (cta_dbg != nullptr && ew == 0 && lane == 0) { cta_dbg[5] = gtime(); cta_dbg[9] = e_wait; cta_dbg[10] = e_work; }
   }
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) TC_STAMP(7);
+  if (cta_dbg != nullptr && threadIdx.x == 0) { cta_dbg[1] = gtime(); cta_dbg[12] = clock64(); }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, static_cast<uint32_t>(g.tmem_cols));
+    tmem_dealloc(tmem_base, 512u);
   }
 }
 
@@ -515,7 +692,7 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t smem_addr) {
   return d;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_wgrad_kernel(const __grid_constant__ WgMaps maps,
+__global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const __grid_constant__ WgMaps maps,
                                                                       const __grid_constant__ WgArgs g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], split_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_bar;
@@ -526,7 +703,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_wgrad_kernel(const __gr
   const int a_chunks = TC_BM / 32, b_chunks = BN / 32;
   const uint32_t raw_bytes = static_cast<uint32_t>(a_chunks + b_chunks) * WG_CHUNK_BYTES;
   const uint32_t stage_bytes = 2 * raw_bytes;
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the address space and
+  // emits LDS / STS instead of generic loads and stores for everything derived from it)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   auto stage_raw = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };   // A chunks then B chunks (hi after split)
   auto stage_lo = [&](int s) { return stage_raw(s) + raw_bytes; };
 
@@ -554,9 +733,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_wgrad_kernel(const __gr
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % S;
-        const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], raw_bytes);
         const int row = (kb0 + it) * WG_KB;
@@ -578,9 +757,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_wgrad_kernel(const __gr
     if (lane == 0) {
       // D = F32, A = B = TF32, both MN-major (bits 15, 16), M = 128, N = BN
       const uint32_t idesc = idesc_tf32(BN) | (1u << 15) | (1u << 16);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % S;
-        const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
         mbar_wait(&full_bar[s], ph);
         mbar_wait(&split_bar[s], ph);
         tc_fence_after();
@@ -616,9 +795,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_wgrad_kernel(const __gr
     float4 colsum[TC_BM / 32];
 #pragma unroll
     for (int c = 0; c < TC_BM / 32; ++c) colsum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int it = 0; it < nkb; ++it) {
-      const int s = it % S;
-      const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
       mbar_wait(&full_bar[s], ph);
       float4* a = reinterpret_cast<float4*>(stage_raw(s));
       float4* l = reinterpret_cast<float4*>(stage_lo(s));
@@ -770,6 +949,7 @@ static unsigned long long* g_tc_dbg = nullptr;
 // accumulator ready, epilogue done, CTA done.  nullptr switches it off.
 extern "C" void ax2d_debug_timing(unsigned long long* buf) { g_tc_dbg = buf; }
 
+
 extern "C" int ax2d_split_tf32(const float* w, int64_t ldw, int rows, int cols, int transpose, float* hi, float* lo,
                                int64_t ldo, ax2d_stream_t stream) {
   AX2D_CHECK_ARG(w != nullptr && hi != nullptr && lo != nullptr && rows > 0 && cols > 0 && ldo >= cols,
@@ -803,11 +983,17 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
   int rc;
   if ((rc = to_out(c, &g.e.c, N, "C", false)) != AX2D_OK) return rc;
   if ((rc = fill_epilogue(ep, M, N, &g.e)) != AX2D_OK) return rc;
-  // tile shape: as few column tiles as fit 256 accumulator columns -- unless the row tiles alone cannot fill the
-  // machine (the [B, 512] head products: 16 row tiles), in which case N is cut into narrower tiles until there is
-  // about one CTA per SM (narrow tiles also get deeper stage rings and the second accumulator)
+  // tile shape: column tiles of at most 192 accumulator columns (two accumulator buffers + the A ring share the 512
+  // TMEM columns), as few as possible without padding N by more than ~6 % -- unless the tiles cannot fill the machine
+  // (the [B, 512] head products: 16 row tiles), in which case N is cut into narrower tiles until there is about one
+  // per SM (narrow tiles also get the second accumulator)
   const int64_t m_tiles = (M + TC_BM - 1) / TC_BM;
-  int n_tiles = static_cast<int>((N + 255) / 256);
+  int n_tiles = static_cast<int>((N + TC_MAX_BN - 1) / TC_MAX_BN);
+  for (int extra = 0; extra < 2; ++extra) {
+    const int bn = static_cast<int>((N + n_tiles - 1) / n_tiles + 31) / 32 * 32;
+    if (static_cast<int64_t>(bn) * n_tiles * 16 <= N * 17) break;
+    ++n_tiles;
+  }
   if (m_tiles * n_tiles < kNumSMs) {
     const int want = static_cast<int>((kNumSMs + m_tiles - 1) / m_tiles);
     const int most = static_cast<int>((N + 31) / 32);
@@ -817,11 +1003,15 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
   BN = (BN + 31) / 32 * 32;
   n_tiles = static_cast<int>((N + BN - 1) / BN);
   g.BN = BN;
-  g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  if (BN <= 128) {          // two CTAs per SM share 512 TMEM columns: a second accumulator fits only for narrow tiles
-    g.acc2 = g.tmem_cols;
-    g.tmem_cols *= 2;
-  }
+  g.n_tiles = n_tiles;
+  AX2D_CHECK_ARG(m_tiles * n_tiles < (1ll << 30), "ax2d_gemm_tc: too many tiles");
+  g.total_tiles = static_cast<int>(m_tiles * n_tiles);
+  g.tmem_cols = 512;
+  g.acc2 = BN <= 96 ? 96 : 0;         // the small-term accumulator fits beside the main one only for narrow tiles
+  // TMEM layouts in use: accumulators at columns {0, 160} with the A ring at 320 (6 slots), or {0, 192} with the
+  // ring at 384 (4 slots).  (A ring starting at column 256 or 288 with six slots hung the kernel on B200 in testing --
+  // cause unknown -- so the accumulator stride is never 128.)
+  g.acc_stride = (BN > 96 && BN <= 160) ? 160 : 192;
   int acc = 0, kb = 0;
   g.n_seg = a->n_seg;
   for (int s = 0; s < a->n_seg; ++s) {
@@ -835,16 +1025,18 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
   g.num_kb = kb;
   if ((rc = make_map(&maps.b_hi, b_hi, K, N, ldb, BN)) != AX2D_OK) return rc;
   if ((rc = make_map(&maps.b_lo, b_lo, K, N, ldb, BN)) != AX2D_OK) return rc;
-  const size_t stage_bytes = 2 * static_cast<size_t>(TC_A_BYTES) + 2 * static_cast<size_t>(BN) * TC_BK * 4;
-  // two CTAs per SM (one's epilogue overlaps the other's main loop; 2 x 256 TMEM columns): <= 110 KB of stages each
-  int stages = static_cast<int>((110 * 1024) / stage_bytes);
-  stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages;
-  stages = stages > g.num_kb ? g.num_kb : stages;
+  const size_t stage_bytes = static_cast<size_t>(TC_A_BYTES) + 2 * static_cast<size_t>(BN) * TC_BK * 4;
+  // one CTA per SM: the stage ring takes what the 227 KB leave after the epilogue's transpose buffers
+  const size_t stg_bytes = static_cast<size_t>(TC_EPI_WARPS) * 32 * 32 * 4;
+  const size_t budget = 227 * 1024 - 1024 - stg_bytes - 512;         // alignment slack, static barriers
+  int stages = static_cast<int>(budget / stage_bytes);
+  g.a_base = 2 * g.acc_stride;
+  const int a_slots = (512 - g.a_base) / (2 * TC_BK);                 // TMEM A ring: one slot per stage
+  stages = stages > a_slots ? a_slots : stages;
   if (stages < 1) stages = 1;
   g.stages = stages;
-  size_t smem = stages * stage_bytes;
-  if (smem < 8 * 32 * 33 * 4) smem = 8 * 32 * 33 * 4;     // epilogue transpose staging
-  smem += 1024;                                          // alignment slack
+  size_t smem = stages * stage_bytes + stg_bytes + 1024;
+  if (smem < 120 * 1024) smem = 120 * 1024;    // never two CTAs on an SM: each allocates all 512 TMEM columns
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -854,7 +1046,7 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
     }
     configured = smem;
   }
-  dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles));
+  dim3 grid(static_cast<unsigned>(g.total_tiles < kNumSMs ? g.total_tiles : kNumSMs));
   gemm_tc_kernel<<<grid, TC_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, g);
   return launch_status("ax2d_gemm_tc");
 }
@@ -960,7 +1152,7 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), static_cast<unsigned>(split));
-  gemm_tc_wgrad_kernel<<<grid, TC_THREADS, smem, st>>>(maps, g);
+  gemm_tc_wgrad_kernel<<<grid, TC_WG_THREADS, smem, st>>>(maps, g);
   rc = launch_status("ax2d_gemm_tc_wgrad");
   if (rc != AX2D_OK || split == 1) return rc;
   return splitk_reduce(g.ws, split, M, N, g.e.c, accumulate, g.db, bias_grad, st);

@@ -179,3 +179,23 @@ def test_gemm_tc_wgrad_matches_float64(rows, gw, xw):
     # deterministic: fixed-order split-K reduction
     dW2 = ops._weight_grad(list(zip(G, gw)), list(zip(X, xw)), rows, No, Ki, DEV)
     assert torch.equal(dW, dW2)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("N", [32, 64, 96, 128, 160, 192, 224, 256, 320, 384, 512, 544])
+def test_gemm_tc_persistent_tiles_every_tile_width(N):
+    """Several tiles per CTA (the persistent loop, both TMEM accumulator buffers, ring wrap-around) for every tile
+    width / TMEM layout the host can choose, with residual + bias epilogue; also guards against a hang."""
+    ops = _ops()
+    M = 148 * 128 * 2 + 77            # > 2 row tiles per SM, ragged tail
+    K = 48
+    rng = np.random.Generator(np.random.PCG64(N))
+    a = _segs(rng, M, [K])
+    W = torch.from_numpy(rng.normal(0, 1.0 / np.sqrt(K), size=(N, K)).astype(np.float32)).to(DEV)
+    bias = torch.from_numpy(rng.normal(0, 0.1, size=N).astype(np.float32)).to(DEV)
+    res = _segs(rng, M, [N])[0]
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm([(a[0], K)], [(W, K)], [(out, N)], M, N, K, bias=bias, resid=[(res, N)])
+    torch.cuda.synchronize()
+    ref = a[0].double() @ W.double().t() + bias.double() + res.double()
+    assert _rel(out, ref) <= 1e-5

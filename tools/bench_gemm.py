@@ -21,11 +21,36 @@ SHAPES = [  # (name, M, K segments, N, epilogue kwargs builder)
 ]
 
 
+def make_case(m, widths, n, kind, dev="cuda"):
+    """Operands and epilogue arguments of one benchmark shape: (a_list, W, c_segs, kwargs)."""
+    k = sum(widths)
+    a = [torch.randn(m, w, device=dev) for w in widths]
+    W = torch.randn(n, k, device=dev) / k ** 0.5
+    bias = torch.randn(n, device=dev)
+    out = torch.empty(m, n, device=dev)
+    pre = torch.empty(m, n, device=dev)
+    res = torch.randn(m, n, device=dev)
+    kw = {}
+    c = [(out, n)]
+    if kind == "act":
+        kw = dict(bias=bias, pre_segs=[(pre, n)], act="silu", drop_p=0.05, drop_seed=1)
+    elif kind == "resid":
+        kw = dict(bias=bias, resid=[(res, n)])
+    elif kind == "io":
+        h = torch.empty(m, n // 2, device=dev); g = torch.empty(m, n // 2, device=dev); z = torch.empty(m, n // 2, device=dev)
+        c = [(h, n // 2), (g, n // 2)]
+        kw = dict(bias=bias, pre_segs=[(z, n // 2), (None, n // 2)], act="silu", act_cols=n // 2)
+    elif kind == "bias":
+        kw = dict(bias=bias)
+    return a, W, c, kw
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--simt", action="store_true")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--shape", type=int, default=-1)
+    ap.add_argument("--plain", action="store_true", help="two eager launches per shape and nothing else (for ncu captures)")
     ap.add_argument("--sweep", action="store_true", help="time vs K (slope = per-k-block cost, intercept = prologue + epilogue)")
     args = ap.parse_args()
     global SHAPES
@@ -38,28 +63,12 @@ def main():
         if args.shape >= 0 and idx != args.shape:
             continue
         k = sum(widths)
-        a = [torch.randn(m, w, device=dev) for w in widths]
-        W = torch.randn(n, k, device=dev) / k ** 0.5
-        bias = torch.randn(n, device=dev)
-        out = torch.empty(m, n, device=dev)
-        pre = torch.empty(m, n, device=dev)
-        res = torch.randn(m, n, device=dev)
-        kw = {}
-        c = [(out, n)]
-        if kind == "act":
-            kw = dict(bias=bias, pre_segs=[(pre, n)], act="silu", drop_p=0.05, drop_seed=1)
-        elif kind == "resid":
-            kw = dict(bias=bias, resid=[(res, n)])
-        elif kind == "io":
-            h = torch.empty(m, n // 2, device=dev); g = torch.empty(m, n // 2, device=dev); z = torch.empty(m, n // 2, device=dev)
-            c = [(h, n // 2), (g, n // 2)]
-            kw = dict(bias=bias, pre_segs=[(z, n // 2), (None, n // 2)], act="silu", act_cols=n // 2)
-        elif kind == "bias":
-            kw = dict(bias=bias)
-        hi, lo = ops.split_tf32(W)
-        for _ in range(3):
+        a, W, c, kw = make_case(m, widths, n, kind, dev)
+        for _ in range(2 if args.plain else 3):
             ops.gemm(list(zip(a, widths)), [(W, k)], c, m, n, k, **kw)
         torch.cuda.synchronize()
+        if args.plain:
+            continue
         # pure device time: `reps` launches captured in a CUDA graph, replayed between two events.  Inputs rotate over
         # several buffers so that they do not stay in L2 between launches.
         nbuf = 4 if m > 10000 else 1
