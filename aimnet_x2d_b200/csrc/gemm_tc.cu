@@ -732,29 +732,31 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const _
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // whole warp, elected issue (see umma_tf32_ts_w)
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
         mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], raw_bytes);
+        __syncwarp();
+        mbar_expect_tx_w(&full_bar[s], raw_bytes);
         const int row = (kb0 + it) * WG_KB;
         unsigned char* dst = stage_raw(s);
         for (int c = 0; c < a_chunks; ++c) {          // columns beyond the last segment: fully out-of-bounds box -> zeros
           const int o = m0 + 32 * c;
           const int sg = find_seg(g.a_start, g.a_nseg, o);
-          tma_load_2d(dst + c * WG_CHUNK_BYTES, &maps.a[sg], &full_bar[s], o - g.a_start[sg], row);
+          tma_load_2d_w(dst + c * WG_CHUNK_BYTES, &maps.a[sg], &full_bar[s], o - g.a_start[sg], row);
         }
         dst += a_chunks * WG_CHUNK_BYTES;
         for (int c = 0; c < b_chunks; ++c) {
           const int i = n0 + 32 * c;
           const int sg = find_seg(g.b_start, g.b_nseg, i);
-          tma_load_2d(dst + c * WG_CHUNK_BYTES, &maps.b[sg], &full_bar[s], i - g.b_start[sg], row);
+          tma_load_2d_w(dst + c * WG_CHUNK_BYTES, &maps.b[sg], &full_bar[s], i - g.b_start[sg], row);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // D = F32, A = B = TF32, both MN-major (bits 15, 16), M = 128, N = BN
       const uint32_t idesc = idesc_tf32(BN) | (1u << 15) | (1u << 16);
       int s = 0;
@@ -763,6 +765,7 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const _
         mbar_wait(&full_bar[s], ph);
         mbar_wait(&split_bar[s], ph);
         tc_fence_after();
+        __syncwarp();
         const uint32_t a_hi = smem_u32(stage_raw(s)), b_hi = a_hi + a_chunks * WG_CHUNK_BYTES;
         const uint32_t a_lo = smem_u32(stage_lo(s)), b_lo = a_lo + a_chunks * WG_CHUNK_BYTES;
 #pragma unroll
@@ -773,17 +776,17 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const _
           const uint32_t first = (it | j) != 0 ? 1u : 0u;
           const uint32_t t_small = tmem_base + static_cast<uint32_t>(g.acc2);    // see gemm_tc_kernel
 #if AX2D_TC_TERMS == 4
-          umma_tf32(t_small, dal, dbl, idesc, first);
-          umma_tf32(t_small, dal, dbh, idesc, 1u);
+          umma_tf32_w(t_small, dal, dbl, idesc, first);
+          umma_tf32_w(t_small, dal, dbh, idesc, 1u);
 #else
-          umma_tf32(t_small, dal, dbh, idesc, first);
+          umma_tf32_w(t_small, dal, dbh, idesc, first);
 #endif
-          umma_tf32(t_small, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, first);
+          umma_tf32_w(t_small, dah, dbl, idesc, 1u);
+          umma_tf32_w(tmem_base, dah, dbh, idesc, first);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit_w(&empty_bar[s]);
       }
-      umma_commit(&acc_bar);
+      umma_commit_w(&acc_bar);
     }
   } else {
     const int t = threadIdx.x - 64;
