@@ -249,11 +249,12 @@ struct TileEpi {
   float* pre; int ldpre;
   const float* res0; int ldres0;
   const float* res1; int ldres1;
+  const float* res2; int ldres2;
   const float* dp; int lddp;
 };
 __device__ __forceinline__ TileEpi tile_epi(const EpiArgs& e, int64_t m0, int n0, int n1, const float* ws) {
   TileEpi t;
-  t.ok = (m0 + TC_BM <= e.M) && e.mask == nullptr && !e.accumulate && e.n_resid <= kEpiPrefetchResid;
+  t.ok = (m0 + TC_BM <= e.M) && e.mask == nullptr && !e.accumulate && e.n_resid <= 3;
   const int cs = find_seg(e.c.start, e.c.n_seg, n0);
   t.ok = t.ok && find_seg(e.c.start, e.c.n_seg, n1 - 1) == cs;
   t.c = e.c.ptr[cs] - e.c.start[cs];           // indexed by absolute column
@@ -277,15 +278,23 @@ __device__ __forceinline__ TileEpi tile_epi(const EpiArgs& e, int64_t m0, int n0
   t.has_dp = e.dact != AX2D_ACT_NONE && n1 <= e.dact_cols;
   t.ok = t.ok && (e.dact == AX2D_ACT_NONE || n1 <= e.dact_cols || n0 >= e.dact_cols);
   t.dp = e.dact_pre; t.lddp = static_cast<int>(e.ld_dact);
-  // the (at most two) residuals either cover the whole column range or none of it; kept in their original order
-  const bool in0 = e.n_resid > 0, in1 = e.n_resid > 1;
-  const bool a0 = in0 && n1 <= e.resid_cols[0], a1 = in1 && n1 <= e.resid_cols[1];
-  t.ok = t.ok && (!in0 || a0 || n0 >= e.resid_cols[0]) && (!in1 || a1 || n0 >= e.resid_cols[1]);
-  t.res0 = a0 ? e.resid[0] : (a1 ? e.resid[1] : nullptr);
-  t.ldres0 = static_cast<int>(a0 ? e.ld_resid[0] : (a1 ? e.ld_resid[1] : 0));
-  t.res1 = (a0 && a1) ? e.resid[1] : nullptr;
-  t.ldres1 = static_cast<int>((a0 && a1) ? e.ld_resid[1] : 0);
-  t.nres = (a0 ? 1 : 0) + (a1 ? 1 : 0);
+  // the (at most three) residuals either cover the whole column range or none of it; kept in their original order
+  // (the last ShellConv projection adds h, the skip projection and the layer input: three)
+  t.res0 = t.res1 = t.res2 = nullptr;
+  t.ldres0 = t.ldres1 = t.ldres2 = 0;
+  t.nres = 0;
+  for (int r = 0; r < 3; ++r) {
+    if (r >= e.n_resid) break;
+    const bool covers = n1 <= e.resid_cols[r];
+    t.ok = t.ok && (covers || n0 >= e.resid_cols[r]);
+    if (!covers) continue;
+    const float* p = e.resid[r];
+    const int ld = static_cast<int>(e.ld_resid[r]);
+    if (t.nres == 0) { t.res0 = p; t.ldres0 = ld; }
+    else if (t.nres == 1) { t.res1 = p; t.ldres1 = ld; }
+    else { t.res2 = p; t.ldres2 = ld; }
+    ++t.nres;
+  }
   return t;
 }
 
@@ -339,14 +348,16 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
         float* ppre = te.pre + mrow * te.ldpre + n;
         const float* pr0 = te.res0 + mrow * te.ldres0 + n;
         const float* pr1 = te.res1 + mrow * te.ldres1 + n;
+        const float* pr2 = te.res2 + mrow * te.ldres2 + n;
         const float* pdp = te.dp + mrow * te.lddp + n;
         const int r0w = lane >> 3;               // this lane's rows: r0w + 4 i
         uint64_t didx = static_cast<uint64_t>(mrow) * static_cast<uint32_t>(N) + static_cast<uint32_t>(n);
 #pragma unroll 4
         for (int i = 0; i < 8; ++i) {          // rows mrow + 4 i
-          float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, dp = r0;
+          float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, dp = r0;
           if (te.nres > 0) r0 = __ldg(reinterpret_cast<const float4*>(pr0));
           if (te.nres > 1) r1 = __ldg(reinterpret_cast<const float4*>(pr1));
+          if (te.nres > 2) r2 = __ldg(reinterpret_cast<const float4*>(pr2));
           if (te.has_dp) dp = __ldg(reinterpret_cast<const float4*>(pdp));
           const float4 s4 = stg4[(r0w + 4 * i) * 8 + (cg ^ ((r0w + 4 * i) & 7))];
           float v[4] = {s4.x + b4.x, s4.y + b4.y, s4.z + b4.z, s4.w + b4.w};
@@ -365,6 +376,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
           }
           v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
           v[0] += r1.x; v[1] += r1.y; v[2] += r1.z; v[3] += r1.w;
+          v[0] += r2.x; v[1] += r2.y; v[2] += r2.z; v[3] += r2.w;
           if constexpr (DACT != AX2D_ACT_NONE) {
             if (te.has_dp) {
               v[0] *= act_bwd_t<DACT>(dp.x) * drop[0];
@@ -378,6 +390,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
           ppre += 4 * te.ldpre;
           pr0 += 4 * te.ldres0;
           pr1 += 4 * te.ldres1;
+          pr2 += 4 * te.ldres2;
           pdp += 4 * te.lddp;
           didx += 4ull * static_cast<uint32_t>(N);
         }
@@ -620,6 +633,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             const int col = n0 + (i % lines) * 32;
             if (te.nres > 0) prefetch_l2(te.res0 + row * te.ldres0 + col);
             if (te.nres > 1) prefetch_l2(te.res1 + row * te.ldres1 + col);
+            if (te.nres > 2) prefetch_l2(te.res2 + row * te.ldres2 + col);
             if (te.has_dp) prefetch_l2(te.dp + row * te.lddp + col);
           }
         }
