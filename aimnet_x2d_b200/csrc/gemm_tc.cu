@@ -131,6 +131,64 @@ __device__ __forceinline__ void umma_tf32_ts_w(uint32_t tmem_d, uint32_t tmem_a,
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One k-block of the projection kernel in ONE statement: the (TC_BK / 8 = 2) k-steps x 4 split terms and the commit
+// that frees the stage, under a single election.  Eight separately elected MMAs cost ~50 cycles of issue each
+// (predicate + R2UR traffic per statement); for the small-M head products that was the whole main loop.
+//   small accumulator: a_lo*b_lo (+)= , a_lo*b_hi, a_hi*b_lo      main accumulator: a_hi*b_hi
+__device__ __forceinline__ void umma_kblock_ts_w(uint32_t t_main, uint32_t t_small, uint32_t a_hi, uint32_t a_lo, uint64_t db_hi,
+                                                 uint64_t db_lo, uint32_t idesc, uint32_t acc_small_first, uint32_t acc_main_first,
+                                                 uint64_t* free_bar) {
+  static_assert(TC_BK == 16, "two k-steps of 8 per k-block");
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, pf, pm, pt;\n\t"
+      ".reg .b32 ah1, al1;\n\t"
+      ".reg .b64 bh1, bl1;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %7, 0;\n\t"
+      "setp.ne.b32 pm, %8, 0;\n\t"
+      "setp.eq.b32 pt, %6, %6;\n\t"
+      "add.u32 ah1, %2, 8;\n\t"
+      "add.u32 al1, %3, 8;\n\t"
+      "add.u64 bh1, %4, 2;\n\t"
+      "add.u64 bl1, %5, 2;\n\t"
+#if AX2D_TC_TERMS == 4
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %5, %6, pf;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, pt;\n\t"
+#else
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, pf;\n\t"
+#endif
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %5, %6, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %4, %6, pm;\n\t"
+#if AX2D_TC_TERMS == 4
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [al1], bl1, %6, pt;\n\t"
+#endif
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [al1], bh1, %6, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah1], bl1, %6, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bh1, %6, pt;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+      "}\n" ::"r"(t_main),
+      "r"(t_small), "r"(a_hi), "r"(a_lo), "l"(db_hi), "l"(db_lo), "r"(idesc), "r"(acc_small_first), "r"(acc_main_first),
+      "r"(smem_u32(free_bar))
+      : "memory");
+}
+// expect_tx + the three tensor-map loads of one k-block (A raw, B hi, B lo), one election
+__device__ __forceinline__ void tma_kblock_w(uint64_t* bar, uint32_t bytes, void* dst_a, const CUtensorMap* map_a, int ka, int m0,
+                                             void* dst_bh, const CUtensorMap* map_bh, void* dst_bl, const CUtensorMap* map_bl,
+                                             int kbcol, int n0) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3, {%4, %5}], [%0];\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%6], [%7, {%10, %11}], [%0];\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%8], [%9, {%10, %11}], [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(bytes), "r"(smem_u32(dst_a)), "l"(reinterpret_cast<uint64_t>(map_a)), "r"(ka), "r"(m0), "r"(smem_u32(dst_bh)),
+      "l"(reinterpret_cast<uint64_t>(map_bh)), "r"(smem_u32(dst_bl)), "l"(reinterpret_cast<uint64_t>(map_bl)), "r"(kbcol), "r"(n0)
+      : "memory");
+}
 __device__ __forceinline__ void umma_tf32_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -519,10 +577,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         mbar_wait(&empty_bar[s], ph ^ 1u);      // the MMAs that read this stage (smem B and TMEM A slot) are done
         __syncwarp();
         while (seg + 1 < g.n_seg && kb >= g.seg_kb_start[seg + 1]) ++seg;
-        mbar_expect_tx_w(&full_bar[s], TC_A_BYTES + 2 * b_bytes);
-        tma_load_2d_w(stage_a(s), &maps.a[seg], &full_bar[s], (kb - g.seg_kb_start[seg]) * TC_BK, m0);
-        tma_load_2d_w(stage_bhi(s), &maps.b_hi, &full_bar[s], kb * TC_BK, n0);
-        tma_load_2d_w(stage_blo(s), &maps.b_lo, &full_bar[s], kb * TC_BK, n0);
+        tma_kblock_w(&full_bar[s], TC_A_BYTES + 2 * b_bytes, stage_a(s), &maps.a[seg], (kb - g.seg_kb_start[seg]) * TC_BK, m0,
+                     stage_bhi(s), &maps.b_hi, stage_blo(s), &maps.b_lo, kb * TC_BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -552,24 +608,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         const uint32_t a_lo = a_hi + TC_BK;
         const uint64_t db_hi = smem_desc_k_sw64(smem_u32(stage_bhi(s)));
         const uint64_t db_lo = smem_desc_k_sw64(smem_u32(stage_blo(s)));
-#pragma unroll
-        for (int jj = 0; jj < TC_BK / 8; ++jj) {
-          const uint64_t adv = static_cast<uint64_t>((jj * 8 * 4) >> 4);     // 32 bytes per k-step inside the swizzle row
-          const uint32_t ak = static_cast<uint32_t>(jj * 8);                 // 8 TMEM columns per k-step
-          // The tensor core's fp32 accumulation truncates, so every MMA into a large accumulator costs up to one
-          // ulp of it.  When TMEM allows (acc2 != 0) the three small terms go to their own accumulator (2^-11 of the
-          // magnitude, so their truncation is negligible) and only hi*hi touches the main one.
-          const uint32_t first = (kb | jj) != 0 ? 1u : 0u;
-#if AX2D_TC_TERMS == 4
-          umma_tf32_ts_w(t_small, a_lo + ak, db_lo + adv, idesc, first);
-          umma_tf32_ts_w(t_small, a_lo + ak, db_hi + adv, idesc, 1u);
-#else
-          umma_tf32_ts_w(t_small, a_lo + ak, db_hi + adv, idesc, first);
-#endif
-          umma_tf32_ts_w(t_small, a_hi + ak, db_lo + adv, idesc, 1u);
-          umma_tf32_ts_w(t_main, a_hi + ak, db_hi + adv, idesc, g.acc2 != 0 ? first : 1u);
-        }
-        umma_commit_w(&empty_bar[s]);      // stage free once these MMAs have read it
+        // The tensor core's fp32 accumulation truncates, so every MMA into a large accumulator costs up to one ulp
+        // of it.  When TMEM allows (acc2 != 0) the three small terms go to their own accumulator (2^-11 of the
+        // magnitude, so their truncation is negligible) and only hi*hi touches the main one.  Per k-step the
+        // descriptors advance by 32 bytes inside the swizzle row (B) and by 8 TMEM columns (A).
+        const uint32_t acc_first = kb != 0 ? 1u : 0u;
+        umma_kblock_ts_w(t_main, t_small, a_hi, a_lo, db_hi, db_lo, idesc, acc_first, g.acc2 != 0 ? acc_first : 1u,
+                         &empty_bar[s]);      // the commit frees the stage once these MMAs have read it
         t_issue += clock64() - c1;
       }
       umma_commit_w(&acc_full[buf]);       // accumulator of this tile complete
