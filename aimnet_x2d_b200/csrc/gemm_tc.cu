@@ -172,6 +172,69 @@ __device__ __forceinline__ void umma_kblock_ts_w(uint32_t t_main, uint32_t t_sma
       "r"(smem_u32(free_bar))
       : "memory");
 }
+// One k-block of the weight-gradient kernel (WG_KB / 8 = 4 k-steps x 4 split terms, both operands from shared memory,
+// descriptors advancing by 1024 bytes = 64 address units per k-step) and the commit, under one election.
+__device__ __forceinline__ void umma_kblock_ss_w(uint32_t t_main, uint32_t t_small, uint64_t dah, uint64_t dal, uint64_t dbh,
+                                                 uint64_t dbl, uint32_t idesc, uint32_t acc_small_first,
+                                                 uint32_t acc_main_first, uint64_t* free_bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, pf, pm, pt;\n\t"
+      ".reg .b64 ah1, al1, bh1, bl1, ah2, al2, bh2, bl2, ah3, al3, bh3, bl3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %7, 0;\n\t"
+      "setp.ne.b32 pm, %9, 0;\n\t"
+      "setp.eq.b32 pt, %6, %6;\n\t"
+      "add.u64 ah1, %2, 64;\n\t"
+      "add.u64 al1, %3, 64;\n\t"
+      "add.u64 bh1, %4, 64;\n\t"
+      "add.u64 bl1, %5, 64;\n\t"
+      "add.u64 ah2, %2, 128;\n\t"
+      "add.u64 al2, %3, 128;\n\t"
+      "add.u64 bh2, %4, 128;\n\t"
+      "add.u64 bl2, %5, 128;\n\t"
+      "add.u64 ah3, %2, 192;\n\t"
+      "add.u64 al3, %3, 192;\n\t"
+      "add.u64 bh3, %4, 192;\n\t"
+      "add.u64 bl3, %5, 192;\n\t"
+#if AX2D_TC_TERMS == 4
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %5, %6, pf;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, pt;\n\t"
+#else
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, pf;\n\t"
+#endif
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %5, %6, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %4, %6, pm;\n\t"
+#if AX2D_TC_TERMS == 4
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al1, bl1, %6, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al1, bh1, %6, pt;\n\t"
+#else
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al1, bh1, %6, pt;\n\t"
+#endif
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], ah1, bl1, %6, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah1, bh1, %6, pt;\n\t"
+#if AX2D_TC_TERMS == 4
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al2, bl2, %6, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al2, bh2, %6, pt;\n\t"
+#else
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al2, bh2, %6, pt;\n\t"
+#endif
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], ah2, bl2, %6, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah2, bh2, %6, pt;\n\t"
+#if AX2D_TC_TERMS == 4
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al3, bl3, %6, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al3, bh3, %6, pt;\n\t"
+#else
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al3, bh3, %6, pt;\n\t"
+#endif
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], ah3, bl3, %6, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah3, bh3, %6, pt;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+      "}\n" ::"r"(t_main),
+      "r"(t_small), "l"(dah), "l"(dal), "l"(dbh), "l"(dbl), "r"(idesc), "r"(acc_small_first), "r"(smem_u32(free_bar)),
+      "r"(acc_main_first)
+      : "memory");
+}
 // expect_tx + the three tensor-map loads of one k-block (A raw, B hi, B lo), one election
 __device__ __forceinline__ void tma_kblock_w(uint64_t* bar, uint32_t bytes, void* dst_a, const CUtensorMap* map_a, int ka, int m0,
                                              void* dst_bh, const CUtensorMap* map_bh, void* dst_bl, const CUtensorMap* map_bl,
@@ -751,22 +814,67 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t smem_addr) {
   return d;
 }
 
+// TMEM columns of the weight-gradient kernel: [0, 160) main accumulator, [160, 320) small-term accumulator,
+// [320, 512) the A ring: three slots of 64 columns (32 contraction rows: hi | lo).
+constexpr int WG_ACC2 = 160;
+constexpr int WG_A_TMEM = 320;
+constexpr int WG_MAX_STAGES = 3;
+constexpr int WG_MAX_BN = 160;
+
+// One k-block (4 k-steps x 4 split terms) with the A operand in tensor memory, and the commit, under one election.
+__device__ __forceinline__ void umma_kblock_wg_w(uint32_t t_main, uint32_t t_small, uint32_t a_hi, uint32_t a_lo, uint64_t dbh,
+                                                 uint64_t dbl, uint32_t idesc, uint32_t acc_first, uint64_t* free_bar) {
+  static_assert(WG_KB == 32, "four k-steps of 8 per k-block");
+#define AX2D_WG_STEP(AH, AL, BH, BL, PF)                                                  \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AL "], " BL ", %6, " PF ";\n\t"        \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AL "], " BH ", %6, pt;\n\t"            \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AH "], " BL ", %6, pt;\n\t"            \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [" AH "], " BH ", %6, " PF ";\n\t"
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, pf, pt;\n\t"
+      ".reg .b32 ah1, al1, ah2, al2, ah3, al3;\n\t"
+      ".reg .b64 bh1, bl1, bh2, bl2, bh3, bl3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %7, 0;\n\t"
+      "setp.eq.b32 pt, %6, %6;\n\t"
+      "add.u32 ah1, %2, 8;\n\t add.u32 al1, %3, 8;\n\t add.u64 bh1, %4, 64;\n\t add.u64 bl1, %5, 64;\n\t"
+      "add.u32 ah2, %2, 16;\n\t add.u32 al2, %3, 16;\n\t add.u64 bh2, %4, 128;\n\t add.u64 bl2, %5, 128;\n\t"
+      "add.u32 ah3, %2, 24;\n\t add.u32 al3, %3, 24;\n\t add.u64 bh3, %4, 192;\n\t add.u64 bl3, %5, 192;\n\t"
+      AX2D_WG_STEP("%2", "%3", "%4", "%5", "pf")
+      AX2D_WG_STEP("ah1", "al1", "bh1", "bl1", "pt")
+      AX2D_WG_STEP("ah2", "al2", "bh2", "bl2", "pt")
+      AX2D_WG_STEP("ah3", "al3", "bh3", "bl3", "pt")
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+      "}\n" ::"r"(t_main),
+      "r"(t_small), "r"(a_hi), "r"(a_lo), "l"(dbh), "l"(dbl), "r"(idesc), "r"(acc_first), "r"(smem_u32(free_bar))
+      : "memory");
+#undef AX2D_WG_STEP
+}
+
+// Roles (one CTA per SM, 10 warps): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 A-splitters
+// (thread = output feature o = TMEM lane: reads its column of the raw G chunk, splits it and stores (hi, lo) into the
+// TMEM A ring; accumulates the fused bias gradient on the way), warps 6..9 B-splitters (rewrite the raw X chunks in
+// place as hi and emit lo beside them; the MN-major swizzled layout is preserved because the split is element-wise).
+// Keeping A out of shared memory removes ~1/3 of the shared-memory traffic that bounded the first version
+// (both operands from shared memory: 288 KB per k-block against 1280 cycles of tensor time).
 __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const __grid_constant__ WgMaps maps,
                                                                       const __grid_constant__ WgArgs g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], split_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_bar;
+  __shared__ __align__(8) uint64_t full_bar[WG_MAX_STAGES], split_bar[WG_MAX_STAGES], empty_bar[WG_MAX_STAGES], acc_bar;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = g.BN, S = g.stages;
   const int a_chunks = TC_BM / 32, b_chunks = BN / 32;
-  const uint32_t raw_bytes = static_cast<uint32_t>(a_chunks + b_chunks) * WG_CHUNK_BYTES;
-  const uint32_t stage_bytes = 2 * raw_bytes;
+  const uint32_t a_bytes = static_cast<uint32_t>(a_chunks) * WG_CHUNK_BYTES, b_bytes = static_cast<uint32_t>(b_chunks) * WG_CHUNK_BYTES;
+  const uint32_t stage_bytes = a_bytes + 2 * b_bytes;
   // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the address space and
   // emits LDS / STS instead of generic loads and stores for everything derived from it)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  auto stage_raw = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };   // A chunks then B chunks (hi after split)
-  auto stage_lo = [&](int s) { return stage_raw(s) + raw_bytes; };
+  auto stage_a = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };     // raw G chunks
+  auto stage_bhi = [&](int s) { return stage_a(s) + a_bytes; };                          // raw X chunks -> hi
+  auto stage_blo = [&](int s) { return stage_a(s) + a_bytes + b_bytes; };
 
   const int m0 = blockIdx.x * TC_BM;
   const int n0 = blockIdx.y * BN;
@@ -784,7 +892,7 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const _
     mbar_init(&acc_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_smem, static_cast<uint32_t>(g.tmem_cols));
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 512u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -792,132 +900,120 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const _
 
   if (warp == 0) {
     // whole warp, elected issue (see umma_tf32_ts_w)
-    {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        __syncwarp();
-        mbar_expect_tx_w(&full_bar[s], raw_bytes);
-        const int row = (kb0 + it) * WG_KB;
-        unsigned char* dst = stage_raw(s);
-        for (int c = 0; c < a_chunks; ++c) {          // columns beyond the last segment: fully out-of-bounds box -> zeros
-          const int o = m0 + 32 * c;
-          const int sg = find_seg(g.a_start, g.a_nseg, o);
-          tma_load_2d_w(dst + c * WG_CHUNK_BYTES, &maps.a[sg], &full_bar[s], o - g.a_start[sg], row);
-        }
-        dst += a_chunks * WG_CHUNK_BYTES;
-        for (int c = 0; c < b_chunks; ++c) {
-          const int i = n0 + 32 * c;
-          const int sg = find_seg(g.b_start, g.b_nseg, i);
-          tma_load_2d_w(dst + c * WG_CHUNK_BYTES, &maps.b[sg], &full_bar[s], i - g.b_start[sg], row);
-        }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      __syncwarp();
+      mbar_expect_tx_w(&full_bar[s], a_bytes + b_bytes);
+      const int row = (kb0 + it) * WG_KB;
+      unsigned char* dst = stage_a(s);
+      for (int c = 0; c < a_chunks; ++c) {          // columns beyond the last segment: fully out-of-bounds box -> zeros
+        const int o = m0 + 32 * c;
+        const int sg = find_seg(g.a_start, g.a_nseg, o);
+        tma_load_2d_w(dst + c * WG_CHUNK_BYTES, &maps.a[sg], &full_bar[s], o - g.a_start[sg], row);
+      }
+      dst = stage_bhi(s);
+      for (int c = 0; c < b_chunks; ++c) {
+        const int i = n0 + 32 * c;
+        const int sg = find_seg(g.b_start, g.b_nseg, i);
+        tma_load_2d_w(dst + c * WG_CHUNK_BYTES, &maps.b[sg], &full_bar[s], i - g.b_start[sg], row);
       }
     }
   } else if (warp == 1) {
-    {
-      // D = F32, A = B = TF32, both MN-major (bits 15, 16), M = 128, N = BN
-      const uint32_t idesc = idesc_tf32(BN) | (1u << 15) | (1u << 16);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
-        mbar_wait(&full_bar[s], ph);
-        mbar_wait(&split_bar[s], ph);
-        tc_fence_after();
-        __syncwarp();
-        const uint32_t a_hi = smem_u32(stage_raw(s)), b_hi = a_hi + a_chunks * WG_CHUNK_BYTES;
-        const uint32_t a_lo = smem_u32(stage_lo(s)), b_lo = a_lo + a_chunks * WG_CHUNK_BYTES;
-#pragma unroll
-        for (int j = 0; j < WG_KB / 8; ++j) {
-          const uint32_t adv = j * 1024;                   // 8 contraction rows = two 4-row swizzle atoms
-          const uint64_t dah = smem_desc_mn_sw128_32b(a_hi + adv), dal = smem_desc_mn_sw128_32b(a_lo + adv);
-          const uint64_t dbh = smem_desc_mn_sw128_32b(b_hi + adv), dbl = smem_desc_mn_sw128_32b(b_lo + adv);
-          const uint32_t first = (it | j) != 0 ? 1u : 0u;
-          const uint32_t t_small = tmem_base + static_cast<uint32_t>(g.acc2);    // see gemm_tc_kernel
-#if AX2D_TC_TERMS == 4
-          umma_tf32_w(t_small, dal, dbl, idesc, first);
-          umma_tf32_w(t_small, dal, dbh, idesc, 1u);
-#else
-          umma_tf32_w(t_small, dal, dbh, idesc, first);
-#endif
-          umma_tf32_w(t_small, dah, dbl, idesc, 1u);
-          umma_tf32_w(tmem_base, dah, dbh, idesc, first);
-        }
-        umma_commit_w(&empty_bar[s]);
-      }
-      umma_commit_w(&acc_bar);
-    }
-  } else {
-    const int t = threadIdx.x - 64;
-    const int n4 = static_cast<int>(raw_bytes / 16);
-    // Fused bias gradient (db[o] = sum_m G[m, o]): the splitters already hold every element of the G tile in
-    // registers.  Float4 #t of every [32 x 32] chunk is always (row t / 8, 16-byte slot t % 8) of that chunk, so
-    // thread t keeps one running float4 per A chunk; only the CTAs of the first column tile do it.
-    const bool want_db = g.db != nullptr && blockIdx.y == 0;
-    float4 colsum[TC_BM / 32];
-#pragma unroll
-    for (int c = 0; c < TC_BM / 32; ++c) colsum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // D = F32, A = B = TF32, A K-major from TMEM, B MN-major (bit 16) from shared memory, M = 128, N = BN
+    const uint32_t idesc = idesc_tf32(BN) | (1u << 16);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
       mbar_wait(&full_bar[s], ph);
-      float4* a = reinterpret_cast<float4*>(stage_raw(s));
-      float4* l = reinterpret_cast<float4*>(stage_lo(s));
-      if (want_db) {
-#pragma unroll
-        for (int c = 0; c < TC_BM / 32; ++c) {
-          const float4 v = a[t + TC_WORKERS * c];
-          colsum[c].x += v.x; colsum[c].y += v.y; colsum[c].z += v.z; colsum[c].w += v.w;
-        }
-      }
-#pragma unroll 4
-      for (int i = t; i < n4; i += TC_WORKERS) {
-        const float4 v = a[i];
-        float4 h, o;
-        split_tf32(v.x, h.x, o.x);
-        split_tf32(v.y, h.y, o.y);
-        split_tf32(v.z, h.z, o.z);
-        split_tf32(v.w, h.w, o.w);
-        a[i] = h;
-        l[i] = o;
-      }
-      fence_proxy_async_smem();
+      mbar_wait(&split_bar[s], ph);
+      tc_fence_after();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&split_bar[s]);
+      const uint32_t a_hi = tmem_base + static_cast<uint32_t>(WG_A_TMEM + s * 2 * WG_KB);
+      // 8 contraction rows per k-step = two 4-row swizzle atoms = 1024 bytes (64 descriptor address units); the three
+      // small terms go to their own accumulator (see gemm_tc_kernel)
+      umma_kblock_wg_w(tmem_base, tmem_base + WG_ACC2, a_hi, a_hi + WG_KB, smem_desc_mn_sw128_32b(smem_u32(stage_bhi(s))),
+                       smem_desc_mn_sw128_32b(smem_u32(stage_blo(s))), idesc, it != 0 ? 1u : 0u, &empty_bar[s]);
+    }
+    umma_commit_w(&acc_bar);
+  } else {
+    const int t = threadIdx.x - 64;
+    const bool a_side = warp < 6;                      // warps 2..5: A-splitters, 6..9: B-splitters
+    const bool want_db = g.db != nullptr && blockIdx.y == 0;
+    float colsum = 0.f;                                // fused bias gradient: db[o] = sum_m G[m, o]
+    int s = 0;
+    uint32_t ph = 0;
+    if (a_side) {
+      const int q = warp & 3;                          // TMEM lane quarter of this warp = chunk of the G tile
+      const float* chunk0 = reinterpret_cast<const float*>(stage_a(0)) + q * (WG_CHUNK_BYTES / 4);
+      for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
+        mbar_wait(&full_bar[s], ph);
+        const float* chunk = chunk0 + static_cast<size_t>(s) * (stage_bytes / 4);
+        const uint32_t slot = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(WG_A_TMEM + s * 2 * WG_KB);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr) {
+            // logical column `lane` of row r: 16-byte slot 2 * ((lane / 8) ^ (r & 3)) + ((lane / 4) & 1)   (Swizzle<2,5,2>);
+            // the 32 lanes of a warp hit 32 different banks
+            const int r = 16 * half + rr;
+            const float v = chunk[r * 32 + (2 * ((lane >> 3) ^ (r & 3)) + ((lane >> 2) & 1)) * 4 + (lane & 3)];
+            colsum += v;
+            float h, o;
+            split_tf32(v, h, o);
+            hi[rr] = __float_as_uint(h);
+            lo[rr] = __float_as_uint(o);
+          }
+          tmem_st16(slot + 16 * half, hi);
+          tmem_st16(slot + WG_KB + 16 * half, lo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);
+      }
+      if (want_db) {
+        const int64_t o = static_cast<int64_t>(m0) + q * 32 + lane;
+        if (o < g.e.M) g.db[static_cast<int64_t>(blockIdx.z) * g.e.M + o] = colsum;
+      }
+    } else {
+      const int tb = t - 128;
+      const int n4 = static_cast<int>(b_bytes / 16);
+      for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
+        mbar_wait(&full_bar[s], ph);
+        float4* h4 = reinterpret_cast<float4*>(stage_bhi(s));
+        float4* l4 = reinterpret_cast<float4*>(stage_blo(s));
+#pragma unroll 5
+        for (int i = tb; i < n4; i += 128) {
+          const float4 v = h4[i];
+          float4 h, o;
+          split_tf32(v.x, h.x, o.x);
+          split_tf32(v.y, h.y, o.y);
+          split_tf32(v.z, h.z, o.z);
+          split_tf32(v.w, h.w, o.w);
+          h4[i] = h;
+          l4[i] = o;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);
+      }
     }
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
-    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 32);     // stage memory is free now
     const EpiCtx cx = epi_ctx(g.e);
-    if (want_db) {
-      // shared memory is free now (all MMAs retired); 256 x 4 float4 behind the epilogue staging area
-      float4* red = reinterpret_cast<float4*>(smem + 8 * 32 * 33 * 4);
-#pragma unroll
-      for (int c = 0; c < TC_BM / 32; ++c) red[c * TC_WORKERS + t] = colsum[c];
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory");      // the 8 worker warps only
-      if (t < TC_BM) {
-        // logical column n of chunk c, row r lives in 32-byte unit (n / 8) ^ (r & 3) of the row (Swizzle<2,5,2>)
-        const int c = t >> 5, n = t & 31;
-        const float* base = reinterpret_cast<const float*>(red + c * TC_WORKERS);
-        float sum = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          const int slot = 2 * ((n >> 3) ^ (r & 3)) + ((n >> 2) & 1);
-          sum += base[(r * 8 + slot) * 4 + (n & 3)];
-        }
-        const int64_t o = static_cast<int64_t>(m0) + t;
-        if (o < g.e.M) g.db[static_cast<int64_t>(blockIdx.z) * g.e.M + o] = sum;
-      }
-    }
     float* ws = g.ws != nullptr ? g.ws + static_cast<int64_t>(blockIdx.z) * g.e.M * g.e.N : nullptr;
     tc_epilogue<AX2D_ACT_NONE, AX2D_ACT_NONE, false>(g.e, BN, ws, cx, tmem_base, stg, m0, n0, warp & 3, lane, (warp - 2) >> 2,
-                                                     static_cast<uint32_t>(g.acc2));
+                                                     static_cast<uint32_t>(WG_ACC2));
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, static_cast<uint32_t>(g.tmem_cols));
+    tmem_dealloc(tmem_base, 512u);
   }
 }
 
@@ -1126,7 +1222,7 @@ extern "C" int ax2d_gemm_tc_wgrad_supported(const ax2d_cmat* a, const ax2d_cmat*
 }
 
 extern "C" int64_t ax2d_gemm_tc_wgrad_workspace(int64_t M, int64_t N, int64_t K) {
-  const int64_t n_tiles = (N + 255) / 256;
+  const int64_t n_tiles = (N + WG_MAX_BN - 1) / WG_MAX_BN;
   const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * n_tiles;
   const int64_t num_kb = (K + WG_KB - 1) / WG_KB;
   int64_t split = (kNumSMs + tiles - 1) / tiles;
@@ -1170,13 +1266,12 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
   }
   for (int s = b->n_seg; s <= AX2D_MAX_SEG; ++s) g.b_start[s] = acc;
   AX2D_CHECK_ARG(acc == N, "ax2d_gemm_tc_wgrad: B segments cover %d columns, expected %lld", acc, (long long)N);
-  const int n_tiles = static_cast<int>((N + 255) / 256);
+  const int n_tiles = static_cast<int>((N + WG_MAX_BN - 1) / WG_MAX_BN);
   int BN = static_cast<int>((N + n_tiles - 1) / n_tiles);
   BN = (BN + 31) / 32 * 32;
   g.BN = BN;
-  g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  g.acc2 = g.tmem_cols;     // one CTA per SM: main + small-term accumulator (<= 512 columns)
-  g.tmem_cols *= 2;
+  g.tmem_cols = 512;        // one CTA per SM: main + small-term accumulator + the A ring
+  g.acc2 = WG_ACC2;
   const int m_tiles = static_cast<int>((M + TC_BM - 1) / TC_BM);
   g.num_kb = static_cast<int>((K + WG_KB - 1) / WG_KB);
   int split = (kNumSMs + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
@@ -1193,15 +1288,16 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
   } else {
     g.db = bias_grad;
   }
-  const size_t stage_bytes = 2 * static_cast<size_t>(TC_BM / 32 + BN / 32) * WG_CHUNK_BYTES;
+  const size_t stage_bytes = static_cast<size_t>(TC_BM / 32 + 2 * (BN / 32)) * WG_CHUNK_BYTES;
   int stages = static_cast<int>((224 * 1024) / stage_bytes);
-  stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages;
+  stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
   stages = stages > g.kb_per_split ? g.kb_per_split : stages;
   if (stages < 1) stages = 1;
   g.stages = stages;
   size_t smem = stages * stage_bytes;
-  const size_t epi_bytes = 8 * 32 * 33 * 4 + (TC_BM / 32) * TC_WORKERS * 16;   // transpose staging + bias-gradient reduce
+  const size_t epi_bytes = 8 * 32 * 32 * 4;        // epilogue transpose staging
   if (smem < epi_bytes) smem = epi_bytes;
+  if (smem < 120 * 1024) smem = 120 * 1024;        // never two CTAs on an SM: each allocates all 512 TMEM columns
   smem += 1024;
   static size_t configured = 0;
   if (smem > configured) {
