@@ -7,23 +7,22 @@
 // (2^-11 operand rounding).  Every operand is therefore split into two TF32-representable terms,
 //   a = a_hi + a_lo,  a_hi = a rounded to 10 explicit mantissa bits,  a_lo = a - a_hi (exact in fp32),
 // (a_lo additionally rounded to TF32: <= 2^-23 |a| dropped), and the product is accumulated in fp32 TMEM as
-//   a_lo*b_lo + a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
-// four kind::tf32 MMAs per k-step.  Every partial product is exact in fp32 (11 x 11 significant bits); what is
-// lost is 2 x 2^-23 relative per product (the rounding of the two lo terms), the same order as an fp32 FMA chain.
+//   a_lo*b_hi + a_hi*b_lo + a_hi*b_hi   (+ a_lo*b_lo with -DAX2D_TC_TERMS=4)
+// three kind::tf32 MMAs per k-step ("3xTF32").  Every partial product is exact in fp32 (11 x 11 significant bits).
 //
-// One CTA computes a 128 x BN output tile (BN <= 256, all of N when it fits):
-//   warp 0      : TMA producer -- per k-block (32 fp32 = one 128-byte swizzle row) one tensor-map load of the raw
-//                 A tile [128 x 32] and of B_hi / B_lo [BN x 32] into a ring of shared-memory stages (SWIZZLE_128B),
+// Persistent kernel, one CTA per SM walking 128 x BN output tiles (BN <= 192), 18 warps:
+//   warp 0      : TMA producer -- per k-block (16 fp32 = one 64-byte swizzle row) one tensor-map load of the raw
+//                 A tile [128 x 16] and of B_hi / B_lo [BN x 16] into a ring of shared-memory stages (SWIZZLE_64B),
 //                 completion on an mbarrier (complete_tx).
-//   warps 2..5  : splitters -- rewrite the raw A tile in place as a_hi and emit a_lo into a second buffer at the
-//                 SAME byte offsets (the split is element-wise, so the swizzled layout is preserved for free), then
-//                 fence.proxy.async + mbarrier arrive.  After the main loop the same warps run the epilogue.
-//   warp 1      : one thread issues the tcgen05.mma instructions (A and B from shared-memory descriptors, the
-//                 accumulator in TMEM), tcgen05.commit releases each stage back to the producer and finally
-//                 signals the epilogue.  The warp also owns the TMEM allocation.
-//   epilogue    : tcgen05.ld (32 lanes x 32 columns per warp) -> shared-memory transpose -> the fused epilogue of
-//                 gemm_common.cuh with row-contiguous 128-bit global accesses (bias, pre-activation copy,
-//                 activation, counter-based dropout, residuals, activation backward, segmented outputs).
+//   warps 2..5  : splitters -- thread = row of the A tile: read the raw row from shared memory, split it and store
+//                 (a_hi, a_lo) into a ring of TENSOR-MEMORY slots (tcgen05.st; lane = row, column = k).
+//   warp 1      : issues the tcgen05.mma instructions (A from TMEM, B from shared-memory descriptors, accumulators in
+//                 TMEM, double-buffered); tcgen05.commit releases each stage back to the producer and hands finished
+//                 accumulators to the epilogue.  The warp also owns the TMEM allocation.
+//   warps 6..17 : epilogue -- tcgen05.ld (32 lanes x 32 columns per warp) -> swizzled shared-memory transpose -> the
+//                 fused epilogue of gemm_common.cuh with row-contiguous 128-bit global accesses (bias,
+//                 pre-activation copy, activation, counter-based dropout, residuals, activation backward, segmented
+//                 outputs) -- of tile i while the other warps already run the main loop of tile i + 1.
 #include <cuda.h>
 
 #include "gemm_common.cuh"
@@ -39,7 +38,10 @@ constexpr int TC_WORKERS = 256;                  // weight-gradient kernel: spli
 constexpr int TC_WG_THREADS = 64 + TC_WORKERS;
 constexpr int TC_MAX_STAGES = 6;
 #ifndef AX2D_TC_TERMS
-#define AX2D_TC_TERMS 4     // 4: lo*lo kept (fp32-level); 3: classic 3xTF32 (drops a 2^-22 relative term)
+#define AX2D_TC_TERMS 3     // 3: classic 3xTF32 (drops a_lo*b_lo, 2^-22 relative per product); 4: keeps it.  Measured on
+                            // the shapes of the model the maximum error against float64 is IDENTICAL with 3 and 4 terms
+                            // (it comes from the tensor core's truncating fp32 accumulation, see acc2), so the default
+                            // spends 25 % fewer MMAs; -DAX2D_TC_TERMS=4 restores the fourth term.
 #endif
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;     // 8 KB
 
@@ -70,17 +72,6 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define TC_STAMP(slot)                                                                             \
-  do {                                                                                             \
-    if (g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0) g.dbg[slot] = gtime();             \
-  } while (0)
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
-      : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -95,42 +86,10 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// A operand from TMEM (lane = row, one 32-bit column per k), B from shared memory
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Warp-collective variants: called by ALL lanes of a converged warp, one elected lane issues.  Inside an
-// `if (lane == 0)` branch the compiler cannot use the uniform datapath these instructions need and wraps every
-// one of them in an ELECT / branch loop with R2UR moves (measured: ~75 cycles per MMA issued, more than the 80
-// cycles a 128 x 160 x 8 MMA occupies the tensor pipe); issued from converged code they cost a few cycles.
-__device__ __forceinline__ void umma_tf32_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, e;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
+// Warp-collective issue: every function below with the suffix _w is called by ALL lanes of a converged warp and
+// elects one lane inside the statement.  Inside an `if (lane == 0)` branch the compiler cannot use the uniform
+// datapath that tcgen05.mma / TMA instructions need and wraps every one of them in an ELECT / branch loop with
+// R2UR moves (measured: ~75 cycles per MMA issued -- as long as a 128 x 160 x 8 MMA occupies the tensor pipe).
 // One k-block of the projection kernel in ONE statement: the (TC_BK / 8 = 2) k-steps x 4 split terms and the commit
 // that frees the stage, under a single election.  Eight separately elected MMAs cost ~50 cycles of issue each
 // (predicate + R2UR traffic per statement); for the small-M head products that was the whole main loop.
@@ -172,69 +131,6 @@ __device__ __forceinline__ void umma_kblock_ts_w(uint32_t t_main, uint32_t t_sma
       "r"(smem_u32(free_bar))
       : "memory");
 }
-// One k-block of the weight-gradient kernel (WG_KB / 8 = 4 k-steps x 4 split terms, both operands from shared memory,
-// descriptors advancing by 1024 bytes = 64 address units per k-step) and the commit, under one election.
-__device__ __forceinline__ void umma_kblock_ss_w(uint32_t t_main, uint32_t t_small, uint64_t dah, uint64_t dal, uint64_t dbh,
-                                                 uint64_t dbl, uint32_t idesc, uint32_t acc_small_first,
-                                                 uint32_t acc_main_first, uint64_t* free_bar) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred e, pf, pm, pt;\n\t"
-      ".reg .b64 ah1, al1, bh1, bl1, ah2, al2, bh2, bl2, ah3, al3, bh3, bl3;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 pf, %7, 0;\n\t"
-      "setp.ne.b32 pm, %9, 0;\n\t"
-      "setp.eq.b32 pt, %6, %6;\n\t"
-      "add.u64 ah1, %2, 64;\n\t"
-      "add.u64 al1, %3, 64;\n\t"
-      "add.u64 bh1, %4, 64;\n\t"
-      "add.u64 bl1, %5, 64;\n\t"
-      "add.u64 ah2, %2, 128;\n\t"
-      "add.u64 al2, %3, 128;\n\t"
-      "add.u64 bh2, %4, 128;\n\t"
-      "add.u64 bl2, %5, 128;\n\t"
-      "add.u64 ah3, %2, 192;\n\t"
-      "add.u64 al3, %3, 192;\n\t"
-      "add.u64 bh3, %4, 192;\n\t"
-      "add.u64 bl3, %5, 192;\n\t"
-#if AX2D_TC_TERMS == 4
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %5, %6, pf;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, pt;\n\t"
-#else
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, pf;\n\t"
-#endif
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %5, %6, pt;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %4, %6, pm;\n\t"
-#if AX2D_TC_TERMS == 4
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al1, bl1, %6, pt;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al1, bh1, %6, pt;\n\t"
-#else
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al1, bh1, %6, pt;\n\t"
-#endif
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], ah1, bl1, %6, pt;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah1, bh1, %6, pt;\n\t"
-#if AX2D_TC_TERMS == 4
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al2, bl2, %6, pt;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al2, bh2, %6, pt;\n\t"
-#else
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al2, bh2, %6, pt;\n\t"
-#endif
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], ah2, bl2, %6, pt;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah2, bh2, %6, pt;\n\t"
-#if AX2D_TC_TERMS == 4
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al3, bl3, %6, pt;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al3, bh3, %6, pt;\n\t"
-#else
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al3, bh3, %6, pt;\n\t"
-#endif
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], ah3, bl3, %6, pt;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah3, bh3, %6, pt;\n\t"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
-      "}\n" ::"r"(t_main),
-      "r"(t_small), "l"(dah), "l"(dal), "l"(dbh), "l"(dbl), "r"(idesc), "r"(acc_small_first), "r"(smem_u32(free_bar)),
-      "r"(acc_main_first)
-      : "memory");
-}
 // expect_tx + the three tensor-map loads of one k-block (A raw, B hi, B lo), one election
 __device__ __forceinline__ void tma_kblock_w(uint64_t* bar, uint32_t bytes, void* dst_a, const CUtensorMap* map_a, int ka, int m0,
                                              void* dst_bh, const CUtensorMap* map_bh, void* dst_bl, const CUtensorMap* map_bl,
@@ -250,17 +146,6 @@ __device__ __forceinline__ void tma_kblock_w(uint64_t* bar, uint32_t bytes, void
       "}\n" ::"r"(smem_u32(bar)),
       "r"(bytes), "r"(smem_u32(dst_a)), "l"(reinterpret_cast<uint64_t>(map_a)), "r"(ka), "r"(m0), "r"(smem_u32(dst_bh)),
       "l"(reinterpret_cast<uint64_t>(map_bh)), "r"(smem_u32(dst_bl)), "l"(reinterpret_cast<uint64_t>(map_bl)), "r"(kbcol), "r"(n0)
-      : "memory");
-}
-__device__ __forceinline__ void umma_tf32_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, e;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
@@ -302,9 +187,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -825,11 +707,18 @@ constexpr int WG_MAX_BN = 160;
 __device__ __forceinline__ void umma_kblock_wg_w(uint32_t t_main, uint32_t t_small, uint32_t a_hi, uint32_t a_lo, uint64_t dbh,
                                                  uint64_t dbl, uint32_t idesc, uint32_t acc_first, uint64_t* free_bar) {
   static_assert(WG_KB == 32, "four k-steps of 8 per k-block");
+#if AX2D_TC_TERMS == 4
 #define AX2D_WG_STEP(AH, AL, BH, BL, PF)                                                  \
   "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AL "], " BL ", %6, " PF ";\n\t"        \
   "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AL "], " BH ", %6, pt;\n\t"            \
   "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AH "], " BL ", %6, pt;\n\t"            \
   "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [" AH "], " BH ", %6, " PF ";\n\t"
+#else
+#define AX2D_WG_STEP(AH, AL, BH, BL, PF)                                                  \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AL "], " BH ", %6, " PF ";\n\t"        \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AH "], " BL ", %6, pt;\n\t"            \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [" AH "], " BH ", %6, " PF ";\n\t"
+#endif
   asm volatile(
       "{\n\t"
       ".reg .pred e, pf, pt;\n\t"
@@ -899,7 +788,7 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const _
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // whole warp, elected issue (see umma_tf32_ts_w)
+    // whole warp, elected issue (see "Warp-collective issue" above)
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
