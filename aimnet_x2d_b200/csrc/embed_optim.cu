@@ -280,22 +280,43 @@ struct PackDesc {           // one rectangular block; 88 bytes (packed.py mirror
 __device__ __forceinline__ float pk_round_tf32(float v) {
   return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
+// 32 x 32 tiles through shared memory so that the transposed copies are written as coalesced rows too
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackDesc* __restrict__ table) {
+  __shared__ float tile[32][33];
   const PackDesc d = table[blockIdx.y];
-  const int total = d.rows * d.cols;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int r = i / d.cols, c = i - r * d.cols;
-    const float v = d.src[static_cast<int64_t>(r) * d.src_ld + c];
-    d.w[static_cast<int64_t>(r) * d.dst_ld + c] = v;
-    if (d.hi != nullptr) {
-      const float h = pk_round_tf32(v), l = pk_round_tf32(v - h);
-      d.hi[static_cast<int64_t>(r) * d.dst_ld + c] = h;
-      d.lo[static_cast<int64_t>(r) * d.dst_ld + c] = l;
-      if (d.hiT != nullptr) {
-        d.hiT[static_cast<int64_t>(c) * d.dstT_ld + r] = h;
-        d.loT[static_cast<int64_t>(c) * d.dstT_ld + r] = l;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tiles_c = (d.cols + 31) / 32, tiles_r = (d.rows + 31) / 32;
+  for (int t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
+    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + ty + 8 * k, c = c0 + tx;
+      float v = 0.f;
+      if (r < d.rows && c < d.cols) {
+        v = d.src[static_cast<int64_t>(r) * d.src_ld + c];
+        d.w[static_cast<int64_t>(r) * d.dst_ld + c] = v;
+        if (d.hi != nullptr) {
+          const float h = pk_round_tf32(v);
+          d.hi[static_cast<int64_t>(r) * d.dst_ld + c] = h;
+          d.lo[static_cast<int64_t>(r) * d.dst_ld + c] = pk_round_tf32(v - h);
+        }
+      }
+      tile[ty + 8 * k][tx] = v;
+    }
+    __syncthreads();
+    if (d.hiT != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, r = r0 + tx;      // transposed: row c of the output, column r
+        if (r < d.rows && c < d.cols) {
+          const float v = tile[tx][ty + 8 * k];
+          const float h = pk_round_tf32(v);
+          d.hiT[static_cast<int64_t>(c) * d.dstT_ld + r] = h;
+          d.loT[static_cast<int64_t>(c) * d.dstT_ld + r] = pk_round_tf32(v - h);
+        }
       }
     }
+    __syncthreads();
   }
 }
 __global__ void __launch_bounds__(256) unpack_grads_kernel(const PackDesc* __restrict__ table) {
@@ -311,8 +332,8 @@ __global__ void __launch_bounds__(256) unpack_grads_kernel(const PackDesc* __res
 extern "C" int ax2d_pack_weights(const void* table, int n_blocks, int max_block_elems, ax2d_stream_t stream) {
   using namespace ax2d;
   AX2D_CHECK_ARG(table != nullptr && n_blocks > 0 && max_block_elems > 0, "ax2d_pack_weights: bad arguments");
-  int gx = (max_block_elems + 255) / 256;
-  gx = gx > 64 ? 64 : gx;
+  int gx = (max_block_elems + 1023) / 1024;       // one CTA per 32 x 32 tile of the largest block (rough: ragged
+  gx = gx > 128 ? 128 : (gx < 1 ? 1 : gx);        // blocks loop)
   dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(n_blocks));
   pack_weights_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<const PackDesc*>(table));
   return launch_status("ax2d_pack_weights");

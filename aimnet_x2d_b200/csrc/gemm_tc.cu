@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int sw = (row >> 1) & 3;
-    int s = 0;
+    int s = 0, prev = -1;   // software pipeline: the TMEM stores of k-block i complete while k-block i + 1 is read and split
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
@@ -588,14 +588,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           split_tf32(v.z, h, o); hi[4 * c + 2] = __float_as_uint(h); lo[4 * c + 2] = __float_as_uint(o);
           split_tf32(v.w, h, o); hi[4 * c + 3] = __float_as_uint(h); lo[4 * c + 3] = __float_as_uint(o);
         }
+        if (prev >= 0) {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split_bar[prev]);
+        }
         const uint32_t slot = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g.a_base + s * 2 * TC_BK);
         tmem_st16(slot, hi);
         tmem_st16(slot + TC_BK, lo);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&split_bar[s]);
+        prev = s;
       }
+    }
+    if (prev >= 0) {
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split_bar[prev]);
     }
   } else {
     // ===================================================================== epilogue warps
