@@ -1119,14 +1119,30 @@ extern "C" int ax2d_gemm_tc_wgrad_supported(const ax2d_cmat* a, const ax2d_cmat*
   return 1;
 }
 
+// How many ways to cut the contraction: at least `by_chain` (accumulation chains of at most 1024 rows), and among the
+// candidates up to 4x that the one that minimises waves x (k-blocks per CTA + fixed cost): 6 tiles x 37 splits = 222
+// CTAs would run 1.5 waves on 148 SMs, 6 x 49 = 294 runs two full ones with 24 instead of 32 k-blocks each.
+static int wgrad_split(int64_t tiles, int64_t num_kb) {
+  const int64_t by_chain = (num_kb + WG_MAX_KB_PER_SPLIT - 1) / WG_MAX_KB_PER_SPLIT;
+  int64_t hi = by_chain * 4 > num_kb ? num_kb : by_chain * 4;
+  const int64_t fill = (kNumSMs + tiles - 1) / tiles;       // enough CTAs for one wave
+  if (hi < fill) hi = fill < num_kb ? fill : num_kb;
+  int64_t best = by_chain > num_kb ? num_kb : by_chain, best_cost = -1;
+  for (int64_t sp = best; sp <= hi; ++sp) {
+    const int64_t per = (num_kb + sp - 1) / sp;
+    const int64_t real = (num_kb + per - 1) / per;                 // no empty split
+    const int64_t waves = (tiles * real + kNumSMs - 1) / kNumSMs;
+    const int64_t cost = waves * (per + 5) * 64 + real;            // prologue + epilogue ~ 5 k-blocks; ties: fewer partials
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = real; }
+  }
+  return static_cast<int>(best);
+}
+
 extern "C" int64_t ax2d_gemm_tc_wgrad_workspace(int64_t M, int64_t N, int64_t K) {
   const int64_t n_tiles = (N + WG_MAX_BN - 1) / WG_MAX_BN;
   const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * n_tiles;
   const int64_t num_kb = (K + WG_KB - 1) / WG_KB;
-  int64_t split = (kNumSMs + tiles - 1) / tiles;
-  const int64_t by_chain = (num_kb + WG_MAX_KB_PER_SPLIT - 1) / WG_MAX_KB_PER_SPLIT;
-  split = split < by_chain ? by_chain : split;
-  split = split > num_kb ? num_kb : split;
+  const int64_t split = wgrad_split(tiles, num_kb);
   return split > 1 ? split * (M * N + M) * 4 : 0;       // partial tiles + partial bias-gradient vectors
 }
 
@@ -1172,10 +1188,7 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
   g.acc2 = WG_ACC2;
   const int m_tiles = static_cast<int>((M + TC_BM - 1) / TC_BM);
   g.num_kb = static_cast<int>((K + WG_KB - 1) / WG_KB);
-  int split = (kNumSMs + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
-  const int by_chain = (g.num_kb + WG_MAX_KB_PER_SPLIT - 1) / WG_MAX_KB_PER_SPLIT;
-  split = split < by_chain ? by_chain : split;
-  split = split > g.num_kb ? g.num_kb : split;
+  int split = wgrad_split(static_cast<int64_t>(m_tiles) * n_tiles, g.num_kb);
   g.kb_per_split = (g.num_kb + split - 1) / split;
   split = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;      // no empty split
   if (split > 1) {
