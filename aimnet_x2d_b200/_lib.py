@@ -63,6 +63,9 @@ _SIGNATURES = {
                               c_void_p, c_int64, c_void_p]),
     "ax2d_embed_fwd": (c_int, [C.POINTER(c_void_p), C.POINTER(c_void_p), c_int, c_int, c_int64, c_void_p, c_int64,
                                c_void_p]),
+    "ax2d_embed_bwd_all_workspace": (c_int64, [c_int64, c_int64, c_int]),
+    "ax2d_embed_bwd_all": (c_int, [c_void_p, c_int64, c_int, c_int, c_int64, C.POINTER(c_void_p), C.POINTER(c_int64),
+                                   C.POINTER(c_void_p), c_void_p, c_void_p]),
     "ax2d_embed_bwd_workspace": (c_int64, [c_int64, c_int]),
     "ax2d_embed_bwd": (c_int, [c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),

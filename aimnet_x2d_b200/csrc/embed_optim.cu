@@ -10,16 +10,73 @@ struct EmbedArgs {
   const int64_t* index[kMaxTables];
 };
 
+// block = (64 float4 columns, 4 rows); a CTA covers kEmbedRowsPerCta atoms (no 64-bit divisions per element)
+constexpr int kEmbedRowsPerCta = 32;
 __global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedArgs a, int n_tables, int E4, int64_t N,
                                                         float* __restrict__ out, int64_t ldo) {
-  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int per_row = n_tables * E4;
-  if (t >= N * per_row) return;
-  const int64_t n = t / per_row;
-  const int c = static_cast<int>(t % per_row);
-  const int tb = c / E4, k = c % E4;
-  const int64_t row = a.index[tb][n];
-  reinterpret_cast<float4*>(out + n * ldo)[c] = __ldg(reinterpret_cast<const float4*>(a.table[tb] + row * E4 * 4) + k);
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * kEmbedRowsPerCta;
+  for (int c = threadIdx.x; c < per_row; c += 64) {
+    const int tb = c / E4, k = c - tb * E4;
+    const int64_t* idx = a.index[tb];
+    const float4* tab = reinterpret_cast<const float4*>(a.table[tb]);
+#pragma unroll 4
+    for (int r = threadIdx.y; r < kEmbedRowsPerCta; r += 4) {
+      const int64_t n = n0 + r;
+      if (n < N) reinterpret_cast<float4*>(out + n * ldo)[c] = __ldg(tab + __ldg(idx + n) * E4 + k);
+    }
+  }
+}
+
+// Backward of all lookups in one pass: thread = gradient column (table t, component e), a CTA walks its slice of the
+// atoms in order and accumulates g[n, column] into a shared-memory copy of the (small) tables at row index[t][n]
+// -- the same thread owns a column for all atoms, so there are no conflicts and the order is the atom order.  Per-CTA
+// partial tables go to the workspace and are summed in CTA order by embed_bwd_all_final_kernel (deterministic).
+struct EmbedBwdArgs {
+  const int64_t* index[kMaxTables];
+  float* g_table[kMaxTables];
+  int row_off[kMaxTables + 1];     // first row of every table in the stacked [total_rows, E] layout
+};
+__global__ void __launch_bounds__(256) embed_bwd_all_kernel(EmbedBwdArgs a, const float* __restrict__ g, int64_t ldg, int n_tables,
+                                                            int E, int64_t N, int64_t rows_per_cta, float* __restrict__ ws) {
+  extern __shared__ float tab[];          // [total_rows][E]
+  const int total = a.row_off[n_tables] * E;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) tab[i] = 0.f;
+  __syncthreads();
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < N ? r0 + rows_per_cta : N;
+  for (int col = threadIdx.x; col < n_tables * E; col += blockDim.x) {
+    const int t = col / E, e = col - t * E;
+    const int64_t* idx = a.index[t];
+    float* base = tab + a.row_off[t] * E + e;
+    int64_t r = r0;
+    for (; r + 4 <= r1; r += 4) {         // loads first, then the (possibly same-address) updates in atom order
+      const int64_t i0 = __ldg(idx + r), i1 = __ldg(idx + r + 1), i2 = __ldg(idx + r + 2), i3 = __ldg(idx + r + 3);
+      const float g0 = __ldg(g + r * ldg + col), g1 = __ldg(g + (r + 1) * ldg + col);
+      const float g2 = __ldg(g + (r + 2) * ldg + col), g3 = __ldg(g + (r + 3) * ldg + col);
+      base[i0 * E] += g0;
+      base[i1 * E] += g1;
+      base[i2 * E] += g2;
+      base[i3 * E] += g3;
+    }
+    for (; r < r1; ++r) base[__ldg(idx + r) * E] += __ldg(g + r * ldg + col);
+  }
+  __syncthreads();
+  float* dst = ws + static_cast<int64_t>(blockIdx.x) * total;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = tab[i];
+}
+__global__ void __launch_bounds__(256) embed_bwd_all_final_kernel(EmbedBwdArgs a, const float* __restrict__ ws, int n_tables, int E,
+                                                                  int n_part) {
+  const int total = a.row_off[n_tables] * E;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float s = 0.f;
+#pragma unroll 8
+  for (int p = 0; p < n_part; ++p) s += __ldg(ws + static_cast<int64_t>(p) * total + i);
+  const int row = i / E;
+  int t = 0;
+  while (t + 1 < n_tables && row >= a.row_off[t + 1]) ++t;
+  a.g_table[t][i - a.row_off[t] * E] = s;
 }
 
 // Two-level fixed-order segment sum over atoms sorted (stably) by table row.
@@ -159,9 +216,12 @@ __global__ void __launch_bounds__(1024) weighted_loss_kernel(const float* __rest
   __shared__ float red[32];
   const float invB = 1.f / static_cast<float>(B);
   float s = 0.f;
-  for (int64_t i = threadIdx.x; i < B * T; i += blockDim.x) {
-    const float d = pred[i] - target[i];
-    const float w = weights[i % T];
+  // 32-bit index arithmetic (the host checks B * T < 2^31): a 64-bit modulo per element made this tiny kernel 20 us
+  const int total = static_cast<int>(B) * T;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const float d = __ldg(pred + i) - __ldg(target + i);
+    const float w = __ldg(weights + (i % T));
     if (kind == 0) {
       s += fabsf(d) * w;
       if (g_pred != nullptr) g_pred[i] = (d > 0.f ? w : (d < 0.f ? -w : 0.f)) * invB;
@@ -196,10 +256,54 @@ extern "C" int ax2d_embed_fwd(const float* const* tables, const int64_t* const* 
     a.table[t] = tables[t];
     a.index[t] = indices[t];
   }
-  const int64_t total = N * n_tables * (emb_dim / 4);
-  embed_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      a, n_tables, emb_dim / 4, N, out, ldo);
+  embed_fwd_kernel<<<static_cast<unsigned>((N + kEmbedRowsPerCta - 1) / kEmbedRowsPerCta), dim3(64, 4), 0,
+                     reinterpret_cast<cudaStream_t>(stream)>>>(a, n_tables, emb_dim / 4, N, out, ldo);
   return launch_status("ax2d_embed_fwd");
+}
+
+static int embed_bwd_all_ctas(int64_t N) {
+  const int64_t by_rows = (N + 63) / 64;               // at least 64 atoms per CTA
+  return static_cast<int>(by_rows < 2 * kNumSMs ? (by_rows < 1 ? 1 : by_rows) : 2 * kNumSMs);
+}
+extern "C" int64_t ax2d_embed_bwd_all_workspace(int64_t N, int64_t total_rows, int emb_dim) {
+  return static_cast<int64_t>(embed_bwd_all_ctas(N)) * total_rows * emb_dim * 4;
+}
+extern "C" int ax2d_embed_bwd_all(const float* g_out, int64_t ldg, int n_tables, int emb_dim, int64_t N,
+                                  const int64_t* const* indices, const int64_t* vocab, float* const* g_tables, void* workspace,
+                                  ax2d_stream_t stream) {
+  AX2D_CHECK_ARG(n_tables > 0 && n_tables <= kMaxTables && emb_dim > 0 && N >= 0, "ax2d_embed_bwd_all: bad arguments");
+  AX2D_CHECK_ARG(g_out != nullptr && workspace != nullptr, "ax2d_embed_bwd_all: null operand");
+  EmbedBwdArgs a;
+  int rows = 0;
+  for (int t = 0; t < n_tables; ++t) {
+    AX2D_CHECK_ARG(indices[t] != nullptr && g_tables[t] != nullptr && vocab[t] > 0, "ax2d_embed_bwd_all: null table operand");
+    a.index[t] = indices[t];
+    a.g_table[t] = g_tables[t];
+    a.row_off[t] = rows;
+    rows += static_cast<int>(vocab[t]);
+  }
+  a.row_off[n_tables] = rows;
+  const size_t smem = static_cast<size_t>(rows) * emb_dim * 4;
+  AX2D_CHECK_ARG(smem <= 200 * 1024, "ax2d_embed_bwd_all: tables of %d rows x %d do not fit shared memory (use ax2d_embed_bwd)",
+                 rows, emb_dim);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(embed_bwd_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      set_error("ax2d_embed_bwd_all: cannot raise the dynamic shared memory limit to %zu: %s", smem, cudaGetErrorString(e));
+      return AX2D_ERR_LAUNCH;
+    }
+    configured = smem;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int ctas = embed_bwd_all_ctas(N);
+  const int64_t rows_per_cta = (N + ctas - 1) / ctas;
+  embed_bwd_all_kernel<<<ctas, 256, smem, st>>>(a, g_out, ldg, n_tables, emb_dim, N, rows_per_cta, static_cast<float*>(workspace));
+  int rc = launch_status("ax2d_embed_bwd_all(partial)");
+  if (rc != AX2D_OK) return rc;
+  const int total = rows * emb_dim;
+  embed_bwd_all_final_kernel<<<(total + 255) / 256, 256, 0, st>>>(a, static_cast<const float*>(workspace), n_tables, emb_dim, ctas);
+  return launch_status("ax2d_embed_bwd_all(final)");
 }
 
 constexpr int kEmbedSplits = 64;
@@ -256,7 +360,7 @@ extern "C" int ax2d_clip_adam(float* p, const float* g, float* m, float* v, int6
 
 extern "C" int ax2d_weighted_loss(const float* pred, const float* target, const float* weights, int64_t B, int T,
                                   int kind, float* loss, float* g_pred, ax2d_stream_t stream) {
-  AX2D_CHECK_ARG(B > 0 && T > 0 && (kind == 0 || kind == 1), "ax2d_weighted_loss: bad arguments");
+  AX2D_CHECK_ARG(B > 0 && T > 0 && (kind == 0 || kind == 1) && B * T < (1ll << 31), "ax2d_weighted_loss: bad arguments");
   weighted_loss_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, target, weights, B, T, kind, loss,
                                                                                g_pred);
   return launch_status("ax2d_weighted_loss");

@@ -482,6 +482,7 @@ class EmbedProjFn(torch.autograd.Function):
              pre_segs=[(zs, Sp), (zo, Dp)], act=opts.act)
         ctx.opts = opts
         ctx.bias = b
+        ctx.indices = indices          # integer inputs: no gradient, kept for the one-pass table gradient
         _keep_packed(ctx, W)
         ctx.save_for_backward(W, e0, zs, zo, *tables)
         return xs, xo
@@ -500,17 +501,30 @@ class EmbedProjFn(torch.autograd.Function):
         dW, db = _param_grads(W, ctx.bias, gz, [(e0, nt * E)], N, Sp + Dp, nt * E, dev)
         de0 = torch.empty_like(e0)
         gemm(gz, [(W, nt * E)], [(de0, nt * E)], N, nt * E, Sp + Dp, trans_b=False)
-        g_tables = []
-        for ti, name in enumerate(opts.names):
-            order, ptr, vocab = opts.gi.embed[name]
-            if vocab != tables[ti].shape[0]:
-                raise RuntimeError(f"embedding index for '{name}' was built for vocab {vocab}, table has "
-                                   f"{tables[ti].shape[0]} rows")
-            gt = torch.empty_like(tables[ti])
-            ws = torch.empty(lib.ax2d_embed_bwd_workspace(vocab, E) // 4, dtype=torch.float32, device=dev)
-            _lib.check(lib.ax2d_embed_bwd(_p(de0), de0.stride(0), ti, E, vocab, _p(order), _p(ptr), _p(gt), _p(ws),
-                                          _stream()), "ax2d_embed_bwd")
-            g_tables.append(gt)
+        g_tables = [torch.empty_like(t) for t in tables]
+        rows = sum(t.shape[0] for t in tables)
+        if rows * E * 4 <= 200 * 1024 and all(t.is_contiguous() and t.shape[1] == E for t in tables):
+            # all tables in one pass through shared memory (fixed summation order)
+            for ti, name in enumerate(opts.names):
+                if name in opts.gi.embed and opts.gi.embed[name][2] != tables[ti].shape[0]:
+                    raise RuntimeError(f"embedding index for '{name}' was built for vocab {opts.gi.embed[name][2]}, table "
+                                       f"has {tables[ti].shape[0]} rows")
+            ws = torch.empty(max(lib.ax2d_embed_bwd_all_workspace(N, rows, E) // 4, 1), dtype=torch.float32, device=dev)
+            ip = (C.c_void_p * nt)(*[i.data_ptr() for i in ctx.indices])
+            gp = (C.c_void_p * nt)(*[t.data_ptr() for t in g_tables])
+            vp = (C.c_int64 * nt)(*[t.shape[0] for t in tables])
+            _lib.check(lib.ax2d_embed_bwd_all(_p(de0), de0.stride(0), nt, E, N, ip, vp, gp, _p(ws), _stream()),
+                       "ax2d_embed_bwd_all")
+        else:
+            for ti, name in enumerate(opts.names):
+                order, ptr, vocab = opts.gi.embed[name]
+                if vocab != tables[ti].shape[0]:
+                    raise RuntimeError(f"embedding index for '{name}' was built for vocab {vocab}, table has "
+                                       f"{tables[ti].shape[0]} rows")
+                gt = g_tables[ti]
+                ws = torch.empty(lib.ax2d_embed_bwd_workspace(vocab, E) // 4, dtype=torch.float32, device=dev)
+                _lib.check(lib.ax2d_embed_bwd(_p(de0), de0.stride(0), ti, E, vocab, _p(order), _p(ptr), _p(gt), _p(ws),
+                                              _stream()), "ax2d_embed_bwd")
         return (None, dW, db, *g_tables, *([None] * nt))
 
 

@@ -158,6 +158,13 @@ int ax2d_cistrans(const float* x, int64_t ldx, int64_t N, int width,
  * ---------------------------------------------------------------------------------------------- */
 int ax2d_embed_fwd(const float* const* tables, const int64_t* const* indices, int n_tables, int emb_dim,
                    int64_t N, float* out, int64_t ldo, ax2d_stream_t stream);
+/* Backward of ALL lookups in one pass (tables small enough for shared memory: sum(vocab) * emb_dim * 4 <= 200 KB):
+ * g_tables[t][v, :] = sum over atoms n with indices[t][n] == v of g_out[n, t * emb_dim : (t + 1) * emb_dim], summed in a
+ * fixed order (atom order inside a CTA's slice, CTA order across slices).  Replaces nn.Embedding's backward
+ * (models/gnn.py:262-274 under autograd). */
+int64_t ax2d_embed_bwd_all_workspace(int64_t N, int64_t total_rows, int emb_dim);
+int ax2d_embed_bwd_all(const float* g_out, int64_t ldg, int n_tables, int emb_dim, int64_t N, const int64_t* const* indices,
+                       const int64_t* vocab, float* const* g_tables, void* workspace, ax2d_stream_t stream);
 int64_t ax2d_embed_bwd_workspace(int64_t vocab, int emb_dim);
 int ax2d_embed_bwd(const float* g_out, int64_t ldg, int table, int emb_dim, int64_t vocab,
                    const int32_t* order, const int32_t* ptr, float* g_table, void* workspace,
