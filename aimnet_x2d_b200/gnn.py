@@ -18,8 +18,8 @@ import torch.nn as nn
 from . import ops
 from .activation import get_activation_function
 from .collate import GraphIndex
-from .layers import (FEATURE_PAD, INDEX_CACHE, MultiLayerPerceptron, ShellConvolutionLayer, _FusedLinear, pad1d,
-                     pad2d)
+from .layers import (FEATURE_PAD, INDEX_CACHE, DropClock, MultiLayerPerceptron, ShellConvolutionLayer, _FusedLinear,
+                     pad1d, pad2d, shared_tick)
 from .packed import PackAnchorFn, PackedWeights
 from .pooling import create_pooling_layer
 
@@ -80,6 +80,7 @@ class GNN(nn.Module):
         final_output_dim = output_dim * 4 if loss_function == "evidential" else output_dim      # gnn.py:136-141
         self.output_layer = _FusedLinear(ffn_hidden_dim * 2, final_output_dim)                  # gnn.py:143
         self.long_range_projection = nn.Linear(hidden_dim, ffn_hidden_dim)                      # dead parameter (Q6)
+        self._clock = DropClock()           # one dropout tick per forward pass for all layers (layers.shared_tick)
         self.use_packed_weights = True      # one pack kernel per forward instead of per-call torch pad / cat / split
         self._packed: Dict[tuple, PackedWeights] = {}
         self.init_weights()
@@ -151,6 +152,16 @@ class GNN(nn.Module):
                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
         """Reference ``gnn.py:197-260``.  ``graph_index`` (optional, from ``MolBatch``) carries the CSR / segment
         offsets emitted at collation; when absent it is rebuilt from the index tensors (and cached)."""
+        dropping = any(m.training and m.p > 0 for m in self.modules() if isinstance(m, nn.Dropout))
+        if not dropping:
+            return self._forward(atom_features, multi_hop_edge_indices, batch_indices, total_charges,
+                                 tetrahedral_indices, cis_indices, trans_indices, graph_index)
+        with shared_tick(self._clock):
+            return self._forward(atom_features, multi_hop_edge_indices, batch_indices, total_charges,
+                                 tetrahedral_indices, cis_indices, trans_indices, graph_index)
+
+    def _forward(self, atom_features, multi_hop_edge_indices, batch_indices, total_charges, tetrahedral_indices,
+                 cis_indices, trans_indices, graph_index=None):
         gi = graph_index
         if gi is None:
             gi = self._index_for(atom_features, multi_hop_edge_indices, batch_indices, total_charges,

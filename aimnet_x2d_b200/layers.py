@@ -75,7 +75,13 @@ INDEX_CACHE = _IndexCache()
 
 
 class DropClock(nn.Module):
-    """Device-side tick for the counter-based dropout of the GEMM epilogues (CUDA-graph friendly)."""
+    """Device-side tick for the counter-based dropout of the GEMM epilogues (CUDA-graph friendly).
+
+    Every dropout site has its own seed; the tick only has to change from one forward pass to the next.  Inside
+    ``GNN.forward`` all sites therefore share ONE tick per pass (``shared_tick``: one add + one snapshot instead of
+    one pair per layer and block); a stand-alone module advances its own."""
+
+    _shared = None          # snapshot of the enclosing model's tick for the running forward pass
 
     def __init__(self):
         super().__init__()
@@ -83,8 +89,27 @@ class DropClock(nn.Module):
         self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
 
     def advance(self) -> torch.Tensor:
+        if DropClock._shared is not None and DropClock._shared.device == self.tick.device:
+            return DropClock._shared
         self.tick.add_(1)
         return self.tick.clone()      # snapshot: backward must see the value of ITS forward
+
+
+class shared_tick:
+    """``with shared_tick(clock):`` -- the dropout sites below use one tick of ``clock`` for this forward pass."""
+
+    def __init__(self, clock: DropClock):
+        self.clock = clock
+
+    def __enter__(self):
+        self.prev = DropClock._shared
+        DropClock._shared = None
+        DropClock._shared = self.clock.advance()
+        return self
+
+    def __exit__(self, *exc):
+        DropClock._shared = self.prev
+        return False
 
 
 class ShellConvolutionLayer(nn.Module):
