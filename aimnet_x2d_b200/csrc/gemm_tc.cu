@@ -30,7 +30,8 @@
 namespace ax2d {
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 16;                        // fp32 per 64-byte swizzle row
+constexpr int TC_BK = 16;                        // fp32 per 64-byte swizzle row (k-block of the generic instance)
+constexpr int TC_BK_WIDE = 32;                   // fp32 per 128-byte swizzle row (instance for K segments % 32 == 0)
 constexpr int TC_SPLIT_WARPS = 4;                // warps 2..5
 constexpr int TC_EPI_WARPS = 12;                 // warps 6..17: three per TMEM lane quarter
 constexpr int TC_THREADS = 32 * (2 + TC_SPLIT_WARPS + TC_EPI_WARPS);   // warp 0 TMA, warp 1 MMA + TMEM
@@ -43,7 +44,6 @@ constexpr int TC_MAX_STAGES = 6;
                             // (it comes from the tensor core's truncating fp32 accumulation, see acc2), so the default
                             // spends 25 % fewer MMAs; -DAX2D_TC_TERMS=4 restores the fourth term.
 #endif
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;     // 8 KB
 
 struct TcMaps {
   CUtensorMap a[AX2D_MAX_SEG];
@@ -131,6 +131,45 @@ __device__ __forceinline__ void umma_kblock_ts_w(uint32_t t_main, uint32_t t_sma
       "r"(smem_u32(free_bar))
       : "memory");
 }
+// The same for 32-wide k-blocks: four k-steps (A advances 8 TMEM columns, B 32 bytes = 2 descriptor units per step).
+__device__ __forceinline__ void umma_kblock_ts32_w(uint32_t t_main, uint32_t t_small, uint32_t a_hi, uint32_t a_lo, uint64_t db_hi,
+                                                   uint64_t db_lo, uint32_t idesc, uint32_t acc_small_first, uint32_t acc_main_first,
+                                                   uint64_t* free_bar) {
+#if AX2D_TC_TERMS == 4
+#define AX2D_TS_STEP(AH, AL, BH, BL, PF, PM)                                              \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AL "], " BL ", %6, " PF ";\n\t"        \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AL "], " BH ", %6, pt;\n\t"            \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AH "], " BL ", %6, pt;\n\t"            \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [" AH "], " BH ", %6, " PM ";\n\t"
+#else
+#define AX2D_TS_STEP(AH, AL, BH, BL, PF, PM)                                              \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AL "], " BH ", %6, " PF ";\n\t"        \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [" AH "], " BL ", %6, pt;\n\t"            \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [" AH "], " BH ", %6, " PM ";\n\t"
+#endif
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, pf, pm, pt;\n\t"
+      ".reg .b32 ah1, al1, ah2, al2, ah3, al3;\n\t"
+      ".reg .b64 bh1, bl1, bh2, bl2, bh3, bl3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %7, 0;\n\t"
+      "setp.ne.b32 pm, %8, 0;\n\t"
+      "setp.eq.b32 pt, %6, %6;\n\t"
+      "add.u32 ah1, %2, 8;\n\t add.u32 al1, %3, 8;\n\t add.u64 bh1, %4, 2;\n\t add.u64 bl1, %5, 2;\n\t"
+      "add.u32 ah2, %2, 16;\n\t add.u32 al2, %3, 16;\n\t add.u64 bh2, %4, 4;\n\t add.u64 bl2, %5, 4;\n\t"
+      "add.u32 ah3, %2, 24;\n\t add.u32 al3, %3, 24;\n\t add.u64 bh3, %4, 6;\n\t add.u64 bl3, %5, 6;\n\t"
+      AX2D_TS_STEP("%2", "%3", "%4", "%5", "pf", "pm")
+      AX2D_TS_STEP("ah1", "al1", "bh1", "bl1", "pt", "pt")
+      AX2D_TS_STEP("ah2", "al2", "bh2", "bl2", "pt", "pt")
+      AX2D_TS_STEP("ah3", "al3", "bh3", "bl3", "pt", "pt")
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+      "}\n" ::"r"(t_main),
+      "r"(t_small), "r"(a_hi), "r"(a_lo), "l"(db_hi), "l"(db_lo), "r"(idesc), "r"(acc_small_first), "r"(acc_main_first),
+      "r"(smem_u32(free_bar))
+      : "memory");
+#undef AX2D_TS_STEP
+}
 // expect_tx + the three tensor-map loads of one k-block (A raw, B hi, B lo), one election
 __device__ __forceinline__ void tma_kblock_w(uint64_t* bar, uint32_t bytes, void* dst_a, const CUtensorMap* map_a, int ka, int m0,
                                              void* dst_bh, const CUtensorMap* map_bh, void* dst_bl, const CUtensorMap* map_bl,
@@ -186,6 +225,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+      "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+      "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -223,6 +273,16 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw64(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(512 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+// The same for the 128-byte swizzle (rows of 128 bytes, 8-row groups of 1024 bytes, layout type 2).
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = bn.
@@ -462,7 +522,11 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
 // TMEM columns (W = acc_stride >= BN, at most 192): [0, W) accumulator 0, [W, 2 W) accumulator 1 (small-term
 // accumulators at +96 when BN <= 96), [2 W, 512) the A ring: 32 columns (hi 16 | lo 16) per pipeline stage.
 constexpr int TC_MAX_BN = 192;
+template <int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcArgs g) {
+  static_assert(BK == 16 || BK == 32, "k-block = one 64-byte or one 128-byte swizzle row of fp32");
+  constexpr int TC_BK = BK;                         // shadows the namespace constant inside this kernel
+  constexpr uint32_t TC_A_BYTES = TC_BM * BK * 4;   // raw A tile of a stage: 8 or 16 KB
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], split_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
@@ -551,15 +615,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         t_wait += c1 - c0;
         const uint32_t a_hi = tmem_base + static_cast<uint32_t>(g.a_base + s * 2 * TC_BK);
         const uint32_t a_lo = a_hi + TC_BK;
-        const uint64_t db_hi = smem_desc_k_sw64(smem_u32(stage_bhi(s)));
-        const uint64_t db_lo = smem_desc_k_sw64(smem_u32(stage_blo(s)));
+        const uint64_t db_hi = BK == 16 ? smem_desc_k_sw64(smem_u32(stage_bhi(s))) : smem_desc_k_sw128(smem_u32(stage_bhi(s)));
+        const uint64_t db_lo = BK == 16 ? smem_desc_k_sw64(smem_u32(stage_blo(s))) : smem_desc_k_sw128(smem_u32(stage_blo(s)));
         // The tensor core's fp32 accumulation truncates, so every MMA into a large accumulator costs up to one ulp
         // of it.  When TMEM allows (acc2 != 0) the three small terms go to their own accumulator (2^-11 of the
         // magnitude, so their truncation is negligible) and only hi*hi touches the main one.  Per k-step the
         // descriptors advance by 32 bytes inside the swizzle row (B) and by 8 TMEM columns (A).
         const uint32_t acc_first = kb != 0 ? 1u : 0u;
-        umma_kblock_ts_w(t_main, t_small, a_hi, a_lo, db_hi, db_lo, idesc, acc_first, g.acc2 != 0 ? acc_first : 1u,
-                         &empty_bar[s]);      // the commit frees the stage once these MMAs have read it
+        if constexpr (BK == 16)
+          umma_kblock_ts_w(t_main, t_small, a_hi, a_lo, db_hi, db_lo, idesc, acc_first, g.acc2 != 0 ? acc_first : 1u,
+                           &empty_bar[s]);    // the commit frees the stage once these MMAs have read it
+        else
+          umma_kblock_ts32_w(t_main, t_small, a_hi, a_lo, db_hi, db_lo, idesc, acc_first, g.acc2 != 0 ? acc_first : 1u,
+                             &empty_bar[s]);
         t_issue += clock64() - c1;
       }
       umma_commit_w(&acc_full[buf]);       // accumulator of this tile complete
@@ -567,11 +635,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     if (cta_dbg != nullptr && lane == 0) { cta_dbg[3] = gtime(); cta_dbg[6] = t_issue; cta_dbg[7] = t_wait; cta_dbg[8] = t_acc; cta_dbg[13] = clock64() - t_loop0; }
   } else if (warp < 2 + TC_SPLIT_WARPS) {
     // ===================================================================== splitters: thread = row of the A tile
-    // raw row (64 bytes in the 64-byte-swizzled stage: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3), which
-    // also makes the 8 rows of a quarter-warp hit 8 different bank groups) -> (hi, lo) -> TMEM lane r, 16 columns each
+    // raw row (64 / 128 bytes in the swizzled stage: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3) for the
+    // 64-byte swizzle, c ^ (r & 7) for the 128-byte one, which also makes the 8 rows of a quarter-warp hit 8 different
+    // bank groups) -> (hi, lo) -> TMEM lane r, BK columns each
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int sw = (row >> 1) & 3;
+    const int sw = BK == 16 ? (row >> 1) & 3 : row & 7;
     int s = 0, prev = -1;   // software pipeline: the TMEM stores of k-block i complete while k-block i + 1 is read and split
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -595,8 +664,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           if (lane == 0) mbar_arrive(&split_bar[prev]);
         }
         const uint32_t slot = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g.a_base + s * 2 * TC_BK);
-        tmem_st16(slot, hi);
-        tmem_st16(slot + TC_BK, lo);
+        if constexpr (BK == 16) {
+          tmem_st16(slot, hi);
+          tmem_st16(slot + TC_BK, lo);
+        } else {
+          tmem_st32(slot, hi);
+          tmem_st32(slot + TC_BK, lo);
+        }
         prev = s;
       }
     }
@@ -1063,47 +1137,66 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
   AX2D_CHECK_ARG(m_tiles * n_tiles < (1ll << 30), "ax2d_gemm_tc: too many tiles");
   g.total_tiles = static_cast<int>(m_tiles * n_tiles);
   g.tmem_cols = 512;
-  g.acc2 = BN <= 96 ? 96 : 0;         // the small-term accumulator fits beside the main one only for narrow tiles
-  // TMEM layouts in use: accumulators at columns {0, 160} with the A ring at 320 (6 slots), or {0, 192} with the
-  // ring at 384 (4 slots).  (A ring starting at column 256 or 288 with six slots hung the kernel on B200 in testing --
-  // cause unknown -- so the accumulator stride is never 128.)
-  g.acc_stride = (BN > 96 && BN <= 160) ? 160 : 192;
+  // k-blocks of 32 fp32 (128-byte swizzle rows) when every A segment allows it, of 16 otherwise: every k-block costs
+  // the producer -> splitter -> MMA chain a fixed ~0.2 us on top of its MMAs, which dominated the [B, 512] head products
+  // (measured: 17.3 vs 19.9 us on [2048, 512] x [512, 512]).  Wide k-blocks halve the number of ring slots, which costs
+  // the big products more than the halved overhead gains (107 -> 130 us on 544 -> 512), so they are used for the
+  // narrow tiles of the small-M products only.
+  bool wide = K % TC_BK_WIDE == 0 && BN <= 64;
+  for (int s = 0; s < a->n_seg; ++s) wide = wide && a->width[s] % TC_BK_WIDE == 0;
+  const int BK = wide ? TC_BK_WIDE : TC_BK;
+  // TMEM layouts (accumulator stride, small-term accumulator offset, first column of the A ring; a slot of the ring
+  // is 2 BK columns).  Only layouts that were run on B200 are used: a ring of six 32-column slots starting at column
+  // 256 or 288 hung the kernel in testing (cause unknown; the same ring with <= 5 slots, or 8 slots under 64-wide
+  // tiles, or starting at 320, runs).
+  if (BN <= 64 && wide) {
+    g.acc_stride = 128; g.acc2 = 64; g.a_base = 256;       // 4 slots of 64
+  } else if (BN <= 96 && !wide) {
+    g.acc_stride = 192; g.acc2 = 96; g.a_base = 384;       // 4 slots of 32
+  } else if (BN <= 160) {
+    g.acc_stride = 160; g.acc2 = 0; g.a_base = 320;        // 6 slots of 32 / 3 slots of 64
+  } else {
+    g.acc_stride = 192; g.acc2 = 0; g.a_base = 384;        // 4 slots of 32 / 2 slots of 64
+  }
   int acc = 0, kb = 0;
   g.n_seg = a->n_seg;
+  const CUtensorMapSwizzle swz = wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   for (int s = 0; s < a->n_seg; ++s) {
     g.seg_kb_start[s] = kb;
-    if ((rc = make_map(&maps.a[s], a->ptr[s], a->width[s], M, a->ld[s], TC_BM)) != AX2D_OK) return rc;
-    kb += a->width[s] / TC_BK;
+    if ((rc = make_map(&maps.a[s], a->ptr[s], a->width[s], M, a->ld[s], TC_BM, BK, swz)) != AX2D_OK) return rc;
+    kb += a->width[s] / BK;
     acc += a->width[s];
   }
   for (int s = a->n_seg; s <= AX2D_MAX_SEG; ++s) g.seg_kb_start[s] = kb;
   AX2D_CHECK_ARG(acc == K, "ax2d_gemm_tc: A segments cover %d columns, expected %lld", acc, (long long)K);
   g.num_kb = kb;
-  if ((rc = make_map(&maps.b_hi, b_hi, K, N, ldb, BN)) != AX2D_OK) return rc;
-  if ((rc = make_map(&maps.b_lo, b_lo, K, N, ldb, BN)) != AX2D_OK) return rc;
-  const size_t stage_bytes = static_cast<size_t>(TC_A_BYTES) + 2 * static_cast<size_t>(BN) * TC_BK * 4;
+  if ((rc = make_map(&maps.b_hi, b_hi, K, N, ldb, BN, BK, swz)) != AX2D_OK) return rc;
+  if ((rc = make_map(&maps.b_lo, b_lo, K, N, ldb, BN, BK, swz)) != AX2D_OK) return rc;
+  const size_t stage_bytes = static_cast<size_t>(TC_BM + 2 * BN) * BK * 4;
   // one CTA per SM: the stage ring takes what the 227 KB leave after the epilogue's transpose buffers
   const size_t stg_bytes = static_cast<size_t>(TC_EPI_WARPS) * 32 * 32 * 4;
   const size_t budget = 227 * 1024 - 1024 - stg_bytes - 512;         // alignment slack, static barriers
   int stages = static_cast<int>(budget / stage_bytes);
-  g.a_base = 2 * g.acc_stride;
-  const int a_slots = (512 - g.a_base) / (2 * TC_BK);                 // TMEM A ring: one slot per stage
+  const int a_slots = (512 - g.a_base) / (2 * BK);                    // TMEM A ring: one slot per stage
   stages = stages > a_slots ? a_slots : stages;
+  stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages;
   if (stages < 1) stages = 1;
   g.stages = stages;
   size_t smem = stages * stage_bytes + stg_bytes + 1024;
   if (smem < 120 * 1024) smem = 120 * 1024;    // never two CTAs on an SM: each allocates all 512 TMEM columns
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[wide]) {
+    cudaError_t e = wide ? cudaFuncSetAttribute(gemm_tc_kernel<TC_BK_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                         : cudaFuncSetAttribute(gemm_tc_kernel<TC_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
       set_error("ax2d_gemm_tc: cannot raise the dynamic shared memory limit to %zu: %s", smem, cudaGetErrorString(e));
       return AX2D_ERR_LAUNCH;
     }
-    configured = smem;
+    configured[wide] = smem;
   }
   dim3 grid(static_cast<unsigned>(g.total_tiles < kNumSMs ? g.total_tiles : kNumSMs));
-  gemm_tc_kernel<<<grid, TC_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, g);
+  if (wide) gemm_tc_kernel<TC_BK_WIDE><<<grid, TC_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, g);
+  else gemm_tc_kernel<TC_BK><<<grid, TC_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, g);
   return launch_status("ax2d_gemm_tc");
 }
 
