@@ -67,6 +67,14 @@ struct TcArgs {
 };
 
 // ---------------------------------------------------------------------------------------------- PTX
+// cycle counter of the development stamps (tools/tc_phases.py); compiled out unless built with -DAX2D_TC_PROFILE
+__device__ __forceinline__ long long tc_clock() {
+#ifdef AX2D_TC_PROFILE
+  return clock64();
+#else
+  return 0;
+#endif
+}
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -553,7 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     cta_dbg[0] = gtime();
     cta_dbg[2] = smid;
-    cta_dbg[11] = clock64();
+    cta_dbg[11] = tc_clock();
   }
 
   if (threadIdx.x == 0) {
@@ -596,22 +604,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     int s = 0, j = 0;
     uint32_t ph = 0;
     long long t_issue = 0, t_wait = 0, t_acc = 0;
-    const long long t_loop0 = clock64();
+    const long long t_loop0 = tc_clock();
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++j) {
       const int buf = j & 1;
-      const long long ca = clock64();
+      const long long ca = tc_clock();
       mbar_wait(&acc_empty[buf], (static_cast<uint32_t>(j >> 1) & 1u) ^ 1u);   // epilogue of tile j - 2 has drained it
       tc_fence_after();
-      t_acc += clock64() - ca;
+      t_acc += tc_clock() - ca;
       const uint32_t t_main = tmem_base + static_cast<uint32_t>(buf * g.acc_stride);
       const uint32_t t_small = t_main + static_cast<uint32_t>(g.acc2);
       for (int kb = 0; kb < num_kb; ++kb, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
-        const long long c0 = clock64();
+        const long long c0 = tc_clock();
         mbar_wait(&full_bar[s], ph);     // B_hi / B_lo have landed
         mbar_wait(&split_bar[s], ph);    // (a_hi, a_lo) are in TMEM
         tc_fence_after();
         __syncwarp();
-        const long long c1 = clock64();
+        const long long c1 = tc_clock();
         t_wait += c1 - c0;
         const uint32_t a_hi = tmem_base + static_cast<uint32_t>(g.a_base + s * 2 * TC_BK);
         const uint32_t a_lo = a_hi + TC_BK;
@@ -628,11 +636,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         else
           umma_kblock_ts32_w(t_main, t_small, a_hi, a_lo, db_hi, db_lo, idesc, acc_first, g.acc2 != 0 ? acc_first : 1u,
                              &empty_bar[s]);
-        t_issue += clock64() - c1;
+        t_issue += tc_clock() - c1;
       }
       umma_commit_w(&acc_full[buf]);       // accumulator of this tile complete
     }
-    if (cta_dbg != nullptr && lane == 0) { cta_dbg[3] = gtime(); cta_dbg[6] = t_issue; cta_dbg[7] = t_wait; cta_dbg[8] = t_acc; cta_dbg[13] = clock64() - t_loop0; }
+    if (cta_dbg != nullptr && lane == 0) { cta_dbg[3] = gtime(); cta_dbg[6] = t_issue; cta_dbg[7] = t_wait; cta_dbg[8] = t_acc; cta_dbg[13] = tc_clock() - t_loop0; }
   } else if (warp < 2 + TC_SPLIT_WARPS) {
     // ===================================================================== splitters: thread = row of the A tile
     // raw row (64 / 128 bytes in the swizzled stage: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3) for the
@@ -698,23 +706,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         // operand) into L2, so that its loads do not each pay an HBM round trip with only two warps per scheduler
         const int n1 = n0 + BN < static_cast<int>(g.e.N) ? n0 + BN : static_cast<int>(g.e.N);
         const TileEpi te = tile_epi(g.e, m0, n0, n1, nullptr);
-        if (te.ok) {
-          const int lines = ((n1 - n0) * 4 + 127) / 128;            // 128-byte lines per row of the tile
+        if (te.ok && (te.nres > 0 || te.has_dp)) {
+          const int lines = ((n1 - n0) * 4 + 127) / 128;            // 128-byte lines per row of the tile (<= 6)
           const int et = threadIdx.x - 32 * (2 + TC_SPLIT_WARPS);
-          for (int i = et; i < TC_BM * lines; i += 32 * TC_EPI_WARPS) {
-            const int64_t row = m0 + i / lines;
-            const int col = n0 + (i % lines) * 32;
-            if (te.nres > 0) prefetch_l2(te.res0 + row * te.ldres0 + col);
-            if (te.nres > 1) prefetch_l2(te.res1 + row * te.ldres1 + col);
-            if (te.nres > 2) prefetch_l2(te.res2 + row * te.ldres2 + col);
-            if (te.has_dp) prefetch_l2(te.dp + row * te.lddp + col);
+          const int l = et & 7;                                      // 8 lanes per row, one line each: no divisions
+          if (l < lines) {
+            const int col = n0 + l * 32;
+            for (int r = et >> 3; r < TC_BM; r += 4 * TC_EPI_WARPS) {
+              const int64_t row = m0 + r;
+              if (te.nres > 0) prefetch_l2(te.res0 + row * te.ldres0 + col);
+              if (te.nres > 1) prefetch_l2(te.res1 + row * te.ldres1 + col);
+              if (te.nres > 2) prefetch_l2(te.res2 + row * te.ldres2 + col);
+              if (te.has_dp) prefetch_l2(te.dp + row * te.lddp + col);
+            }
           }
         }
       }
-      const long long ce0 = clock64();
+      const long long ce0 = tc_clock();
       mbar_wait(&acc_full[buf], static_cast<uint32_t>(j >> 1) & 1u);
       tc_fence_after();
-      const long long ce1 = clock64();
+      const long long ce1 = tc_clock();
       e_wait += ce1 - ce0;
       if (cta_dbg != nullptr && j == 0 && ew == 0 && lane == 0) cta_dbg[4] = gtime();
       AX2D_EPI_DISPATCH(g.e.act, g.e.dact, dropping, {
@@ -726,13 +737,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      e_work += clock64() - ce1;
+      e_work += tc_clock() - ce1;
     }
     if (cta_dbg != nullptr && ew == 0 && lane == 0) { cta_dbg[5] = gtime(); cta_dbg[9] = e_wait; cta_dbg[10] = e_work; }
   }
   tc_fence_before();
   __syncthreads();
-  if (cta_dbg != nullptr && threadIdx.x == 0) { cta_dbg[1] = gtime(); cta_dbg[12] = clock64(); }
+  if (cta_dbg != nullptr && threadIdx.x == 0) { cta_dbg[1] = gtime(); cta_dbg[12] = tc_clock(); }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);

@@ -1,4 +1,5 @@
-"""Development aid: phase timestamps (globaltimer, ns) of CTA (0,0) of the tensor-core projection kernel."""
+"""Development aid: per-CTA phase timestamps (globaltimer) and cycle accounting of the tensor-core projection kernel.
+The cycle counters need a profile build: AX2D_NVCC_EXTRA=-DAX2D_TC_PROFILE python aimnet_x2d_b200/build.py"""
 import ctypes as C
 import os
 import sys
