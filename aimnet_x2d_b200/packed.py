@@ -50,6 +50,8 @@ class PackedWeights:
 
     def __init__(self, device):
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:       # "cuda" -> the current device, as tensors report it
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.mats: Dict[str, _Matrix] = {}
         self.tensors: Dict[str, torch.Tensor] = {}
         self._table = None

@@ -1,0 +1,120 @@
+"""GPU: the small C-ABI kernels around the projections, each against a float64 torch restatement of what it replaces:
+one-pass embedding backward (nn.Embedding autograd, gnn.py:262-274), weight packing / gradient collection
+(packed.PackedWeights) and the weighted loss (losses.py:14-87)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _lib():
+    from aimnet_x2d_b200 import _lib
+    return _lib
+
+
+@pytest.mark.parametrize("N,E,vocabs", [(5000, 64, (119, 9, 7, 7)), (37, 16, (5, 3)), (1, 4, (2,)), (70001, 32, (300, 2, 11))])
+def test_embed_bwd_all_matches_index_add(N, E, vocabs):
+    L = _lib()
+    lib = L.load()
+    rng = np.random.Generator(np.random.PCG64(N + E))
+    nt = len(vocabs)
+    # skewed indices (a few hot rows, like atom types), every table row possible
+    idx = [torch.from_numpy(np.minimum(rng.geometric(0.3, size=N) - 1, v - 1).astype(np.int64)).to(DEV) for v in vocabs]
+    g = torch.from_numpy(rng.normal(size=(N, nt * E)).astype(np.float32)).to(DEV)
+    outs = [torch.full((v, E), float("nan"), device=DEV) for v in vocabs]
+    rows = sum(vocabs)
+    ws = torch.empty(max(lib.ax2d_embed_bwd_all_workspace(N, rows, E) // 4, 1), dtype=torch.float32, device=DEV)
+    ip = (C.c_void_p * nt)(*[i.data_ptr() for i in idx])
+    gp = (C.c_void_p * nt)(*[o.data_ptr() for o in outs])
+    vp = (C.c_int64 * nt)(*vocabs)
+    L.check(lib.ax2d_embed_bwd_all(C.c_void_p(g.data_ptr()), g.stride(0), nt, E, N, ip, vp, gp, C.c_void_p(ws.data_ptr()),
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ax2d_embed_bwd_all")
+    torch.cuda.synchronize()
+    for t, v in enumerate(vocabs):
+        ref = torch.zeros((v, E), dtype=torch.float64, device=DEV).index_add_(0, idx[t], g[:, t * E:(t + 1) * E].double())
+        scale = float(ref.abs().max()) + 1e-30
+        assert float((outs[t].double() - ref).abs().max()) <= 1e-5 * scale, f"table {t}"
+        assert torch.all(outs[t][ref.abs().sum(1) == 0] == 0)          # untouched rows are exact zeros
+
+
+def test_embed_bwd_all_is_deterministic():
+    L = _lib()
+    lib = L.load()
+    N, E, vocabs = 20000, 64, (119, 9)
+    rng = np.random.Generator(np.random.PCG64(3))
+    idx = [torch.from_numpy(rng.integers(0, v, size=N).astype(np.int64)).to(DEV) for v in vocabs]
+    g = torch.from_numpy(rng.normal(size=(N, 2 * E)).astype(np.float32)).to(DEV)
+    res = []
+    for _ in range(2):
+        outs = [torch.empty((v, E), device=DEV) for v in vocabs]
+        ws = torch.empty(lib.ax2d_embed_bwd_all_workspace(N, sum(vocabs), E) // 4, dtype=torch.float32, device=DEV)
+        L.check(lib.ax2d_embed_bwd_all(C.c_void_p(g.data_ptr()), g.stride(0), 2, E, N,
+                                       (C.c_void_p * 2)(*[i.data_ptr() for i in idx]), (C.c_int64 * 2)(*vocabs),
+                                       (C.c_void_p * 2)(*[o.data_ptr() for o in outs]), C.c_void_p(ws.data_ptr()),
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ax2d_embed_bwd_all")
+        res.append([o.cpu().numpy() for o in outs])
+    assert all(np.array_equal(a, b) for a, b in zip(*res))
+
+
+def test_pack_weights_and_unpack_grads():
+    """Blocks of two parameters into one padded matrix: packed fp32 copy, TF32 terms (hi + lo == w up to 2^-22, hi has
+    13 zero mantissa bits), transposed terms, zero padding untouched; gradients scattered back additively."""
+    from aimnet_x2d_b200.packed import PackedWeights
+    torch.manual_seed(0)
+    a = torch.nn.Parameter(torch.randn(37, 50, device=DEV))
+    b = torch.nn.Parameter(torch.randn(21, device=DEV))
+    pk = PackedWeights(DEV)
+    pk.add("W", 64, 96, [(a, 0, 37, 0, 20, 0, 0), (a, 5, 37, 20, 50, 0, 32)])     # two column chunks, padded apart
+    pk.add("b", 1, 32, [(b, 0, 1, 0, 21, 0, 0)], vector=True)
+    pk.finalize()
+    pk.refresh()
+    W, info = pk["W"], pk["W"]._ax2d
+    want = torch.zeros(64, 96, device=DEV)
+    want[:37, :20] = a.data[:, :20]
+    want[:32, 32:62] = a.data[5:37, 20:50]
+    assert torch.equal(W, want)
+    assert torch.equal(pk["b"][:21], b.data) and torch.all(pk["b"][21:] == 0)
+    assert torch.all((info.hi.view(torch.int32) & 0x1FFF) == 0) and torch.all((info.lo.view(torch.int32) & 0x1FFF) == 0)
+    assert float((info.hi.double() + info.lo.double() - W.double()).abs().max()) <= 2.0 ** -22 * float(W.abs().max())
+    assert torch.equal(info.hiT, info.hi.t()) and torch.equal(info.loT, info.lo.t())
+    # gradients: written into the packed buffers by the kernels, collected additively into .grad
+    a.grad = torch.ones_like(a)
+    info.grad.copy_(torch.arange(64 * 96, device=DEV, dtype=torch.float32).view(64, 96))
+    pk["b"]._ax2d.grad.fill_(2.0)
+    pk.dirty = True
+    pk.unpack_grads()
+    ga = torch.ones(37, 50, device=DEV)
+    full = torch.arange(64 * 96, device=DEV, dtype=torch.float32).view(64, 96)
+    ga[:, :20] += full[:37, :20]
+    ga[5:37, 20:50] += full[:32, 32:62]
+    assert torch.equal(a.grad, ga)
+    assert torch.equal(b.grad, torch.full((21,), 2.0, device=DEV))
+    assert not pk.dirty and torch.all(info.grad == 0)              # cleared for the next step
+    # a parameter update shows up after the next refresh
+    with torch.no_grad():
+        a.mul_(0.5)
+    pk.refresh()
+    assert torch.equal(pk["W"][:37, :20], a.data[:, :20])
+
+
+@pytest.mark.parametrize("kind", ["l1", "mse"])
+@pytest.mark.parametrize("B,T", [(2112, 12), (7, 1), (1, 3)])
+def test_weighted_loss_kernel(kind, B, T):
+    import aimnet_x2d_b200 as ax
+    rng = np.random.Generator(np.random.PCG64(B * 31 + T))
+    pred = torch.from_numpy(rng.normal(size=(B, T)).astype(np.float32)).to(DEV).requires_grad_(True)
+    tgt = torch.from_numpy(rng.normal(size=(B, T)).astype(np.float32)).to(DEV)
+    w = torch.from_numpy(rng.uniform(0.5, 2.0, size=T).astype(np.float32))
+    crit = (ax.WeightedL1Loss if kind == "l1" else ax.WeightedMSELoss)(w).to(DEV)
+    loss = crit(pred, tgt)
+    loss.backward()
+    p64 = pred.detach().double().requires_grad_(True)
+    d = p64 - tgt.double()
+    ref = ((d.abs() if kind == "l1" else d * d) * w.double().to(DEV)).sum(1).mean()      # losses.py:36-43, 71-78
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
+    assert float((pred.grad.double() - p64.grad).abs().max()) <= 1e-5 * float(p64.grad.abs().max())
