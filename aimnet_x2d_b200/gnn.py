@@ -143,6 +143,8 @@ class GNN(nn.Module):
         if F4 == self.post_pooling_projection.out_features:      # the segments of the output layer are unpadded
             self.skip_transform.declare_packed(pk, "skip", [F4], [F4])
             self.output_layer.declare_packed(pk, "out", [F4, F4], [F4, F4])
+        if hasattr(self.pooling, "declare_packed"):
+            self.pooling.declare_packed(pk, "pool")
         pk.finalize()
         return pk
 
@@ -205,7 +207,10 @@ class GNN(nn.Module):
             partial_charges = x[:, 0].clone()
 
         atom_emb = self.concat_self_other(([x_self, x], [S, D]), packed=use("cso"))                # gnn.py:245-246
-        x_pooled, attention_weights = self.pooling(atom_emb, batch_indices, graph_index=gi)        # gnn.py:249
+        if pk is not None and "pool.W" in pk:
+            x_pooled, attention_weights = self.pooling(atom_emb, batch_indices, graph_index=gi, packed=(pk, "pool"))
+        else:
+            x_pooled, attention_weights = self.pooling(atom_emb, batch_indices, graph_index=gi)    # gnn.py:249
         v = self.post_pooling_projection(x_pooled, packed=use("ppp"))                              # gnn.py:252
         v = self.ffn(v, packed=use("ffn"))                                                         # gnn.py:253
         skip = self.skip_transform(v, packed=use("skip"))                                          # gnn.py:256

@@ -545,6 +545,7 @@ class AttnPoolFn(torch.autograd.Function):
         _lib.check(lib.ax2d_attn_pool_fwd(_p(x), F, _p(gi.seg_ptr), B, N, F, heads, _p(w), _p(b), _p(temperature),
                                           _p(pooled), _p(attn), _p(z), gi.max_seg, _stream()), "ax2d_attn_pool_fwd")
         ctx.gi = gi
+        ctx.packed_wb = (w, b) if packed_info(w) is not None else None
         ctx.save_for_backward(x, w, temperature, attn, z)
         return pooled, attn
 
@@ -557,8 +558,13 @@ class AttnPoolFn(torch.autograd.Function):
         heads, B = w.shape[0], gi.num_graphs
         dev = x.device
         gx = torch.empty_like(x)
-        gw = torch.empty_like(w)
-        gb = torch.empty(heads, dtype=torch.float32, device=dev)
+        iw = ib = None
+        if ctx.packed_wb is not None:      # gradients go to the packed buffers (collected into .grad by one kernel)
+            iw, ib = packed_info(ctx.packed_wb[0]), packed_info(ctx.packed_wb[1])
+            if iw.written or ib is None:
+                iw = ib = None             # (a pooling layer applied twice in one backward: ordinary autograd path)
+        gw = torch.empty_like(w) if iw is None else iw.grad
+        gb = torch.empty(heads, dtype=torch.float32, device=dev) if ib is None else ib.grad
         gT = torch.empty((), dtype=torch.float32, device=dev)
         ws = torch.empty(lib.ax2d_attn_pool_bwd_workspace(B, F, heads) // 4, dtype=torch.float32, device=dev)
         if g_pooled is None:
@@ -567,6 +573,10 @@ class AttnPoolFn(torch.autograd.Function):
         _lib.check(lib.ax2d_attn_pool_bwd(_p(x), F, _p(gi.seg_ptr), B, N, F, heads, _p(w), _p(temperature), _p(attn),
                                           _p(z), _p(g_pooled.contiguous()), _p(g_attn), _p(gx), F, _p(gw), _p(gb),
                                           _p(gT), _p(ws), gi.max_seg, _stream()), "ax2d_attn_pool_bwd")
+        if iw is not None:
+            iw.written = True
+            iw.owner.dirty = True
+            return gx, None, None, gT, None
         return gx, gw, gb, gT, None
 
 

@@ -77,15 +77,25 @@ class MultiHeadAttentionPoolingLayer(nn.Module):
             self.register_buffer("temperature", torch.tensor(initial_temperature))
         self.dropout = nn.Dropout(dropout_prob)
 
+    def declare_packed(self, pk, prefix: str) -> None:
+        """The stacked head weights [heads, F] / biases [heads] in a ``packed.PackedWeights`` (one gather per forward
+        and one gradient collection per backward instead of cat + per-parameter gradient accumulation)."""
+        F_ = self.attention_weights[0].in_features
+        heads = len(self.attention_weights)
+        pk.add(f"{prefix}.W", heads, ops.pad_to(F_, 4), [(l.weight, 0, 1, 0, F_, h, 0) for h, l in enumerate(self.attention_weights)])
+        pk.add(f"{prefix}.b", 1, heads, [(l.bias, 0, 1, 0, 1, 0, h) for h, l in enumerate(self.attention_weights)], vector=True)
+
     def forward(self, x: torch.Tensor, batch_indices: Optional[torch.Tensor],
-                graph_index: Optional[GraphIndex] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                graph_index: Optional[GraphIndex] = None, packed=None) -> Tuple[torch.Tensor, torch.Tensor]:
         gi = _segments_for(x, batch_indices, graph_index)
         F_ = x.shape[1]
         Fp = ops.pad_to(F_, 4)
-        w = torch.cat([l.weight for l in self.attention_weights], dim=0)          # [heads, F]
-        b = torch.cat([l.bias for l in self.attention_weights], dim=0)            # [heads]
-        pooled, attn = ops.AttnPoolFn.apply(pad_cols(x, Fp).contiguous(), pad_cols(w, Fp).contiguous(), b,
-                                            self.temperature, gi)
+        if packed is not None:
+            w, b = packed[0][f"{packed[1]}.W"], packed[0][f"{packed[1]}.b"]
+        else:
+            w = pad_cols(torch.cat([l.weight for l in self.attention_weights], dim=0), Fp).contiguous()   # [heads, F]
+            b = torch.cat([l.bias for l in self.attention_weights], dim=0)                               # [heads]
+        pooled, attn = ops.AttnPoolFn.apply(pad_cols(x, Fp).contiguous(), w, b, self.temperature, gi)
         if Fp != F_:
             pooled = pooled[:, :F_]
         if self.dropout.p > 0:                                                    # pooling.py:169-170
