@@ -65,14 +65,21 @@ __global__ void __launch_bounds__(256) embed_bwd_all_kernel(EmbedBwdArgs a, cons
   float* dst = ws + static_cast<int64_t>(blockIdx.x) * total;
   for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = tab[i];
 }
+// eight lanes per output element: lane z sums the partials z, z + 8, ..., a shuffle tree combines them (fixed order)
 __global__ void __launch_bounds__(256) embed_bwd_all_final_kernel(EmbedBwdArgs a, const float* __restrict__ ws, int n_tables, int E,
                                                                   int n_part) {
   const int total = a.row_off[n_tables] * E;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int z0 = threadIdx.x & 7;
   float s = 0.f;
-#pragma unroll 8
-  for (int p = 0; p < n_part; ++p) s += __ldg(ws + static_cast<int64_t>(p) * total + i);
+  if (i < total) {
+#pragma unroll 4
+    for (int p = z0; p < n_part; p += 8) s += __ldg(ws + static_cast<int64_t>(p) * total + i);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (i >= total || z0 != 0) return;
   const int row = i / E;
   int t = 0;
   while (t + 1 < n_tables && row >= a.row_off[t + 1]) ++t;
@@ -218,10 +225,12 @@ __global__ void __launch_bounds__(1024) weighted_loss_kernel(const float* __rest
   float s = 0.f;
   // 32-bit index arithmetic (the host checks B * T < 2^31): a 64-bit modulo per element made this tiny kernel 20 us
   const int total = static_cast<int>(B) * T;
+  int col = threadIdx.x % T;                       // weight index of element i, advanced without a modulo per element
+  const int step = blockDim.x % T;
 #pragma unroll 4
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+  for (int i = threadIdx.x; i < total; i += blockDim.x, col = col + step >= T ? col + step - T : col + step) {
     const float d = __ldg(pred + i) - __ldg(target + i);
-    const float w = __ldg(weights + (i % T));
+    const float w = __ldg(weights + col);
     if (kind == 0) {
       s += fabsf(d) * w;
       if (g_pred != nullptr) g_pred[i] = (d > 0.f ? w : (d < 0.f ? -w : 0.f)) * invB;
@@ -263,7 +272,7 @@ extern "C" int ax2d_embed_fwd(const float* const* tables, const int64_t* const* 
 
 static int embed_bwd_all_ctas(int64_t N) {
   const int64_t by_rows = (N + 63) / 64;               // at least 64 atoms per CTA
-  return static_cast<int>(by_rows < 2 * kNumSMs ? (by_rows < 1 ? 1 : by_rows) : 2 * kNumSMs);
+  return static_cast<int>(by_rows < kNumSMs ? (by_rows < 1 ? 1 : by_rows) : kNumSMs);
 }
 extern "C" int64_t ax2d_embed_bwd_all_workspace(int64_t N, int64_t total_rows, int emb_dim) {
   return static_cast<int64_t>(embed_bwd_all_ctas(N)) * total_rows * emb_dim * 4;
@@ -302,7 +311,8 @@ extern "C" int ax2d_embed_bwd_all(const float* g_out, int64_t ldg, int n_tables,
   int rc = launch_status("ax2d_embed_bwd_all(partial)");
   if (rc != AX2D_OK) return rc;
   const int total = rows * emb_dim;
-  embed_bwd_all_final_kernel<<<(total + 255) / 256, 256, 0, st>>>(a, static_cast<const float*>(workspace), n_tables, emb_dim, ctas);
+  embed_bwd_all_final_kernel<<<(8 * total + 255) / 256, 256, 0, st>>>(a, static_cast<const float*>(workspace), n_tables, emb_dim,
+                                                                      ctas);
   return launch_status("ax2d_embed_bwd_all(final)");
 }
 
