@@ -382,14 +382,17 @@ extern "C" int ax2d_weighted_loss(const float* pred, const float* target, const 
 // destination and is never written), split into the two TF32 terms of the tensor-core path (plain and transposed:
 // forward / data-gradient operands), and -- the other way round -- the packed weight gradients are accumulated
 // into the parameters' .grad storage.
-struct PackDesc {           // one rectangular block; 88 bytes (packed.py mirrors the layout)
+struct PackDesc {           // one rectangular block; 112 bytes (packed.py mirrors the layout)
   const float* src;         // parameter block [rows, cols], leading dimension src_ld
   float* grad_dst;          // same block inside the parameter's .grad (may be null: frozen parameter)
   float* w;                 // packed fp32 copy              [.., dst_ld]
   float* hi; float* lo;     // TF32 split of it (may be null: bias vectors)
   float* hiT; float* loT;   // transposed split              [.., dstT_ld] (may be null)
   const float* g;           // packed gradient block          [.., dst_ld]
-  int32_t rows, cols, src_ld, dst_ld, dstT_ld, pad;
+  const float* part;        // split-K partials of the whole packed matrix [split][p_rows][p_cols] left behind by the
+                            // weight-gradient kernel (null / split == 0: none); summed here in split order
+  int32_t rows, cols, src_ld, dst_ld, dstT_ld;
+  int32_t split, p_rows, p_cols, dr, dc;   // (dr, dc): position of this block inside the packed matrix
 };
 __device__ __forceinline__ float pk_round_tf32(float v) {
   return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
@@ -439,7 +442,16 @@ __global__ void __launch_bounds__(256) unpack_grads_kernel(const PackDesc* __res
   const int total = d.rows * d.cols;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int r = i / d.cols, c = i - r * d.cols;
-    d.grad_dst[static_cast<int64_t>(r) * d.src_ld + c] += d.g[static_cast<int64_t>(r) * d.dst_ld + c];
+    float acc = d.g[static_cast<int64_t>(r) * d.dst_ld + c];
+    if (d.split > 0) {      // deferred split-K reduction: fixed order z = 0, 1, ... (deterministic)
+      const float* p = d.part + static_cast<int64_t>(d.dr + r) * d.p_cols + d.dc + c;
+      const int64_t plane = static_cast<int64_t>(d.p_rows) * d.p_cols;
+      float s = 0.f;
+#pragma unroll 8
+      for (int z = 0; z < d.split; ++z) s += __ldg(p + z * plane);
+      acc += s;
+    }
+    d.grad_dst[static_cast<int64_t>(r) * d.src_ld + c] += acc;
   }
 }
 
@@ -456,7 +468,7 @@ extern "C" int ax2d_unpack_grads(const void* table, int n_blocks, int max_block_
   using namespace ax2d;
   AX2D_CHECK_ARG(table != nullptr && n_blocks > 0 && max_block_elems > 0, "ax2d_unpack_grads: bad arguments");
   int gx = (max_block_elems + 255) / 256;
-  gx = gx > 64 ? 64 : gx;
+  gx = gx > 200 ? 200 : gx;         // one element per thread for the large blocks: their partial sums are latency-bound
   dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(n_blocks));
   unpack_grads_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<const PackDesc*>(table));
   return launch_status("ax2d_unpack_grads");

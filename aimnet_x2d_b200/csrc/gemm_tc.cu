@@ -1242,6 +1242,11 @@ static int wgrad_split(int64_t tiles, int64_t num_kb) {
   return static_cast<int>(best);
 }
 
+extern "C" int ax2d_gemm_tc_wgrad_splits(int64_t M, int64_t N, int64_t K) {
+  const int64_t n_tiles = (N + WG_MAX_BN - 1) / WG_MAX_BN;
+  return wgrad_split(((M + TC_BM - 1) / TC_BM) * n_tiles, (K + WG_KB - 1) / WG_KB);
+}
+
 extern "C" int64_t ax2d_gemm_tc_wgrad_workspace(int64_t M, int64_t N, int64_t K) {
   const int64_t n_tiles = (N + WG_MAX_BN - 1) / WG_MAX_BN;
   const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * n_tiles;
@@ -1295,6 +1300,7 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
   int split = wgrad_split(static_cast<int64_t>(m_tiles) * n_tiles, g.num_kb);
   g.kb_per_split = (g.num_kb + split - 1) / split;
   split = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;      // no empty split
+  g.e.accumulate = (split == 1 && accumulate == 1) ? 1 : 0;      // partial tiles are plain stores; the reduce accumulates
   if (split > 1) {
     AX2D_CHECK_ARG(workspace != nullptr, "ax2d_gemm_tc_wgrad: workspace required (ax2d_gemm_tc_wgrad_workspace)");
     AX2D_CHECK_ALIGN(workspace);
@@ -1323,10 +1329,12 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
     }
     configured = smem;
   }
+  AX2D_CHECK_ARG(accumulate != 2 || split > 1, "ax2d_gemm_tc_wgrad: accumulate == 2 (leave the partials) needs more than one split "
+                                              "(ax2d_gemm_tc_wgrad_splits)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), static_cast<unsigned>(split));
   gemm_tc_wgrad_kernel<<<grid, TC_WG_THREADS, smem, st>>>(maps, g);
   rc = launch_status("ax2d_gemm_tc_wgrad");
-  if (rc != AX2D_OK || split == 1) return rc;
-  return splitk_reduce(g.ws, split, M, N, g.e.c, accumulate, g.db, bias_grad, st);
+  if (rc != AX2D_OK || split == 1 || accumulate == 2) return rc;
+  return splitk_reduce(g.ws, split, M, N, g.e.c, accumulate == 1, g.db, bias_grad, st);
 }

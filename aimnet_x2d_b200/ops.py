@@ -246,6 +246,37 @@ def _weight_grad(g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device, bias:
     return dW, out_bias
 
 
+DEFER_SPLITK_REDUCE = True      # packed weights: the gradient-collect kernel sums the split-K partials (no reduce launches)
+
+
+def _deferred_weight_grad(iw, ib, g_segs, x_segs, M_rows: int, Nout: int, Kin: int) -> bool:
+    """Tensor-core weight gradient that leaves its split-K partial tiles (and partial bias vectors) in a persistent
+    workspace of the packed matrix; ``ax2d_unpack_grads`` sums them in split order while it scatters the gradients,
+    which saves one reduce launch per matrix and step.  False: not applicable (caller takes the ordinary path)."""
+    if not (DEFER_SPLITK_REDUCE and USE_TENSOR_CORES and M_rows >= TC_MIN_ROWS):
+        return False
+    lib = _lib.load()
+    a, b = _mat(g_segs), _mat(x_segs)
+    if not lib.ax2d_gemm_tc_wgrad_supported(C.byref(a), C.byref(b), Nout, Kin, M_rows):
+        return False
+    splits = lib.ax2d_gemm_tc_wgrad_splits(Nout, Kin, M_rows)
+    if splits <= 1 or tuple(iw.grad.shape) != (Nout, Kin):
+        return False
+    ws = iw.owner.workspace(iw.name, lib.ax2d_gemm_tc_wgrad_workspace(Nout, Kin, M_rows))
+    c = _mat([(iw.grad, Kin)])              # not written in this mode
+    want_bias = ib is not None
+    call = lambda: _lib.check(lib.ax2d_gemm_tc_wgrad(C.byref(a), C.byref(b), C.byref(c), Nout, Kin, M_rows, 2,
+                                                     _p(ib.grad) if want_bias else None, _p(ws), _stream()), "ax2d_gemm_tc_wgrad")
+    if TIMER is None:
+        call()
+    else:
+        TIMER.launch("gemm_tc_wgrad", call, nbytes=4 * M_rows * (Nout + Kin), flops=2 * M_rows * Nout * Kin)
+    iw.partials = (ws.data_ptr(), splits, Nout, Kin)
+    if want_bias:
+        ib.partials = (ws.data_ptr() + 4 * splits * Nout * Kin, splits, 1, Nout)
+    return True
+
+
 def _param_grads(W, b, g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device):
     """(dW, db) for autograd.  For packed weights (``packed.PackedWeights``) the gradients go straight into the packed
     gradient buffers -- collected into ``.grad`` by ONE kernel at the end of backward -- and autograd gets (None, None)."""
@@ -257,7 +288,9 @@ def _param_grads(W, b, g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device)
     ib = packed_info(b)
     if b is not None and ib is None:
         raise RuntimeError("a packed weight needs a packed bias")
-    if not iw.written:
+    if not iw.written and _deferred_weight_grad(iw, ib, g_segs, x_segs, M_rows, Nout, Kin):
+        pass
+    elif not iw.written:
         _weight_grad(g_segs, x_segs, M_rows, Nout, Kin, device, bias=b is not None, out=iw.grad,
                      out_bias=None if b is None else ib.grad)
     else:           # a weight shared by several calls (stereochemical_embedding_2 serves every layer): sum them

@@ -18,19 +18,22 @@ import torch
 from . import _lib
 
 _DESC = np.dtype([("src", "u8"), ("grad", "u8"), ("w", "u8"), ("hi", "u8"), ("lo", "u8"), ("hiT", "u8"), ("loT", "u8"),
-                  ("g", "u8"), ("rows", "i4"), ("cols", "i4"), ("src_ld", "i4"), ("dst_ld", "i4"), ("dstT_ld", "i4"),
-                  ("pad", "i4")])
-assert _DESC.itemsize == 88
+                  ("g", "u8"), ("part", "u8"), ("rows", "i4"), ("cols", "i4"), ("src_ld", "i4"), ("dst_ld", "i4"),
+                  ("dstT_ld", "i4"), ("split", "i4"), ("p_rows", "i4"), ("p_cols", "i4"), ("dr", "i4"), ("dc", "i4")])
+assert _DESC.itemsize == 112
 
 
 class PackInfo:
     """Attached to a packed weight tensor as ``t._ax2d``: its TF32 terms (plain and transposed) and the buffer its
     gradient is written to."""
-    __slots__ = ("hi", "lo", "hiT", "loT", "grad", "owner", "written")
+    __slots__ = ("hi", "lo", "hiT", "loT", "grad", "owner", "written", "name", "partials")
 
-    def __init__(self, hi, lo, hiT, loT, grad, owner):
-        self.hi, self.lo, self.hiT, self.loT, self.grad, self.owner = hi, lo, hiT, loT, grad, owner
+    def __init__(self, hi, lo, hiT, loT, grad, owner, name=""):
+        self.hi, self.lo, self.hiT, self.loT, self.grad, self.owner, self.name = hi, lo, hiT, loT, grad, owner, name
         self.written = False      # the gradient buffer already holds a contribution of the running backward pass
+        # split-K partials the weight-gradient kernel left for this matrix in the running backward pass:
+        # (data_ptr, splits, rows, cols) -- summed by the gradient-collect kernel instead of a reduce launch per matrix
+        self.partials = None
 
 
 def packed_info(t) -> Optional[PackInfo]:
@@ -59,6 +62,7 @@ class PackedWeights:
         self._n_blocks = 0
         self._max_elems = 1
         self.dirty = False
+        self._workspaces: Dict[str, torch.Tensor] = {}     # persistent split-K workspaces, one per matrix
 
     # a derived cache: copies / pickles of the owning module rebuild their own
     def __deepcopy__(self, memo):
@@ -91,10 +95,10 @@ class PackedWeights:
             t = self.w[sl].view(shape)
             gr = self.grad[sl].view(shape)
             if m.vector:
-                info = PackInfo(None, None, None, None, gr, self)
+                info = PackInfo(None, None, None, None, gr, self, m.name)
             else:
                 info = PackInfo(self.hi[sl].view(shape), self.lo[sl].view(shape), self.hiT[sl].view(m.cols, m.rows),
-                                self.loT[sl].view(m.cols, m.rows), gr, self)
+                                self.loT[sl].view(m.cols, m.rows), gr, self, m.name)
             t._ax2d = info
             self.tensors[m.name] = t
         self._n_blocks = sum(len(m.blocks) for m in self.mats.values())
@@ -112,8 +116,17 @@ class PackedWeights:
 
     def _key(self, with_grads: bool):
         ps = self._params()
+        parts = tuple((n, t._ax2d.partials) for n, t in self.tensors.items() if t._ax2d.partials is not None) if with_grads else None
         return (tuple(p.data_ptr() for p in ps),
-                tuple((p.grad.data_ptr() if p.grad is not None else 0) for p in ps) if with_grads else None)
+                tuple((p.grad.data_ptr() if p.grad is not None else 0) for p in ps) if with_grads else None, parts)
+
+    def workspace(self, name: str, nbytes: int) -> torch.Tensor:
+        """Persistent split-K workspace of one matrix (its partial tiles must outlive the backward pass)."""
+        ws = self._workspaces.get(name)
+        if ws is None or ws.numel() * 4 < nbytes:
+            ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=self.device)
+            self._workspaces[name] = ws
+        return ws
 
     def _build(self, with_grads: bool) -> None:
         rec = np.zeros(self._n_blocks, dtype=_DESC)
@@ -138,6 +151,10 @@ class PackedWeights:
                 d["rows"], d["cols"] = r1 - r0, c1 - c0
                 d["src_ld"] = (c1 - c0) if p.dim() == 1 else ld
                 d["dst_ld"], d["dstT_ld"] = m.cols, m.rows
+                part = self.tensors[m.name]._ax2d.partials if with_grads else None
+                if part is not None:
+                    d["part"], d["split"], d["p_rows"], d["p_cols"] = part
+                    d["dr"], d["dc"] = dr, dc
                 i += 1
         host = torch.from_numpy(rec.view(np.uint8).copy())
         if self._table is None:
@@ -153,7 +170,7 @@ class PackedWeights:
                     p.grad = torch.zeros_like(p)
         key = self._key(with_grads)
         if self._table is None or self._table_key is None or key[0] != self._table_key[0] or (
-                with_grads and key[1] != self._table_key[1]):
+                with_grads and (key[1] != self._table_key[1] or key[2] != self._table_key[2])):
             self._build(with_grads)
 
     # ------------------------------------------------------------------ the two launches
@@ -161,6 +178,7 @@ class PackedWeights:
         self.grad.zero_()
         for t in self.tensors.values():
             t._ax2d.written = False
+            t._ax2d.partials = None
         self.dirty = False
 
     def refresh(self) -> None:

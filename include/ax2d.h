@@ -223,6 +223,10 @@ int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* b_lo, int64
  * already stages -- replaces a separate ax2d_colsum pass. */
 int     ax2d_gemm_tc_wgrad_supported(const ax2d_cmat* a, const ax2d_cmat* b, int64_t M, int64_t N, int64_t K);
 int64_t ax2d_gemm_tc_wgrad_workspace(int64_t M, int64_t N, int64_t K);
+/* Number of row splits the kernel uses for this shape.  With accumulate == 2 (and more than one split) the call leaves
+ * the partial tiles [splits][M][N] followed by the partial bias vectors [splits][M] in `workspace` and does not reduce
+ * them: ax2d_unpack_grads sums them, in split order, while it scatters the gradients (c and bias_grad are not written). */
+int     ax2d_gemm_tc_wgrad_splits(int64_t M, int64_t N, int64_t K);
 int     ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const ax2d_mat* c, int64_t M, int64_t N, int64_t K,
                            int accumulate, float* bias_grad, void* workspace, ax2d_stream_t stream);
 /* elementwise g_pre[m,n] = g[m,n] * act'(pre[m,n]) for n < width (width % 4 == 0). */

@@ -37,8 +37,19 @@ def _run(model, b, steps=2):
     return outs, grads
 
 
+@pytest.fixture
+def immediate_reduce():
+    """The packed path normally leaves the split-K partials of the weight gradients to the gradient-collect kernel
+    (a different, equally fixed summation order); with the reduce done per matrix the two paths are bit-identical."""
+    from aimnet_x2d_b200 import ops
+    old = ops.DEFER_SPLITK_REDUCE
+    ops.DEFER_SPLITK_REDUCE = False
+    yield
+    ops.DEFER_SPLITK_REDUCE = old
+
+
 @pytest.mark.parametrize("stereo,charges", [(False, False), (True, True)])
-def test_packed_path_is_bit_identical_to_per_call_path(stereo, charges):
+def test_packed_path_is_bit_identical_to_per_call_path(stereo, charges, immediate_reduce):
     from aimnet_x2d_b200 import synthetic as S
     b = S.make_batch(77, 48, 3, "druglike" if stereo else "qm9", num_targets=3, stereo=stereo).to(DEV)
     m_p, m_l = _model(stereo, charges, True), _model(stereo, charges, False)
@@ -53,7 +64,25 @@ def test_packed_path_is_bit_identical_to_per_call_path(stereo, charges):
         np.testing.assert_allclose(g_p[k], g_l[k], rtol=3e-7, atol=1e-12, err_msg=k)
 
 
-def test_packed_first_step_gradients_bitwise():
+@pytest.mark.parametrize("stereo,charges", [(False, False), (True, True)])
+def test_deferred_splitk_reduce_matches_immediate_reduce(stereo, charges):
+    """Default packed path (partials summed by ax2d_unpack_grads) against the per-call path: same values up to the
+    rounding of a different summation order; and deterministic from run to run."""
+    from aimnet_x2d_b200 import ops, synthetic as S
+    assert ops.DEFER_SPLITK_REDUCE
+    b = S.make_batch(81, 64, 3, "druglike" if stereo else "qm9", num_targets=3, stereo=stereo).to(DEV)
+    o_p, g_p = _run(_model(stereo, charges, True), b)
+    o_q, g_q = _run(_model(stereo, charges, True), b)
+    o_l, g_l = _run(_model(stereo, charges, False), b)
+    for a, c in zip(o_p, o_l):
+        assert np.array_equal(a, c)
+    for k in g_l:
+        assert np.array_equal(g_p[k], g_q[k]), k                      # deterministic
+        scale = float(np.abs(g_l[k]).max()) + 1e-30
+        assert float(np.abs(g_p[k] - g_l[k]).max()) <= 2e-6 * scale, k
+
+
+def test_packed_first_step_gradients_bitwise(immediate_reduce):
     from aimnet_x2d_b200 import synthetic as S
     b = S.make_batch(78, 32, 3, "qm9", num_targets=3).to(DEV)
     _, g_p = _run(_model(False, False, True), b, steps=1)
@@ -62,7 +91,7 @@ def test_packed_first_step_gradients_bitwise():
         assert np.array_equal(g_p[k], g_l[k]), k
 
 
-def test_packed_follows_parameter_updates_and_state_dict():
+def test_packed_follows_parameter_updates_and_state_dict(immediate_reduce):
     """The packed operands are a cache: an optimiser step / load_state_dict must show up in the next forward."""
     import aimnet_x2d_b200 as ax
     from aimnet_x2d_b200 import synthetic as S
