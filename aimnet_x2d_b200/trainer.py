@@ -65,6 +65,30 @@ def _batch_tensors(b: MolBatch):
     return ts
 
 
+_ARENA_ALIGN = 256
+
+
+def _arena_layout(tensors):
+    """Byte offsets of the batch tensors inside one contiguous buffer (256-byte aligned) and its size."""
+    offs, n = [], 0
+    for t in tensors:
+        offs.append(n)
+        n += (t.numel() * t.element_size() + _ARENA_ALIGN - 1) // _ARENA_ALIGN * _ARENA_ALIGN
+    return offs, max(n, _ARENA_ALIGN)
+
+
+class HostBatch:
+    """A padded batch packed into ONE pinned host buffer with the layout of a captured step's device slot
+    (``GraphedTrainStep.pack``): the whole batch crosses PCIe as a single copy, which can be issued ahead of time
+    (``prefetch``) so that it overlaps the previous step."""
+
+    def __init__(self, arena: torch.Tensor, signature):
+        self.arena, self.signature = arena, signature
+
+    def nbytes(self) -> int:
+        return int(self.arena.numel())
+
+
 class GraphedTrainStep:
     """The same training step captured ONCE as CUDA graphs and replayed for every batch of the same static
     signature (``collate.pad_batch``): no per-kernel host work is left in the loop, which is what lets a ~3 ms GPU
@@ -83,6 +107,11 @@ class GraphedTrainStep:
         self.signature = None
         self.graph_fb = self.graph_opt = None
         self.loss = None
+        self.slot_arena = self.stage_arena = None
+        self._offsets = None
+        self._staged = None
+        self._copy_stream = None
+        self._stage_ready = self._stage_free = None
 
     def _fwd_bwd(self) -> torch.Tensor:
         bd, opt = self.slot, self.optimizer
@@ -101,6 +130,19 @@ class GraphedTrainStep:
         opt = self.optimizer
         self.slot = padded.to(self.device)
         self.signature = static_signature(padded)
+        # every tensor of the slot becomes a view of one device buffer (in place: all references stay valid), so that a
+        # HostBatch arrives with a single copy
+        ts = _batch_tensors(self.slot)
+        self._offsets, total = _arena_layout(ts)
+        self.slot_arena = torch.zeros(total, dtype=torch.uint8, device=self.device)
+        self.stage_arena = torch.zeros(total, dtype=torch.uint8, device=self.device)
+        for t, o in zip(ts, self._offsets):
+            if t.numel():
+                view = self.slot_arena[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+                view.copy_(t)
+                t.set_(view)
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._stage_ready, self._stage_free = torch.cuda.Event(), torch.cuda.Event()
         saved = [t.clone() for t in (opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.step_count)]
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
@@ -133,6 +175,48 @@ class GraphedTrainStep:
             if dst.numel():
                 dst.copy_(src, non_blocking=True)
 
+    def pack(self, padded: MolBatch) -> HostBatch:
+        """Pack a padded host batch into one pinned buffer with the slot's layout (host-side work of the data loader)."""
+        if self.slot_arena is None:
+            raise RuntimeError("capture() first: the layout of the host buffer is the captured slot's")
+        if static_signature(padded) != self.signature:
+            raise RuntimeError("batch does not match the static signature the step was captured for")
+        arena = torch.zeros(self.slot_arena.numel(), dtype=torch.uint8).pin_memory()
+        for src, dst, o in zip(_batch_tensors(padded), _batch_tensors(self.slot), self._offsets):
+            if tuple(src.shape) != tuple(dst.shape) or src.dtype != dst.dtype:
+                raise RuntimeError(f"static slot tensor {tuple(dst.shape)} vs batch tensor {tuple(src.shape)}")
+            if src.numel():
+                arena[o:o + src.numel() * src.element_size()].view(src.dtype).view(src.shape).copy_(src)
+        return HostBatch(arena, self.signature)
+
+    def prefetch(self, hb: HostBatch) -> None:
+        """Start the host-to-device copy of a later batch on a side stream; it overlaps whatever the main stream runs."""
+        if hb.signature != self.signature:
+            raise RuntimeError("batch does not match the static signature the step was captured for")
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free)       # the staging buffer has been consumed
+            self.stage_arena.copy_(hb.arena, non_blocking=True)
+            self._stage_ready.record(self._copy_stream)
+        self._staged = hb
+        del main
+
+    def _load_host(self, hb: HostBatch) -> None:
+        if hb.signature != self.signature:
+            raise RuntimeError("batch does not match the static signature the step was captured for")
+        main = torch.cuda.current_stream(self.device)
+        if self._staged is hb:                                    # prefetched: one device-to-device copy
+            main.wait_event(self._stage_ready)
+            self.slot_arena.copy_(self.stage_arena, non_blocking=True)
+            self._stage_free.record(main)
+            self._staged = None
+        else:
+            self.slot_arena.copy_(hb.arena, non_blocking=True)
+
+    def load_arena(self, arena: torch.Tensor) -> None:
+        """A batch that already lives on the device as one packed buffer (``HostBatch.arena.to(device)``)."""
+        self.slot_arena.copy_(arena, non_blocking=True)
+
     def replay(self) -> torch.Tensor:
         self.graph_fb.replay()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -140,9 +224,18 @@ class GraphedTrainStep:
         self.graph_opt.replay()
         return self.loss
 
-    def __call__(self, padded: MolBatch, return_float: bool = True):
-        if self.graph_fb is None:
-            self.capture(padded)
-        self.load(padded)
+    def __call__(self, padded, return_float: bool = True, prefetch: Optional[HostBatch] = None):
+        """``padded``: a padded ``MolBatch`` (one copy per tensor) or a ``HostBatch`` from ``pack`` (one copy, possibly
+        already under way).  ``prefetch``: the ``HostBatch`` of a later call, copied while this step runs."""
+        if isinstance(padded, HostBatch):
+            if self.graph_fb is None:
+                raise RuntimeError("capture() with a padded MolBatch before passing HostBatch objects")
+            self._load_host(padded)
+        else:
+            if self.graph_fb is None:
+                self.capture(padded)
+            self.load(padded)
         loss = self.replay()
+        if prefetch is not None:
+            self.prefetch(prefetch)
         return float(loss.item()) if return_float else loss

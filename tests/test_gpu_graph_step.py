@@ -188,3 +188,40 @@ def test_stereo_batches_pad_to_a_static_shape_and_replay():
         assert float(le) == graphed(b), it
     torch.cuda.synchronize()
     assert torch.equal(o_g.flat_param, o_e.flat_param)
+
+
+def test_host_batch_single_copy_and_prefetch_equal_per_tensor_loads():
+    """GraphedTrainStep with HostBatch objects (one pinned buffer per batch, one copy, optionally prefetched on a side
+    stream) must produce exactly the losses and parameters of the per-tensor load path."""
+    import aimnet_x2d_b200 as ax
+    from aimnet_x2d_b200 import synthetic as S
+    from aimnet_x2d_b200.collate import pad_batch
+    from aimnet_x2d_b200.trainer import GraphedTrainStep
+    raws = [S.make_batch(60 + i, 24, 3, "qm9", num_targets=3) for i in range(4)]
+    n_pad = max(b.graph_index.num_atoms for b in raws) + 64
+    e_cap = max(b.graph_index.num_edges for b in raws) + 64
+    first = [pad_batch(b, n_pad, e_cap, 8) for b in raws]
+    t_cap = max(p.graph_index.n_tiles for p in first) + 2
+    me_cap = max(p.graph_index.max_tile_edges for p in first)
+    padded = [pad_batch(b, n_pad, e_cap, 8, t_cap, max_tile_edges=me_cap).pin_memory() for b in raws]
+    crit = ax.WeightedL1Loss(torch.linspace(0.5, 1.5, 3)).to(DEV)
+    m_a, m_b = _model(), _model()
+    for m in (m_a, m_b):
+        m.eval()                          # no dropout: the two runs must agree bit for bit
+        m.train(False)
+    s_a = GraphedTrainStep(m_a, crit, ax.FlatAdam(m_a.parameters(), lr=1e-3), DEV)
+    s_b = GraphedTrainStep(m_b, crit, ax.FlatAdam(m_b.parameters(), lr=1e-3), DEV)
+    s_a.capture(padded[0])
+    s_b.capture(padded[0])
+    packed = [s_b.pack(p) for p in padded]
+    order = [0, 1, 2, 3, 1, 0, 3]
+    la, lb = [], []
+    for k, i in enumerate(order):
+        la.append(s_a(padded[i]))
+        nxt = packed[order[k + 1]] if k + 1 < len(order) and k % 2 == 0 else None     # prefetched and direct copies mixed
+        lb.append(s_b(packed[i], prefetch=nxt))
+    assert la == lb
+    for (k, p), (_, q) in zip(m_a.named_parameters(), m_b.named_parameters()):
+        assert torch.equal(p, q), k
+    with pytest.raises(RuntimeError):
+        s_b.pack(pad_batch(raws[0], n_pad + 32, e_cap, 8, t_cap, max_tile_edges=me_cap))
