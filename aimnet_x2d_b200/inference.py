@@ -12,8 +12,8 @@ from typing import Dict, Optional
 
 import torch
 
-from .collate import MolBatch, static_signature
-from .trainer import _batch_tensors
+from .collate import MolBatch
+from .trainer import HostBatch, StaticSlot
 
 
 class InferenceStep:
@@ -52,7 +52,7 @@ class InferenceStep:
         return self.device_step(batch.to(self.device, non_blocking=True))
 
 
-class GraphedInferenceStep:
+class GraphedInferenceStep(StaticSlot):
     """CUDA-graph replay of ``InferenceStep.device_step`` for padded batches of one static signature.  The returned
     tensors are static device buffers (valid until the next call)."""
 
@@ -65,8 +65,7 @@ class GraphedInferenceStep:
         self.result = None
 
     def capture(self, padded: MolBatch, warmup: int = 2) -> None:
-        self.slot = padded.to(self.device)
-        self.signature = static_signature(padded)
+        self._make_slot(padded)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -79,19 +78,21 @@ class GraphedInferenceStep:
             self.result = self.eager.device_step(self.slot)
         torch.cuda.synchronize()
 
-    def load(self, padded: MolBatch) -> None:
-        if static_signature(padded) != self.signature:
-            raise RuntimeError("batch does not match the static signature the step was captured for")
-        for dst, src in zip(_batch_tensors(self.slot), _batch_tensors(padded)):
-            if dst.numel():
-                dst.copy_(src, non_blocking=True)
-
     def replay(self):
         self.graph.replay()
         return self.result
 
-    def __call__(self, padded: MolBatch):
-        if self.graph is None:
-            self.capture(padded)
-        self.load(padded)
-        return self.replay()
+    def __call__(self, padded, prefetch: Optional[HostBatch] = None):
+        """``padded``: a padded ``MolBatch`` or a ``HostBatch`` (``pack``); ``prefetch``: the ``HostBatch`` of a later call."""
+        if isinstance(padded, HostBatch):
+            if self.graph is None:
+                raise RuntimeError("capture() with a padded MolBatch before passing HostBatch objects")
+            self._load_host(padded)
+        else:
+            if self.graph is None:
+                self.capture(padded)
+            self.load(padded)
+        res = self.replay()
+        if prefetch is not None:
+            self.prefetch(prefetch)
+        return res

@@ -89,45 +89,20 @@ class HostBatch:
         return int(self.arena.numel())
 
 
-class GraphedTrainStep:
-    """The same training step captured ONCE as CUDA graphs and replayed for every batch of the same static
-    signature (``collate.pad_batch``): no per-kernel host work is left in the loop, which is what lets a ~3 ms GPU
-    step run at GPU speed (the eager path needs ~10 ms of Python / launch time for its ~250 launches).
+class StaticSlot:
+    """The static device copy of a padded batch that captured graphs read, kept as views of ONE device buffer, and the
+    ways a batch gets into it: per tensor (``load``), as one packed buffer from the host (``HostBatch``, optionally
+    prefetched on a side stream) or from the device (``load_arena``)."""
 
-    Per step: H2D copies of the batch into the static device slot -> graph A (zero_grad, forward, loss, backward)
-    -> [world > 1: ONE NCCL all-reduce of the flat gradient arena] -> graph B (clip + Adam).  The loss is a static
-    device scalar; ``__call__`` reads it back like ``trainer.py:169`` does.
-    """
+    slot: Optional[MolBatch] = None
+    signature = None
+    slot_arena = stage_arena = None
+    _offsets = None
+    _staged = None
+    _copy_stream = None
+    _stage_ready = _stage_free = None
 
-    def __init__(self, model: torch.nn.Module, criterion: torch.nn.Module, optimizer: FlatAdam, device=None):
-        self.eager = TrainStep(model, criterion, optimizer, device)
-        self.model, self.criterion, self.optimizer = model, criterion, optimizer
-        self.device = self.eager.device
-        self.slot: Optional[MolBatch] = None
-        self.signature = None
-        self.graph_fb = self.graph_opt = None
-        self.loss = None
-        self.slot_arena = self.stage_arena = None
-        self._offsets = None
-        self._staged = None
-        self._copy_stream = None
-        self._stage_ready = self._stage_free = None
-
-    def _fwd_bwd(self) -> torch.Tensor:
-        bd, opt = self.slot, self.optimizer
-        opt.zero_grad()
-        out, _, _ = self.model(bd.atom_features_map, bd.multi_hop_edge_indices, bd.batch_indices, bd.total_charges,
-                               bd.final_tetrahedral_chiral_tensor, bd.final_cis_tensor, bd.final_trans_tensor,
-                               graph_index=bd.graph_index)
-        n = getattr(bd, "num_real_graphs", out.shape[0])          # dummy (padding) molecules carry no loss
-        loss = self.criterion(out[:n], bd.targets[:n])
-        loss.backward()
-        return loss.detach()
-
-    def capture(self, padded: MolBatch, warmup: int = 3) -> None:
-        """Allocate the static slot from ``padded`` (a host batch from ``pad_batch``), run ``warmup`` eager steps on a
-        side stream (their effect on parameters / optimiser state is rolled back), then capture."""
-        opt = self.optimizer
+    def _make_slot(self, padded: MolBatch) -> None:
         self.slot = padded.to(self.device)
         self.signature = static_signature(padded)
         # every tensor of the slot becomes a view of one device buffer (in place: all references stay valid), so that a
@@ -143,32 +118,12 @@ class GraphedTrainStep:
                 t.set_(view)
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._stage_ready, self._stage_free = torch.cuda.Event(), torch.cuda.Event()
-        saved = [t.clone() for t in (opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.step_count)]
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self._fwd_bwd()
-                opt.all_reduce_grads()
-                opt.step()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_fb):
-            self.loss = self._fwd_bwd()
-        self.graph_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_opt):
-            opt.step()
-        with torch.no_grad():
-            for dst, src in zip((opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.step_count), saved):
-                dst.copy_(src)
-        torch.cuda.synchronize()
 
     def load(self, padded: MolBatch) -> None:
-        """H2D copies of a padded host batch into the static slot (pinned source => asynchronous)."""
+        """H2D copies of a padded host batch into the static slot, tensor by tensor (pinned source => asynchronous)."""
         if static_signature(padded) != self.signature:
             raise RuntimeError("batch does not match the static signature the step was captured for; pad it with the "
-                               "same capacities (collate.pad_batch) or capture a new GraphedTrainStep")
+                               "same capacities (collate.pad_batch) or capture a new step")
         for dst, src in zip(_batch_tensors(self.slot), _batch_tensors(padded)):
             if dst.shape != src.shape:
                 raise RuntimeError(f"static slot tensor {tuple(dst.shape)} vs batch tensor {tuple(src.shape)}")
@@ -193,13 +148,11 @@ class GraphedTrainStep:
         """Start the host-to-device copy of a later batch on a side stream; it overlaps whatever the main stream runs."""
         if hb.signature != self.signature:
             raise RuntimeError("batch does not match the static signature the step was captured for")
-        main = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(self._stage_free)       # the staging buffer has been consumed
             self.stage_arena.copy_(hb.arena, non_blocking=True)
             self._stage_ready.record(self._copy_stream)
         self._staged = hb
-        del main
 
     def _load_host(self, hb: HostBatch) -> None:
         if hb.signature != self.signature:
@@ -216,6 +169,63 @@ class GraphedTrainStep:
     def load_arena(self, arena: torch.Tensor) -> None:
         """A batch that already lives on the device as one packed buffer (``HostBatch.arena.to(device)``)."""
         self.slot_arena.copy_(arena, non_blocking=True)
+
+
+class GraphedTrainStep(StaticSlot):
+    """The same training step captured ONCE as CUDA graphs and replayed for every batch of the same static
+    signature (``collate.pad_batch``): no per-kernel host work is left in the loop, which is what lets a ~3 ms GPU
+    step run at GPU speed (the eager path needs ~10 ms of Python / launch time for its ~250 launches).
+
+    Per step: H2D copies of the batch into the static device slot -> graph A (zero_grad, forward, loss, backward)
+    -> [world > 1: ONE NCCL all-reduce of the flat gradient arena] -> graph B (clip + Adam).  The loss is a static
+    device scalar; ``__call__`` reads it back like ``trainer.py:169`` does.
+    """
+
+    def __init__(self, model: torch.nn.Module, criterion: torch.nn.Module, optimizer: FlatAdam, device=None):
+        self.eager = TrainStep(model, criterion, optimizer, device)
+        self.model, self.criterion, self.optimizer = model, criterion, optimizer
+        self.device = self.eager.device
+        self.slot: Optional[MolBatch] = None
+        self.signature = None
+        self.graph_fb = self.graph_opt = None
+        self.loss = None
+
+    def _fwd_bwd(self) -> torch.Tensor:
+        bd, opt = self.slot, self.optimizer
+        opt.zero_grad()
+        out, _, _ = self.model(bd.atom_features_map, bd.multi_hop_edge_indices, bd.batch_indices, bd.total_charges,
+                               bd.final_tetrahedral_chiral_tensor, bd.final_cis_tensor, bd.final_trans_tensor,
+                               graph_index=bd.graph_index)
+        n = getattr(bd, "num_real_graphs", out.shape[0])          # dummy (padding) molecules carry no loss
+        loss = self.criterion(out[:n], bd.targets[:n])
+        loss.backward()
+        return loss.detach()
+
+    def capture(self, padded: MolBatch, warmup: int = 3) -> None:
+        """Allocate the static slot from ``padded`` (a host batch from ``pad_batch``), run ``warmup`` eager steps on a
+        side stream (their effect on parameters / optimiser state is rolled back), then capture."""
+        opt = self.optimizer
+        self._make_slot(padded)
+        saved = [t.clone() for t in (opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.step_count)]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._fwd_bwd()
+                opt.all_reduce_grads()
+                opt.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fb):
+            self.loss = self._fwd_bwd()
+        self.graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_opt):
+            opt.step()
+        with torch.no_grad():
+            for dst, src in zip((opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.step_count), saved):
+                dst.copy_(src)
+        torch.cuda.synchronize()
 
     def replay(self) -> torch.Tensor:
         self.graph_fb.replay()
