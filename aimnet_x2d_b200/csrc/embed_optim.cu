@@ -439,19 +439,38 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackDesc* __res
 __global__ void __launch_bounds__(256) unpack_grads_kernel(const PackDesc* __restrict__ table) {
   const PackDesc d = table[blockIdx.y];
   if (d.grad_dst == nullptr) return;
-  const int total = d.rows * d.cols;
+  // four consecutive columns per thread: the split-K partials (the bulk of the traffic) are read as float4 whenever the
+  // packed side is 16-byte aligned; the parameter side (.grad, arbitrary width) is written element by element
+  const int quads = (d.cols + 3) >> 2;
+  const int total = d.rows * quads;
+  const int64_t plane = static_cast<int64_t>(d.p_rows) * d.p_cols;
+  const bool vec = d.split > 0 && (d.p_cols & 3) == 0 && (d.dc & 3) == 0 && (reinterpret_cast<uintptr_t>(d.part) & 15u) == 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int r = i / d.cols, c = i - r * d.cols;
-    float acc = d.g[static_cast<int64_t>(r) * d.dst_ld + c];
+    const int r = i / quads, c0 = (i - r * quads) * 4;
+    const int nc = d.cols - c0 < 4 ? d.cols - c0 : 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (d.split > 0) {      // deferred split-K reduction: fixed order z = 0, 1, ... (deterministic)
-      const float* p = d.part + static_cast<int64_t>(d.dr + r) * d.p_cols + d.dc + c;
-      const int64_t plane = static_cast<int64_t>(d.p_rows) * d.p_cols;
-      float s = 0.f;
+      const float* p = d.part + static_cast<int64_t>(d.dr + r) * d.p_cols + d.dc + c0;
+      if (vec && nc == 4) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-      for (int z = 0; z < d.split; ++z) s += __ldg(p + z * plane);
-      acc += s;
+        for (int z = 0; z < d.split; ++z) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(p + z * plane));
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        acc[0] = s.x; acc[1] = s.y; acc[2] = s.z; acc[3] = s.w;
+      } else {
+        for (int j = 0; j < nc; ++j) {
+          float s = 0.f;
+#pragma unroll 8
+          for (int z = 0; z < d.split; ++z) s += __ldg(p + z * plane + j);
+          acc[j] = s;
+        }
+      }
     }
-    d.grad_dst[static_cast<int64_t>(r) * d.src_ld + c] += acc;
+    const float* gp = d.g + static_cast<int64_t>(r) * d.dst_ld + c0;
+    float* dst = d.grad_dst + static_cast<int64_t>(r) * d.src_ld + c0;
+    for (int j = 0; j < nc; ++j) dst[j] += gp[j] + acc[j];
   }
 }
 
@@ -467,8 +486,8 @@ extern "C" int ax2d_pack_weights(const void* table, int n_blocks, int max_block_
 extern "C" int ax2d_unpack_grads(const void* table, int n_blocks, int max_block_elems, ax2d_stream_t stream) {
   using namespace ax2d;
   AX2D_CHECK_ARG(table != nullptr && n_blocks > 0 && max_block_elems > 0, "ax2d_unpack_grads: bad arguments");
-  int gx = (max_block_elems + 255) / 256;
-  gx = gx > 200 ? 200 : gx;         // one element per thread for the large blocks: their partial sums are latency-bound
+  int gx = (max_block_elems / 4 + 255) / 256;
+  gx = gx > 100 ? 100 : (gx < 1 ? 1 : gx);     // ~one quad per thread for the large blocks: their partial sums are latency-bound
   dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(n_blocks));
   unpack_grads_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<const PackDesc*>(table));
   return launch_status("ax2d_unpack_grads");
