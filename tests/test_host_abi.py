@@ -281,3 +281,37 @@ def test_packed_weight_table_matches_per_call_packing(collapsed):
     assert not any("packed" in k for k in m.state_dict())
     m._packed[("cpu", collapsed)] = pk
     assert copy.deepcopy(m)._packed[("cpu", collapsed)] is None
+
+
+def test_wgrad_split_plan_host_logic():
+    """ax2d_gemm_tc_wgrad_splits / _workspace are pure host arithmetic: chains of at most 1024 rows per accumulator,
+    split count chosen to minimise waves x chain length on 148 SMs, workspace = partial tiles + partial bias vectors."""
+    from aimnet_x2d_b200 import _lib
+    lib = _lib.load()
+    rows = 37632                                   # C2 step: atoms of a padded 2048-molecule batch
+    expect = {(160, 160): 74, (320, 320): 49, (544, 256): 44, (512, 544): 37}
+    for (m, n), want in expect.items():
+        sp = lib.ax2d_gemm_tc_wgrad_splits(m, n, rows)
+        assert sp == want, (m, n, sp)
+        assert sp >= -(-rows // 1024)                                  # accumulation chains <= 1024 rows
+        assert lib.ax2d_gemm_tc_wgrad_workspace(m, n, rows) == sp * (m * n + m) * 4
+    # tiny contraction: one split, no workspace
+    assert lib.ax2d_gemm_tc_wgrad_splits(4096, 512, 32) == 1
+    assert lib.ax2d_gemm_tc_wgrad_workspace(4096, 512, 32) == 0
+    # monotone sanity over a sweep: never fewer splits than the chain cap, never more than one per k-block
+    for k in (1, 31, 32, 33, 1000, 5000, 100000):
+        for (m, n) in ((32, 32), (160, 160), (512, 1024)):
+            sp = lib.ax2d_gemm_tc_wgrad_splits(m, n, k)
+            assert -(-k // 1024) <= sp <= -(-k // 32), (m, n, k, sp)
+
+
+def test_arena_layout_is_aligned_and_disjoint():
+    import torch
+    from aimnet_x2d_b200.trainer import _arena_layout
+    ts = [torch.zeros(7, dtype=torch.int64), torch.zeros(0), torch.zeros((3, 5)), torch.zeros(1000, dtype=torch.int32)]
+    offs, total = _arena_layout(ts)
+    assert all(o % 256 == 0 for o in offs) and total % 256 == 0
+    spans = [(o, o + t.numel() * t.element_size()) for o, t in zip(offs, ts)]
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0
+    assert spans[-1][1] <= total
