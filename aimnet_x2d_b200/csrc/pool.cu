@@ -172,6 +172,114 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_fwd_kernel(
   }
 }
 
+// Forward for molecules of at most kDirectRows atoms (every drug-like batch): the same arithmetic in the same order
+// as attn_pool_fwd_kernel, but x is NOT staged in shared memory -- pass 1 reads each row from global memory (one
+// coalesced warp-wide read per row), pass 2 reads the molecule's rows again, which L2 still holds.  With ~10 KB of
+// shared memory instead of ~68 KB per CTA an SM holds 12-16 molecules at a time instead of 3, which is what this
+// latency-bound kernel (a few dependent phases over ~36 KB per molecule) needs.  The head weights (8 KB, the same for
+// every CTA) are read through L1 instead of being copied to shared memory first.
+constexpr int kDirectRows = 256;
+__global__ void __launch_bounds__(kPoolThreads) attn_pool_fwd_direct_kernel(
+    const float* __restrict__ x, const int32_t* __restrict__ seg_ptr, int64_t N, int F, int heads,
+    const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ temperature,
+    float* __restrict__ pooled, float* __restrict__ attn, float* __restrict__ zbuf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* as = reinterpret_cast<float*>(smem_raw);                 // [heads, kDirectRows]  scores then weights
+  float* abar = as + static_cast<size_t>(heads) * kDirectRows;    // [kDirectRows]
+
+  const int g = blockIdx.x;
+  const int n0 = seg_ptr[g], n1 = seg_ptr[g + 1];
+  const int n = n1 - n0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int F4 = F >> 2;
+  const bool fits = n <= kDirectRows;      // a molecule beyond the hint: scores / weights go through global memory
+  float4* pooled4 = reinterpret_cast<float4*>(pooled + static_cast<int64_t>(g) * F);
+  if (n == 0) {   // torch_scatter leaves untouched segments at 0
+    for (int c = tid; c < F4; c += kPoolThreads) pooled4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float T = __ldg(temperature);
+  const float4* w4 = reinterpret_cast<const float4*>(w);          // 8 KB shared by every CTA: served by L1
+
+  // ---- pass 1: scores z[h,i] = (w_h . x_i + b_h) / T            (pooling.py:134-140)
+  const float4* xg = reinterpret_cast<const float4*>(x + static_cast<int64_t>(n0) * F);
+  for (int i = warp; i < n; i += kPoolThreads / 32) {
+    float dot[kMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) dot[h] = 0.f;
+    const float4* xr = xg + static_cast<size_t>(i) * F4;
+    // (unrolling this loop so that the row's four loads issue together costs 90 registers and occupancy: 75 vs 60 us)
+    for (int c = lane; c < F4; c += 32) {
+      const float4 xv = __ldg(xr + c);
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h)
+        if (h < heads) {
+          const float4 wv = __ldg(w4 + h * F4 + c);
+          dot[h] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h)
+      if (h < heads) {
+        const float s = warp_sum(dot[h]);
+        if (lane == 0) {
+          const float z = (s + __ldg(b + h)) / T;
+          zbuf[static_cast<int64_t>(h) * N + n0 + i] = z;
+          if (fits) as[h * kDirectRows + i] = z;
+        }
+      }
+  }
+  __syncthreads();
+
+  // ---- softmax per (head, molecule)                              (pooling.py:144-145, scatter_softmax)
+  for (int h = warp; h < heads; h += kPoolThreads / 32) {
+    float* zrow = fits ? as + h * kDirectRows : zbuf + static_cast<int64_t>(h) * N + n0;
+    float m = -INFINITY;
+    for (int i = lane; i < n; i += 32) m = fmaxf(m, zrow[i]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int i = lane; i < n; i += 32) s += expf(zrow[i] - m);
+    s = warp_sum(s);
+    float* arow = attn + static_cast<int64_t>(h) * N + n0;
+    for (int i = lane; i < n; i += 32) {
+      const float a = expf(zrow[i] - m) / s;
+      arow[i] = a;
+      if (fits) zrow[i] = a;
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 2: pooled = mean_h sum_i a[h,i] x_i                  (pooling.py:150-161)
+  if (fits) {
+    for (int i = tid; i < n; i += kPoolThreads) {
+      float sacc = 0.f;
+      for (int h = 0; h < heads; ++h) sacc += as[h * kDirectRows + i];
+      abar[i] = sacc;
+    }
+    __syncthreads();
+  }
+  const float inv_h = 1.f / static_cast<float>(heads);
+  for (int c = tid; c < F4; c += kPoolThreads) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+      float a;
+      if (fits) {
+        a = abar[i];
+      } else {
+        a = 0.f;
+        for (int h = 0; h < heads; ++h) a += attn[static_cast<int64_t>(h) * N + n0 + i];
+      }
+      const float4 xv = __ldg(xg + static_cast<size_t>(i) * F4 + c);
+      acc.x += a * xv.x;
+      acc.y += a * xv.y;
+      acc.z += a * xv.z;
+      acc.w += a * xv.w;
+    }
+    pooled4[c] = make_float4(acc.x * inv_h, acc.y * inv_h, acc.z * inv_h, acc.w * inv_h);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ backward
 // Formulas: SURVEY.md appendix C6.  d_i = (1/H) G_g . x_i ; da[h,i] = d_i (+ Ga[h,i]) ;
 // dz[h,i] = a[h,i] (da[h,i] - sum_j a[h,j] da[h,j]) ; gx_i = (sum_h a[h,i]/H) G_g + (1/T) sum_h dz[h,i] w_h ;
@@ -499,6 +607,14 @@ extern "C" int ax2d_attn_pool_fwd(const float* x, int64_t ldx, const int32_t* se
   AX2D_CHECK_ALIGN(w);
   AX2D_CHECK_ALIGN(pooled);
   if (B <= 0) return AX2D_OK;
+  if (max_rows_hint > 0 && max_rows_hint <= kDirectRows) {       // every molecule fits the score buffer: no x staging
+    const size_t smem_d = static_cast<size_t>(heads + 1) * kDirectRows * 4;
+    if (smem_d > 48 * 1024)
+      cudaFuncSetAttribute(attn_pool_fwd_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_d));
+    attn_pool_fwd_direct_kernel<<<static_cast<unsigned>(B), kPoolThreads, smem_d, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, seg_ptr, N, F, heads, w, b, temperature, pooled, attn, z);
+    return launch_status("ax2d_attn_pool_fwd");
+  }
   const int CH = pool_chunk_rows(F, heads, max_rows_hint, false);
   const size_t smem = (static_cast<size_t>(CH) * F + static_cast<size_t>(heads) * F + static_cast<size_t>(heads) * CH + CH) * 4;
   if (smem > 48 * 1024)

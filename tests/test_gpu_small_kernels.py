@@ -118,3 +118,40 @@ def test_weighted_loss_kernel(kind, B, T):
     ref.backward()
     assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
     assert float((pred.grad.double() - p64.grad).abs().max()) <= 1e-5 * float(p64.grad.abs().max())
+
+
+@pytest.mark.parametrize("hint", [8, 300, 1000])
+def test_attn_pool_fwd_direct_and_staged_kernels(hint):
+    """hint <= 256 selects the kernel that reads x straight from global memory; a molecule larger than the hint (300
+    atoms against hint 8) must still be handled (scores through global memory); hint 1000 selects the staged kernel.
+    Reference: pooling.py:134-161 in float64."""
+    L = _lib()
+    lib = L.load()
+    rng = np.random.Generator(np.random.PCG64(hint))
+    sizes = [300, 5, 0, 40, 1, 29]
+    N, F, heads = sum(sizes), 64, 4
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32), device=DEV)
+    x = torch.from_numpy(rng.normal(size=(N, F)).astype(np.float32)).to(DEV)
+    w = torch.from_numpy(rng.normal(size=(heads, F)).astype(np.float32) / 8).to(DEV)
+    b = torch.from_numpy(rng.normal(size=heads).astype(np.float32)).to(DEV)
+    T = torch.tensor(0.7, device=DEV)
+    pooled = torch.full((len(sizes), F), float("nan"), device=DEV)
+    attn = torch.full((heads, N), float("nan"), device=DEV)
+    z = torch.full((heads, N), float("nan"), device=DEV)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    L.check(lib.ax2d_attn_pool_fwd(P(x), F, P(seg), len(sizes), N, F, heads, P(w), P(b), P(T), P(pooled), P(attn), P(z), hint,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ax2d_attn_pool_fwd")
+    torch.cuda.synchronize()
+    zz = (x.double() @ w.double().t() + b.double()) / 0.7                                     # [N, heads]
+    ref_pooled = torch.zeros((len(sizes), F), dtype=torch.float64, device=DEV)
+    ref_attn = torch.zeros((heads, N), dtype=torch.float64, device=DEV)
+    o = 0
+    for g, n in enumerate(sizes):
+        if n:
+            a = torch.softmax(zz[o:o + n], dim=0)                                             # per head over the molecule
+            ref_attn[:, o:o + n] = a.t()
+            ref_pooled[g] = (a.t().unsqueeze(2) * x[o:o + n].double().unsqueeze(0)).sum(1).mean(0)
+        o += n
+    assert float((attn.double() - ref_attn).abs().max()) <= 1e-6
+    assert float((pooled.double() - ref_pooled).abs().max()) <= 1e-5 * float(ref_pooled.abs().max())
+    assert float((z.double() - zz.t()).abs().max()) <= 1e-5 * float(zz.abs().max())
