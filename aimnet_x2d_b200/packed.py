@@ -63,6 +63,11 @@ class PackedWeights:
         self._max_elems = 1
         self.dirty = False
         self._workspaces: Dict[str, torch.Tensor] = {}     # persistent split-K workspaces, one per matrix
+        # Buffers a captured CUDA graph may still read are never freed or rewritten: a second step captured on the same
+        # model with other shapes gets its own descriptor table (one per configuration) and, if it needs a larger
+        # workspace, the old one stays alive.
+        self._tables: Dict[tuple, torch.Tensor] = {}
+        self._retired: List[torch.Tensor] = []
 
     # a derived cache: copies / pickles of the owning module rebuild their own
     def __deepcopy__(self, memo):
@@ -124,6 +129,8 @@ class PackedWeights:
         """Persistent split-K workspace of one matrix (its partial tiles must outlive the backward pass)."""
         ws = self._workspaces.get(name)
         if ws is None or ws.numel() * 4 < nbytes:
+            if ws is not None:
+                self._retired.append(ws)
             ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=self.device)
             self._workspaces[name] = ws
         return ws
@@ -156,12 +163,10 @@ class PackedWeights:
                     d["part"], d["split"], d["p_rows"], d["p_cols"] = part
                     d["dr"], d["dc"] = dr, dc
                 i += 1
-        host = torch.from_numpy(rec.view(np.uint8).copy())
-        if self._table is None:
-            self._table = host.to(self.device)
-        else:                       # in place: a captured CUDA graph keeps reading this buffer
-            self._table.copy_(host)
-        self._table_key = self._key(with_grads)
+        key = self._key(with_grads)
+        self._table = torch.from_numpy(rec.view(np.uint8).copy()).to(self.device)
+        self._tables[key] = self._table
+        self._table_key = key
 
     def _ensure(self, with_grads: bool) -> None:
         if with_grads:
@@ -169,8 +174,13 @@ class PackedWeights:
                 if p.requires_grad and p.grad is None:
                     p.grad = torch.zeros_like(p)
         key = self._key(with_grads)
-        if self._table is None or self._table_key is None or key[0] != self._table_key[0] or (
-                with_grads and (key[1] != self._table_key[1] or key[2] != self._table_key[2])):
+        if self._table is not None and self._table_key is not None and key[0] == self._table_key[0] and (
+                not with_grads or (key[1] == self._table_key[1] and key[2] == self._table_key[2])):
+            return                                       # the current table fits (a refresh only needs the parameters)
+        cached = self._tables.get(key)
+        if cached is not None:
+            self._table, self._table_key = cached, key
+        else:
             self._build(with_grads)
 
     # ------------------------------------------------------------------ the two launches

@@ -225,3 +225,45 @@ def test_host_batch_single_copy_and_prefetch_equal_per_tensor_loads():
         assert torch.equal(p, q), k
     with pytest.raises(RuntimeError):
         s_b.pack(pad_batch(raws[0], n_pad + 32, e_cap, 8, t_cap, max_tile_edges=me_cap))
+
+
+def test_two_captured_steps_of_different_shapes_share_one_model():
+    """Two GraphedTrainSteps with different static signatures on the SAME model and optimiser, replayed alternately:
+    the packed-weight descriptor tables and split-K workspaces a captured graph reads must survive the other capture.
+    Checked against the eager step on a twin model."""
+    import aimnet_x2d_b200 as ax
+    from aimnet_x2d_b200 import synthetic as S
+    from aimnet_x2d_b200.collate import pad_batch
+    from aimnet_x2d_b200.trainer import GraphedTrainStep, TrainStep
+    crit = ax.WeightedL1Loss(torch.linspace(0.5, 1.5, 3)).to(DEV)
+
+    def padded(seed, graphs, extra):
+        raw = S.make_batch(seed, graphs, 3, "qm9", num_targets=3)
+        return pad_batch(raw, raw.graph_index.num_atoms + extra, raw.graph_index.num_edges + extra, 8).pin_memory()
+
+    small, big = padded(90, 24, 40), padded(91, 96, 200)          # different atom / tile / molecule counts
+    m_g, m_e = _model(), _model()
+    for m in (m_g, m_e):
+        m.train(False)
+    o_g, o_e = ax.FlatAdam(m_g.parameters(), lr=1e-3), ax.FlatAdam(m_e.parameters(), lr=1e-3)
+    s_small, s_big = GraphedTrainStep(m_g, crit, o_g, DEV), GraphedTrainStep(m_g, crit, o_g, DEV)
+    s_small.capture(small)
+    s_big.capture(big)                                             # larger workspaces, another descriptor table
+
+    class PaddedEager(TrainStep):
+        def device_step(self, bd):
+            self.optimizer.zero_grad()
+            out, _, _ = _fwd(self.model, bd)
+            loss = self.criterion(out[: bd.num_real_graphs], bd.targets[: bd.num_real_graphs])
+            loss.backward()
+            self.optimizer.step()
+            return loss.detach()
+
+    eager = PaddedEager(m_e, crit, o_e, DEV)
+    for which in (0, 1, 0, 0, 1, 1, 0):
+        b, st = (small, s_small) if which == 0 else (big, s_big)
+        lg = st(b)
+        le = float(eager(b))
+        assert abs(lg - le) <= 1e-6 * max(abs(le), 1.0), (which, lg, le)
+    for (k, p), (_, q) in zip(m_g.named_parameters(), m_e.named_parameters()):
+        assert float((p - q).abs().max()) <= 1e-6 * (float(q.abs().max()) + 1e-12), k
