@@ -50,7 +50,7 @@ WORKLOADS = {
 }
 T_TARGETS = 12
 AGG_DRAM_TRAFFIC = 25.6e6     # bytes per forward launch, ncu capture profiles/r1e_agg_tiles_full.txt
-DENSE_SHARE_OF_STEP = 0.85    # gemm_tc + gemm_tc_wgrad + split-K sums share of the step, profiles/r1n_launches_graph_step.csv
+DENSE_SHARE_OF_STEP = 0.85    # gemm_tc + gemm_tc_wgrad + split-K sums share of the step, profiles/r1o_launches_graph_step.csv
 RING = 4            # distinct batches per rank, rotated every step (per-step working set >> 126 MB L2)
 
 
@@ -435,7 +435,7 @@ def ours_arm(args, wl):
                           "peak_source": "0.5 x measured sustained bf16 (MEASURED_PEAKS.json); the split issues 3 tf32 "
                                          "MMAs per useful product, so frac <= 0.33 by construction",
                           "useful_tflops_over_whole_step": tf_step, "share_of_step": DENSE_SHARE_OF_STEP,
-                          "share_source": "profiles/r1n_launches_graph_step.csv (ncu --graph-profiling node)",
+                          "share_source": "profiles/r1o_launches_graph_step.csv (ncu --graph-profiling node)",
                           "launches_per_step": sum(ks[k]["launches"] for k in dense) / n_prof}
         h2d = packed[0].nbytes() if graphs else host[0].nbytes()
         cpu = None
