@@ -423,7 +423,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
         const float* pdp = te.dp + mrow * te.lddp + n;
         const int r0w = lane >> 3;               // this lane's rows: r0w + 4 i
         uint64_t didx = static_cast<uint64_t>(mrow) * static_cast<uint32_t>(N) + static_cast<uint32_t>(n);
-#pragma unroll 4
+#pragma unroll 2      // measured on the C2 shapes: 2 beats 1 (too little in flight) and 4 / 8 (instruction-cache pressure)
         for (int i = 0; i < 8; ++i) {          // rows mrow + 4 i
           float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, dp = r0;
           if (te.nres > 0) r0 = __ldg(reinterpret_cast<const float4*>(pr0));
