@@ -369,6 +369,57 @@ __device__ __forceinline__ TileEpi tile_epi(const EpiArgs& e, int64_t m0, int n0
   return t;
 }
 
+// The eight rows (r0w + 4 i) of one 32 x 32 chunk that a lane finishes on the CTA-uniform path: NRES residuals.
+template <int ACT, int DACT, bool DROP, int NRES>
+__device__ __forceinline__ void lean_rows(const TileEpi& te, const EpiCtx& cx, const float4* stg4, int r0w, int cg, float4 b4,
+                                          float* pc, float* ppre, const float* pr0, const float* pr1, const float* pr2,
+                                          const float* pdp, uint64_t didx, int N) {
+#pragma unroll 2      // measured on the C2 shapes: 2 beats 1 (too little in flight) and 4 / 8 (instruction-cache pressure)
+  for (int i = 0; i < 8; ++i) {          // rows mrow + 4 i
+    float4 r0, r1, r2, dp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (NRES > 0) r0 = __ldg(reinterpret_cast<const float4*>(pr0));
+    if constexpr (NRES > 1) r1 = __ldg(reinterpret_cast<const float4*>(pr1));
+    if constexpr (NRES > 2) r2 = __ldg(reinterpret_cast<const float4*>(pr2));
+    if constexpr (DACT != AX2D_ACT_NONE) {
+      if (te.has_dp) dp = __ldg(reinterpret_cast<const float4*>(pdp));
+    }
+    const float4 s4 = stg4[(r0w + 4 * i) * 8 + (cg ^ ((r0w + 4 * i) & 7))];
+    float v[4] = {s4.x + b4.x, s4.y + b4.y, s4.z + b4.z, s4.w + b4.w};
+    if (te.has_pre) *reinterpret_cast<float4*>(ppre) = make_float4(v[0], v[1], v[2], v[3]);
+    float drop[4] = {1.f, 1.f, 1.f, 1.f};
+    if constexpr (DROP) drop_scale4(cx, didx, drop);
+    if constexpr (ACT != AX2D_ACT_NONE) {
+      if (te.act) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = act_fwd_t<ACT>(v[j]);
+      }
+    }
+    if constexpr (DROP && DACT == AX2D_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= drop[j];
+    }
+    if constexpr (NRES > 0) { v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; }
+    if constexpr (NRES > 1) { v[0] += r1.x; v[1] += r1.y; v[2] += r1.z; v[3] += r1.w; }
+    if constexpr (NRES > 2) { v[0] += r2.x; v[1] += r2.y; v[2] += r2.z; v[3] += r2.w; }
+    if constexpr (DACT != AX2D_ACT_NONE) {
+      if (te.has_dp) {
+        v[0] *= act_bwd_t<DACT>(dp.x) * drop[0];
+        v[1] *= act_bwd_t<DACT>(dp.y) * drop[1];
+        v[2] *= act_bwd_t<DACT>(dp.z) * drop[2];
+        v[3] *= act_bwd_t<DACT>(dp.w) * drop[3];
+      }
+    }
+    *reinterpret_cast<float4*>(pc) = make_float4(v[0], v[1], v[2], v[3]);
+    pc += 4 * te.ldc;
+    ppre += 4 * te.ldpre;
+    if constexpr (NRES > 0) pr0 += 4 * te.ldres0;
+    if constexpr (NRES > 1) pr1 += 4 * te.ldres1;
+    if constexpr (NRES > 2) pr2 += 4 * te.ldres2;
+    if constexpr (DACT != AX2D_ACT_NONE) pdp += 4 * te.lddp;
+    if constexpr (DROP) didx += 4ull * static_cast<uint32_t>(N);
+  }
+}
+
 // Epilogue of one warp: its 32 accumulator rows (TMEM lanes 32 q .. 32 q + 31), 32 columns at a time:
 // tcgen05.ld (lane = row, registers = columns) -> shared-memory transpose -> 8 lanes per row, float4 per lane, so
 // every global access of the fused epilogue is a row-contiguous 128-byte segment.
@@ -423,47 +474,14 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
         const float* pdp = te.dp + mrow * te.lddp + n;
         const int r0w = lane >> 3;               // this lane's rows: r0w + 4 i
         uint64_t didx = static_cast<uint64_t>(mrow) * static_cast<uint32_t>(N) + static_cast<uint32_t>(n);
-#pragma unroll 2      // measured on the C2 shapes: 2 beats 1 (too little in flight) and 4 / 8 (instruction-cache pressure)
-        for (int i = 0; i < 8; ++i) {          // rows mrow + 4 i
-          float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, dp = r0;
-          if (te.nres > 0) r0 = __ldg(reinterpret_cast<const float4*>(pr0));
-          if (te.nres > 1) r1 = __ldg(reinterpret_cast<const float4*>(pr1));
-          if (te.nres > 2) r2 = __ldg(reinterpret_cast<const float4*>(pr2));
-          if (te.has_dp) dp = __ldg(reinterpret_cast<const float4*>(pdp));
-          const float4 s4 = stg4[(r0w + 4 * i) * 8 + (cg ^ ((r0w + 4 * i) & 7))];
-          float v[4] = {s4.x + b4.x, s4.y + b4.y, s4.z + b4.z, s4.w + b4.w};
-          if (te.has_pre) *reinterpret_cast<float4*>(ppre) = make_float4(v[0], v[1], v[2], v[3]);
-          float drop[4] = {1.f, 1.f, 1.f, 1.f};
-          if constexpr (DROP) drop_scale4(cx, didx, drop);
-          if constexpr (ACT != AX2D_ACT_NONE) {
-            if (te.act) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = act_fwd_t<ACT>(v[j]);
-            }
-          }
-          if constexpr (DROP && DACT == AX2D_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] *= drop[j];
-          }
-          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-          v[0] += r1.x; v[1] += r1.y; v[2] += r1.z; v[3] += r1.w;
-          v[0] += r2.x; v[1] += r2.y; v[2] += r2.z; v[3] += r2.w;
-          if constexpr (DACT != AX2D_ACT_NONE) {
-            if (te.has_dp) {
-              v[0] *= act_bwd_t<DACT>(dp.x) * drop[0];
-              v[1] *= act_bwd_t<DACT>(dp.y) * drop[1];
-              v[2] *= act_bwd_t<DACT>(dp.z) * drop[2];
-              v[3] *= act_bwd_t<DACT>(dp.w) * drop[3];
-            }
-          }
-          *reinterpret_cast<float4*>(pc) = make_float4(v[0], v[1], v[2], v[3]);
-          pc += 4 * te.ldc;
-          ppre += 4 * te.ldpre;
-          pr0 += 4 * te.ldres0;
-          pr1 += 4 * te.ldres1;
-          pr2 += 4 * te.ldres2;
-          pdp += 4 * te.lddp;
-          didx += 4ull * static_cast<uint32_t>(N);
+        // the row loop is compiled once per residual count: without it every row carried the zero-initialisation,
+        // predicated loads, adds and pointer bookkeeping of three optional residuals (~25 of ~87 instructions per
+        // float4 row of the plain SiLU epilogue)
+        switch (te.nres) {
+          case 0: lean_rows<ACT, DACT, DROP, 0>(te, cx, stg4, r0w, cg, b4, pc, ppre, pr0, pr1, pr2, pdp, didx, N); break;
+          case 1: lean_rows<ACT, DACT, DROP, 1>(te, cx, stg4, r0w, cg, b4, pc, ppre, pr0, pr1, pr2, pdp, didx, N); break;
+          case 2: lean_rows<ACT, DACT, DROP, 2>(te, cx, stg4, r0w, cg, b4, pc, ppre, pr0, pr1, pr2, pdp, didx, N); break;
+          default: lean_rows<ACT, DACT, DROP, 3>(te, cx, stg4, r0w, cg, b4, pc, ppre, pr0, pr1, pr2, pdp, didx, N); break;
         }
       }
     } else if (n < N) {
