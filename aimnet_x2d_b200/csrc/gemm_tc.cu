@@ -369,9 +369,23 @@ __device__ __forceinline__ TileEpi tile_epi(const EpiArgs& e, int64_t m0, int n0
   return t;
 }
 
+// 128-bit shared-memory load from a 32-bit shared address.  The address comes out of an opaque asm statement (pin32), so
+// the compiler keeps it in a register instead of re-deriving it from the thread index in every iteration, which at
+// the kernel's 96-register cap it otherwise does (~20 instructions per two rows).
+__device__ __forceinline__ uint32_t pin32(uint32_t v) {
+  asm volatile("mov.u32 %0, %0;" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 // The eight rows (r0w + 4 i) of one 32 x 32 chunk that a lane finishes on the CTA-uniform path: NRES residuals.
+// s_even / s_odd: shared addresses of this lane's float4 in rows r0w and r0w + 4 (row r0w + 4 i is 1024 (i / 2) bytes
+// further: 8 rows of 128 bytes; the swizzle term (row & 7) only depends on the parity of i).
 template <int ACT, int DACT, bool DROP, int NRES>
-__device__ __forceinline__ void lean_rows(const TileEpi& te, const EpiCtx& cx, const float4* stg4, int r0w, int cg, float4 b4,
+__device__ __forceinline__ void lean_rows(const TileEpi& te, const EpiCtx& cx, uint32_t s_even, uint32_t s_odd, float4 b4,
                                           float* pc, float* ppre, const float* pr0, const float* pr1, const float* pr2,
                                           const float* pdp, uint64_t didx, int N) {
 #pragma unroll 2      // measured on the C2 shapes: 2 beats 1 (too little in flight) and 4 / 8 (instruction-cache pressure)
@@ -383,7 +397,7 @@ __device__ __forceinline__ void lean_rows(const TileEpi& te, const EpiCtx& cx, c
     if constexpr (DACT != AX2D_ACT_NONE) {
       if (te.has_dp) dp = __ldg(reinterpret_cast<const float4*>(pdp));
     }
-    const float4 s4 = stg4[(r0w + 4 * i) * 8 + (cg ^ ((r0w + 4 * i) & 7))];
+    const float4 s4 = lds128(((i & 1) ? s_odd : s_even) + static_cast<uint32_t>(i >> 1) * 1024u);
     float v[4] = {s4.x + b4.x, s4.y + b4.y, s4.z + b4.z, s4.w + b4.w};
     if (te.has_pre) *reinterpret_cast<float4*>(ppre) = make_float4(v[0], v[1], v[2], v[3]);
     float drop[4] = {1.f, 1.f, 1.f, 1.f};
@@ -477,11 +491,14 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
         // the row loop is compiled once per residual count: without it every row carried the zero-initialisation,
         // predicated loads, adds and pointer bookkeeping of three optional residuals (~25 of ~87 instructions per
         // float4 row of the plain SiLU epilogue)
+        const int sw0 = cg ^ r0w;
+        const uint32_t s_even = pin32(smem_u32(stg4 + r0w * 8 + sw0));
+        const uint32_t s_odd = pin32(smem_u32(stg4 + (r0w + 4) * 8 + (sw0 ^ 4)));
         switch (te.nres) {
-          case 0: lean_rows<ACT, DACT, DROP, 0>(te, cx, stg4, r0w, cg, b4, pc, ppre, pr0, pr1, pr2, pdp, didx, N); break;
-          case 1: lean_rows<ACT, DACT, DROP, 1>(te, cx, stg4, r0w, cg, b4, pc, ppre, pr0, pr1, pr2, pdp, didx, N); break;
-          case 2: lean_rows<ACT, DACT, DROP, 2>(te, cx, stg4, r0w, cg, b4, pc, ppre, pr0, pr1, pr2, pdp, didx, N); break;
-          default: lean_rows<ACT, DACT, DROP, 3>(te, cx, stg4, r0w, cg, b4, pc, ppre, pr0, pr1, pr2, pdp, didx, N); break;
+          case 0: lean_rows<ACT, DACT, DROP, 0>(te, cx, s_even, s_odd, b4, pc, ppre, pr0, pr1, pr2, pdp, didx, N); break;
+          case 1: lean_rows<ACT, DACT, DROP, 1>(te, cx, s_even, s_odd, b4, pc, ppre, pr0, pr1, pr2, pdp, didx, N); break;
+          case 2: lean_rows<ACT, DACT, DROP, 2>(te, cx, s_even, s_odd, b4, pc, ppre, pr0, pr1, pr2, pdp, didx, N); break;
+          default: lean_rows<ACT, DACT, DROP, 3>(te, cx, s_even, s_odd, b4, pc, ppre, pr0, pr1, pr2, pdp, didx, N); break;
         }
       }
     } else if (n < N) {
