@@ -315,3 +315,24 @@ def test_arena_layout_is_aligned_and_disjoint():
     for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
         assert a1 <= b0
     assert spans[-1][1] <= total
+
+
+def test_shared_dropout_tick_host_logic():
+    """layers.shared_tick: every dropout site below shares ONE tick per forward pass of the enclosing model; outside
+    of it a site advances its own clock (CPU tensors: pure host logic)."""
+    import torch
+    from aimnet_x2d_b200.layers import DropClock, shared_tick
+    model_clock, site_a, site_b = DropClock(), DropClock(), DropClock()
+    assert site_a.seed != site_b.seed                            # the masks differ through the per-site seeds
+    with shared_tick(model_clock):
+        t1, t2 = site_a.advance(), site_b.advance()
+        assert t1 is t2 and int(t1) == 1
+        with shared_tick(model_clock):                           # nested forward (a model inside a model)
+            assert int(site_a.advance()) == 2
+        assert site_a.advance() is t1                            # the outer pass keeps its tick
+    assert int(model_clock.tick) == 2 and int(site_a.tick) == 0 and int(site_b.tick) == 0
+    own = site_a.advance()                                       # stand-alone module: its own clock
+    assert int(own) == 1 and int(site_a.tick) == 1 and DropClock._shared is None
+    snapshot = site_a.advance()
+    site_a.advance()
+    assert int(snapshot) == 2                                    # a snapshot: backward sees the value of ITS forward
