@@ -89,6 +89,7 @@ _SIGNATURES = {
     "ax2d_sqnorm": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ax2d_clip_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float,
                                c_float, c_float, c_float, c_void_p, c_void_p]),
+    "ax2d_clip_adam_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ax2d_pack_weights": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "ax2d_unpack_grads": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "ax2d_weighted_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),

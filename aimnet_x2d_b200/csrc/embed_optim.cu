@@ -214,6 +214,44 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
   }
 }
 
+// The same update with every hyper-parameter read from DEVICE memory, hyper = {grad_scale, max_norm, lr, beta1, beta2,
+// eps}: a CUDA-graph-captured step then follows learning-rate schedulers (the host rewrites the six floats between
+// replays) instead of replaying the values that were current at capture time.
+__global__ void __launch_bounds__(256) clip_adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                            float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                            const float* __restrict__ norm2, const float* __restrict__ hyper,
+                                                            const int64_t* __restrict__ step) {
+  __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+  const float grad_scale = hyper[0], max_norm = hyper[1], lr = hyper[2], beta1 = hyper[3], beta2 = hyper[4], eps = hyper[5];
+  if (threadIdx.x == 0) {
+    const double t = static_cast<double>(step[0]);
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), t);
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), t);
+    s_step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+    s_bc2_sqrt = static_cast<float>(sqrt(bc2));
+    float coef = grad_scale;
+    if (max_norm > 0.f) {
+      const float total = sqrtf(norm2[0]) * grad_scale;
+      const float c = max_norm / (total + 1e-6f);
+      coef *= c < 1.f ? c : 1.f;
+    }
+    s_coef = coef;
+  }
+  __syncthreads();
+  const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float w1 = 1.f - beta1, w2 = 1.f - beta2;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = m[i] + (gi - m[i]) * w1;
+    const float vi = v[i] * beta2 + w2 * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+
 // ----------------------------------------------------------------------------------------- loss
 __global__ void __launch_bounds__(1024) weighted_loss_kernel(const float* __restrict__ pred,
                                                              const float* __restrict__ target,
@@ -366,6 +404,17 @@ extern "C" int ax2d_clip_adam(float* p, const float* g, float* m, float* v, int6
   clip_adam_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, n, norm2, grad_scale, max_norm, lr, beta1, beta2, eps, step);
   return launch_status("ax2d_clip_adam");
+}
+
+extern "C" int ax2d_clip_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* norm2,
+                                  const float* hyper, const int64_t* step, ax2d_stream_t stream) {
+  AX2D_CHECK_ARG(n >= 0 && step != nullptr && hyper != nullptr && norm2 != nullptr, "ax2d_clip_adam_dev: bad arguments");
+  if (n == 0) return AX2D_OK;
+  int64_t blocks = (n + 255) / 256;
+  blocks = blocks > kNumSMs * 8 ? kNumSMs * 8 : blocks;
+  clip_adam_dev_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, norm2,
+                                                                                                            hyper, step);
+  return launch_status("ax2d_clip_adam_dev");
 }
 
 extern "C" int ax2d_weighted_loss(const float* pred, const float* target, const float* weights, int64_t B, int T,

@@ -93,13 +93,15 @@ struct EpiCtx {      // per-thread constants of the epilogue
 __device__ __forceinline__ EpiCtx epi_ctx(const EpiArgs& g) {
   EpiCtx c;
   c.dropping = g.mask != nullptr || g.drop_p > 0.f;
-  c.inv_keep = g.drop_p > 0.f ? 1.f / (1.f - g.drop_p) : 1.f;
+  c.thresh = static_cast<uint32_t>(g.drop_p * 65536.f + 0.5f);
+  // the keep probability that is actually realised is (65536 - thresh) / 65536 (p quantised to 16 bits): scale by ITS
+  // reciprocal so that E[mask] == 1 exactly
+  c.inv_keep = g.drop_p > 0.f ? 65536.f / static_cast<float>(65536u - (c.thresh < 65535u ? c.thresh : 65535u)) : 1.f;
   const uint64_t seed = g.drop_seed + (g.drop_tick != nullptr
                                            ? __ldg(reinterpret_cast<const unsigned long long*>(g.drop_tick)) * 0xD1B54A32D192ED03ull
                                            : 0ull);
   c.seed_lo = static_cast<uint32_t>(seed);
   c.seed_hi = static_cast<uint32_t>(seed >> 32);
-  c.thresh = static_cast<uint32_t>(g.drop_p * 65536.f + 0.5f);
   uint32_t h = c.seed_hi;
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   c.base0 = h ^ c.seed_lo;
@@ -114,7 +116,10 @@ __device__ __forceinline__ void drop_scale4(const EpiCtx& cx, uint64_t idx, floa
   const uint32_t lo = static_cast<uint32_t>(idx >> 2), hi = static_cast<uint32_t>(idx >> 34);
   const uint32_t base = hi == 0u ? cx.base0 : (mix32(hi ^ cx.seed_hi) ^ cx.seed_lo);
   const uint32_t h0 = mix32((lo * 0x9E3779B1u) ^ base);
-  const uint32_t h1 = h0 * 0x9E3779B1u + 0x7F4A7C15u;
+  // second 32 bits: a multiply-xorshift round of h0 (not an affine map of it: under h0 * odd + c the low half of h1 would
+  // be a function of the low half of h0 alone and the keep decisions of elements 0 / 2 and 1 / 3 would be coupled)
+  uint32_t h1 = (h0 ^ (h0 >> 15)) * 0x2C1B3C6Du;
+  h1 ^= h1 >> 12;
   d[0] = (h0 & 0xFFFFu) >= cx.thresh ? cx.inv_keep : 0.f;
   d[1] = (h0 >> 16) >= cx.thresh ? cx.inv_keep : 0.f;
   d[2] = (h1 & 0xFFFFu) >= cx.thresh ? cx.inv_keep : 0.f;

@@ -8,6 +8,7 @@ checkpoints round-trip with the reference.
 """
 from __future__ import annotations
 
+import weakref
 from collections import OrderedDict
 from typing import List, Optional
 
@@ -47,27 +48,53 @@ def pack_chunked(w: torch.Tensor, rows_pad: int, n_chunks: int, chunk: int, chun
 
 
 class _IndexCache:
-    """Small LRU of GraphIndex objects rebuilt on the fly when the caller passes raw index tensors."""
+    """Small LRU of GraphIndex objects rebuilt on the fly when the caller passes raw index tensors.
+
+    An entry is keyed on the IDENTITY of the index tensors (the Python objects, or the base tensor of a view plus the
+    view's geometry) and their autograd version counters, and it holds weak references to those objects: it is only
+    served while every one of them is still alive, is the same object and has not been written in place.  Addresses are
+    never part of the key -- the caching allocator hands a freed block to the next batch, so a different batch of the same
+    shape routinely reappears at the same ``data_ptr``."""
 
     def __init__(self, size: int = 8):
         self.size = size
-        self.items: "OrderedDict[tuple, GraphIndex]" = OrderedDict()
+        self.items: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+    @staticmethod
+    def _root(t):
+        base = t._base if t._base is not None else t
+        return base
 
     @staticmethod
     def key(*tensors, extra=()):
         k = []
         for t in tensors:
-            k.append(None if t is None else (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t._version, str(t.device)))
-        return tuple(k) + tuple(extra)
+            if t is None:
+                k.append(None)
+                continue
+            k.append((id(_IndexCache._root(t)), t.storage_offset(), tuple(t.shape), tuple(t.stride()), t._version,
+                      str(t.device), str(t.dtype)))
+        return (tuple(k) + tuple(extra), tuple(tensors))
 
     def get(self, key, builder):
-        if key in self.items:
-            self.items.move_to_end(key)
-            return self.items[key]
+        key, tensors = key
+        hit = self.items.get(key)
+        if hit is not None:
+            gi, refs = hit
+            roots = [None if t is None else self._root(t) for t in tensors]
+            if len(refs) == len(roots) and all((r is None and o is None) or (r is not None and r() is o)
+                                               for r, o in zip(refs, roots)):
+                self.items.move_to_end(key)
+                return gi
+            del self.items[key]            # id() of a dead object was reused by another tensor
         gi = builder()
-        self.items[key] = gi
+        refs = [None if t is None else weakref.ref(self._root(t)) for t in tensors]
+        self.items[key] = (gi, refs)
         while len(self.items) > self.size:
             self.items.popitem(last=False)
+        # drop entries whose tensors died (their ids may be reused)
+        for k in [k for k, (_, rs) in self.items.items() if any(r is not None and r() is None for r in rs)]:
+            del self.items[k]
         return gi
 
 

@@ -36,6 +36,10 @@ class PackInfo:
         self.partials = None
 
 
+def _capturing(device) -> bool:
+    return device.type == "cuda" and torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 def packed_info(t) -> Optional[PackInfo]:
     return None if t is None else getattr(t, "_ax2d", None)
 
@@ -50,6 +54,8 @@ class PackedWeights:
     """``add(name, rows, cols, blocks)`` declares a packed matrix built from rectangular blocks of parameters:
     ``blocks = [(param, r0, r1, c0, c1, dst_r, dst_c), ...]`` (for a bias: rows = 1, r0 = 0, r1 = 1, columns = entries).
     ``finalize()`` allocates the (zero) arenas; ``refresh()`` / ``unpack_grads()`` launch the two kernels."""
+
+    MAX_TABLES = 16          # descriptor tables kept (LRU); tables a captured CUDA graph reads are never dropped
 
     def __init__(self, device):
         self.device = torch.device(device)
@@ -67,6 +73,7 @@ class PackedWeights:
         # model with other shapes gets its own descriptor table (one per configuration) and, if it needs a larger
         # workspace, the old one stays alive.
         self._tables: Dict[tuple, torch.Tensor] = {}
+        self._pinned = set()
         self._retired: List[torch.Tensor] = []
 
     # a derived cache: copies / pickles of the owning module rebuild their own
@@ -164,9 +171,21 @@ class PackedWeights:
                     d["dr"], d["dc"] = dr, dc
                 i += 1
         key = self._key(with_grads)
+        if _capturing(self.device):
+            # a pageable host-to-device copy is illegal inside a capture; the eager warm-up passes of capture() build every
+            # table the captured pass needs, so getting here means the capture was started cold
+            raise RuntimeError("packed-weight descriptor table would have to be built during CUDA graph capture; run "
+                               "at least one eager step with the same parameters / gradients first")
         self._table = torch.from_numpy(rec.view(np.uint8).copy()).to(self.device)
         self._tables[key] = self._table
         self._table_key = key
+        # bounded: a stock optimiser with zero_grad(set_to_none=True) hands out fresh .grad tensors every step, i.e. a new
+        # key per step.  Tables a captured graph reads (``_pinned``) are never dropped.
+        while len(self._tables) > self.MAX_TABLES:
+            victim = next((k for k in self._tables if k not in self._pinned and k != key), None)
+            if victim is None:
+                break
+            del self._tables[victim]
 
     def _ensure(self, with_grads: bool) -> None:
         if with_grads:
@@ -176,12 +195,17 @@ class PackedWeights:
         key = self._key(with_grads)
         if self._table is not None and self._table_key is not None and key[0] == self._table_key[0] and (
                 not with_grads or (key[1] == self._table_key[1] and key[2] == self._table_key[2])):
+            if _capturing(self.device):
+                self._pinned.add(self._table_key)
             return                                       # the current table fits (a refresh only needs the parameters)
         cached = self._tables.get(key)
         if cached is not None:
+            self._tables[key] = self._tables.pop(key)          # most recently used last
             self._table, self._table_key = cached, key
         else:
             self._build(with_grads)
+        if _capturing(self.device):
+            self._pinned.add(self._table_key)
 
     # ------------------------------------------------------------------ the two launches
     def _clear_grads(self) -> None:

@@ -231,6 +231,7 @@ class GraphedTrainStep(StaticSlot):
         self.graph_fb.replay()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             self.optimizer.all_reduce_grads()
+        self.optimizer.sync_hyper()          # LR schedulers: the captured update reads its hyper-parameters from device memory
         self.graph_opt.replay()
         return self.loss
 

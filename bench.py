@@ -128,10 +128,14 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ workloads
+def batch_seed(wl, rank, i):
+    cfg_id = {"c2": 2, "c3": 3, "c4": 4, "c4q": 4, "c5": 5}[wl["name"]]
+    return 1234 + cfg_id * 1000 + rank * 97 + i
+
+
 def make_batches(wl, rank, n):
     from aimnet_x2d_b200 import synthetic as S
-    cfg_id = {"c2": 2, "c3": 3, "c5": 5}[wl["name"]]
-    return [S.make_batch(1234 + cfg_id * 1000 + rank * 97 + i, wl["graphs"], wl["hops"], wl["kind"], T_TARGETS,
+    return [S.make_batch(batch_seed(wl, rank, i), wl["graphs"], wl["hops"], wl["kind"], T_TARGETS,
                          stereo=wl["stereo"]) for i in range(n)]
 
 
@@ -151,9 +155,105 @@ def build_model(wl, device):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_step_fn(wl, batch):
-    """One reference training step on the CPU through the oracle port (test infrastructure used as the baseline
-    checker leg only): returns a closure that runs zero_grad/forward/L1/backward/clip/Adam once."""
+# Nothing below imports aimnet_x2d_b200 (importing the package maps libax2d.so): the reference arm's process must contain
+# the reference's own code only.  Molecules come from aimnet_x2d_b200/molgen.py loaded BY FILE PATH (numpy only), shell
+# edges and collation from oracle/graph_port.py (restatement of datasets/features.py:97-150, molecular.py:339-458).
+def _molgen():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ax2d_molgen", os.path.join(ROOT, "aimnet_x2d_b200", "molgen.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def ref_batch(wl, seed, n):
+    """The synthetic batch of ``synthetic.make_batch(seed, n, ...)`` in the reference's Batch layout (dict of torch tensors)."""
+    from oracle import graph_port as GP
+    mg = _molgen()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    mols = [mg.make_molecule(rng, wl["kind"], T_TARGETS, wl["stereo"]) for _ in range(n)]
+    for m in mols:
+        m["hops"] = GP.shell_edges_bfs(m["num_atoms"], m["bonds"], wl["hops"])
+    c = GP.collate(mols)
+    t = torch.from_numpy
+    return dict(atom_features_map={k: t(v) for k, v in c["atom_features_map"].items()},
+                multi_hop_edge_indices=t(c["multi_hop_edge_indices"]), batch_indices=t(c["batch_indices"]),
+                total_charges=t(c["total_charges"]), final_tetrahedral_chiral_tensor=t(c["final_tetrahedral_chiral_tensor"]),
+                final_cis_tensor=t(np.ascontiguousarray(c["final_cis_tensor"])),
+                final_trans_tensor=t(np.ascontiguousarray(c["final_trans_tensor"])), targets=t(c["targets"]))
+
+
+_SHAPE_CACHE = {}
+
+
+def common_config(wl, world):
+    """The `config` object both arms print (identical for the same workload and --gpus): the workload and its sizes.  Atom /
+    edge counts are those of the first full-size batch of rank 0 (seed 1234 + 1000 * config id)."""
+    key = wl["name"]
+    if key not in _SHAPE_CACHE:
+        b = ref_batch(wl, batch_seed(wl, 0, 0), wl["graphs"])
+        _SHAPE_CACHE[key] = (int(b["batch_indices"].shape[0]), int(b["multi_hop_edge_indices"].shape[0]))
+    n_atoms, n_edges = _SHAPE_CACHE[key]
+    return {"workload": wl["desc"], "graphs_per_gpu": wl["graphs"], "global_batch": wl["graphs"] * world,
+            "atoms_per_batch": n_atoms, "edges_per_batch": n_edges, "targets": T_TARGETS,
+            "dropout": 0.0 if wl.get("mode") == "inference" else 0.05, "hidden": wl["hidden"], "hops": wl["hops"],
+            "layers": wl["layers"], "parallelism": f"dp{world}"}
+
+
+def staged_reference():
+    """oracle/_ref (the UNMODIFIED reference modules staged by oracle/stage_ref.py) if present and checksum-clean."""
+    from oracle import stage_ref
+    if not stage_ref.verify():
+        stage_ref.stage()                       # build container: /root/reference is there; on the GPU box this is a no-op
+    return stage_ref.src_dir() if stage_ref.verify() else None
+
+
+def cpu_step_fn(wl, b):
+    """One training step of the reference on the CPU; returns (closure, kind).
+
+    kind "reference": models.gnn.GNN / models.losses.WeightedL1Loss imported unmodified from oracle/_ref/src, driven through
+    the reference's own API exactly as training/trainer.py:130-165 does (zero_grad(set_to_none) -> forward ->
+    criterion -> backward -> clip_grad_norm_(1.0) -> Adam(2.5e-4).step() -> loss.item()), stock nn.Dropout active.
+    kind "port": oracle/model_port.py when the staged reference is missing (it always exists; same op sequence)."""
+    from oracle import scatter_port
+    mode = wl.get("mode", "train")
+    ref_src = staged_reference()
+    args = (b["atom_features_map"], b["multi_hop_edge_indices"], b["batch_indices"], b["total_charges"],
+            b["final_tetrahedral_chiral_tensor"], b["final_cis_tensor"], b["final_trans_tensor"])
+    if ref_src is not None:
+        sys.modules["torch_scatter"] = scatter_port          # third-party wheel (pinned 2.1.2), absent from this image
+        if ref_src not in sys.path:
+            sys.path.insert(0, ref_src)
+        from models.gnn import GNN as RefGNN
+        from models.losses import WeightedL1Loss as RefL1
+        torch.manual_seed(0)
+        sizes = {"atom_type": 119, "hydrogen_count": 9, "degree": 7, "hybridization": 7}
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):         # the reference prints "[GNN] Model weights initialized"
+            model = RefGNN(sizes, wl["hidden"], T_TARGETS, num_shells=wl["hops"], num_message_passing_layers=wl["layers"],
+                           task_type="multitask", use_partial_charges=wl["charges"], use_stereochemistry=wl["stereo"])
+        if mode == "inference":
+            model.eval()
+
+            def infer():
+                with torch.no_grad():
+                    out, _, q = model(*args)
+                return float(out[0, 0])
+            return infer, "reference"
+        model.train()
+        crit = RefL1(torch.ones(T_TARGETS))
+        opt = torch.optim.Adam(model.parameters(), lr=2.5e-4)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            out, _, _ = model(*args)
+            loss = crit(out, b["targets"])
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            return float(loss.item())
+        return step, "reference"
+
     from oracle import model_port as MP
     from oracle.fixtures import det_state
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -164,28 +264,25 @@ def cpu_step_fn(wl, batch):
     for v in P.values():
         v.requires_grad_(True)
     state = dict(m=[torch.zeros_like(P[k]) for k in keys], v=[torch.zeros_like(P[k]) for k in keys])
-    ob = dict(atom_features_map=batch.atom_features_map, multi_hop_edge_indices=batch.multi_hop_edge_indices,
-              batch_indices=batch.batch_indices, total_charges=batch.total_charges,
-              final_tetrahedral_chiral_tensor=batch.final_tetrahedral_chiral_tensor,
-              final_cis_tensor=batch.final_cis_tensor, final_trans_tensor=batch.final_trans_tensor)
     w = torch.ones(T_TARGETS)
-    N = int(batch.batch_indices.shape[0])
+    N = int(b["batch_indices"].shape[0])
+    B = int(b["targets"].shape[0])
     D = int(0.3 * wl["hidden"])
     step_no = [0]
 
     def masks():
-        # dropout is part of the reference step (p = 0.05 in the conv MLPs and the FFN); Bernoulli masks drawn per
-        # step like nn.Dropout does
         keep = 0.95
         conv = [[(torch.rand(N, D) < keep).float() / keep for _ in range(2)] for _ in range(wl["layers"])]
-        ffn = [(torch.rand(wl["graphs_sample"], wl["hidden"]) < keep).float() / keep for _ in range(3)]
+        ffn = [(torch.rand(B, wl["hidden"]) < keep).float() / keep for _ in range(3)]
         return dict(conv=conv, ffn=ffn)
 
     def step():
         for v in P.values():
             v.grad = None
-        out, _, _, _ = MP.gnn_forward(P, cfg, ob, dropout=masks())
-        loss = MP.weighted_l1(out, batch.targets, w)
+        out, _, _, _ = MP.gnn_forward(P, cfg, b, dropout=masks() if mode != "inference" else None)
+        if mode == "inference":
+            return float(out[0, 0])
+        loss = MP.weighted_l1(out, b["targets"], w)
         loss.backward()
         ks = [k for k in keys if P[k].grad is not None]
         step_no[0] += 1
@@ -194,38 +291,35 @@ def cpu_step_fn(wl, batch):
                              dict(m=[state["m"][keys.index(k)] for k in ks], v=[state["v"][keys.index(k)] for k in ks]),
                              step=step_no[0])
         return float(loss.detach())
-    return step
+    return step, "port"
 
 
 def run_cpu(wl, steps, warmup, budget_s):
     """Time the CPU path on a bounded sample: the sample size (molecules per step) is chosen from a probe step so
     that warmup + steps fit in ``budget_s`` seconds; capped at the workload's own batch."""
-    from aimnet_x2d_b200 import synthetic as S
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     wl = dict(wl)
     probe_n = min(128, wl["graphs"])
-    wl["graphs_sample"] = probe_n
-    b = S.make_batch(99, probe_n, wl["hops"], wl["kind"], T_TARGETS, stereo=wl["stereo"])
-    fn = cpu_step_fn(wl, b)
+    fn, kind = cpu_step_fn(wl, ref_batch(wl, 99, probe_n))
     fn()
     t0 = time.perf_counter(); fn(); t_probe = time.perf_counter() - t0
     per_mol = t_probe / probe_n
     n = int(min(wl["graphs"], max(probe_n, budget_s / max(steps + warmup, 1) / per_mol)))
     n = max(64, (n // 64) * 64)
-    wl["graphs_sample"] = n
-    b = S.make_batch(1234 + 2000, n, wl["hops"], wl["kind"], T_TARGETS, stereo=wl["stereo"])
-    fn = cpu_step_fn(wl, b)
+    fn, kind = cpu_step_fn(wl, ref_batch(wl, batch_seed(wl, 0, 0), n))
     for _ in range(warmup):
         fn()
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
     t = sum(ts) / len(ts)
-    return dict(value=n / t, unit="molecules/s", cores=cores, kind="port",
+    what = ("the UNMODIFIED reference modules (models.gnn.GNN, models.losses.WeightedL1Loss, torch.optim.Adam, "
+            "clip_grad_norm_) staged from /root/reference/src by oracle/stage_ref.py; torch_scatter 2.1.2 = oracle/scatter_port.py"
+            if kind == "reference" else "oracle/model_port.py restatement of the reference step (oracle/_ref not staged)")
+    return dict(value=n / t, unit="molecules/s", cores=cores, kind=kind,
                 sample=f"{n}-molecule batch of the same workload (full batch {wl['graphs']}), {steps} timed steps after "
-                       f"{warmup} warm-up, mean {t * 1e3:.1f} ms/step, torch CPU threads={cores}; oracle/model_port.py "
-                       f"restatement of the reference step"), t * 1e3, n
+                       f"{warmup} warm-up, mean {t * 1e3:.1f} ms/step, torch CPU threads={cores}; {what}"), t * 1e3, n
 
 
 def reference_arm(args, wl):
@@ -233,12 +327,17 @@ def reference_arm(args, wl):
     if rank != 0:
         return
     base, ms, n = run_cpu(wl, args.steps, max(args.warmup, 1), budget_s=150.0)
-    line = {"impl": "reference", "metric": "train molecules/sec", "value": base["value"], "unit": "molecules/s",
+    inference = wl.get("mode") == "inference"
+    line = {"impl": "reference", "metric": "inference molecules/sec" if inference else "train molecules/sec",
+            "value": base["value"], "unit": "molecules/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "sample_molecules_per_step": n},
+            "config": common_config(wl, args.gpus),
+            "sample_molecules_per_step": n,
+            "note": "ONE CPU process on rank 0 whatever --gpus says: only the N=1 line of the GPU arm is comparable with this number",
             "cpu_baseline": base,
-            "e2e": {"value": base["value"], "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": base["value"], "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "loaded_native": [m for m in ("aimnet_x2d_b200",) if m in sys.modules]}
     print(json.dumps(line), flush=True)
 
 

@@ -255,6 +255,12 @@ int ax2d_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, cons
                    float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
                    const int64_t* step, ax2d_stream_t stream);
 
+/* The same update with the hyper-parameters in DEVICE memory: hyper[6] = {grad_scale, max_norm, lr, beta1, beta2, eps}.
+ * A captured CUDA graph of the step then follows the reference's learning-rate schedulers
+ * (training/trainer.py:60-93, 268-271: ReduceLROnPlateau & co. rewrite param_group['lr'] between steps). */
+int ax2d_clip_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* norm2,
+                       const float* hyper, const int64_t* step, ax2d_stream_t stream);
+
 /* Packed weights: ONE launch gathers every projection weight / bias from its reference-shaped parameter into the
  * padded, packed layouts the kernels read (plus the two TF32 terms, plain and transposed), and one launch adds the
  * packed weight gradients back into the parameters' gradients.  `table` is a DEVICE array of n_blocks 96-byte block

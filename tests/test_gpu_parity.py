@@ -65,6 +65,12 @@ def exact_model_grads(g):
     return _EXACT[key]
 
 
+# Entries (fixture -> parameter names) that may pass on the float64 criterion below instead of the primary bar: heavily
+# cancelling sums of the deterministic-weight fixtures where the reference's OWN fp32 value is further than 1e-5 of the
+# tensor scale from the float64 evaluation of the same formulas.  Anything not named here must meet the primary bar.
+FALLBACK_ALLOWED = {}
+
+
 def close_or_as_exact_as_reference(got, ref32, exact, what):
     """Primary bar: |got - ref32| <= 1e-5 * scale.  Fallback for ill-conditioned entries: the CUDA result must be as
     close to the float64 value as the bar plus the reference's OWN distance from it,
@@ -279,7 +285,9 @@ def test_gnn_matches_reference(name, use_graph_index):
             if "g_" + k in g:
                 note = close_or_as_exact_as_reference(gr, g["g_" + k], exact_model_grads(g)[k], "grad " + k)
                 if note:
-                    print("[fallback criterion]", note)
+                    # the float64 criterion is only accepted for the entries NAMED in FALLBACK_ALLOWED; anywhere else a
+                    # miss of the primary 1e-5 bar fails the test
+                    assert k in FALLBACK_ALLOWED.get(name, ()), f"[fallback criterion not allowed for {name}] {note}"
                     continue
             assert abs(np.linalg.norm(gr.astype(np.float64)) - ref_norm) <= 2 * RTOL_F32 * max(ref_norm, 1e-12) + 1e-12, \
                 f"norm of grad {k}: {np.linalg.norm(gr.astype(np.float64)):.9e} vs {ref_norm:.9e}"
@@ -459,3 +467,162 @@ def test_no_edges_batch_skips_message_passing():
     out, _, _ = model({k: v.to(DEV) for k, v in feats.items()}, empty.to(DEV), bi.to(DEV), torch.zeros(3, device=DEV),
                       torch.empty((0, 4), dtype=torch.long, device=DEV), empty.to(DEV), empty.to(DEV))
     assert_close(out.detach().cpu().numpy(), ro.numpy(), RTOL_F32, "no-edge batch output")
+
+
+# --------------------------------------------------------------------------------------------- full-size train step
+def _train_step_pair(cfg, T, seed, batch, weights, lr=2.5e-4):
+    """One optimisation step (zero_grad, forward, WeightedL1Loss, backward, clip_grad_norm_(1.0), Adam) on the CUDA path
+    and on the CPU oracle, same deterministic weights, dropout 0.  Returns (cuda, oracle) dicts."""
+    ax = _ax()
+    P = det_state(gnn_shapes(cfg, T), seed)
+    model = ax.GNN(FEATURE_SIZES, cfg["hidden_dim"], T, num_shells=cfg["num_shells"],
+                   num_message_passing_layers=cfg["num_message_passing_layers"], task_type="multitask",
+                   use_partial_charges=cfg.get("use_partial_charges", False),
+                   use_stereochemistry=cfg.get("use_stereochemistry", False), ffn_dropout=0.0, shell_conv_dropout=0.0)
+    model.load_state_dict(P, strict=True)
+    model.to(DEV).train()
+    opt = ax.FlatAdam(model.parameters(), lr=lr, max_grad_norm=1.0)
+    opt.zero_grad()
+    bd = batch.to(DEV)
+    out, attn, q = model(bd.atom_features_map, bd.multi_hop_edge_indices, bd.batch_indices, bd.total_charges,
+                         bd.final_tetrahedral_chiral_tensor, bd.final_cis_tensor, bd.final_trans_tensor,
+                         graph_index=bd.graph_index)
+    loss = ax.WeightedL1Loss(weights).to(DEV)(out, bd.targets)
+    loss.backward()
+    grads = {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters()}
+    before = {k: p.detach().cpu().numpy().copy() for k, p in model.named_parameters()}
+    opt.step()
+    torch.cuda.synchronize()
+    after = {k: p.detach().cpu().numpy().copy() for k, p in model.named_parameters()}
+    cuda = dict(loss=float(loss), out=out.detach().cpu().numpy(), grads=grads, before=before, after=after,
+                norm=float(opt.grad_norm()), q=None if q is None else q.detach().cpu().numpy())
+
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    ob = dict(atom_features_map=batch.atom_features_map, multi_hop_edge_indices=batch.multi_hop_edge_indices,
+              batch_indices=batch.batch_indices, total_charges=batch.total_charges,
+              final_tetrahedral_chiral_tensor=batch.final_tetrahedral_chiral_tensor,
+              final_cis_tensor=batch.final_cis_tensor, final_trans_tensor=batch.final_trans_tensor)
+    ro, _, rq, _ = MP.gnn_forward(Pr, cfg, ob)
+    rl = MP.weighted_l1(ro, batch.targets, weights)
+    rl.backward()
+    rg = {k: (v.grad.numpy().copy() if v.grad is not None else np.zeros(tuple(v.shape), np.float32)) for k, v in Pr.items()}
+    keys = [k for k in Pr if Pr[k].grad is not None]
+    state = dict(m=[torch.zeros_like(Pr[k]) for k in keys], v=[torch.zeros_like(Pr[k]) for k in keys])
+    with torch.no_grad():
+        total = MP.clip_and_adam([Pr[k] for k in keys], [Pr[k].grad for k in keys], state, step=1, lr=lr)
+    oracle = dict(loss=float(rl), out=ro.detach().numpy(), grads=rg, after={k: v.detach().numpy() for k, v in Pr.items()},
+                  norm=total, q=None if rq is None else rq.detach().numpy())
+    return cuda, oracle
+
+
+def _check_train_step(cuda, oracle, lr, full_matrices):
+    assert_close(cuda["out"], oracle["out"], RTOL_F32, "output (full size)")
+    assert abs(cuda["loss"] - oracle["loss"]) <= RTOL_F32 * abs(oracle["loss"]), (cuda["loss"], oracle["loss"])
+    assert abs(cuda["norm"] - oracle["norm"]) <= RTOL_F32 * oracle["norm"], (cuda["norm"], oracle["norm"])
+    if oracle["q"] is not None:
+        assert_close(cuda["q"], oracle["q"], RTOL_F32, "partial charges (full size)")
+    for k, ref in oracle["grads"].items():
+        got = cuda["grads"][k]
+        if is_softmax_bias(k):
+            ws = float(np.max(np.abs(oracle["grads"][k.replace(".bias", ".weight")])))
+            assert float(np.max(np.abs(got))) <= RTOL_F32 * ws and float(np.max(np.abs(ref))) <= RTOL_F32 * ws, k
+            continue
+        rn = float(np.linalg.norm(ref.astype(np.float64)))
+        gn = float(np.linalg.norm(got.astype(np.float64)))
+        assert abs(gn - rn) <= RTOL_F32 * max(rn, 1e-30), f"gradient norm of {k}: {gn:.9e} vs {rn:.9e}"
+        if any(s in k for s in full_matrices) or ref.size <= 1 << 16:
+            assert_close(got, ref, RTOL_F32, "grad (full size) " + k)
+    # one clip + Adam step.  Adam's first update is lr * g / (|g| + 1e-8), i.e. +-lr wherever |g| >> 1e-8: entries whose
+    # gradient is at the rounding level of the sum that produced it move by a noise-determined fraction of lr in the
+    # reference as well, so they are excluded (|g_ref| < 1e-4 of the tensor's largest gradient) and counted.
+    skipped = total = 0
+    for k, ref in oracle["after"].items():
+        if is_softmax_bias(k):
+            continue
+        g = np.abs(oracle["grads"][k])
+        firm = g >= 1e-4 * max(float(g.max()), 1e-30)
+        total += g.size
+        skipped += int(g.size - firm.sum())
+        diff = np.abs(cuda["after"][k].astype(np.float64) - ref)
+        scale = float(np.max(np.abs(ref))) if ref.size else 0.0
+        assert float(np.max(np.where(firm, diff, 0.0), initial=0.0)) <= RTOL_F32 * scale + 1e-30, f"parameter after one step: {k}"
+        assert float(np.max(diff, initial=0.0)) <= 2.0 * lr * 1.001, k         # nothing moves by more than +-lr either way
+    return skipped, total
+
+
+def test_full_size_c2_train_step():
+    """BASELINE configs[1] at its real size (2048 QM9-shaped molecules, hidden 512, 3 hops x 3 layers, 12 targets, dropout
+    off): loss, output, total gradient norm (the clip coefficient), every gradient norm, the full gradients of the shell
+    convolution matrices and of every small tensor, and the parameters after one clip + Adam step, against the CPU oracle
+    at 1e-5.  Weight gradients here are sums over ~37 k atom rows (up to 37 split-K chains of 1024 rows)."""
+    from aimnet_x2d_b200 import synthetic as S
+    cfg = dict(hidden_dim=512, num_shells=3, num_message_passing_layers=3)
+    batch = S.make_batch(1234 + 2000 + 7, 2048, 3, "qm9", 12)
+    w = torch.linspace(0.5, 1.5, 12)
+    cuda, oracle = _train_step_pair(cfg, 12, 11, batch, w)
+    skipped, total = _check_train_step(cuda, oracle, 2.5e-4, ("input_proj.weight", "linear_1.weight", "linear_2.weight",
+                                                              "global_skip_proj.weight", "concat_self_other.weight"))
+    # the excluded entries are mostly the structurally zero gradients of quirk Q1 (hop chunks 2..H of input_proj /
+    # global_skip_proj) and of the dead parameters (long_range_projection): about a quarter of all entries by construction
+    assert skipped <= 0.35 * total, (skipped, total)
+
+
+def test_full_size_c3_train_step():
+    """One drug-like batch with stereo features and partial charges (BASELINE configs[2], B = 256): same comparison."""
+    from aimnet_x2d_b200 import synthetic as S
+    cfg = dict(hidden_dim=512, num_shells=3, num_message_passing_layers=3, use_partial_charges=True,
+               use_stereochemistry=True)
+    batch = S.make_batch(1234 + 3000 + 7, 256, 3, "drug", 12, stereo=True)
+    w = torch.ones(12)
+    cuda, oracle = _train_step_pair(cfg, 12, 13, batch, w)
+    _check_train_step(cuda, oracle, 2.5e-4, ("input_proj.weight", "linear_1.weight", "linear_2.weight",
+                                             "global_skip_proj.weight", "stereochemical_embedding_2.weight"))
+
+
+def test_same_shape_batches_without_graph_index_are_not_served_a_stale_index():
+    """Two DIFFERENT batches with identical tensor shapes, the first one freed before the second is moved to the device (so
+    the caching allocator hands out the same addresses), through ``model(...)`` WITHOUT ``graph_index``: each must get its
+    own CSR / segments (reference callers: evaluator / predictor, training/trainer.py:116-159)."""
+    import gc
+    ax = _ax()
+    from aimnet_x2d_b200 import synthetic as S
+    mols = S.make_molecules(31, 24, 3, "qm9", 4)
+    # same molecules in a different order: every index tensor keeps its shape, the contents differ
+    order = list(range(len(mols)))[::-1]
+    b1 = ax.MolBatch.from_data_list([S.to_data(m) for m in mols], FEATURE_SIZES)
+    b2 = ax.MolBatch.from_data_list([S.to_data(mols[i]) for i in order], FEATURE_SIZES)
+    assert b1.batch_indices.shape == b2.batch_indices.shape and b1.multi_hop_edge_indices.shape == b2.multi_hop_edge_indices.shape
+    assert not torch.equal(b1.batch_indices, b2.batch_indices)
+    torch.manual_seed(0)
+    model = ax.GNN(FEATURE_SIZES, 128, 4, num_shells=3, num_message_passing_layers=2, shell_conv_dropout=0.0,
+                   ffn_dropout=0.0).to(DEV).eval()
+
+    def run(b, with_index):
+        bd = b.to(DEV)
+        args = (bd.atom_features_map, bd.multi_hop_edge_indices, bd.batch_indices, bd.total_charges,
+                bd.final_tetrahedral_chiral_tensor, bd.final_cis_tensor, bd.final_trans_tensor)
+        with torch.no_grad():
+            out = model(*args, graph_index=bd.graph_index)[0] if with_index else model(*args)[0]
+        res = out.cpu().numpy().copy()
+        ptrs = (bd.batch_indices.data_ptr(), bd.multi_hop_edge_indices.data_ptr())
+        del bd, args, out
+        gc.collect()
+        return res, ptrs
+
+    ref1, _ = run(b1, True)
+    ref2, _ = run(b2, True)
+    assert not np.allclose(ref1, ref2)
+    got1, p1 = run(b1, False)
+    got2, p2 = run(b2, False)               # same shapes, (very likely) the same device addresses as batch 1
+    assert np.array_equal(got1, ref1)
+    assert np.array_equal(got2, ref2), f"stale GraphIndex served (addresses reused: {p1 == p2})"
+    assert np.array_equal(got2[::-1], got1) or np.allclose(got2[::-1], got1, rtol=1e-5, atol=1e-6)
+    # pooling alone keys on batch_indices only: same N, different molecule boundaries
+    pool = ax.MultiHeadAttentionPoolingLayer(32, num_heads=2).to(DEV)
+    x = torch.randn(10, 32, device=DEV)
+    for sizes in ([3, 7], [6, 4], [5, 5]):
+        bi = torch.repeat_interleave(torch.arange(2), torch.tensor(sizes)).to(DEV)
+        pooled, attn = pool(x, bi)
+        s = attn[0].detach().cpu().numpy()
+        assert abs(s[: sizes[0]].sum() - 1.0) < 1e-5 and abs(s[sizes[0]:].sum() - 1.0) < 1e-5, sizes
+        del bi

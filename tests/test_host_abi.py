@@ -336,3 +336,31 @@ def test_shared_dropout_tick_host_logic():
     snapshot = site_a.advance()
     site_a.advance()
     assert int(snapshot) == 2                                    # a snapshot: backward sees the value of ITS forward
+
+
+def test_index_cache_is_keyed_on_tensor_identity_not_addresses():
+    """a freed batch's addresses are reused by the next batch of the same shape; the cache must miss."""
+    from aimnet_x2d_b200.layers import _IndexCache
+    cache = _IndexCache(size=4)
+    built = []
+
+    def builder(tag):
+        def f():
+            built.append(tag)
+            return tag
+        return f
+
+    a = torch.arange(12).reshape(6, 2)
+    assert cache.get(cache.key(a[:, 0], a[:, 1], extra=(6,)), builder("a")) == "a"
+    assert cache.get(cache.key(a[:, 0], a[:, 1], extra=(6,)), builder("a2")) == "a"       # same base, same geometry: hit
+    a.add_(1)                                                                              # written in place: miss
+    assert cache.get(cache.key(a[:, 0], a[:, 1], extra=(6,)), builder("a3")) == "a3"
+    ident = id(a)
+    del a
+    b = torch.arange(12).reshape(6, 2) * 2                                                 # new object (often the same id / address)
+    got = cache.get(cache.key(b[:, 0], b[:, 1], extra=(6,)), builder("b"))
+    assert got == "b", f"stale entry served (id reused: {id(b) == ident})"
+    assert built == ["a", "a3", "b"]
+    # no tensors in the key: content-free entries are shared
+    assert cache.get(cache.key(extra=("all", 5, "cpu")), builder("all")) == "all"
+    assert cache.get(cache.key(extra=("all", 5, "cpu")), builder("all2")) == "all"
