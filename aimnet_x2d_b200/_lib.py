@@ -81,6 +81,16 @@ _SIGNATURES = {
     "ax2d_gemm_tc_wgrad_workspace": (c_int64, [c_int64, c_int64, c_int64]),
     "ax2d_gemm_tc_wgrad": (c_int, [C.POINTER(CMat), C.POINTER(CMat), C.POINTER(CMat), c_int64, c_int64, c_int64, c_int,
                                    c_void_p, c_void_p, c_void_p]),
+    "ax2d_gemm_bf16_supported": (c_int, [C.POINTER(CMat), c_int64, c_int64, c_int64]),
+    "ax2d_gemm_bf16": (c_int, [C.POINTER(CMat), c_void_p, c_int64, C.POINTER(CMat), c_int, c_int64, c_int64, c_int64,
+                               C.POINTER(Epilogue), c_void_p]),
+    "ax2d_gemm_bf16_wgrad_supported": (c_int, [C.POINTER(CMat), C.POINTER(CMat), c_int64, c_int64, c_int64]),
+    "ax2d_gemm_bf16_wgrad_splits": (c_int, [c_int64, c_int64, c_int64]),
+    "ax2d_gemm_bf16_wgrad_workspace": (c_int64, [c_int64, c_int64, c_int64]),
+    "ax2d_gemm_bf16_wgrad": (c_int, [C.POINTER(CMat), C.POINTER(CMat), C.POINTER(CMat), c_int64, c_int64, c_int64, c_int,
+                                     c_void_p, c_void_p, c_void_p]),
+    "ax2d_convert": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p]),
+    "ax2d_act_bwd_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     "ax2d_act_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     "ax2d_tick": (c_int, [c_void_p, c_void_p]),
     "ax2d_colsum_workspace": (c_int64, [c_int64, c_int64]),

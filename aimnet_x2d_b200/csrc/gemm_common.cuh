@@ -90,16 +90,16 @@ struct EpiCtx {      // per-thread constants of the epilogue
   uint32_t seed_lo, seed_hi, thresh;
   uint32_t base0;    // seed mix for linear indices below 2^34 (every realistic matrix)
 };
-__device__ __forceinline__ EpiCtx epi_ctx(const EpiArgs& g) {
+__device__ __forceinline__ EpiCtx epi_ctx_seed(float drop_p, uint64_t drop_seed, const uint64_t* drop_tick, bool has_mask = false) {
   EpiCtx c;
-  c.dropping = g.mask != nullptr || g.drop_p > 0.f;
-  c.thresh = static_cast<uint32_t>(g.drop_p * 65536.f + 0.5f);
+  c.dropping = has_mask || drop_p > 0.f;
+  c.thresh = static_cast<uint32_t>(drop_p * 65536.f + 0.5f);
   // the keep probability that is actually realised is (65536 - thresh) / 65536 (p quantised to 16 bits): scale by ITS
   // reciprocal so that E[mask] == 1 exactly
-  c.inv_keep = g.drop_p > 0.f ? 65536.f / static_cast<float>(65536u - (c.thresh < 65535u ? c.thresh : 65535u)) : 1.f;
-  const uint64_t seed = g.drop_seed + (g.drop_tick != nullptr
-                                           ? __ldg(reinterpret_cast<const unsigned long long*>(g.drop_tick)) * 0xD1B54A32D192ED03ull
-                                           : 0ull);
+  c.inv_keep = drop_p > 0.f ? 65536.f / static_cast<float>(65536u - (c.thresh < 65535u ? c.thresh : 65535u)) : 1.f;
+  const uint64_t seed = drop_seed + (drop_tick != nullptr
+                                         ? __ldg(reinterpret_cast<const unsigned long long*>(drop_tick)) * 0xD1B54A32D192ED03ull
+                                         : 0ull);
   c.seed_lo = static_cast<uint32_t>(seed);
   c.seed_hi = static_cast<uint32_t>(seed >> 32);
   uint32_t h = c.seed_hi;
@@ -107,6 +107,7 @@ __device__ __forceinline__ EpiCtx epi_ctx(const EpiArgs& g) {
   c.base0 = h ^ c.seed_lo;
   return c;
 }
+__device__ __forceinline__ EpiCtx epi_ctx(const EpiArgs& g) { return epi_ctx_seed(g.drop_p, g.drop_seed, g.drop_tick, g.mask != nullptr); }
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;

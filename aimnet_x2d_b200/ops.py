@@ -70,8 +70,8 @@ def _need_cuda(*ts):
                                f"{t.device} tensor")
 
 
-def _mat(segs: Sequence, allow_none: bool = False) -> CMat:
-    """segs: sequence of (tensor | None, width) -- 2-D fp32 tensors with unit column stride."""
+def _mat(segs: Sequence, allow_none: bool = False, dtype=torch.float32) -> CMat:
+    """segs: sequence of (tensor | None, width) -- 2-D tensors of ``dtype`` with unit column stride."""
     m = CMat()
     if len(segs) > MAX_SEG:
         raise RuntimeError(f"at most {MAX_SEG} segments are supported, got {len(segs)}")
@@ -83,8 +83,8 @@ def _mat(segs: Sequence, allow_none: bool = False) -> CMat:
             m.ptr[i], m.ld[i] = None, 4
         else:
             _need_cuda(t)
-            if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
-                raise RuntimeError(f"segment must be a 2-D fp32 tensor with unit column stride, got {t.dtype} "
+            if t.dtype != dtype or t.dim() != 2 or t.stride(1) != 1:
+                raise RuntimeError(f"segment must be a 2-D {dtype} tensor with unit column stride, got {t.dtype} "
                                    f"{tuple(t.shape)} strides {t.stride()}")
             m.ptr[i], m.ld[i] = t.data_ptr(), t.stride(0)
         m.width[i] = int(w)
@@ -157,6 +157,87 @@ def gemm(a_segs, b_segs, c_segs, M: int, N: int, K: int, trans_a: bool = False, 
         call()
     else:
         TIMER.launch("gemm", call, nbytes=4 * (M * K + K * N + M * N), flops=2 * M * N * K)
+
+
+BF16 = torch.bfloat16
+DT_CODES = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def gemm_bf16(a_segs, w: torch.Tensor, c_segs, M: int, N: int, K: int, *, bias=None, pre_segs=None, act=None, act_cols=None,
+              drop_p: float = 0.0, drop_seed: int = 0, drop_tick=None, resid=(), dact_pre=None, dact=None, dact_cols=None,
+              out_dtype=torch.bfloat16) -> None:
+    """C = epilogue(A W^T) on the tensor cores in bf16 (fp32 accumulation): ``a_segs`` bf16 column segments, ``w`` bf16
+    [N, K] (K-major), ``c_segs`` segments of ``out_dtype`` (bf16 or fp32), epilogue operands bf16, ``bias`` fp32."""
+    lib = _lib.load()
+    a = _mat(a_segs, dtype=BF16)
+    c = _mat(c_segs, dtype=out_dtype)
+    if w.dtype != BF16 or w.dim() != 2 or w.stride(1) != 1 or w.shape[0] < N or w.shape[1] < K:
+        raise RuntimeError(f"bf16 weight operand must be a [{N}, {K}] K-major bf16 matrix, got {w.dtype} {tuple(w.shape)}")
+    ep = Epilogue()
+    ep.bias = None if bias is None else bias.data_ptr()
+    if bias is not None and bias.dtype != torch.float32:
+        raise RuntimeError("bias stays fp32 in the bf16 configuration")
+    if pre_segs:
+        ep.pre = _mat(pre_segs, allow_none=True, dtype=BF16)
+    ep.act = ACT_CODES[act]
+    ep.act_cols = int(N if act_cols is None else act_cols)
+    ep.drop_p, ep.drop_seed = float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF
+    ep.drop_tick = None if drop_tick is None else drop_tick.data_ptr()
+    if resid:
+        ep.resid = _mat([(r, wd) for r, wd in resid], dtype=BF16)
+    if dact_pre is not None:
+        if dact_pre.dtype != BF16:
+            raise RuntimeError("dact_pre must be bf16")
+        ep.dact_pre, ep.ld_dact, ep.dact = dact_pre.data_ptr(), dact_pre.stride(0), ACT_CODES[dact]
+        ep.dact_cols = int(N if dact_cols is None else dact_cols)
+    call = lambda: _lib.check(lib.ax2d_gemm_bf16(C.byref(a), _p(w), w.stride(0), C.byref(c), DT_CODES[out_dtype], M, N, K,
+                                                 C.byref(ep), _stream()), "ax2d_gemm_bf16")
+    if TIMER is None:
+        call()
+    else:
+        TIMER.launch("gemm_bf16", call, nbytes=2 * (M * K + K * N + M * N), flops=2 * M * N * K)
+
+
+def weight_grad_bf16(g_segs, x_segs, M_rows: int, Nout: int, Kin: int, bias: bool = False, out=None, out_bias=None, ws=None,
+                     leave_partials: bool = False):
+    """dW[o, i] = sum_r G[r, o] X[r, i] (fp32) from bf16 activations; with ``bias`` also db[o] = sum_r G[r, o].
+    ``leave_partials``: the fp32 split partials stay in ``ws`` (summed later by ``ax2d_unpack_grads``); returns the split count."""
+    lib = _lib.load()
+    a, b = _mat(g_segs, dtype=BF16), _mat(x_segs, dtype=BF16)
+    if not lib.ax2d_gemm_bf16_wgrad_supported(C.byref(a), C.byref(b), Nout, Kin, M_rows):
+        raise RuntimeError(f"bf16 weight gradient [{Nout}, {Kin}] over {M_rows} rows: segment widths must be multiples of 32")
+    dev = g_segs[0][0].device
+    if ws is None:
+        ws = torch.empty(max(lib.ax2d_gemm_bf16_wgrad_workspace(Nout, Kin, M_rows) // 4, 1), dtype=torch.float32, device=dev)
+    if leave_partials:
+        call = lambda: _lib.check(lib.ax2d_gemm_bf16_wgrad(C.byref(a), C.byref(b), None, Nout, Kin, M_rows, 2, None, _p(ws),
+                                                           _stream()), "ax2d_gemm_bf16_wgrad")
+    else:
+        dW = torch.empty((Nout, Kin), dtype=torch.float32, device=dev) if out is None else out
+        db = (torch.empty(Nout, dtype=torch.float32, device=dev) if out_bias is None else out_bias) if bias else None
+        c = _mat([(dW, Kin)])
+        call = lambda: _lib.check(lib.ax2d_gemm_bf16_wgrad(C.byref(a), C.byref(b), C.byref(c), Nout, Kin, M_rows, 0, _p(db),
+                                                           _p(ws), _stream()), "ax2d_gemm_bf16_wgrad")
+    if TIMER is None:
+        call()
+    else:
+        TIMER.launch("gemm_bf16_wgrad", call, nbytes=2 * M_rows * (Nout + Kin), flops=2 * M_rows * Nout * Kin)
+    if leave_partials:
+        return lib.ax2d_gemm_bf16_wgrad_splits(Nout, Kin, M_rows)
+    return (dW, db) if bias else dW
+
+
+def convert(x: torch.Tensor, dtype) -> torch.Tensor:
+    """fp32 <-> bf16 copy of a 2-D matrix (width % 8 == 0) through ax2d_convert."""
+    if x.dtype == dtype:
+        return x
+    x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    out = torch.empty(x2.shape, dtype=dtype, device=x.device)
+    _lib.check(_lib.load().ax2d_convert(_p(x2), x2.stride(0), DT_CODES[x.dtype], _p(out), out.stride(0), DT_CODES[dtype],
+                                        x2.shape[0], x2.shape[1], _stream()), "ax2d_convert")
+    return out.reshape(x.shape)
 
 
 def colsum(segs, M: int, N: int, out: torch.Tensor, accumulate: bool = False) -> None:

@@ -229,6 +229,34 @@ int64_t ax2d_gemm_tc_wgrad_workspace(int64_t M, int64_t N, int64_t K);
 int     ax2d_gemm_tc_wgrad_splits(int64_t M, int64_t N, int64_t K);
 int     ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const ax2d_mat* c, int64_t M, int64_t N, int64_t K,
                            int accumulate, float* bias_grad, void* workspace, ax2d_stream_t stream);
+/* ------------------------------------------------------------------------------------------------
+ * bf16 configuration (BASELINE configs[3]; reference mixed precision: training/trainer.py:133-149, cli.py:236).
+ * Activations and the packed weight copies are bf16, accumulation is fp32 (TMEM), master weights / weight gradients /
+ * optimiser state stay fp32.  In these entry points the `float*` members of ax2d_cmat / ax2d_mat / ax2d_epilogue.pre /
+ * .resid / .dact_pre point to BF16 data (leading dimensions in bf16 elements, multiples of 8); `bias` stays fp32.
+ *   ax2d_gemm_bf16:  C[M,N] = epilogue(A B^T), A column-segmented, B = bf16 [N,K] (K-major; ldb), C = c_dtype (AX2D_BF16 or
+ *     AX2D_F32) in up to 4 column segments.  Epilogue as ax2d_gemm (bias, pre copy, act, hash dropout, <= 3 residuals,
+ *     act' * dropout); explicit masks and `accumulate` are not supported.  act_cols / dact_cols / residual widths / pre
+ *     segment boundaries must coincide with output-segment boundaries or multiples of the column tile.
+ *   ax2d_gemm_bf16_wgrad:  C[M,N] (fp32) (+)= A^T B over the K rows, segment widths % 32 == 0.  The workspace
+ *     (ax2d_gemm_bf16_wgrad_workspace) is always required; accumulate: 0 write, 1 add, 2 leave the fp32 partials
+ *     [splits][M][N] + [splits][M] (bias) in the workspace for ax2d_unpack_grads.  bias_grad: optional [M] column sums of A.
+ * ---------------------------------------------------------------------------------------------- */
+int     ax2d_gemm_bf16_supported(const ax2d_cmat* a, int64_t M, int64_t N, int64_t K);
+int     ax2d_gemm_bf16(const ax2d_cmat* a, const void* b, int64_t ldb, const ax2d_mat* c, int c_dtype,
+                       int64_t M, int64_t N, int64_t K, const ax2d_epilogue* ep, ax2d_stream_t stream);
+int     ax2d_gemm_bf16_wgrad_supported(const ax2d_cmat* a, const ax2d_cmat* b, int64_t M, int64_t N, int64_t K);
+int     ax2d_gemm_bf16_wgrad_splits(int64_t M, int64_t N, int64_t K);
+int64_t ax2d_gemm_bf16_wgrad_workspace(int64_t M, int64_t N, int64_t K);
+int     ax2d_gemm_bf16_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const ax2d_mat* c, int64_t M, int64_t N, int64_t K,
+                             int accumulate, float* bias_grad, void* workspace, ax2d_stream_t stream);
+/* fp32 <-> bf16 copy of an [M, width] matrix (width, ldi, ldo multiples of 8). */
+int     ax2d_convert(const void* in, int64_t ldi, int in_dtype, void* out, int64_t ldo, int out_dtype, int64_t M, int width,
+                     ax2d_stream_t stream);
+/* bf16 variant of ax2d_act_bwd (width % 8 == 0). */
+int     ax2d_act_bwd_bf16(const void* g, int64_t ldg, const void* pre, int64_t ldp, void* out, int64_t ldo, int64_t M,
+                          int width, int act, ax2d_stream_t stream);
+
 /* elementwise g_pre[m,n] = g[m,n] * act'(pre[m,n]) for n < width (width % 4 == 0). */
 int ax2d_act_bwd(const float* g, int64_t ldg, const float* pre, int64_t ldp, float* out, int64_t ldo,
                  int64_t M, int width, int act, ax2d_stream_t stream);
