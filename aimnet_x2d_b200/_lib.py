@@ -66,6 +66,10 @@ _SIGNATURES = {
     "ax2d_embed_bwd_all_workspace": (c_int64, [c_int64, c_int64, c_int]),
     "ax2d_embed_bwd_all": (c_int, [c_void_p, c_int64, c_int, c_int, c_int64, C.POINTER(c_void_p), C.POINTER(c_int64),
                                    C.POINTER(c_void_p), c_void_p, c_void_p]),
+    "ax2d_embed_fwd_bf16": (c_int, [C.POINTER(c_void_p), C.POINTER(c_void_p), c_int, c_int, c_int64, c_void_p, c_int64,
+                                    c_void_p]),
+    "ax2d_embed_bwd_all_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int64, C.POINTER(c_void_p), C.POINTER(c_int64),
+                                        C.POINTER(c_void_p), c_void_p, c_void_p]),
     "ax2d_embed_bwd_workspace": (c_int64, [c_int64, c_int]),
     "ax2d_embed_bwd": (c_int, [c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
@@ -108,6 +112,35 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 _lib = None
 
+# Optional per-launch timer (ops.KernelTimer) -- when set, every kernel-enqueueing entry point is bracketed by a pair of
+# CUDA events on the launching stream (inside a CUDA-graph capture: external event-record nodes, so the durations are
+# those of the launches INSIDE the replayed step).  None: the calls go straight to the library.
+TIMER_HOOK = [None]
+_UNTIMED_MARKS = ("_host_", "_workspace", "_supported", "_splits", "abi_version", "error_string", "last_error",
+                  "launch_count")
+
+
+class _TimedLib:
+    """Thin proxy over the CDLL: same attributes; kernel launches go through ``TIMER_HOOK[0].bracket`` when a timer is set."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.startswith("ax2d_") or any(m in name for m in _UNTIMED_MARKS):
+            setattr(self, name, fn)
+            return fn
+
+        def call(*args):
+            t = TIMER_HOOK[0]
+            if t is None:
+                return fn(*args)
+            return t.bracket(name, fn, args)
+
+        setattr(self, name, call)
+        return call
+
 
 def load():
     """Load libax2d.so once; raise loudly when it is absent (no CPU / eager fallback exists)."""
@@ -125,8 +158,8 @@ def load():
         fn.argtypes = args
     if lib.ax2d_abi_version() != 1:
         raise RuntimeError("libax2d.so ABI version mismatch; rebuild")
-    _lib = lib
-    return lib
+    _lib = _TimedLib(lib)
+    return _lib
 
 
 def check(rc: int, what: str) -> None:

@@ -278,6 +278,210 @@ __global__ void __launch_bounds__(AGG_CONSUMERS + 32, 2) agg_tiles_kernel(
   AGG_STAMP(15);
 }
 
+// ------------------------------------------------------------------------------------------------ bf16 features
+// The same persistent tile pipeline for bf16 rows (BASELINE configs[3]): the staged tile is half the bytes, FOUR lanes own
+// one output row (lane j accumulates the 16-byte units j, j + 4, ... = 8 bf16 each, in fp32 registers, CSR order), the
+// result is rounded to bf16 once per row.  V = width / 32 units per lane.
+__device__ __forceinline__ void bf8_add(float* acc, const uint4& u) {
+  acc[0] += __uint_as_float(u.x << 16); acc[1] += __uint_as_float(u.x & 0xFFFF0000u);
+  acc[2] += __uint_as_float(u.y << 16); acc[3] += __uint_as_float(u.y & 0xFFFF0000u);
+  acc[4] += __uint_as_float(u.z << 16); acc[5] += __uint_as_float(u.z & 0xFFFF0000u);
+  acc[6] += __uint_as_float(u.w << 16); acc[7] += __uint_as_float(u.w & 0xFFFF0000u);
+}
+__device__ __forceinline__ uint32_t bf2_pack(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint4 ld_nc_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_na_u4(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <int V>
+__global__ void __launch_bounds__(AGG_CONSUMERS + 32, 2) agg_tiles_bf16_kernel(
+    const uint16_t* __restrict__ x, uint16_t* __restrict__ out, int64_t ldo, const int32_t* __restrict__ rowptr,
+    const int32_t* __restrict__ col, const uint16_t* __restrict__ addend, int64_t ld_addend,
+    const int4* __restrict__ tile_info, int n_tiles, int stages, uint32_t x_bytes, uint32_t rp_bytes, uint32_t col_bytes) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[AGG_STAGES], empty[AGG_STAGES];
+  __shared__ int4 s_info[AGG_STAGES];
+  constexpr int U = 4 * V;                      // 16-byte units per row
+  const uint32_t stage_bytes = x_bytes + rp_bytes + col_bytes;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_my = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], AGG_CONSUMERS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == AGG_CONSUMERS / 32) {
+    // ================================================================= producer warp (as in agg_tiles_kernel)
+    for (int base = 0; base < n_my; base += 32) {
+      int4 mine = make_int4(0, 0, 0, 0);
+      if (base + lane < n_my) mine = __ldg(tile_info + first + static_cast<int64_t>(base + lane) * stride);
+      const int cnt = n_my - base < 32 ? n_my - base : 32;
+      for (int j = 0; j < cnt; ++j) {
+        const int it = base + j;
+        int4 inf;
+        inf.x = __shfl_sync(0xffffffffu, mine.x, j);
+        inf.y = __shfl_sync(0xffffffffu, mine.y, j);
+        inf.z = __shfl_sync(0xffffffffu, mine.z, j);
+        inf.w = __shfl_sync(0xffffffffu, mine.w, j);
+        if (lane == 0) {
+          const int s = it % stages;
+          mbar_wait(&empty[s], (static_cast<uint32_t>(it / stages) & 1u) ^ 1u);
+          unsigned char* dst = smem_raw + static_cast<size_t>(s) * stage_bytes;
+          const uint32_t xb = static_cast<uint32_t>(inf.y - inf.x) * U * 16;
+          const int rs = inf.x & ~3, es = inf.z & ~3;
+          const uint32_t rb = static_cast<uint32_t>((inf.y + 1 - rs + 3) & ~3) * 4;
+          const uint32_t cb = static_cast<uint32_t>((inf.w - es + 3) & ~3) * 4;
+          s_info[s] = inf;
+          mbar_expect_tx(&full[s], xb + rb + cb);
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(x) + static_cast<int64_t>(inf.x) * (U * 16);
+          for (uint32_t off = 0; off < xb; off += 16384) {
+            const uint32_t n = xb - off < 16384u ? xb - off : 16384u;
+            bulk_g2s(dst + off, src + off, n, &full[s]);
+          }
+          bulk_g2s(dst + x_bytes, rowptr + rs, rb, &full[s]);
+          if (cb > 0) bulk_g2s(dst + x_bytes + rp_bytes, col + es, cb, &full[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // =================================================================== consumers: 4 lanes per row, 64 rows per CTA pass
+  constexpr int n_groups = AGG_CONSUMERS / 4;
+  const int lane4 = lane & 3;
+  const int group = threadIdx.x >> 2;
+  const unsigned gmask = 0xfu << (threadIdx.x & 28);
+  for (int it = 0; it < n_my; ++it) {
+    const int s = it % stages;
+    mbar_wait(&full[s], static_cast<uint32_t>(it / stages) & 1u);
+    const int4 inf = s_info[s];
+    const unsigned char* st = smem_raw + static_cast<size_t>(s) * stage_bytes;
+    const uint4* xs = reinterpret_cast<const uint4*>(st) + lane4;
+    const int32_t* rp = reinterpret_cast<const int32_t*>(st + x_bytes) - (inf.x & ~3);
+    const int32_t* cs = reinterpret_cast<const int32_t*>(st + x_bytes + rp_bytes) - (inf.z & ~3);
+    for (int r = inf.x + group; r < inf.y; r += n_groups) {
+      const int beg = rp[r], end = rp[r + 1];
+      uint4 add4[V];
+      if (addend != nullptr) {
+        const uint4* a = reinterpret_cast<const uint4*>(addend + static_cast<int64_t>(r) * ld_addend) + lane4;
+#pragma unroll
+        for (int v = 0; v < V; ++v) add4[v] = ld_nc_u4(a + 4 * v);
+      }
+      float acc[V][8];
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[v][e] = 0.f;
+      for (int k = beg; k < end; k += 4) {
+        const int my_c = (k + lane4 < end) ? (cs[k + lane4] - inf.x) * U : 0;
+        const int cnt = end - k < 4 ? end - k : 4;
+        int j = 0;
+        for (; j + 2 <= cnt; j += 2) {            // two neighbour rows in flight; additions stay in CSR order
+          const uint4* ra = xs + __shfl_sync(gmask, my_c, j, 4);
+          const uint4* rb = xs + __shfl_sync(gmask, my_c, j + 1, 4);
+          uint4 ta[V], tb[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            ta[v] = ra[4 * v];
+            tb[v] = rb[4 * v];
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            bf8_add(acc[v], ta[v]);
+            bf8_add(acc[v], tb[v]);
+          }
+        }
+        if (j < cnt) {
+          const uint4* ra = xs + __shfl_sync(gmask, my_c, j, 4);
+#pragma unroll
+          for (int v = 0; v < V; ++v) bf8_add(acc[v], ra[4 * v]);
+        }
+      }
+      if (addend != nullptr) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) bf8_add(acc[v], add4[v]);
+      }
+      uint4* o = reinterpret_cast<uint4*>(out + static_cast<int64_t>(r) * ldo) + lane4;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        st_na_u4(o + 4 * v, make_uint4(bf2_pack(acc[v][0], acc[v][1]), bf2_pack(acc[v][2], acc[v][3]),
+                                        bf2_pack(acc[v][4], acc[v][5]), bf2_pack(acc[v][6], acc[v][7])));
+    }
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+    }
+  }
+}
+
+// general bf16 path (any CSR, width % 8 == 0): one warp per output row, lanes over the 16-byte units
+__global__ void __launch_bounds__(256) agg_generic_bf16_kernel(const uint16_t* __restrict__ x, int64_t ldx, uint16_t* __restrict__ out,
+                                                               int64_t ldo, const int32_t* __restrict__ rowptr,
+                                                               const int32_t* __restrict__ col, const uint16_t* __restrict__ addend,
+                                                               int64_t ld_addend, int64_t n_out_rows, int w8) {
+  const int warps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * warps + (threadIdx.x >> 5);
+  if (r >= n_out_rows) return;
+  const int beg = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
+  for (int c = lane; c < w8; c += 32) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = beg; k < end; ++k)
+      bf8_add(acc, __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(__ldg(col + k)) * ldx) + c));
+    if (addend != nullptr) bf8_add(acc, __ldg(reinterpret_cast<const uint4*>(addend + r * ld_addend) + c));
+    reinterpret_cast<uint4*>(out + r * ldo)[c] = make_uint4(bf2_pack(acc[0], acc[1]), bf2_pack(acc[2], acc[3]),
+                                                            bf2_pack(acc[4], acc[5]), bf2_pack(acc[6], acc[7]));
+  }
+}
+
+template <int V>
+static int launch_agg_bf16(const uint16_t* x, uint16_t* out, int64_t ldo, const int32_t* rowptr, const int32_t* col,
+                           const uint16_t* addend, int64_t ld_addend, const int32_t* tile_info, int64_t n_tiles, int max_tile_rows,
+                           int max_tile_edges, cudaStream_t st) {
+  const size_t xb = static_cast<size_t>(max_tile_rows) * V * 4 * 16;
+  const size_t rb = (static_cast<size_t>(max_tile_rows) + 8) * 4 / 16 * 16 + 16;
+  const size_t cb = (static_cast<size_t>(max_tile_edges) + 8) * 4 / 16 * 16 + 16;
+  const size_t stage = xb + rb + cb;
+  if (stage > 220 * 1024) {
+    set_error("ax2d_agg: tile of %d rows / %d edges needs %zu bytes of shared memory", max_tile_rows, max_tile_edges, stage);
+    return AX2D_ERR_UNSUPPORTED;
+  }
+  int ctas_per_sm = 2;
+  int stages = static_cast<int>((110 * 1024) / stage);
+  if (stages < 2) {
+    stages = static_cast<int>((220 * 1024) / stage);
+    ctas_per_sm = 1;
+  }
+  stages = stages > AGG_STAGES ? AGG_STAGES : stages;
+  const size_t smem = stage * stages;
+  auto kern = agg_tiles_bf16_kernel<V>;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = smem;
+  }
+  int64_t grid = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
+  grid = grid > n_tiles ? n_tiles : grid;
+  kern<<<static_cast<unsigned>(grid), AGG_CONSUMERS + 32, smem, st>>>(
+      x, out, ldo, rowptr, col, addend, ld_addend, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles), stages,
+      static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb));
+  return launch_status("ax2d_agg");
+}
+
 // generic width (multiple of 4, not of 32): one lane per float4 column, strided over the row
 __global__ void __launch_bounds__(256) agg_generic_kernel(const float* __restrict__ x, int64_t ldx,
                                                           float* __restrict__ out, int64_t ldo,
@@ -358,8 +562,41 @@ extern "C" int ax2d_agg(const void* x, int64_t ldx, int64_t n_src_rows, void* ou
                         const int32_t* tile_info, int64_t n_tiles, int max_tile_rows, int max_tile_edges, int dtype,
                         ax2d_stream_t stream) {
   using namespace ax2d;
+  if (dtype == AX2D_BF16) {
+    // bf16 rows (leading dimensions in bf16 elements): fp32 accumulation in CSR order, one rounding per output row
+    AX2D_CHECK_ARG(width > 0 && width % 8 == 0, "ax2d_agg: bf16 width %d must be a positive multiple of 8", width);
+    AX2D_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0 && ldx >= width && ldo >= width, "ax2d_agg: bad leading dimensions");
+    AX2D_CHECK_ARG(addend == nullptr || ld_addend % 8 == 0, "ax2d_agg: bad addend leading dimension");
+    AX2D_CHECK_ALIGN(x);
+    AX2D_CHECK_ALIGN(out);
+    AX2D_CHECK_ALIGN(addend);
+    if (n_out_rows <= 0) return AX2D_OK;
+    cudaStream_t st16 = reinterpret_cast<cudaStream_t>(stream);
+    const uint16_t* xh = static_cast<const uint16_t*>(x);
+    uint16_t* oh = static_cast<uint16_t*>(out);
+    const uint16_t* ah = static_cast<const uint16_t*>(addend);
+    if (tile_info != nullptr && width % 32 == 0 && width <= 32 * 16) {
+      AX2D_CHECK_ARG(n_out_rows == n_src_rows && ldx == width && n_tiles > 0 && max_tile_rows > 0 && max_tile_edges >= 0,
+                     "ax2d_agg: tiled mode needs n_out_rows == n_src_rows, ldx == width, width %% 32 == 0");
+      AX2D_CHECK_ALIGN(tile_info);
+      AX2D_CHECK_ALIGN(rowptr);
+      AX2D_CHECK_ALIGN(col);
+#define AX2D_AGG16_CASE(V) \
+  case V: return launch_agg_bf16<V>(xh, oh, ldo, rowptr, col, ah, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, st16);
+      switch (width / 32) {
+        AX2D_AGG16_CASE(1) AX2D_AGG16_CASE(2) AX2D_AGG16_CASE(3) AX2D_AGG16_CASE(4) AX2D_AGG16_CASE(5) AX2D_AGG16_CASE(6)
+        AX2D_AGG16_CASE(7) AX2D_AGG16_CASE(8) AX2D_AGG16_CASE(9) AX2D_AGG16_CASE(10) AX2D_AGG16_CASE(11) AX2D_AGG16_CASE(12)
+        AX2D_AGG16_CASE(13) AX2D_AGG16_CASE(14) AX2D_AGG16_CASE(15) AX2D_AGG16_CASE(16)
+      }
+#undef AX2D_AGG16_CASE
+    }
+    const int warps = 8;
+    agg_generic_bf16_kernel<<<static_cast<unsigned>((n_out_rows + warps - 1) / warps), warps * 32, 0, st16>>>(
+        xh, ldx, oh, ldo, rowptr, col, ah, ld_addend, n_out_rows, width / 8);
+    return launch_status("ax2d_agg");
+  }
   if (dtype != AX2D_F32) {
-    set_error("ax2d_agg: dtype %d not supported (f32 only in this build)", dtype);
+    set_error("ax2d_agg: dtype %d not supported", dtype);
     return AX2D_ERR_DTYPE;
   }
   AX2D_CHECK_ARG(width > 0 && width % 4 == 0, "ax2d_agg: width %d must be a positive multiple of 4", width);

@@ -28,6 +28,32 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedArgs a, int n_table
   }
 }
 
+// bf16 output (BASELINE configs[3]): the fp32 table rows are rounded on the way out; 8 columns (16 bytes) per thread
+__global__ void __launch_bounds__(256) embed_fwd_bf16_kernel(EmbedArgs a, int n_tables, int E8, int64_t N,
+                                                             uint16_t* __restrict__ out, int64_t ldo) {
+  const int per_row = n_tables * E8;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * kEmbedRowsPerCta;
+  for (int c = threadIdx.x; c < per_row; c += 64) {
+    const int tb = c / E8, k = c - tb * E8;
+    const int64_t* idx = a.index[tb];
+    const float4* tab = reinterpret_cast<const float4*>(a.table[tb]);
+#pragma unroll 4
+    for (int r = threadIdx.y; r < kEmbedRowsPerCta; r += 4) {
+      const int64_t n = n0 + r;
+      if (n < N) {
+        const float4* src = tab + (__ldg(idx + n) * E8 + k) * 2;
+        const float4 u = __ldg(src), v = __ldg(src + 1);
+        uint4 o;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(u.y), "f"(u.x));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(u.w), "f"(u.z));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(v.y), "f"(v.x));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(v.w), "f"(v.z));
+        reinterpret_cast<uint4*>(out + n * ldo)[c] = o;
+      }
+    }
+  }
+}
+
 // Backward of all lookups in one pass: thread = gradient column (table t, component e), a CTA walks its slice of the
 // atoms in order and accumulates g[n, column] into a shared-memory copy of the (small) tables at row index[t][n]
 // -- the same thread owns a column for all atoms, so there are no conflicts and the order is the atom order.  Per-CTA
@@ -37,7 +63,10 @@ struct EmbedBwdArgs {
   float* g_table[kMaxTables];
   int row_off[kMaxTables + 1];     // first row of every table in the stacked [total_rows, E] layout
 };
-__global__ void __launch_bounds__(256) embed_bwd_all_kernel(EmbedBwdArgs a, const float* __restrict__ g, int64_t ldg, int n_tables,
+__device__ __forceinline__ float embed_g(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float embed_g(const uint16_t* p) { return __uint_as_float(static_cast<uint32_t>(__ldg(p)) << 16); }
+template <typename GT>
+__global__ void __launch_bounds__(256) embed_bwd_all_kernel(EmbedBwdArgs a, const GT* __restrict__ g, int64_t ldg, int n_tables,
                                                             int E, int64_t N, int64_t rows_per_cta, float* __restrict__ ws) {
   extern __shared__ float tab[];          // [total_rows][E]
   const int total = a.row_off[n_tables] * E;
@@ -52,14 +81,14 @@ __global__ void __launch_bounds__(256) embed_bwd_all_kernel(EmbedBwdArgs a, cons
     int64_t r = r0;
     for (; r + 4 <= r1; r += 4) {         // loads first, then the (possibly same-address) updates in atom order
       const int64_t i0 = __ldg(idx + r), i1 = __ldg(idx + r + 1), i2 = __ldg(idx + r + 2), i3 = __ldg(idx + r + 3);
-      const float g0 = __ldg(g + r * ldg + col), g1 = __ldg(g + (r + 1) * ldg + col);
-      const float g2 = __ldg(g + (r + 2) * ldg + col), g3 = __ldg(g + (r + 3) * ldg + col);
+      const float g0 = embed_g(g + r * ldg + col), g1 = embed_g(g + (r + 1) * ldg + col);
+      const float g2 = embed_g(g + (r + 2) * ldg + col), g3 = embed_g(g + (r + 3) * ldg + col);
       base[i0 * E] += g0;
       base[i1 * E] += g1;
       base[i2 * E] += g2;
       base[i3 * E] += g3;
     }
-    for (; r < r1; ++r) base[__ldg(idx + r) * E] += __ldg(g + r * ldg + col);
+    for (; r < r1; ++r) base[__ldg(idx + r) * E] += embed_g(g + r * ldg + col);
   }
   __syncthreads();
   float* dst = ws + static_cast<int64_t>(blockIdx.x) * total;
@@ -308,6 +337,23 @@ extern "C" int ax2d_embed_fwd(const float* const* tables, const int64_t* const* 
   return launch_status("ax2d_embed_fwd");
 }
 
+extern "C" int ax2d_embed_fwd_bf16(const float* const* tables, const int64_t* const* indices, int n_tables, int emb_dim,
+                                   int64_t N, void* out, int64_t ldo, ax2d_stream_t stream) {
+  AX2D_CHECK_ARG(n_tables >= 1 && n_tables <= kMaxTables, "ax2d_embed_fwd_bf16: n_tables=%d not in [1,%d]", n_tables, kMaxTables);
+  AX2D_CHECK_ARG(emb_dim > 0 && emb_dim % 8 == 0 && ldo % 8 == 0, "ax2d_embed_fwd_bf16: emb_dim and ldo must be multiples of 8");
+  AX2D_CHECK_ALIGN(out);
+  if (N <= 0) return AX2D_OK;
+  EmbedArgs a;
+  for (int t = 0; t < n_tables; ++t) {
+    AX2D_CHECK_ALIGN(tables[t]);
+    a.table[t] = tables[t];
+    a.index[t] = indices[t];
+  }
+  embed_fwd_bf16_kernel<<<static_cast<unsigned>((N + kEmbedRowsPerCta - 1) / kEmbedRowsPerCta), dim3(64, 4), 0,
+                          reinterpret_cast<cudaStream_t>(stream)>>>(a, n_tables, emb_dim / 8, N, static_cast<uint16_t*>(out), ldo);
+  return launch_status("ax2d_embed_fwd_bf16");
+}
+
 static int embed_bwd_all_ctas(int64_t N) {
   const int64_t by_rows = (N + 63) / 64;               // at least 64 atoms per CTA
   return static_cast<int>(by_rows < kNumSMs ? (by_rows < 1 ? 1 : by_rows) : kNumSMs);
@@ -315,9 +361,9 @@ static int embed_bwd_all_ctas(int64_t N) {
 extern "C" int64_t ax2d_embed_bwd_all_workspace(int64_t N, int64_t total_rows, int emb_dim) {
   return static_cast<int64_t>(embed_bwd_all_ctas(N)) * total_rows * emb_dim * 4;
 }
-extern "C" int ax2d_embed_bwd_all(const float* g_out, int64_t ldg, int n_tables, int emb_dim, int64_t N,
-                                  const int64_t* const* indices, const int64_t* vocab, float* const* g_tables, void* workspace,
-                                  ax2d_stream_t stream) {
+static int embed_bwd_all_impl(const void* g_out, int g_bf16, int64_t ldg, int n_tables, int emb_dim, int64_t N,
+                              const int64_t* const* indices, const int64_t* vocab, float* const* g_tables, void* workspace,
+                              ax2d_stream_t stream) {
   AX2D_CHECK_ARG(n_tables > 0 && n_tables <= kMaxTables && emb_dim > 0 && N >= 0, "ax2d_embed_bwd_all: bad arguments");
   AX2D_CHECK_ARG(g_out != nullptr && workspace != nullptr, "ax2d_embed_bwd_all: null operand");
   EmbedBwdArgs a;
@@ -335,7 +381,9 @@ extern "C" int ax2d_embed_bwd_all(const float* g_out, int64_t ldg, int n_tables,
                  rows, emb_dim);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(embed_bwd_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(embed_bwd_all_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(embed_bwd_all_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
       set_error("ax2d_embed_bwd_all: cannot raise the dynamic shared memory limit to %zu: %s", smem, cudaGetErrorString(e));
       return AX2D_ERR_LAUNCH;
@@ -345,13 +393,29 @@ extern "C" int ax2d_embed_bwd_all(const float* g_out, int64_t ldg, int n_tables,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int ctas = embed_bwd_all_ctas(N);
   const int64_t rows_per_cta = (N + ctas - 1) / ctas;
-  embed_bwd_all_kernel<<<ctas, 256, smem, st>>>(a, g_out, ldg, n_tables, emb_dim, N, rows_per_cta, static_cast<float*>(workspace));
+  if (g_bf16)
+    embed_bwd_all_kernel<uint16_t><<<ctas, 256, smem, st>>>(a, static_cast<const uint16_t*>(g_out), ldg, n_tables, emb_dim, N,
+                                                            rows_per_cta, static_cast<float*>(workspace));
+  else
+    embed_bwd_all_kernel<float><<<ctas, 256, smem, st>>>(a, static_cast<const float*>(g_out), ldg, n_tables, emb_dim, N, rows_per_cta,
+                                                         static_cast<float*>(workspace));
   int rc = launch_status("ax2d_embed_bwd_all(partial)");
   if (rc != AX2D_OK) return rc;
   const int total = rows * emb_dim;
   embed_bwd_all_final_kernel<<<(8 * total + 255) / 256, 256, 0, st>>>(a, static_cast<const float*>(workspace), n_tables, emb_dim,
                                                                       ctas);
   return launch_status("ax2d_embed_bwd_all(final)");
+}
+
+extern "C" int ax2d_embed_bwd_all(const float* g_out, int64_t ldg, int n_tables, int emb_dim, int64_t N,
+                                  const int64_t* const* indices, const int64_t* vocab, float* const* g_tables, void* workspace,
+                                  ax2d_stream_t stream) {
+  return embed_bwd_all_impl(g_out, 0, ldg, n_tables, emb_dim, N, indices, vocab, g_tables, workspace, stream);
+}
+extern "C" int ax2d_embed_bwd_all_bf16(const void* g_out, int64_t ldg, int n_tables, int emb_dim, int64_t N,
+                                       const int64_t* const* indices, const int64_t* vocab, float* const* g_tables, void* workspace,
+                                       ax2d_stream_t stream) {
+  return embed_bwd_all_impl(g_out, 1, ldg, n_tables, emb_dim, N, indices, vocab, g_tables, workspace, stream);
 }
 
 constexpr int kEmbedSplits = 64;
@@ -431,7 +495,7 @@ extern "C" int ax2d_weighted_loss(const float* pred, const float* target, const 
 // destination and is never written), split into the two TF32 terms of the tensor-core path (plain and transposed:
 // forward / data-gradient operands), and -- the other way round -- the packed weight gradients are accumulated
 // into the parameters' .grad storage.
-struct PackDesc {           // one rectangular block; 112 bytes (packed.py mirrors the layout)
+struct PackDesc {           // one rectangular block; 128 bytes (packed.py mirrors the layout)
   const float* src;         // parameter block [rows, cols], leading dimension src_ld
   float* grad_dst;          // same block inside the parameter's .grad (may be null: frozen parameter)
   float* w;                 // packed fp32 copy              [.., dst_ld]
@@ -442,7 +506,14 @@ struct PackDesc {           // one rectangular block; 112 bytes (packed.py mirro
                             // weight-gradient kernel (null / split == 0: none); summed here in split order
   int32_t rows, cols, src_ld, dst_ld, dstT_ld;
   int32_t split, p_rows, p_cols, dr, dc;   // (dr, dc): position of this block inside the packed matrix
+  uint16_t* wb;             // bf16 copy (operand of ax2d_gemm_bf16)            [.., dst_ld]   (may be null)
+  uint16_t* wbT;            // transposed bf16 copy (data-gradient operand)      [.., dstT_ld]  (may be null)
 };
+__device__ __forceinline__ uint16_t pk_bf16(float v) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(v));
+  return static_cast<uint16_t>(r & 0xFFFFu);
+}
 __device__ __forceinline__ float pk_round_tf32(float v) {
   return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
@@ -466,19 +537,23 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackDesc* __res
           d.hi[static_cast<int64_t>(r) * d.dst_ld + c] = h;
           d.lo[static_cast<int64_t>(r) * d.dst_ld + c] = pk_round_tf32(v - h);
         }
+        if (d.wb != nullptr) d.wb[static_cast<int64_t>(r) * d.dst_ld + c] = pk_bf16(v);
       }
       tile[ty + 8 * k][tx] = v;
     }
     __syncthreads();
-    if (d.hiT != nullptr) {
+    if (d.hiT != nullptr || d.wbT != nullptr) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int c = c0 + ty + 8 * k, r = r0 + tx;      // transposed: row c of the output, column r
         if (r < d.rows && c < d.cols) {
           const float v = tile[tx][ty + 8 * k];
-          const float h = pk_round_tf32(v);
-          d.hiT[static_cast<int64_t>(c) * d.dstT_ld + r] = h;
-          d.loT[static_cast<int64_t>(c) * d.dstT_ld + r] = pk_round_tf32(v - h);
+          if (d.hiT != nullptr) {
+            const float h = pk_round_tf32(v);
+            d.hiT[static_cast<int64_t>(c) * d.dstT_ld + r] = h;
+            d.loT[static_cast<int64_t>(c) * d.dstT_ld + r] = pk_round_tf32(v - h);
+          }
+          if (d.wbT != nullptr) d.wbT[static_cast<int64_t>(c) * d.dstT_ld + r] = pk_bf16(v);
         }
       }
     }

@@ -82,6 +82,10 @@ class GNN(nn.Module):
         self.long_range_projection = nn.Linear(hidden_dim, ffn_hidden_dim)                      # dead parameter (Q6)
         self._clock = DropClock()           # one dropout tick per forward pass for all layers (layers.shared_tick)
         self.use_packed_weights = True      # one pack kernel per forward instead of per-call torch pad / cat / split
+        # torch.bfloat16: activations / saved tensors / packed weight copies in bf16, fp32 accumulation, fp32 master weights
+        # and gradients (BASELINE configs[3]).  None: follow torch.autocast (the reference's mixed precision,
+        # training/trainer.py:133-149) -- bf16 inside ``torch.autocast("cuda", dtype=torch.bfloat16)``, fp32 otherwise.
+        self.compute_dtype = None
         self._packed: Dict[tuple, PackedWeights] = {}
         self.init_weights()
 
@@ -101,7 +105,7 @@ class GNN(nn.Module):
 
         return INDEX_CACHE.get(key, build)
 
-    def _packed_weights(self, gi: GraphIndex) -> Optional[PackedWeights]:
+    def _packed_weights(self, gi: GraphIndex, bf16: bool = False) -> Optional[PackedWeights]:
         """The packed operands of every projection of this model for the hop layout of ``gi`` (built once per device
         and layout), or None when the per-call path has to be used: embedding widths that need padding, parameters
         that are not all trainable fp32 CUDA tensors (the gradients are collected behind the first embedding table)."""
@@ -110,18 +114,31 @@ class GNN(nn.Module):
         t0 = self.atom_type_embedding.weight
         if not t0.is_cuda or t0.dtype != torch.float32 or (torch.is_grad_enabled() and not t0.requires_grad):
             return None
-        key = (str(t0.device), bool(gi.collapsed))
+        key = (str(t0.device), bool(gi.collapsed), bool(bf16))
         pk = self._packed.get(key)
         if pk is not None:
             return pk
         if any(p.dtype != torch.float32 or p.device != t0.device for p in self.parameters()):
             return None
-        pk = self._declare_packed(t0.device, bool(gi.collapsed))
+        pk = self._declare_packed(t0.device, bool(gi.collapsed), bf16)
         if pk is not None:
             self._packed[key] = pk
         return pk
 
-    def _declare_packed(self, device, collapsed: bool) -> Optional[PackedWeights]:
+    def _bf16_active(self) -> bool:
+        if self.compute_dtype is not None:
+            if self.compute_dtype not in (torch.float32, torch.bfloat16):
+                raise ValueError("compute_dtype must be torch.float32, torch.bfloat16 or None (follow autocast)")
+            return self.compute_dtype == torch.bfloat16
+        if torch.is_autocast_enabled():
+            dt = torch.get_autocast_gpu_dtype()
+            if dt != torch.bfloat16:
+                raise RuntimeError(f"autocast dtype {dt} is not supported by the B200 path: use torch.bfloat16 (fp32 "
+                                   "accumulation, no GradScaler needed) or disable autocast")
+            return True
+        return False
+
+    def _declare_packed(self, device, collapsed: bool, bf16: bool = False) -> Optional[PackedWeights]:
         D, S = self.x_other_dim, self.x_self_dim
         Dp, Sp = ops.pad_to(D, FEATURE_PAD), ops.pad_to(S, FEATURE_PAD)
         ntE = self.embedding_dim * len(FEATURE_ORDER)
@@ -142,10 +159,14 @@ class GNN(nn.Module):
         self.ffn.declare_packed(pk, "ffn")
         if F4 == self.post_pooling_projection.out_features:      # the segments of the output layer are unpadded
             self.skip_transform.declare_packed(pk, "skip", [F4], [F4])
-            self.output_layer.declare_packed(pk, "out", [F4, F4], [F4, F4])
+            # bf16: the output width is padded to 32 (tensor-core operands of the backward products need 16-byte rows)
+            self.output_layer.declare_packed(pk, "out", [F4, F4], [F4, F4],
+                                             n_out=ops.pad_to(self.output_layer.out_features, 32) if bf16 else None)
         if hasattr(self.pooling, "declare_packed"):
             self.pooling.declare_packed(pk, "pool")
         pk.finalize()
+        if bf16:
+            pk.enable_bf16()
         return pk
 
     def forward(self, atom_features: Dict[str, torch.Tensor], multi_hop_edge_indices: torch.Tensor,
@@ -168,6 +189,11 @@ class GNN(nn.Module):
         if gi is None:
             gi = self._index_for(atom_features, multi_hop_edge_indices, batch_indices, total_charges,
                                  tetrahedral_indices, cis_indices, trans_indices)
+        bf16 = self._bf16_active()
+        dt = torch.bfloat16 if bf16 else torch.float32
+        if bf16 and (self.hidden_dim % 32 or self.post_pooling_projection.out_features % 32 or (self.embedding_dim * 4) % 32):
+            raise ValueError("the bf16 configuration needs hidden_dim, ffn_hidden_dim and 4 * embedding_dim to be multiples "
+                             "of 32 (16-byte rows for the tensor-core operands)")
         D, S = self.x_other_dim, self.x_self_dim
         Dp, Sp = ops.pad_to(D, FEATURE_PAD), ops.pad_to(S, FEATURE_PAD)
         E = self.embedding_dim
@@ -176,7 +202,10 @@ class GNN(nn.Module):
         if Ep != E:
             tables = [pad2d(t, t.shape[0], Ep) for t in tables]
         nt = len(FEATURE_ORDER)
-        pk = self._packed_weights(gi)
+        pk = self._packed_weights(gi, bf16)
+        if bf16 and pk is None:
+            raise RuntimeError("the bf16 configuration needs the packed-weight path (trainable fp32 CUDA parameters, "
+                               "embedding_dim % 4 == 0, use_packed_weights = True)")
         use = (lambda name: (pk, name) if f"{name}.W" in pk or f"{name}.W_io" in pk or f"{name}.0.W1" in pk else None) \
             if pk is not None else (lambda name: None)
         if pk is not None:
@@ -190,21 +219,22 @@ class GNN(nn.Module):
             W_ep = torch.cat([pad2d(Wp[:S], Sp, nt * Ep), pad2d(Wp[S:], Dp, nt * Ep)], dim=0)
             bp = self.embedding_projection.bias
             b_ep = torch.cat([pad1d(bp[:S], Sp), pad1d(bp[S:], Dp)], dim=0)
-        opts = ops._Opts(act=self.activation_type, names=FEATURE_ORDER, emb_dim=Ep, s_pad=Sp, d_pad=Dp, gi=gi)
+        opts = ops._Opts(act=self.activation_type, names=FEATURE_ORDER, emb_dim=Ep, s_pad=Sp, d_pad=Dp, gi=gi, dtype=dt)
         x_self, x = ops.EmbedProjFn.apply(opts, W_ep, b_ep, *tables,
                                           *[atom_features[k].contiguous() for k in FEATURE_ORDER])   # gnn.py:220-231
 
         if multi_hop_edge_indices.numel() > 0:                                                     # gnn.py:287
             for i, layer in enumerate(self.message_passing_layers):
                 if self.use_partial_charges:                                                       # gnn.py:290-293
-                    x = ops.ChargeEqFn.apply(x, total_charges, gi)
+                    # bf16: fp32 equilibration on up-cast values (the reference crashes here under autocast, quirk Q5)
+                    x = ops.cast(ops.ChargeEqFn.apply(ops.cast(x, torch.float32), total_charges, gi), dt)
                 if self.use_stereochemistry:                                                       # gnn.py:296-299
                     x = self._apply_stereochemistry(x, gi, D, Dp, use("stereo2"))
                 x = layer.forward_padded(x, gi, add_input=True, packed=use(f"mp.{i}"))             # gnn.py:302-306
 
         partial_charges = None
         if self.use_partial_charges and D >= 2:                                                    # gnn.py:240-242
-            partial_charges = x[:, 0].clone()
+            partial_charges = x[:, 0].float().clone()
 
         atom_emb = self.concat_self_other(([x_self, x], [S, D]), packed=use("cso"))                # gnn.py:245-246
         if pk is not None and "pool.W" in pk:
@@ -215,13 +245,20 @@ class GNN(nn.Module):
         v = self.ffn(v, packed=use("ffn"))                                                         # gnn.py:253
         skip = self.skip_transform(v, packed=use("skip"))                                          # gnn.py:256
         Fh = v.shape[1]
-        output = self.output_layer(([v, skip], [Fh, Fh]), packed=use("out"))                       # gnn.py:257-258
+        if bf16:        # fp32 outputs (they feed the loss), computed 32 columns wide and cut back to the real targets
+            T = self.output_layer.out_features
+            output = self.output_layer(([v, skip], [Fh, Fh], ops.pad_to(T, 32)), packed=use("out"),
+                                       out_dtype=torch.float32)[:, :T]
+        else:
+            output = self.output_layer(([v, skip], [Fh, Fh]), packed=use("out"))                   # gnn.py:257-258
         return output, attention_weights, partial_charges
 
     def _apply_stereochemistry(self, x: torch.Tensor, gi: GraphIndex, D: int, Dp: int, packed=None) -> torch.Tensor:
         """Reference ``gnn.py:310-327``: Linear([x | cis_trans(x) | tetra(x)])."""
-        ct = ops.CisTransFn.apply(x, gi) if gi.cistrans is not None else x          # identity when empty (gnn.py:475-476)
-        tt = ops.TetraFn.apply(x, D, gi) if gi.tetra is not None else x             # identity when empty (gnn.py:402-403)
+        dt = x.dtype
+        x32 = ops.cast(x, torch.float32) if (gi.cistrans is not None or gi.tetra is not None) else x   # bf16: fp32 terms
+        ct = ops.cast(ops.CisTransFn.apply(x32, gi), dt) if gi.cistrans is not None else x   # identity when empty (gnn.py:475-476)
+        tt = ops.cast(ops.TetraFn.apply(x32, D, gi), dt) if gi.tetra is not None else x      # identity when empty (gnn.py:402-403)
         return self.stereochemical_embedding_2(([x, ct, tt], [D, D, D], Dp), packed=packed)  # padded [N, Dp], pads = 0
 
     # ------------------------------------------------------------------------------------------ misc API

@@ -268,7 +268,7 @@ class _FusedLinear(nn.Linear):
         if self.bias is not None:
             pk.add(f"{prefix}.b", 1, n_out, [(self.bias, 0, 1, 0, self.out_features, 0, 0)], vector=True)
 
-    def forward(self, x, packed=None):  # type: ignore[override]
+    def forward(self, x, packed=None, out_dtype=None):  # type: ignore[override]
         if isinstance(x, (list, tuple)):
             segs, true_widths = x[0], x[1]   # ([tensors], [true widths][, padded out width]) -- internal convention
             widths = [s.shape[1] for s in segs]
@@ -286,7 +286,7 @@ class _FusedLinear(nn.Linear):
                     off += tw
                 W = cols[0] if len(cols) == 1 else torch.cat(cols, dim=1)
                 b = pad1d(self.bias, n_out)
-            out = ops.LinearFn.apply(ops._Opts(widths=widths, n_out=n_out), W, b, *segs)
+            out = ops.LinearFn.apply(ops._Opts(widths=widths, n_out=n_out, out_dtype=out_dtype), W, b, *segs)
             return out if (n_out == self.out_features or len(x) > 2) else out[:, : self.out_features]
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])

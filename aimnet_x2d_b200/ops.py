@@ -19,27 +19,58 @@ from ._lib import ACT_CODES, CMat, Epilogue, MAX_SEG, SEG_MODES
 class KernelTimer:
     """CUDA-event timing of individual C-ABI launches on the launching (= torch current) stream.
 
-    ``bench.py`` installs one over the timed region to obtain the live per-launch durations that the
-    roofline fractions are computed from.  Inactive (``TIMER is None``) it costs one attribute test."""
+    Installed with ``with timer:`` (sets ``_lib.TIMER_HOOK``); every kernel-enqueueing entry point of libax2d is then
+    bracketed by an event pair.  While a CUDA graph is being captured the events are *external* event-record nodes of
+    the graph: after a replay ``summary()`` gives the duration of every launch INSIDE the replayed step, which is what
+    ``bench.py`` computes its roofline fractions and per-kernel shares from (an event pair around a single ~20 us launch
+    issued eagerly from Python mostly measures the launch path)."""
 
     def __init__(self):
         self.events = {}          # name -> list of (start, stop, algorithmic_bytes, flops)
+        self._meta = (0, 0)
+        self._alias = None
+
+    def __enter__(self):
+        global TIMER
+        self._prev = (_lib.TIMER_HOOK[0], TIMER)
+        _lib.TIMER_HOOK[0] = self
+        TIMER = self
+        return self
+
+    def __exit__(self, *exc):
+        global TIMER
+        _lib.TIMER_HOOK[0], TIMER = self._prev
+        return False
+
+    def bracket(self, name, fn, args):
+        ext = torch.cuda.is_current_stream_capturing()
+        a = torch.cuda.Event(enable_timing=True, external=ext)
+        b = torch.cuda.Event(enable_timing=True, external=ext)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        nbytes, flops = self._meta
+        self._meta = (0, 0)
+        self.events.setdefault(self._alias or name, []).append((a, b, nbytes, flops))
+        return rc
 
     def launch(self, name, fn, nbytes=0, flops=0):
-        a = torch.cuda.Event(enable_timing=True)
-        b = torch.cuda.Event(enable_timing=True)
-        a.record()
-        fn()
-        b.record()
-        self.events.setdefault(name, []).append((a, b, nbytes, flops))
+        """Attach the algorithmic bytes / flops of the next launch (recorded under ``name``)."""
+        self._meta, self._alias = (nbytes, flops), name
+        try:
+            fn()
+        finally:
+            self._meta, self._alias = (0, 0), None
 
-    def summary(self):
-        """name -> dict(launches, ms_total, ms_avg, bytes_avg, flops_avg); call after a device synchronize."""
+    def summary(self, replays: int = 1):
+        """name -> dict(launches, ms_total, ms_avg, bytes_avg, flops_avg); call after a device synchronize.  For events
+        recorded inside a captured graph the values are those of the LAST replay."""
         out = {}
         for name, evs in self.events.items():
             ms = [a.elapsed_time(b) for a, b, _, _ in evs]
             out[name] = dict(launches=len(evs), ms_total=sum(ms), ms_avg=sum(ms) / len(ms),
-                             bytes_avg=sum(e[2] for e in evs) / len(evs), flops_avg=sum(e[3] for e in evs) / len(evs))
+                             bytes_avg=sum(e[2] for e in evs) / len(evs), flops_avg=sum(e[3] for e in evs) / len(evs),
+                             bytes_total=sum(e[2] for e in evs), flops_total=sum(e[3] for e in evs))
         return out
 
 
@@ -112,6 +143,20 @@ def gemm(a_segs, b_segs, c_segs, M: int, N: int, K: int, trans_a: bool = False, 
          drop_tick=None, resid=(), dact_pre=None, dact=None, dact_cols=None, accumulate: bool = False,
          split_k: int = 1) -> None:
     lib = _lib.load()
+    if a_segs[0][0].dtype == BF16:          # bf16 configuration: activations bf16, weights from the bf16 packed copies
+        if trans_a or split_k != 1 or len(b_segs) != 1 or mask is not None or accumulate:
+            raise RuntimeError("bf16 projections support C = epilogue(A W^T) / (A W) with one weight operand only")
+        w = b_segs[0][0]
+        info = packed_info(w)
+        if info is not None and info.wb is not None:
+            wb = info.wb if trans_b else info.wbT
+            if tuple(wb.shape) != (N, K):
+                raise RuntimeError(f"packed bf16 weight {tuple(wb.shape)} does not match the contraction ({N}, {K})")
+        else:                               # stand-alone module: derive the operand per call
+            wb = (w[:N, :K] if trans_b else w[:K, :N].t()).to(BF16).contiguous()
+        return gemm_bf16(a_segs, wb, c_segs, M, N, K, bias=bias, pre_segs=pre_segs, act=act, act_cols=act_cols, drop_p=drop_p,
+                         drop_seed=drop_seed, drop_tick=drop_tick, resid=resid, dact_pre=dact_pre, dact=dact,
+                         dact_cols=dact_cols, out_dtype=c_segs[0][0].dtype)
     a, b, c = _mat(a_segs), _mat(b_segs), _mat(c_segs)
     ep = Epilogue()
     ep.bias = None if bias is None else bias.data_ptr()
@@ -249,6 +294,11 @@ def colsum(segs, M: int, N: int, out: torch.Tensor, accumulate: bool = False) ->
 
 def act_bwd(g: torch.Tensor, pre: torch.Tensor, act: str) -> torch.Tensor:
     out = torch.empty_like(pre)
+    if pre.dtype == BF16:
+        g = convert(g, BF16)
+        _lib.check(_lib.load().ax2d_act_bwd_bf16(_p(g), g.stride(0), _p(pre), pre.stride(0), _p(out), out.stride(0),
+                                                 pre.shape[0], pre.shape[1], ACT_CODES[act], _stream()), "ax2d_act_bwd_bf16")
+        return out
     _lib.check(_lib.load().ax2d_act_bwd(_p(g), g.stride(0), _p(pre), pre.stride(0), _p(out), out.stride(0),
                                         pre.shape[0], pre.shape[1], ACT_CODES[act], _stream()), "ax2d_act_bwd")
     return out
@@ -268,17 +318,20 @@ def agg(x: torch.Tensor, gi, transpose: bool = False, addend: Optional[torch.Ten
     rows = N if transpose else gi.num_rows
     out = torch.empty((rows, width), dtype=x.dtype, device=x.device)
     rowptr, col, info = (gi.rowptr_t, gi.col_t, gi.tile_info_t) if transpose else (gi.rowptr, gi.col, gi.tile_info)
+    es = x.element_size()
+    if x.dtype not in DT_CODES or (addend is not None and addend.dtype != x.dtype):
+        raise RuntimeError(f"aggregation runs on fp32 or bf16 features, got {x.dtype}")
     tiled = (gi.tile_local and gi.collapsed and x.stride(0) == width and width % 32 == 0 and info is not None
-             and gi.max_tile_rows * width * 4 + gi.max_tile_edges * 4 <= 200 * 1024 and gi.n_tiles > 0)
+             and gi.max_tile_rows * width * es + gi.max_tile_edges * 4 <= 200 * 1024 and gi.n_tiles > 0)
     call = lambda: _lib.check(lib.ax2d_agg(_p(x), x.stride(0), x.shape[0], _p(out), out.stride(0), rows, _p(rowptr),
                                            _p(col), _p(addend), 0 if addend is None else addend.stride(0), width,
                                            _p(info) if tiled else None, gi.n_tiles if tiled else 0,
-                                           gi.max_tile_rows if tiled else 0, gi.max_tile_edges if tiled else 0, 0,
-                                           _stream()), "ax2d_agg")
+                                           gi.max_tile_rows if tiled else 0, gi.max_tile_edges if tiled else 0,
+                                           DT_CODES[x.dtype], _stream()), "ax2d_agg")
     if TIMER is None:
         call()
     else:
-        TIMER.launch("agg", call, nbytes=agg_bytes(x.shape[0], rows, gi.num_edges, width, addend is not None))
+        TIMER.launch("agg", call, nbytes=agg_bytes(x.shape[0], rows, gi.num_edges, width, addend is not None, es))
     return out
 
 
@@ -304,6 +357,8 @@ def _weight_grad(g_segs, x_segs, M_rows: int, Nout: int, Kin: int, device, bias:
     if tuple(dW.shape) != (Nout, Kin) or not dW.is_contiguous():
         raise RuntimeError(f"weight-gradient buffer {tuple(dW.shape)} vs ({Nout}, {Kin})")
     lib = _lib.load()
+    if g_segs[0][0].dtype == BF16:
+        return weight_grad_bf16(g_segs, x_segs, M_rows, Nout, Kin, bias=bias, out=dW, out_bias=out_bias)
     if USE_TENSOR_CORES and M_rows >= TC_MIN_ROWS:
         a, b, c = _mat(g_segs), _mat(x_segs), _mat([(dW, Kin)])
         if lib.ax2d_gemm_tc_wgrad_supported(C.byref(a), C.byref(b), Nout, Kin, M_rows):
@@ -334,9 +389,18 @@ def _deferred_weight_grad(iw, ib, g_segs, x_segs, M_rows: int, Nout: int, Kin: i
     """Tensor-core weight gradient that leaves its split-K partial tiles (and partial bias vectors) in a persistent
     workspace of the packed matrix; ``ax2d_unpack_grads`` sums them in split order while it scatters the gradients,
     which saves one reduce launch per matrix and step.  False: not applicable (caller takes the ordinary path)."""
+    lib = _lib.load()
+    if g_segs[0][0].dtype == BF16:
+        if not DEFER_SPLITK_REDUCE or tuple(iw.grad.shape) != (Nout, Kin):
+            return False
+        ws = iw.owner.workspace(iw.name, lib.ax2d_gemm_bf16_wgrad_workspace(Nout, Kin, M_rows))
+        splits = weight_grad_bf16(g_segs, x_segs, M_rows, Nout, Kin, ws=ws, leave_partials=True)
+        iw.partials = (ws.data_ptr(), splits, Nout, Kin)
+        if ib is not None:
+            ib.partials = (ws.data_ptr() + 4 * splits * Nout * Kin, splits, 1, Nout)
+        return True
     if not (DEFER_SPLITK_REDUCE and USE_TENSOR_CORES and M_rows >= TC_MIN_ROWS):
         return False
-    lib = _lib.load()
     a, b = _mat(g_segs), _mat(x_segs)
     if not lib.ax2d_gemm_tc_wgrad_supported(C.byref(a), C.byref(b), Nout, Kin, M_rows):
         return False
@@ -411,7 +475,7 @@ class LinearFn(torch.autograd.Function):
         _need_cuda(W, *a)
         M = a[0].shape[0]
         K = sum(opts.widths)
-        out = torch.empty((M, opts.n_out), dtype=torch.float32, device=W.device)
+        out = torch.empty((M, opts.n_out), dtype=getattr(opts, "out_dtype", None) or a[0].dtype, device=W.device)
         gemm(list(zip(a, opts.widths)), [(W, K)], [(out, opts.n_out)], M, opts.n_out, K, bias=b)
         ctx.opts = opts
         ctx.bias = b
@@ -425,9 +489,13 @@ class LinearFn(torch.autograd.Function):
         (W,) = _packed_or(ctx, W)
         opts = ctx.opts
         g = g.contiguous()
+        if g.dtype != a[0].dtype:            # fp32 outputs of the bf16 configuration (the last layer feeds the loss)
+            if g.shape[1] % 8 != 0:
+                g = torch.nn.functional.pad(g, (0, 8 - g.shape[1] % 8))
+            g = convert(g, a[0].dtype)
         M, Np, K = g.shape[0], opts.n_out, sum(opts.widths)
         gs = [(g, Np)]
-        d_a = [torch.empty((M, w), dtype=torch.float32, device=g.device) for w in opts.widths]
+        d_a = [torch.empty((M, w), dtype=a[0].dtype, device=g.device) for w in opts.widths]
         gemm(gs, [(W, K)], list(zip(d_a, opts.widths)), M, K, Np, trans_a=False, trans_b=False)
         dW, db = _param_grads(W, ctx.bias, gs, list(zip(a, opts.widths)), M, Np, K, g.device)
         return (None, dW, db, *d_a)
@@ -442,7 +510,7 @@ class MLPBlockFn(torch.autograd.Function):
     def forward(ctx, opts, h, W1, b1, W2, b2):
         _need_cuda(h, W1, W2)
         M, Wi, Wo = h.shape[0], opts.w_in, opts.w_out
-        u = torch.empty((M, Wo), dtype=torch.float32, device=h.device)
+        u = torch.empty((M, Wo), dtype=h.dtype, device=h.device)
         t = torch.empty_like(u)
         out = torch.empty_like(u)
         gemm([(h, Wi)], [(W1, Wi)], [(t, Wo)], M, Wo, Wi, bias=b1, pre_segs=[(u, Wo)], act=opts.act,
@@ -495,7 +563,7 @@ class ShellConvFn(torch.autograd.Function):
         ag = agg(x, gi)                                                     # layers.py:133-167
         a_segs = ShellConvFn._segments(x, ag, Di)
         K = Di * len(a_segs)
-        z0 = torch.empty((N, Do), dtype=torch.float32, device=dev)
+        z0 = torch.empty((N, Do), dtype=x.dtype, device=dev)
         h = torch.empty_like(z0)
         gskip = torch.empty_like(z0)
         gemm(a_segs, [(W_io, K)], [(h, Do), (gskip, Do)], N, 2 * Do, K, bias=b_io,
@@ -559,7 +627,7 @@ class ShellConvFn(torch.autograd.Function):
         K = Di * len(a_segs)
         gz = [(dz0, Do), (g, Do)]
         dW_io, db_io = _param_grads(W_io, b_io, gz, a_segs, N, 2 * Do, K, dev)
-        dx1 = torch.empty((N, Di), dtype=torch.float32, device=dev)
+        dx1 = torch.empty((N, Di), dtype=ag.dtype, device=dev)
         dag = torch.empty_like(ag)
         c_segs = ShellConvFn._segments(dx1, dag, Di)
         gemm(gz, [(W_io, K)], c_segs, N, K, 2 * Do, trans_b=False,
@@ -581,16 +649,20 @@ class EmbedProjFn(torch.autograd.Function):
         lib = _lib.load()
         N, E = indices[0].shape[0], opts.emb_dim
         dev = W.device
-        e0 = torch.empty((N, nt * E), dtype=torch.float32, device=dev)
+        dt = getattr(opts, "dtype", torch.float32)
+        e0 = torch.empty((N, nt * E), dtype=dt, device=dev)
         tp = (C.c_void_p * nt)(*[t.data_ptr() for t in tables])
         ip = (C.c_void_p * nt)(*[i.data_ptr() for i in indices])
         for i in indices:
             if i.dtype != torch.int64 or not i.is_contiguous():
                 raise RuntimeError("atom feature indices must be contiguous int64 tensors")
-        _lib.check(lib.ax2d_embed_fwd(tp, ip, nt, E, N, _p(e0), e0.stride(0), _stream()), "ax2d_embed_fwd")
+        if dt == BF16:
+            _lib.check(lib.ax2d_embed_fwd_bf16(tp, ip, nt, E, N, _p(e0), e0.stride(0), _stream()), "ax2d_embed_fwd_bf16")
+        else:
+            _lib.check(lib.ax2d_embed_fwd(tp, ip, nt, E, N, _p(e0), e0.stride(0), _stream()), "ax2d_embed_fwd")
         Sp, Dp = opts.s_pad, opts.d_pad
-        xs = torch.empty((N, Sp), dtype=torch.float32, device=dev)
-        xo = torch.empty((N, Dp), dtype=torch.float32, device=dev)
+        xs = torch.empty((N, Sp), dtype=dt, device=dev)
+        xo = torch.empty((N, Dp), dtype=dt, device=dev)
         zs, zo = torch.empty_like(xs), torch.empty_like(xo)
         gemm([(e0, nt * E)], [(W, nt * E)], [(xs, Sp), (xo, Dp)], N, Sp + Dp, nt * E, bias=b,
              pre_segs=[(zs, Sp), (zo, Dp)], act=opts.act)
@@ -627,9 +699,11 @@ class EmbedProjFn(torch.autograd.Function):
             ip = (C.c_void_p * nt)(*[i.data_ptr() for i in ctx.indices])
             gp = (C.c_void_p * nt)(*[t.data_ptr() for t in g_tables])
             vp = (C.c_int64 * nt)(*[t.shape[0] for t in tables])
-            _lib.check(lib.ax2d_embed_bwd_all(_p(de0), de0.stride(0), nt, E, N, ip, vp, gp, _p(ws), _stream()),
-                       "ax2d_embed_bwd_all")
+            fn = lib.ax2d_embed_bwd_all_bf16 if de0.dtype == BF16 else lib.ax2d_embed_bwd_all
+            _lib.check(fn(_p(de0), de0.stride(0), nt, E, N, ip, vp, gp, _p(ws), _stream()), "ax2d_embed_bwd_all")
         else:
+            if de0.dtype == BF16:
+                de0 = convert(de0, torch.float32)
             for ti, name in enumerate(opts.names):
                 order, ptr, vocab = opts.gi.embed[name]
                 if vocab != tables[ti].shape[0]:
@@ -640,6 +714,24 @@ class EmbedProjFn(torch.autograd.Function):
                 _lib.check(lib.ax2d_embed_bwd(_p(de0), de0.stride(0), ti, E, vocab, _p(order), _p(ptr), _p(gt), _p(ws),
                                               _stream()), "ax2d_embed_bwd")
         return (None, dW, db, *g_tables, *([None] * nt))
+
+
+class CastFn(torch.autograd.Function):
+    """fp32 <-> bf16 through ``ax2d_convert`` (the bf16 configuration runs segmented softmax, charge equilibration and
+    the stereo terms in fp32 on up-cast values)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src = x.dtype
+        return convert(x, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return convert(g.contiguous(), ctx.src), None
+
+
+def cast(x: torch.Tensor, dtype) -> torch.Tensor:
+    return x if x.dtype == dtype else CastFn.apply(x, dtype)
 
 
 # ----------------------------------------------------------------------------------------------- segment ops

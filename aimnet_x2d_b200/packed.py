@@ -19,17 +19,19 @@ from . import _lib
 
 _DESC = np.dtype([("src", "u8"), ("grad", "u8"), ("w", "u8"), ("hi", "u8"), ("lo", "u8"), ("hiT", "u8"), ("loT", "u8"),
                   ("g", "u8"), ("part", "u8"), ("rows", "i4"), ("cols", "i4"), ("src_ld", "i4"), ("dst_ld", "i4"),
-                  ("dstT_ld", "i4"), ("split", "i4"), ("p_rows", "i4"), ("p_cols", "i4"), ("dr", "i4"), ("dc", "i4")])
-assert _DESC.itemsize == 112
+                  ("dstT_ld", "i4"), ("split", "i4"), ("p_rows", "i4"), ("p_cols", "i4"), ("dr", "i4"), ("dc", "i4"),
+                  ("wb", "u8"), ("wbT", "u8")])
+assert _DESC.itemsize == 128
 
 
 class PackInfo:
     """Attached to a packed weight tensor as ``t._ax2d``: its TF32 terms (plain and transposed) and the buffer its
     gradient is written to."""
-    __slots__ = ("hi", "lo", "hiT", "loT", "grad", "owner", "written", "name", "partials")
+    __slots__ = ("hi", "lo", "hiT", "loT", "grad", "owner", "written", "name", "partials", "wb", "wbT")
 
     def __init__(self, hi, lo, hiT, loT, grad, owner, name=""):
         self.hi, self.lo, self.hiT, self.loT, self.grad, self.owner, self.name = hi, lo, hiT, loT, grad, owner, name
+        self.wb = self.wbT = None  # bf16 copies [rows, cols] / [cols, rows] (``PackedWeights.enable_bf16``)
         self.written = False      # the gradient buffer already holds a contribution of the running backward pass
         # split-K partials the weight-gradient kernel left for this matrix in the running backward pass:
         # (data_ptr, splits, rows, cols) -- summed by the gradient-collect kernel instead of a reduce launch per matrix
@@ -74,6 +76,8 @@ class PackedWeights:
         # workspace, the old one stays alive.
         self._tables: Dict[tuple, torch.Tensor] = {}
         self._pinned = set()
+        self.bf16 = False
+        self.wb = self.wbT = None
         self._retired: List[torch.Tensor] = []
 
     # a derived cache: copies / pickles of the owning module rebuild their own
@@ -116,6 +120,25 @@ class PackedWeights:
         self._n_blocks = sum(len(m.blocks) for m in self.mats.values())
         self._max_elems = max([1] + [(b[2] - b[1]) * (b[4] - b[3]) for m in self.mats.values() for b in m.blocks])
 
+    def enable_bf16(self) -> None:
+        """Also keep bf16 copies of every matrix (plain and transposed) for the bf16 configuration: written by the same
+        pack launch, read by ``ax2d_gemm_bf16``."""
+        if self.bf16:
+            return
+        n = self.w.numel()
+        self.wb = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
+        self.wbT = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
+        for m in self.mats.values():
+            if m.vector:
+                continue
+            sl = slice(m.off, m.off + m.rows * m.cols)
+            info = self.tensors[m.name]._ax2d
+            info.wb = self.wb[sl].view(m.rows, m.cols)
+            info.wbT = self.wbT[sl].view(m.cols, m.rows)
+        self.bf16 = True
+        self._table = self._table_key = None          # descriptor tables carry the new pointers
+        self._tables = {k: v for k, v in self._tables.items() if k in self._pinned}
+
     def __getitem__(self, name: str) -> torch.Tensor:
         return self.tensors[name]
 
@@ -129,7 +152,7 @@ class PackedWeights:
     def _key(self, with_grads: bool):
         ps = self._params()
         parts = tuple((n, t._ax2d.partials) for n, t in self.tensors.items() if t._ax2d.partials is not None) if with_grads else None
-        return (tuple(p.data_ptr() for p in ps),
+        return (tuple(p.data_ptr() for p in ps) + (self.bf16,),
                 tuple((p.grad.data_ptr() if p.grad is not None else 0) for p in ps) if with_grads else None, parts)
 
     def workspace(self, name: str, nbytes: int) -> torch.Tensor:
@@ -162,6 +185,8 @@ class PackedWeights:
                 if not m.vector:
                     d["hi"], d["lo"] = self.hi.data_ptr() + dst_off, self.lo.data_ptr() + dst_off
                     d["hiT"], d["loT"] = self.hiT.data_ptr() + dstT_off, self.loT.data_ptr() + dstT_off
+                    if self.bf16:
+                        d["wb"], d["wbT"] = self.wb.data_ptr() + dst_off // 2, self.wbT.data_ptr() + dstT_off // 2
                 d["rows"], d["cols"] = r1 - r0, c1 - c0
                 d["src_ld"] = (c1 - c0) if p.dim() == 1 else ld
                 d["dst_ld"], d["dstT_ld"] = m.cols, m.rows

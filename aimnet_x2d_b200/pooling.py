@@ -42,8 +42,9 @@ class _SegmentPooling(nn.Module):
                 graph_index: Optional[GraphIndex] = None) -> Tuple[torch.Tensor, None]:
         gi = _segments_for(x, batch_indices, graph_index)
         F_ = x.shape[1]
-        xp = pad_cols(x, ops.pad_to(F_, 4)).contiguous()
-        out = ops.SegPoolFn.apply(xp, self.mode, gi)
+        dt = x.dtype
+        xp = pad_cols(x, ops.pad_to(F_, 8 if dt != torch.float32 else 4)).contiguous()
+        out = ops.cast(ops.SegPoolFn.apply(ops.cast(xp, torch.float32), self.mode, gi), dt)     # bf16 features: fp32 reduction
         return (out[:, :F_] if out.shape[1] != F_ else out), None
 
 
@@ -95,7 +96,12 @@ class MultiHeadAttentionPoolingLayer(nn.Module):
         else:
             w = pad_cols(torch.cat([l.weight for l in self.attention_weights], dim=0), Fp).contiguous()   # [heads, F]
             b = torch.cat([l.bias for l in self.attention_weights], dim=0)                               # [heads]
-        pooled, attn = ops.AttnPoolFn.apply(pad_cols(x, Fp).contiguous(), w, b, self.temperature, gi)
+        # bf16 features: scores, the segmented softmax and the weighted sum run in fp32 on up-cast values
+        dt = x.dtype
+        if dt != torch.float32 and Fp % 8:
+            raise ValueError("bf16 attention pooling needs input_dim % 8 == 0")
+        pooled, attn = ops.AttnPoolFn.apply(ops.cast(pad_cols(x, Fp).contiguous(), torch.float32), w, b, self.temperature, gi)
+        pooled = ops.cast(pooled, dt)
         if Fp != F_:
             pooled = pooled[:, :F_]
         if self.dropout.p > 0:                                                    # pooling.py:169-170

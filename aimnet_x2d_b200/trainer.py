@@ -201,9 +201,12 @@ class GraphedTrainStep(StaticSlot):
         loss.backward()
         return loss.detach()
 
-    def capture(self, padded: MolBatch, warmup: int = 3) -> None:
+    def capture(self, padded: MolBatch, warmup: int = 3, timer=None) -> None:
         """Allocate the static slot from ``padded`` (a host batch from ``pad_batch``), run ``warmup`` eager steps on a
-        side stream (their effect on parameters / optimiser state is rolled back), then capture."""
+        side stream (their effect on parameters / optimiser state is rolled back), then capture.  ``timer``: an
+        ``ops.KernelTimer`` installed during the capture only -- its event pairs become nodes of the graphs, so every
+        replay measures each launch inside the step."""
+        import contextlib
         opt = self.optimizer
         self._make_slot(padded)
         saved = [t.clone() for t in (opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.step_count)]
@@ -217,11 +220,12 @@ class GraphedTrainStep(StaticSlot):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_fb):
-            self.loss = self._fwd_bwd()
-        self.graph_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_opt):
-            opt.step()
+        with (timer if timer is not None else contextlib.nullcontext()):
+            with torch.cuda.graph(self.graph_fb):
+                self.loss = self._fwd_bwd()
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt):
+                opt.step()
         with torch.no_grad():
             for dst, src in zip((opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.step_count), saved):
                 dst.copy_(src)

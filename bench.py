@@ -47,10 +47,19 @@ WORKLOADS = {
                     "iteration per GPU, batch-sharded, no collectives, fp32"),
     "c3": dict(kind="drug", graphs=1024, hops=3, layers=3, hidden=512, stereo=True, charges=True,
                desc="BASELINE configs[2]: synthetic drug-like graphs (20-70 heavy atoms), stereo + charges, 1024/GPU, fp32"),
+    # foundation config: FIXED global batch of 8192 molecules -> 8192 / world per GPU (strong scaling), bf16
+    "c4": dict(kind="drug", graphs=8192, hops=4, layers=6, hidden=512, stereo=False, charges=False, dtype="bf16",
+               global_batch=8192, ring=16,
+               desc="BASELINE configs[3]: foundation-scale, hidden 512, 6 message-passing layers x 4 hops, bf16, 8192-molecule "
+                    "global batch of drug-like graphs (C3 generator), device-resident ring of 16 pre-collated CSR batches"),
+    "c4q": dict(kind="qm9", graphs=8192, hops=4, layers=6, hidden=512, stereo=False, charges=False, dtype="bf16",
+                global_batch=8192, ring=16,
+                desc="BASELINE configs[3], QM9-shaped variant: hidden 512, 6 layers x 4 hops, bf16, 8192-molecule global batch, "
+                     "device-resident ring of 16 pre-collated CSR batches"),
+    "c2b": dict(kind="qm9", graphs=2048, hops=3, layers=3, hidden=512, stereo=False, charges=False, dtype="bf16",
+                desc="configs[1] shapes run in the bf16 configuration (not a BASELINE line: kernel comparison with c2)"),
 }
 T_TARGETS = 12
-AGG_DRAM_TRAFFIC = 25.6e6     # bytes per forward launch, ncu capture profiles/r1e_agg_tiles_full.txt
-DENSE_SHARE_OF_STEP = 0.85    # gemm_tc + gemm_tc_wgrad + split-K sums share of the step, profiles/r1o_launches_graph_step.csv
 RING = 4            # distinct batches per rank, rotated every step (per-step working set >> 126 MB L2)
 
 
@@ -129,14 +138,28 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------ workloads
 def batch_seed(wl, rank, i):
-    cfg_id = {"c2": 2, "c3": 3, "c4": 4, "c4q": 4, "c5": 5}[wl["name"]]
+    cfg_id = {"c2": 2, "c2b": 2, "c3": 3, "c4": 4, "c4q": 4, "c5": 5}[wl["name"]]
     return 1234 + cfg_id * 1000 + rank * 97 + i
 
 
 def make_batches(wl, rank, n):
+    """`n` distinct pre-collated batches of wl['graphs'] molecules.  Up to 4: independently generated; larger rings draw
+    their batches (seeded, without replacement) from a pool of 1.5 x graphs molecules generated once, so that building a
+    16-batch ring does not take minutes of host time."""
     from aimnet_x2d_b200 import synthetic as S
-    return [S.make_batch(batch_seed(wl, rank, i), wl["graphs"], wl["hops"], wl["kind"], T_TARGETS,
-                         stereo=wl["stereo"]) for i in range(n)]
+    from aimnet_x2d_b200.collate import MolBatch
+    B = wl["graphs"]
+    if n <= 4:
+        return [S.make_batch(batch_seed(wl, rank, i), B, wl["hops"], wl["kind"], T_TARGETS, stereo=wl["stereo"]) for i in range(n)]
+    rows = 32
+    pool = S.make_molecules(batch_seed(wl, rank, 0), B + B // 2, wl["hops"], wl["kind"], T_TARGETS, wl["stereo"])
+    data = [S.to_data(m) for m in pool]
+    rng = np.random.Generator(np.random.PCG64(batch_seed(wl, rank, 1)))
+    out = []
+    for _ in range(n):
+        pick = rng.permutation(len(data))[:B]
+        out.append(MolBatch.from_data_list([data[i] for i in pick], S.FEATURE_SIZES, rows))
+    return out
 
 
 def model_cfg(wl):
@@ -151,6 +174,8 @@ def build_model(wl, device):
     model = ax.GNN(FEATURE_SIZES, wl["hidden"], T_TARGETS, num_shells=wl["hops"], num_message_passing_layers=wl["layers"],
                    task_type="multitask", use_partial_charges=wl["charges"], use_stereochemistry=wl["stereo"])
     model.init_weights()                                   # trainer.py:206-209
+    if wl.get("dtype") == "bf16":
+        model.compute_dtype = torch.bfloat16               # bf16 activations, fp32 accumulation / master weights / gradients
     return model.to(device).train()
 
 
@@ -342,28 +367,23 @@ def reference_arm(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def time_agg_launches(dev_batches, width=160, reps=48):
-    """Average device time of one ax2d_agg launch (forward and fused-addend backward alternating, the ring's batches
-    and fresh feature buffers rotating so that inputs do not stay in L2): the launches are captured in a CUDA graph
-    and the replay is bracketed by CUDA events, so no host time sits between them (an event pair around a single
-    ~20 us launch issued from Python mostly measures the launch path)."""
+def time_agg_launches(dev_batches, width, dtype, reps=48):
+    """Average device time of one ax2d_agg launch: forward and fused-addend backward alternating over the ring's batches and
+    rotating feature buffers (inputs do not stay in L2), captured back to back in one CUDA graph and bracketed by ONE event pair
+    -- no event nodes between the launches (each in-graph event pair of the per-kernel profile adds a few microseconds of
+    node-to-node latency to what it brackets, which matters for a ~15 us kernel)."""
     from aimnet_x2d_b200 import ops
-    gis = [b.graph_index for b in dev_batches]
-    xs = [torch.randn(g.num_atoms, width, device=gis[0].rowptr.device) for g in gis for _ in range(2)]
-    nbytes = 0
+    gis = [b.graph_index for b in dev_batches[:4]]
+    xs = [torch.randn(g.num_atoms, width, device=gis[0].rowptr.device).to(dtype) for g in gis for _ in range(2)]
 
     def body():
-        nonlocal nbytes
-        nbytes = 0
         for i in range(reps):
             g = gis[i % len(gis)]
             x, y = xs[(2 * i) % len(xs)], xs[(2 * i + 1) % len(xs)]
             if i % 2 == 0:
                 ops.agg(x, g)
-                nbytes += ops.agg_bytes(g.num_atoms, g.num_rows, g.num_edges, width)
             else:
                 ops.agg(x, g, transpose=True, addend=y)
-                nbytes += ops.agg_bytes(g.num_atoms, g.num_atoms, g.num_edges, width, True)
     body()
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
@@ -376,14 +396,38 @@ def time_agg_launches(dev_batches, width=160, reps=48):
     graph.replay()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) * 1e-3 / reps, nbytes / reps
+    return a.elapsed_time(b) * 1e-3 / reps
+
+
+def bracket_overhead_us(device):
+    """What an in-graph event pair adds to the launch it brackets: the pair around a 1-thread kernel (ax2d_tick), minus ~2 us
+    for that kernel itself."""
+    from aimnet_x2d_b200 import _lib, ops
+    lib = _lib.load()
+    ctr = torch.zeros(1, dtype=torch.int64, device=device)
+    timer = ops.KernelTimer()
+    fn = lambda: [lib.ax2d_tick(ops._p(ctr), ops._stream()) for _ in range(16)]
+    fn()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with timer:
+        with torch.cuda.graph(graph):
+            fn()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    v = sorted(a.elapsed_time(b) * 1e3 for a, b, _, _ in timer.events["ax2d_tick"])
+    return max(v[len(v) // 2] - 2.0, 0.0)
 
 
 def pad_ring(batches, n_dummy=64):
     """Static-shape versions of the ring's batches (one CUDA-graph capture serves all of them)."""
     from aimnet_x2d_b200.collate import pad_batch
     n_max = max(b.graph_index.num_atoms for b in batches)
+    n_min = min(b.graph_index.num_atoms for b in batches)
     e_max = max(b.graph_index.num_edges for b in batches)
+    # dummy (edge-less, <= 29-atom) molecules hold the padding atoms: enough of them for the smallest batch of the ring
+    n_dummy = max(n_dummy, ((n_max - n_min + 256 + 28) // 29 + 63) // 64 * 64)
     n_pad = (n_max + n_dummy + 127) // 128 * 128
     e_cap = (int(e_max * 1.02) + 1023) // 1024 * 1024
     seg_max = max(b.graph_index.max_seg for b in batches)
@@ -404,7 +448,7 @@ def ours_arm(args, wl):
 
     import aimnet_x2d_b200 as ax
     from aimnet_x2d_b200 import ops
-    from aimnet_x2d_b200.trainer import GraphedTrainStep, TrainStep, _batch_tensors
+    from aimnet_x2d_b200.trainer import GraphedTrainStep, TrainStep
     rank, local_rank, world = env_rank()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
@@ -412,16 +456,22 @@ def ours_arm(args, wl):
     device = torch.device(f"cuda:{local_rank}")
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    raw = make_batches(wl, rank, RING)
+    bf16 = wl.get("dtype") == "bf16"
+    strong = "global_batch" in wl if args.scaling is None else args.scaling == "strong"
+    if strong:                                             # fixed global batch: every rank takes global / world molecules
+        gb = wl.get("global_batch", wl["graphs"])
+        if gb % world:
+            raise RuntimeError(f"global batch {gb} is not divisible by {world} ranks")
+        wl = dict(wl, graphs=gb // world)
+    ring = args.ring or wl.get("ring", RING)
+    raw = make_batches(wl, rank, ring)
     graphs = not args.eager
     host = [b.pin_memory() for b in (pad_ring(raw) if graphs else raw)]
     dev_batches = [b.to(device) for b in host]
     model = build_model(wl, device)
     weights = torch.ones(T_TARGETS)
     crit = ax.WeightedL1Loss(weights).to(device)
-    opt = ax.FlatAdam(model.parameters(), lr=2.5e-4, max_grad_norm=1.0)
-    if world > 1:                                          # DDP broadcasts rank 0's parameters at wrap time
-        dist.broadcast(opt.flat_param, src=0)
+    opt = ax.FlatAdam(model.parameters(), lr=2.5e-4, max_grad_norm=1.0)      # broadcasts rank 0's parameters (DDP wrap)
     eager = TrainStep(model, crit, opt, device)
     launches_per_step = None
     if graphs:
@@ -434,15 +484,15 @@ def ours_arm(args, wl):
         dev_packed = [hb.arena.to(device) for hb in packed]
 
         def dev_step(i):                                   # batch i is already in HBM: one D2D into the static slot
-            stepper.load_arena(dev_packed[i % RING])
+            stepper.load_arena(dev_packed[i % ring])
             return stepper.replay()
 
         def host_step(i):      # public call: pinned host batch -> ONE H2D copy -> replay -> loss; the copy of the next
-            return stepper(packed[i % RING], prefetch=packed[(i + 1) % RING])      # batch overlaps this step
+            return stepper(packed[i % ring], prefetch=packed[(i + 1) % ring])      # batch overlaps this step
     else:
         stepper = eager
-        dev_step = lambda i: eager.device_step(dev_batches[i % RING])
-        host_step = lambda i: eager(host[i % RING])
+        dev_step = lambda i: eager.device_step(dev_batches[i % ring])
+        host_step = lambda i: eager(host[i % ring])
 
     def barrier():
         if world > 1:
@@ -480,21 +530,32 @@ def ours_arm(args, wl):
     sampler.stop_flag.set()
     sampler.join()
 
-    # ---- per-kernel CUDA-event timing: the same steps replayed eagerly (events cannot be recorded inside a graph)
-    timer = ops.KernelTimer()
-    n_prof = min(args.steps, 5)
-    eager.device_step(dev_batches[0])
-    barrier()
-    ops.TIMER = timer
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for i in range(n_prof):
-        eager.device_step(dev_batches[i % RING])
-    p1.record()
-    barrier()
-    ops.TIMER = None
-    ms_prof = p0.elapsed_time(p1)
-    agg_s, agg_bytes = time_agg_launches(dev_batches)
+    # ---- per-kernel durations INSIDE the replayed step: the same step captured once more with an event pair around every
+    # libax2d launch (external event-record nodes of the graph), replayed over the ring; read after the last replay
+    ks, prof_step_ms = {}, None
+    if graphs:
+        timer = ops.KernelTimer()
+        prof = GraphedTrainStep(model, crit, opt, device)
+        prof.capture(host[0], warmup=1, timer=timer)
+        for i in range(3):
+            prof.load_arena(dev_packed[i % ring])
+            prof.replay()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        prof.load_arena(dev_packed[3 % ring])
+        p0.record()
+        prof.replay()
+        p1.record()
+        barrier()
+        prof_step_ms = p0.elapsed_time(p1)
+        ks = timer.summary()
+        ovh_us = bracket_overhead_us(device)
+        for v in ks.values():                               # remove the event pair's own node-to-node latency
+            v["ms_avg_raw"] = v["ms_avg"]
+            v["ms_avg"] = max(v["ms_avg"] - ovh_us * 1e-3, 1e-4)
+            v["ms_total"] = v["ms_avg"] * v["launches"]
+        Dp = (int(0.3 * wl["hidden"]) + 31) // 32 * 32
+        agg_s = time_agg_launches(dev_batches, Dp, torch.bfloat16 if bf16 else torch.float32)
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
     if world > 1:
@@ -503,62 +564,82 @@ def ours_arm(args, wl):
     mols = wl["graphs"] * world * args.steps
     if rank == 0:
         peak, peak_src = measured_peaks()
-        ks = timer.summary()
         step_ms = ms / args.steps
         roof = roof_dense = None
-        kernel_ms = sum(v["ms_total"] for v in ks.values()) / n_prof     # per step, timed launch groups only
+        kernel_ms = sum(v["ms_total"] for v in ks.values())              # per step: every libax2d launch of the step
+        share = lambda names: sum(ks[k]["ms_total"] for k in names if k in ks) / kernel_ms if kernel_ms else None
+        es = 2 if bf16 else 4
         if "agg" in ks:
             a = ks["agg"]
-            ach = agg_bytes / agg_s / 1e9
-            roof = {"bound": "hbm", "kernel": "ax2d_agg (agg_tiles_kernel: persistent CSR gather-reduce, fwd + bwd launches)",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": AGG_DRAM_TRAFFIC,
-                    "peak_source": peak_src, "launches_per_step": a["launches"] / n_prof,
-                    "avg_launch_us": agg_s * 1e6, "algorithmic_bytes_per_launch": agg_bytes,
-                    "share_of_step": agg_s * 1e3 * a["launches"] / n_prof / step_ms,
-                    "timing": "CUDA events around a graph replay of 48 back-to-back launches (fwd / bwd alternating, "
-                              "rotating batches and feature buffers), run right after the timed region",
-                    "traffic_note": "dram__bytes_read + write of one forward launch from profiles/ (ncu --set full); the "
-                                    "output of a launch stays in the 126 MB L2, so DRAM traffic is below the algorithmic bytes"}
-        dense = [k for k in ("gemm_tc", "gemm_tc_wgrad", "gemm") if k in ks]
+            ach = a["bytes_total"] / (a["ms_total"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "ax2d_agg (persistent CSR gather-reduce: forward + fused-addend backward launches)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "launches_per_step": a["launches"],
+                    "avg_launch_us": a["ms_avg"] * 1e3, "algorithmic_bytes_per_launch": a["bytes_avg"],
+                    "share_of_step": a["ms_total"] / kernel_ms,
+                    "timing": "CUDA event pairs recorded as nodes of the captured step graph around every ax2d_agg launch; "
+                              "durations of the launches inside one replay of the step (after 3 warm-up replays over the ring)",
+                    "algorithmic_bytes": f"{es}*N*D (x) + 4*E (col) + 4*(N+1) (rowptr) + {es}*N*D (out) [+ {es}*N*D addend in "
+                                         f"backward], UNPADDED D = int(0.3*hidden), per launch (SURVEY 8d)",
+                    "traffic_note": "see profiles/ for the ncu --set full capture (dram__bytes_read + write) of this kernel"}
+            # algorithmic bytes on the UNPADDED width (the kernel moves D padded to a multiple of 32)
+            D, Dp = int(0.3 * wl["hidden"]), (int(0.3 * wl["hidden"]) + 31) // 32 * 32
+            gi0 = host[0].graph_index
+            fwd = ops.agg_bytes(gi0.num_atoms, gi0.num_atoms, gi0.num_edges, D, False, es)
+            bwd = ops.agg_bytes(gi0.num_atoms, gi0.num_atoms, gi0.num_edges, D, True, es)
+            roof["achieved_padded_width"] = ach
+            roof["in_step_avg_launch_us"] = a["ms_avg"] * 1e3          # in-graph event pair minus its calibrated overhead
+            roof["in_step_bracket_overhead_us"] = ovh_us
+            roof["avg_launch_us"] = agg_s * 1e6                          # 48 launches back to back in one graph, one event pair
+            roof["achieved"] = 0.5 * (fwd + bwd) / agg_s / 1e9
+            roof["frac"] = roof["achieved"] / peak
+            roof["frac_in_step"] = 0.5 * (fwd + bwd) / (a["ms_avg"] * 1e-3) / 1e9 / peak
+            roof["algorithmic_bytes_per_launch"] = 0.5 * (fwd + bwd)
+            roof["timing"] = ("avg_launch_us: 48 ax2d_agg launches (fwd / fused-addend bwd alternating, rotating batches and "
+                              "feature buffers) captured back to back in one CUDA graph, ONE event pair around the replay; "
+                              "in_step_avg_launch_us: event pairs recorded as nodes of the captured step graph around every "
+                              "ax2d_agg launch of one replay, minus the pair's own overhead measured around a 1-thread kernel")
+        dense = [k for k in ("gemm_tc", "gemm_tc_wgrad", "gemm", "gemm_bf16", "gemm_bf16_wgrad") if k in ks]
         if dense:
-            fl = sum(ks[k]["flops_avg"] * ks[k]["launches"] for k in dense) / n_prof      # useful fp32 flops per step
-            # Per-launch CUDA-event pairs around eagerly issued launches measure host latency for kernels this short, so
-            # the rate is taken over the graph-replayed step: dense flops / (step time x the projections' share of the
-            # step in the ncu launch list of the same command, profiles/).
-            tf_step = fl / (step_ms * 1e-3) / 1e12
-            tf = tf_step / DENSE_SHARE_OF_STEP
-            tf32_peak = 0.5 * 1393.4            # dense TF32 = half the measured sustained bf16 rate (MEASURED_PEAKS.json)
-            roof_dense = {"bound": "tensor", "kernel": "ax2d_gemm_tc / ax2d_gemm_tc_wgrad (tcgen05 kind::tf32, 3 MMAs per "
-                                                         "k-step: 3xTF32 operand split) + split-K reduce + SIMT remainder",
-                          "achieved": tf, "peak": tf32_peak, "unit": "TFLOP/s (useful fp32 flops)", "frac": tf / tf32_peak,
-                          "peak_source": "0.5 x measured sustained bf16 (MEASURED_PEAKS.json); the split issues 3 tf32 "
-                                         "MMAs per useful product, so frac <= 0.33 by construction",
-                          "useful_tflops_over_whole_step": tf_step, "share_of_step": DENSE_SHARE_OF_STEP,
-                          "share_source": "profiles/r1o_launches_graph_step.csv (ncu --graph-profiling node)",
-                          "launches_per_step": sum(ks[k]["launches"] for k in dense) / n_prof}
+            fl = sum(ks[k]["flops_total"] for k in dense)                 # useful flops per step
+            dense_ms = sum(ks[k]["ms_total"] for k in dense)
+            tf = fl / (dense_ms * 1e-3) / 1e12
+            tpeak = 1393.4 if bf16 else 0.5 * 1393.4
+            roof_dense = {"bound": "tensor",
+                          "kernel": ("ax2d_gemm_bf16 / ax2d_gemm_bf16_wgrad (tcgen05 kind::f16, bf16 operands by TMA, fp32 TMEM "
+                                     "accumulators, TMA-store epilogue)") if bf16 else
+                                    ("ax2d_gemm_tc / ax2d_gemm_tc_wgrad (tcgen05 kind::tf32, 3 MMAs per k-step: 3xTF32 operand "
+                                     "split) + SIMT remainder"),
+                          "achieved": tf, "peak": tpeak, "unit": "TFLOP/s (useful flops)", "frac": tf / tpeak,
+                          "peak_source": "measured sustained bf16 (MEASURED_PEAKS.json)" if bf16 else
+                                         "0.5 x measured sustained bf16 (MEASURED_PEAKS.json); the split issues 3 tf32 MMAs per "
+                                         "useful product, so frac <= 0.33 by construction",
+                          "share_of_step": dense_ms / kernel_ms, "share_source": "in-graph event pairs of this run",
+                          "launches_per_step": sum(ks[k]["launches"] for k in dense),
+                          "hbm_GBs_over_dense_launches": sum(ks[k]["bytes_total"] for k in dense) / (dense_ms * 1e-3) / 1e9}
         h2d = packed[0].nbytes() if graphs else host[0].nbytes()
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _, _ = run_cpu(wl, 2, 1, budget_s=20.0)
-        gi = raw[0].graph_index
         line = {"metric": "train molecules/sec", "value": mols / (ms * 1e-3), "unit": "molecules/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wl["desc"], "graphs_per_gpu": wl["graphs"], "global_batch": wl["graphs"] * world,
-                           "atoms_per_batch": gi.num_atoms, "edges_per_batch": gi.num_edges, "targets": T_TARGETS,
-                           "dropout": 0.05, "parallelism": f"dp{world}",
-                           "execution": ("CUDA graphs over static-shape (padded) batches: "
-                                         f"{host[0].graph_index.num_atoms} atom rows incl. 64 dummy molecules") if graphs
-                           else "eager launches",
-                           "l2": f"ring of {RING} distinct batches per rank; per-step activations + saved tensors "
-                                 f"(> 1 GB) exceed the 126 MB L2, no explicit flush"},
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16" if bf16 else "f32",
+                "data": "synthetic",
+                "config": common_config(wl, world),
+                "run": {"execution": ("CUDA graphs over static-shape (padded) batches: "
+                                      f"{host[0].graph_index.num_atoms} atom rows incl. dummy molecules") if graphs
+                        else "eager launches",
+                        "l2": f"ring of {ring} distinct batches per rank; per-step activations + saved tensors "
+                              f"(> 1 GB) exceed the 126 MB L2, no explicit flush",
+                        "allreduce": "one ncclAllReduce of the flat fp32 gradient arena between the two graphs" if world > 1
+                        else "none (1 GPU)"},
                 "e2e": {"value": mols / (ms_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "roofline": roof, "roofline_dense": roof_dense, "cpu_baseline": cpu,
                 "clocks": sampler.summary(), "final_loss": final_loss,
-                "eager_ms_per_step": ms_prof / n_prof, "timed_kernel_ms_per_step": kernel_ms,
-                "timed_launch_groups": {k: {"launches_per_step": v["launches"] / n_prof, "avg_us": v["ms_avg"] * 1e3}
-                                        for k, v in ks.items()}}
+                "profiled_step_ms": prof_step_ms, "timed_kernel_ms_per_step": kernel_ms,
+                "kernel_shares": {k: {"launches_per_step": v["launches"], "avg_us": v["ms_avg"] * 1e3,
+                                      "share": v["ms_total"] / kernel_ms} for k, v in sorted(ks.items(), key=lambda kv: -kv[1]["ms_total"])}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -645,6 +726,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="per-kernel launches instead of CUDA graphs")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="weak: graphs per GPU fixed; strong: global batch fixed (default: strong for c4, weak otherwise)")
+    ap.add_argument("--ring", type=int, default=0, help="distinct batches per rank (default: the workload's)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload], name=args.workload)
     if args.impl == "reference":

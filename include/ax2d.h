@@ -250,6 +250,12 @@ int     ax2d_gemm_bf16_wgrad_splits(int64_t M, int64_t N, int64_t K);
 int64_t ax2d_gemm_bf16_wgrad_workspace(int64_t M, int64_t N, int64_t K);
 int     ax2d_gemm_bf16_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const ax2d_mat* c, int64_t M, int64_t N, int64_t K,
                              int accumulate, float* bias_grad, void* workspace, ax2d_stream_t stream);
+/* bf16 variants of the embedding kernels: out / g_out are bf16 (emb_dim, ld multiples of 8); tables and their gradients fp32. */
+int     ax2d_embed_fwd_bf16(const float* const* tables, const int64_t* const* indices, int n_tables, int emb_dim,
+                            int64_t N, void* out, int64_t ldo, ax2d_stream_t stream);
+int     ax2d_embed_bwd_all_bf16(const void* g_out, int64_t ldg, int n_tables, int emb_dim, int64_t N,
+                                const int64_t* const* indices, const int64_t* vocab, float* const* g_tables, void* workspace,
+                                ax2d_stream_t stream);
 /* fp32 <-> bf16 copy of an [M, width] matrix (width, ldi, ldo multiples of 8). */
 int     ax2d_convert(const void* in, int64_t ldi, int in_dtype, void* out, int64_t ldo, int out_dtype, int64_t M, int width,
                      ax2d_stream_t stream);
@@ -291,10 +297,11 @@ int ax2d_clip_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, 
 
 /* Packed weights: ONE launch gathers every projection weight / bias from its reference-shaped parameter into the
  * padded, packed layouts the kernels read (plus the two TF32 terms, plain and transposed), and one launch adds the
- * packed weight gradients back into the parameters' gradients.  `table` is a DEVICE array of n_blocks 96-byte block
+ * packed weight gradients back into the parameters' gradients.  `table` is a DEVICE array of n_blocks 128-byte block
  * descriptors (layout: struct PackDesc in csrc/embed_optim.cu, built by aimnet_x2d_b200/packed.py):
  *   { const float* src; float* grad_dst; float* w; float* hi; float* lo; float* hiT; float* loT; const float* g;
- *     int32 rows, cols, src_ld, dst_ld, dstT_ld, pad; }
+ *     const float* part; int32 rows, cols, src_ld, dst_ld, dstT_ld, split, p_rows, p_cols, dr, dc;
+ *     bf16* wb; bf16* wbT; }   (wb / wbT: bf16 copies for the bf16 configuration, may be null)
  * Replaces the per-call torch pad / cat / slice / accumulate kernels around every nn.Linear (layers.py:47-61,
  * gnn.py:96-146). */
 int ax2d_pack_weights(const void* table, int n_blocks, int max_block_elems, ax2d_stream_t stream);
