@@ -278,6 +278,205 @@ __global__ void __launch_bounds__(AGG_CONSUMERS + 32, 2) agg_tiles_kernel(
   AGG_STAMP(15);
 }
 
+__device__ __forceinline__ uint32_t bf2_pack(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// ------------------------------------------------------------------------------------------------ warp-per-row consumers
+// Second-generation persistent tile kernel (fp32 and bf16 rows).  Same producer / stage ring as agg_tiles_kernel; the
+// consumers differ: ONE WARP owns an output row.  Lane l accumulates the 32-bit words l, l + 32, ... of the row (fp32: one
+// column per word, bf16: two), so every shared-memory load of a neighbour row is a conflict-free 128-byte wavefront and --
+// the point -- every loop bound (the row's degree) is WARP-UNIFORM: the 8-lanes-per-row mapping above lets the four rows of
+// a warp diverge on their degrees, and the hardware then issues each row's instructions separately with 8 active lanes
+// (measured: ~33 issue slots per (row, edge); per-CTA %globaltimer stamps showed 2.3 us per 21-row tile, all of it
+// instruction issue).  Here one instruction serves a whole row: ~13 issue slots per (row, edge).  EDGES neighbour rows are
+// loaded before the first of them is added, the additions stay strictly in CSR order (bit-exact).
+constexpr int AGG2_WARPS = 8;             // consumer warps per CTA (+ 1 producer warp)
+constexpr int AGG2_EDGES = 4;             // neighbour rows in flight per warp
+template <int V, bool BF16>
+__global__ void __launch_bounds__(32 * (AGG2_WARPS + 1), 3) agg_rows_kernel(
+    const uint32_t* __restrict__ x, uint32_t* __restrict__ out, int64_t ldo_w, const int32_t* __restrict__ rowptr,
+    const int32_t* __restrict__ col, const uint32_t* __restrict__ addend, int64_t lda_w, const int4* __restrict__ tile_info,
+    int n_tiles, int stages, int words, uint32_t x_bytes, uint32_t rp_bytes, uint32_t col_bytes, int dbg_flags) {
+  // words: 32-bit words per row (fp32: width, bf16: width / 2); V = ceil(words / 32) words per lane
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[AGG_STAGES], empty[AGG_STAGES];
+  __shared__ int4 s_info[AGG_STAGES];
+  const uint32_t stage_bytes = x_bytes + rp_bytes + col_bytes;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_my = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  AGG_STAMP(0);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], AGG2_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == AGG2_WARPS) {
+    // ================================================================= producer warp
+    const uint32_t row_bytes = static_cast<uint32_t>(words) * 4u;
+    for (int base = 0; base < n_my; base += 32) {
+      int4 mine = make_int4(0, 0, 0, 0);
+      if (base + lane < n_my) mine = __ldg(tile_info + first + static_cast<int64_t>(base + lane) * stride);
+      const int cnt = n_my - base < 32 ? n_my - base : 32;
+      for (int j = 0; j < cnt; ++j) {
+        const int it = base + j;
+        int4 inf;
+        inf.x = __shfl_sync(0xffffffffu, mine.x, j);
+        inf.y = __shfl_sync(0xffffffffu, mine.y, j);
+        inf.z = __shfl_sync(0xffffffffu, mine.z, j);
+        inf.w = __shfl_sync(0xffffffffu, mine.w, j);
+        if (lane == 0) {
+          const int s = it % stages;
+          mbar_wait(&empty[s], (static_cast<uint32_t>(it / stages) & 1u) ^ 1u);
+          unsigned char* dst = smem_raw + static_cast<size_t>(s) * stage_bytes;
+          const uint32_t xb = static_cast<uint32_t>(inf.y - inf.x) * row_bytes;
+          const int rs = inf.x & ~3, es = inf.z & ~3;
+          const uint32_t rb = static_cast<uint32_t>((inf.y + 1 - rs + 3) & ~3) * 4;
+          const uint32_t cb = static_cast<uint32_t>((inf.w - es + 3) & ~3) * 4;
+          s_info[s] = inf;
+          mbar_expect_tx(&full[s], xb + rb + cb);
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(x) + static_cast<int64_t>(inf.x) * row_bytes;
+          for (uint32_t off = 0; off < xb; off += 16384) {
+            const uint32_t n = xb - off < 16384u ? xb - off : 16384u;
+            bulk_g2s(dst + off, src + off, n, &full[s]);
+          }
+          bulk_g2s(dst + x_bytes, rowptr + rs, rb, &full[s]);
+          if (cb > 0) bulk_g2s(dst + x_bytes + rp_bytes, col + es, cb, &full[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // =================================================================== consumers: one warp per row
+  bool on[V];                                   // word lane + 32 v exists (only the last slot can be partial)
+#pragma unroll
+  for (int v = 0; v < V; ++v) on[v] = lane + 32 * v < words;
+  constexpr int A = BF16 ? 2 : 1;               // fp32 accumulators per word
+  AGG_STAMP(1);
+  for (int it = 0; it < n_my; ++it) {
+    const int s = it % stages;
+    mbar_wait(&full[s], static_cast<uint32_t>(it / stages) & 1u);
+    if (it < 6) AGG_STAMP(2 + 2 * it);
+    const int4 inf = s_info[s];
+    const unsigned char* st = smem_raw + static_cast<size_t>(s) * stage_bytes;
+    const uint32_t* xs = reinterpret_cast<const uint32_t*>(st) + lane;
+    const int32_t* rp = reinterpret_cast<const int32_t*>(st + x_bytes) - (inf.x & ~3);             // indexed by global row
+    const int32_t* cs = reinterpret_cast<const int32_t*>(st + x_bytes + rp_bytes) - (inf.z & ~3);  // indexed by global edge
+    for (int r = inf.x + warp; r < inf.y; r += AGG2_WARPS) {
+      const int beg = rp[r], end = rp[r + 1];
+      uint32_t addw[V];
+      if (addend != nullptr) {
+        const uint32_t* a = addend + static_cast<int64_t>(r) * lda_w + lane;
+#pragma unroll
+        for (int v = 0; v < V; ++v) addw[v] = on[v] ? __ldg(a + 32 * v) : 0u;
+      }
+      float acc[V][A];
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < A; ++e) acc[v][e] = 0.f;
+      auto add_word = [&](int v, uint32_t w) {
+        if constexpr (BF16) {
+          acc[v][0] += __uint_as_float(w << 16);
+          acc[v][1] += __uint_as_float(w & 0xFFFF0000u);
+        } else {
+          acc[v][0] += __uint_as_float(w);
+        }
+      };
+      for (int k = beg; k < ((dbg_flags & 1) ? beg : end); k += 32) {
+        const int cnt = end - k < 32 ? end - k : 32;
+        const int my_off = lane < cnt ? (cs[k + lane] - inf.x) * words : 0;       // one coalesced index load per 32 edges
+        int j = 0;
+        for (; j + AGG2_EDGES <= cnt; j += AGG2_EDGES) {
+          uint32_t t[AGG2_EDGES][V];
+#pragma unroll
+          for (int e = 0; e < AGG2_EDGES; ++e) {
+            const uint32_t* row = xs + __shfl_sync(0xffffffffu, my_off, j + e);
+#pragma unroll
+            for (int v = 0; v < V; ++v) t[e][v] = (v + 1 < V || on[v]) ? row[32 * v] : 0u;
+          }
+#pragma unroll
+          for (int e = 0; e < AGG2_EDGES; ++e)
+#pragma unroll
+            for (int v = 0; v < V; ++v) add_word(v, t[e][v]);
+        }
+        for (; j < cnt; ++j) {
+          const uint32_t* row = xs + __shfl_sync(0xffffffffu, my_off, j);
+          uint32_t t[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) t[v] = (v + 1 < V || on[v]) ? row[32 * v] : 0u;
+#pragma unroll
+          for (int v = 0; v < V; ++v) add_word(v, t[v]);
+        }
+      }
+      if (addend != nullptr) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) add_word(v, addw[v]);
+      }
+      uint32_t* o = out + static_cast<int64_t>(r) * ldo_w + lane;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        uint32_t w;
+        if constexpr (BF16) w = bf2_pack(acc[v][0], acc[v][1]);
+        else w = __float_as_uint(acc[v][0]);
+        if ((v + 1 < V || on[v]) && !(dbg_flags & 2)) o[32 * v] = w;
+      }
+    }
+    __syncwarp();
+    if (it < 6) AGG_STAMP(3 + 2 * it);
+    if (lane == 0) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+    }
+  }
+  AGG_STAMP(15);
+}
+
+static int g_agg_debug_ctas = 0, g_agg_debug_stages = 0, g_agg_use_rows = 1, g_agg_debug_flags = 0;
+template <int V, bool BF16>
+static int launch_agg_rows(const void* x, void* out, int64_t ldo, const int32_t* rowptr, const int32_t* col, const void* addend,
+                           int64_t ld_addend, const int32_t* tile_info, int64_t n_tiles, int max_tile_rows, int max_tile_edges,
+                           int width, cudaStream_t st) {
+  const int words = BF16 ? width / 2 : width;
+  const size_t xb = (static_cast<size_t>(max_tile_rows) * words * 4 + 15) / 16 * 16;
+  const size_t rb = (static_cast<size_t>(max_tile_rows) + 8) * 4 / 16 * 16 + 16;
+  const size_t cb = (static_cast<size_t>(max_tile_edges) + 8) * 4 / 16 * 16 + 16;
+  const size_t stage = xb + rb + cb;
+  if (stage > 220 * 1024) {
+    set_error("ax2d_agg: tile of %d rows / %d edges needs %zu bytes of shared memory", max_tile_rows, max_tile_edges, stage);
+    return AX2D_ERR_UNSUPPORTED;
+  }
+  // as many CTAs per SM as give each a ring of >= 3 stages (at most 3 CTAs: 27 warps), else fewer CTAs with what fits
+  int ctas_per_sm = 3;
+  while (ctas_per_sm > 1 && (220 * 1024 / ctas_per_sm) / stage < 3) --ctas_per_sm;
+  if (g_agg_debug_ctas > 0) ctas_per_sm = g_agg_debug_ctas;
+  int stages = static_cast<int>((220 * 1024 / ctas_per_sm) / stage);
+  stages = stages > AGG_STAGES ? AGG_STAGES : (stages < 1 ? 1 : stages);
+  if (g_agg_debug_stages > 0 && g_agg_debug_stages <= stages) stages = g_agg_debug_stages;
+  const size_t smem = stage * stages;
+  auto kern = agg_rows_kernel<V, BF16>;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = smem;
+  }
+  int64_t grid = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
+  grid = grid > n_tiles ? n_tiles : grid;
+  const int esz = BF16 ? 2 : 4;
+  kern<<<static_cast<unsigned>(grid), 32 * (AGG2_WARPS + 1), smem, st>>>(
+      static_cast<const uint32_t*>(x), static_cast<uint32_t*>(out), ldo * esz / 4, rowptr, col, static_cast<const uint32_t*>(addend),
+      ld_addend * esz / 4, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles), stages, words,
+      static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb), g_agg_debug_flags);
+  return launch_status("ax2d_agg");
+}
+
 // ------------------------------------------------------------------------------------------------ bf16 features
 // The same persistent tile pipeline for bf16 rows (BASELINE configs[3]): the staged tile is half the bytes, FOUR lanes own
 // one output row (lane j accumulates the 16-byte units j, j + 4, ... = 8 bf16 each, in fp32 registers, CSR order), the
@@ -287,11 +486,6 @@ __device__ __forceinline__ void bf8_add(float* acc, const uint4& u) {
   acc[2] += __uint_as_float(u.y << 16); acc[3] += __uint_as_float(u.y & 0xFFFF0000u);
   acc[4] += __uint_as_float(u.z << 16); acc[5] += __uint_as_float(u.z & 0xFFFF0000u);
   acc[6] += __uint_as_float(u.w << 16); acc[7] += __uint_as_float(u.w & 0xFFFF0000u);
-}
-__device__ __forceinline__ uint32_t bf2_pack(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
 }
 __device__ __forceinline__ uint4 ld_nc_u4(const uint4* p) {
   uint4 r;
@@ -552,6 +746,14 @@ static int launch_agg(const float* x, int64_t ldx, float* out, int64_t ldo, int6
 
 }  // namespace ax2d
 
+// development aid (not part of include/ax2d.h): CTAs per SM / stages of the warp-per-row kernel (0 = automatic) and whether
+// it is used at all (0: the first-generation 8-lanes-per-row kernels)
+extern "C" void ax2d_debug_agg_config(int ctas_per_sm, int stages, int use_rows_kernel) {
+  ax2d::g_agg_debug_ctas = ctas_per_sm;
+  ax2d::g_agg_debug_stages = stages & 0xff;
+  ax2d::g_agg_debug_flags = stages >> 8;          // development: bit 0 skip the edge loop, bit 1 skip the stores
+  ax2d::g_agg_use_rows = use_rows_kernel;
+}
 // development aid (not part of include/ax2d.h): 16 x u64 device buffer receiving %globaltimer stamps of CTA 0
 extern "C" void ax2d_debug_agg_timing(unsigned long long* buf) {
   cudaMemcpyToSymbol(ax2d::g_agg_dbg, &buf, sizeof(buf));
@@ -582,7 +784,9 @@ extern "C" int ax2d_agg(const void* x, int64_t ldx, int64_t n_src_rows, void* ou
       AX2D_CHECK_ALIGN(rowptr);
       AX2D_CHECK_ALIGN(col);
 #define AX2D_AGG16_CASE(V) \
-  case V: return launch_agg_bf16<V>(xh, oh, ldo, rowptr, col, ah, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, st16);
+  case V: return g_agg_use_rows \
+      ? launch_agg_rows<(V + 1) / 2, true>(xh, oh, ldo, rowptr, col, ah, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, width, st16) \
+      : launch_agg_bf16<V>(xh, oh, ldo, rowptr, col, ah, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, st16);
       switch (width / 32) {
         AX2D_AGG16_CASE(1) AX2D_AGG16_CASE(2) AX2D_AGG16_CASE(3) AX2D_AGG16_CASE(4) AX2D_AGG16_CASE(5) AX2D_AGG16_CASE(6)
         AX2D_AGG16_CASE(7) AX2D_AGG16_CASE(8) AX2D_AGG16_CASE(9) AX2D_AGG16_CASE(10) AX2D_AGG16_CASE(11) AX2D_AGG16_CASE(12)
@@ -625,7 +829,9 @@ extern "C" int ax2d_agg(const void* x, int64_t ldx, int64_t n_src_rows, void* ou
     return launch_status("ax2d_agg");
   }
 #define AX2D_AGG_CASE(V) \
-  case V: return launch_agg<V>(xf, ldx, of, ldo, n_out_rows, rowptr, col, af, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, st);
+  case V: return (tile_info != nullptr && g_agg_use_rows) \
+      ? launch_agg_rows<V, false>(xf, of, ldo, rowptr, col, af, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, width, st) \
+      : launch_agg<V>(xf, ldx, of, ldo, n_out_rows, rowptr, col, af, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, st);
   switch (width / 32) {
     AX2D_AGG_CASE(1) AX2D_AGG_CASE(2) AX2D_AGG_CASE(3) AX2D_AGG_CASE(4) AX2D_AGG_CASE(5) AX2D_AGG_CASE(6)
     AX2D_AGG_CASE(7) AX2D_AGG_CASE(8) AX2D_AGG_CASE(9) AX2D_AGG_CASE(10) AX2D_AGG_CASE(11) AX2D_AGG_CASE(12)
