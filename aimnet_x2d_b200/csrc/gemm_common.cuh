@@ -89,9 +89,11 @@ struct EpiCtx {      // per-thread constants of the epilogue
   float inv_keep;
   uint32_t seed_lo, seed_hi, thresh;
   uint32_t base0;    // seed mix for linear indices below 2^34 (every realistic matrix)
+  float acc_scale;   // 1, or the truncation compensation of a tensor-core accumulator (gemm_tc.cu: tc_acc_scale)
 };
 __device__ __forceinline__ EpiCtx epi_ctx_seed(float drop_p, uint64_t drop_seed, const uint64_t* drop_tick, bool has_mask = false) {
   EpiCtx c;
+  c.acc_scale = 1.f;
   c.dropping = has_mask || drop_p > 0.f;
   c.thresh = static_cast<uint32_t>(drop_p * 65536.f + 0.5f);
   // the keep probability that is actually realised is (65536 - thresh) / 65536 (p quantised to 16 bits): scale by ITS
@@ -188,7 +190,9 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& g, const EpiCtx& cx, c
                                            const EpiOperands& o, float a0, float a1, float a2, float a3,
                                            int64_t row = -1) {
   if (row < 0) row = m;
-  float v[4] = {a0 + k.bias.x, a1 + k.bias.y, a2 + k.bias.z, a3 + k.bias.w};
+  // (fma with acc_scale == 1 is the plain sum, bit for bit)
+  float v[4] = {fmaf(a0, cx.acc_scale, k.bias.x), fmaf(a1, cx.acc_scale, k.bias.y), fmaf(a2, cx.acc_scale, k.bias.z),
+                fmaf(a3, cx.acc_scale, k.bias.w)};
   if (k.pre != nullptr) *reinterpret_cast<float4*>(k.pre + m * k.ldpre) = make_float4(v[0], v[1], v[2], v[3]);
   float drop[4] = {1.f, 1.f, 1.f, 1.f};
   if constexpr (DROP) {

@@ -44,6 +44,7 @@ struct TcArgs {
   int tmem_cols;
   int acc2;                            // column offset of the small-term accumulator (0: single accumulator)
   int n_tiles, total_tiles;            // projection kernel: column tiles per row tile, all tiles
+  float acc_scale;                     // truncation compensation of the main accumulator (tc_acc_scale)
   int acc_stride;                      // TMEM columns between the two accumulator buffers
   int a_base;                          // first TMEM column of the A ring
 };
@@ -149,7 +150,8 @@ __device__ __forceinline__ void lean_rows(const TileEpi& te, const EpiCtx& cx, u
       if (te.has_dp) dp = __ldg(reinterpret_cast<const float4*>(pdp));
     }
     const float4 s4 = lds128(((i & 1) ? s_odd : s_even) + static_cast<uint32_t>(i >> 1) * 1024u);
-    float v[4] = {s4.x + b4.x, s4.y + b4.y, s4.z + b4.z, s4.w + b4.w};
+    float v[4] = {fmaf(s4.x, cx.acc_scale, b4.x), fmaf(s4.y, cx.acc_scale, b4.y), fmaf(s4.z, cx.acc_scale, b4.z),
+                  fmaf(s4.w, cx.acc_scale, b4.w)};
     if (te.has_pre) *reinterpret_cast<float4*>(ppre) = make_float4(v[0], v[1], v[2], v[3]);
     float drop[4] = {1.f, 1.f, 1.f, 1.f};
     if constexpr (DROP) drop_scale4(cx, didx, drop);
@@ -191,10 +193,24 @@ __device__ __forceinline__ void lean_rows(const TileEpi& te, const EpiCtx& cx, u
 // ws != nullptr: raw partial sums go to the split-K workspace slice [M, N] at ws instead of the output segments.
 // Inlined into the kernel on purpose: `e` is then known to live in the (immutable, constant-cached) kernel parameter
 // space; behind a real call it degrades to generic loads that must be re-issued after every global store.
+// The tensor core adds into its fp32 accumulator with TRUNCATION: every MMA that touches an accumulator of magnitude |c|
+// loses on average a fixed fraction of ulp(c), always towards zero.  Measured on B200 against float64 (tools/tc_bias.py,
+// profiles/): zero-mean operands -> mean signed relative error of the result = -0.27 x 2^-24 per MMA into the accumulator,
+// the same coefficient for K = 160 ... 1024 and every tile layout (-9.6e-7 at K = 160, -3.3e-6 at K = 544); the SIMT
+// kernel's is < 1e-9.  It is a BIAS, not noise: through the ~20 products between the embeddings and the loss it adds up
+// (the full-size C2 step was 1.4e-5 low in the loss, C3 outputs 2.5e-5 of their scale off -- over the 1e-5 bar) instead
+// of averaging out.  The epilogue therefore scales the main accumulator by 1 + 0.27 n 2^-24 (n = MMAs accumulated into
+// it): one FFMA that replaces the FADD of the bias / small-term sum, no extra instruction.  What remains is zero-mean.
+__host__ __device__ __forceinline__ float tc_acc_scale(int n_mma) { return 1.f + 0.27f * static_cast<float>(n_mma) * 5.9604645e-8f; }
+
 template <int ACT, int DACT, bool DROP>
-__device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws, const EpiCtx& cx, uint32_t tmem_base,
+__device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws, const EpiCtx& cx_in, uint32_t tmem_base,
                                          float* stg, int m0, int n0, int q, int lane, int first_chunk, uint32_t acc2,
-                                         unsigned long long* dbg = nullptr, int chunk_step = 64) {
+                                         float acc_scale, unsigned long long* dbg = nullptr, int chunk_step = 64) {
+  // with a separate small-term accumulator the scale is applied to the main one where the two are summed; otherwise where
+  // the bias is added (lean_rows / epi_finish)
+  EpiCtx cx = cx_in;
+  cx.acc_scale = acc2 != 0 ? 1.f : acc_scale;
   const int64_t M = e.M;
   const int N = static_cast<int>(e.N);
   const int cg = lane & 7;
@@ -213,7 +229,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiArgs& e, int BN, float* ws,
         tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc2 + static_cast<uint32_t>(c0 + 16 * hh), r2);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          r[16 * hh + j] = __float_as_uint(__uint_as_float(r[16 * hh + j]) + __uint_as_float(r2[j]));
+          r[16 * hh + j] = __float_as_uint(fmaf(__uint_as_float(r[16 * hh + j]), acc_scale, __uint_as_float(r2[j])));
       }
     }
     // transpose through shared memory with 128-bit accesses: row `lane` stores its eight float4 column groups at
@@ -516,7 +532,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       if (cta_dbg != nullptr && j == 0 && ew == 0 && lane == 0) cta_dbg[4] = gtime();
       AX2D_EPI_DISPATCH(g.e.act, g.e.dact, dropping, {
         tc_epilogue<ACT, DACT, DROP>(g.e, BN, nullptr, cx, tmem_base + static_cast<uint32_t>(buf * g.acc_stride), stg, m0, n0,
-                                     warp & 3, lane, ew >> 2, static_cast<uint32_t>(g.acc2),
+                                     warp & 3, lane, ew >> 2, static_cast<uint32_t>(g.acc2), g.acc_scale,
                                      (cta_dbg != nullptr && ew == 0 && lane == 0 && j == 0) ? cta_dbg + 8 : nullptr,
                                      32 * (TC_EPI_WARPS / 4));
       });
@@ -775,8 +791,9 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const _
     float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 32);     // stage memory is free now
     const EpiCtx cx = epi_ctx(g.e);
     float* ws = g.ws != nullptr ? g.ws + static_cast<int64_t>(blockIdx.z) * g.e.M * g.e.N : nullptr;
+    // main accumulator: one hi*hi MMA per k-step, four k-steps per k-block
     tc_epilogue<AX2D_ACT_NONE, AX2D_ACT_NONE, false>(g.e, BN, ws, cx, tmem_base, stg, m0, n0, warp & 3, lane, (warp - 2) >> 2,
-                                                     static_cast<uint32_t>(WG_ACC2));
+                                                     static_cast<uint32_t>(WG_ACC2), tc_acc_scale(4 * nkb));
   }
   tc_fence_before();
   __syncthreads();
@@ -925,6 +942,8 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
   for (int s = a->n_seg; s <= AX2D_MAX_SEG; ++s) g.seg_kb_start[s] = kb;
   AX2D_CHECK_ARG(acc == K, "ax2d_gemm_tc: A segments cover %d columns, expected %lld", acc, (long long)K);
   g.num_kb = kb;
+  // MMAs accumulated into the main accumulator per output: K / 8 k-steps x (hi*hi only | all split terms)
+  g.acc_scale = tc_acc_scale(static_cast<int>(K / 8) * (g.acc2 != 0 ? 1 : AX2D_TC_TERMS));
   if ((rc = make_map(&maps.b_hi, b_hi, K, N, ldb, BN, BK, swz)) != AX2D_OK) return rc;
   if ((rc = make_map(&maps.b_lo, b_lo, K, N, ldb, BN, BK, swz)) != AX2D_OK) return rc;
   const size_t stage_bytes = static_cast<size_t>(TC_BM + 2 * BN) * BK * 4;

@@ -49,12 +49,10 @@ def test_gemm_tc_matches_float64(M, widths, N):
     ops.TC_MIN_ROWS = 1
     try:
         t = ops.KernelTimer()
-        ops.TIMER = t
-        ops.gemm(list(zip(a, widths)), [(W, K)], [(out, N)], M, N, K, bias=bias)
-        ops.TIMER = None
+        with t:
+            ops.gemm(list(zip(a, widths)), [(W, K)], [(out, N)], M, N, K, bias=bias)
         assert "gemm_tc" in t.events, "the tensor-core kernel was not selected"
     finally:
-        ops.TIMER = None
         ops.TC_MIN_ROWS = old
     ref = torch.cat(a, 1).double() @ W.double().t() + bias.double()
     err = _rel(out, ref)
@@ -159,12 +157,10 @@ def test_gemm_tc_wgrad_matches_float64(rows, gw, xw):
     ops.TC_MIN_ROWS = 1
     try:
         t = ops.KernelTimer()
-        ops.TIMER = t
-        dW, db = ops._weight_grad(list(zip(G, gw)), list(zip(X, xw)), rows, No, Ki, DEV, bias=True)
-        ops.TIMER = None
+        with t:
+            dW, db = ops._weight_grad(list(zip(G, gw)), list(zip(X, xw)), rows, No, Ki, DEV, bias=True)
         assert "gemm_tc_wgrad" in t.events
     finally:
-        ops.TIMER = None
         ops.TC_MIN_ROWS = old
     Gd, Xd = torch.cat(G, 1).double(), torch.cat(X, 1).double()
     ref = Gd.t() @ Xd

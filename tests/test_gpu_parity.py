@@ -515,7 +515,20 @@ def _train_step_pair(cfg, T, seed, batch, weights, lr=2.5e-4):
     return cuda, oracle
 
 
-def _check_train_step(cuda, oracle, lr, full_matrices):
+def _exact_bias_grads(cfg, T, seed, batch, weights):
+    """float64 evaluation of the oracle step (CPU): gradients of the bias vectors only, computed when one of them misses
+    the primary bar (see _check_train_step)."""
+    P = {k: v.double().requires_grad_(True) for k, v in det_state(gnn_shapes(cfg, T), seed).items()}
+    ob = dict(atom_features_map=batch.atom_features_map, multi_hop_edge_indices=batch.multi_hop_edge_indices,
+              batch_indices=batch.batch_indices, total_charges=batch.total_charges.double(),
+              final_tetrahedral_chiral_tensor=batch.final_tetrahedral_chiral_tensor,
+              final_cis_tensor=batch.final_cis_tensor, final_trans_tensor=batch.final_trans_tensor)
+    out, _, _, _ = MP.gnn_forward(P, cfg, ob)
+    MP.weighted_l1(out, batch.targets.double(), weights.double()).backward()
+    return {k: v.grad.numpy() for k, v in P.items() if k.endswith(".bias") and v.grad is not None}
+
+
+def _check_train_step(cuda, oracle, lr, full_matrices, exact_bias=None):
     assert_close(cuda["out"], oracle["out"], RTOL_F32, "output (full size)")
     assert abs(cuda["loss"] - oracle["loss"]) <= RTOL_F32 * abs(oracle["loss"]), (cuda["loss"], oracle["loss"])
     assert abs(cuda["norm"] - oracle["norm"]) <= RTOL_F32 * oracle["norm"], (cuda["norm"], oracle["norm"])
@@ -531,7 +544,16 @@ def _check_train_step(cuda, oracle, lr, full_matrices):
         gn = float(np.linalg.norm(got.astype(np.float64)))
         assert abs(gn - rn) <= RTOL_F32 * max(rn, 1e-30), f"gradient norm of {k}: {gn:.9e} vs {rn:.9e}"
         if any(s in k for s in full_matrices) or ref.size <= 1 << 16:
-            assert_close(got, ref, RTOL_F32, "grad (full size) " + k)
+            try:
+                assert_close(got, ref, RTOL_F32, "grad (full size) " + k)
+            except AssertionError:
+                # Bias gradients are column sums over ALL atoms of mixed-sign terms (|sum| << sum |terms|): the reference's
+                # own fp32 value is then further than 1e-5 of the scale from the exact sum.  For `.bias` entries ONLY the
+                # float64 criterion of close_or_as_exact_as_reference applies; everything else must meet the primary bar.
+                if not (k.endswith(".bias") and exact_bias is not None):
+                    raise
+                note = close_or_as_exact_as_reference(got, ref, exact_bias()[k], "grad (full size) " + k)
+                print("[float64 criterion, bias gradient]", note)
     # one clip + Adam step.  Adam's first update is lr * g / (|g| + 1e-8), i.e. +-lr wherever |g| >> 1e-8: entries whose
     # gradient is at the rounding level of the sum that produced it move by a noise-determined fraction of lr in the
     # reference as well, so they are excluded (|g_ref| < 1e-4 of the tensor's largest gradient) and counted.
@@ -575,8 +597,14 @@ def test_full_size_c3_train_step():
     batch = S.make_batch(1234 + 3000 + 7, 256, 3, "drug", 12, stereo=True)
     w = torch.ones(12)
     cuda, oracle = _train_step_pair(cfg, 12, 13, batch, w)
+    cache = {}
+
+    def exact():
+        if not cache:
+            cache.update(_exact_bias_grads(cfg, 12, 13, batch, w))
+        return cache
     _check_train_step(cuda, oracle, 2.5e-4, ("input_proj.weight", "linear_1.weight", "linear_2.weight",
-                                             "global_skip_proj.weight", "stereochemical_embedding_2.weight"))
+                                             "global_skip_proj.weight", "stereochemical_embedding_2.weight"), exact)
 
 
 def test_same_shape_batches_without_graph_index_are_not_served_a_stale_index():
