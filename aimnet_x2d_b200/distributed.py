@@ -74,6 +74,30 @@ def gather_ndarray_to_rank0(arr: np.ndarray, device: str = "cpu") -> np.ndarray:
     return np.array([], dtype=arr.dtype)
 
 
+def gather_tensor_to_rank0(t: torch.Tensor) -> torch.Tensor:
+    """Device-resident replacement of ``gather_ndarray_to_rank0`` for the evaluation path (``training/evaluator.py:158-187``):
+    rows of ``t`` ([n_r, ...], different n_r per rank) are exchanged with ONE size all_gather + ONE padded all_gather on the
+    tensor's own device (NCCL for CUDA tensors) -- no ``.cpu().numpy()`` round trip, no float cast, no pickling.  Rank 0 gets
+    the concatenation in rank order, the other ranks an empty tensor."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return t
+    W = dist.get_world_size()
+    size = torch.tensor([t.shape[0]], dtype=torch.long, device=t.device)
+    sizes = torch.zeros(W, dtype=torch.long, device=t.device)
+    dist.all_gather_into_tensor(sizes, size)
+    sizes = [int(s) for s in sizes.tolist()]
+    mx = max(sizes) if sizes else 0
+    local = t.contiguous()
+    if local.shape[0] < mx:
+        local = torch.cat([local, local.new_zeros((mx - local.shape[0],) + tuple(local.shape[1:]))], 0)
+    out = local.new_empty((W * mx,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, local)
+    if dist.get_rank() != 0:
+        return t.new_empty((0,) + tuple(t.shape[1:]))
+    out = out.view((W, mx) + tuple(local.shape[1:]))
+    return torch.cat([out[r, : sizes[r]] for r in range(W)], 0)
+
+
 def gather_strings_to_rank0(local_list: List[str], device: str = "cpu") -> List[str]:
     """``distributed.py:98-144``."""
     if not (dist.is_available() and dist.is_initialized()):

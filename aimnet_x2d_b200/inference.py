@@ -96,3 +96,149 @@ class GraphedInferenceStep(StaticSlot):
         if prefetch is not None:
             self.prefetch(prefetch)
         return res
+
+
+# ------------------------------------------------------------------------------------------------ output plumbing
+class ShardedOutputWriter:
+    """Per-rank output files for inference / embedding extraction -- every rank writes what it computed, nothing is
+    gathered while the job runs (reference: ranks pickle partial results and rank 0 merges them,
+    ``inference/pipeline.py:637-701``, ``inference/embeddings.py:376-498``; the evaluation path pads and all_gathers every
+    array, ``utils/distributed.py:49-95``).
+
+    Layout under ``directory``: ``<field>.rank<r>.bin`` (raw little-endian rows appended batch by batch) and
+    ``index.rank<r>.json`` ({field: {dtype, row_shape, rows}}; ragged per-atom fields additionally get ``<field>_ptr`` = the
+    molecule offsets).  ``merge_rank_outputs`` concatenates the rank files in rank order into ``.npy`` arrays."""
+
+    def __init__(self, directory: str, rank: int = 0, world_size: int = 1):
+        import os
+        self.dir, self.rank, self.world = directory, int(rank), int(world_size)
+        os.makedirs(directory, exist_ok=True)
+        self._fh = {}
+        self._index = {}
+        self._atoms = 0
+
+    def _file(self, field: str, arr):
+        import os
+        if field not in self._fh:
+            self._fh[field] = open(os.path.join(self.dir, f"{field}.rank{self.rank}.bin"), "wb")
+            self._index[field] = {"dtype": str(arr.dtype), "row_shape": list(arr.shape[1:]), "rows": 0}
+        meta = self._index[field]
+        if str(arr.dtype) != meta["dtype"] or list(arr.shape[1:]) != meta["row_shape"]:
+            raise ValueError(f"field '{field}': rows of {arr.dtype}{list(arr.shape[1:])} after {meta['dtype']}{meta['row_shape']}")
+        return self._fh[field]
+
+    def append(self, field: str, rows) -> None:
+        """Rows of a per-molecule field ([B, ...]) -- a host array or a (pinned) CPU tensor."""
+        import numpy as np
+        arr = np.ascontiguousarray(rows.numpy() if isinstance(rows, torch.Tensor) else rows)
+        self._file(field, arr).write(arr.tobytes())
+        self._index[field]["rows"] += int(arr.shape[0])
+
+    def append_ragged(self, field: str, values, counts) -> None:
+        """A per-atom field (e.g. partial charges [N]) with the number of atoms of each molecule of the batch."""
+        import numpy as np
+        counts = np.asarray(counts, dtype=np.int64)
+        self.append(field, values)
+        ptr = self._atoms + np.concatenate([[0], np.cumsum(counts)])[:-1]
+        self.append(field + "_ptr", ptr.astype(np.int64))
+        self._atoms += int(counts.sum())
+
+    def close(self) -> None:
+        import json
+        import os
+        for fh in self._fh.values():
+            fh.close()
+        self._fh = {}
+        with open(os.path.join(self.dir, f"index.rank{self.rank}.json"), "w") as fh:
+            json.dump({"world_size": self.world, "fields": self._index, "atoms": self._atoms}, fh)
+
+
+def merge_rank_outputs(directory: str, world_size: int) -> Dict[str, "np.ndarray"]:
+    """Rank 0, after a barrier: concatenate the per-rank files in rank order (contiguous rank shards of the input,
+    ``distributed.shard_indices``, therefore come back in input order).  Writes ``<field>.npy`` and returns the arrays;
+    ``*_ptr`` offsets are rebased onto the merged per-atom array."""
+    import json
+    import os
+
+    import numpy as np
+    idx = []
+    for r in range(world_size):
+        with open(os.path.join(directory, f"index.rank{r}.json")) as fh:
+            idx.append(json.load(fh))
+    out = {}
+    atom_base = np.concatenate([[0], np.cumsum([i["atoms"] for i in idx])])
+    for field in idx[0]["fields"]:
+        parts = []
+        for r in range(world_size):
+            meta = idx[r]["fields"].get(field)
+            if meta is None or meta["rows"] == 0:
+                continue
+            a = np.fromfile(os.path.join(directory, f"{field}.rank{r}.bin"), dtype=np.dtype(meta["dtype"]))
+            a = a.reshape([meta["rows"]] + meta["row_shape"])
+            if field.endswith("_ptr"):
+                a = a + atom_base[r]
+            parts.append(a)
+        if parts:
+            out[field] = np.concatenate(parts, 0)
+            np.save(os.path.join(directory, field + ".npy"), out[field])
+    return out
+
+
+class EmbeddingExtractor:
+    """Forward-only pass over a sequence of (padded) batches with results streamed to a ``ShardedOutputWriter``: ONE forward
+    per batch yields predictions, pooled embeddings and partial charges (the reference runs the model twice per batch for
+    embeddings, ``inference/embeddings.py:109-119``), device-to-host copies go through two pinned buffers so that the copy of
+    batch i overlaps the forward of batch i + 1, and nothing is gathered across ranks."""
+
+    def __init__(self, step, writer: ShardedOutputWriter, fields=("outputs", "embeddings", "partial_charges")):
+        self.step, self.writer, self.fields = step, writer, tuple(fields)
+        self._host = [None, None]
+        self._event = [None, None]
+        self._pending = [None, None]
+
+    def _flush(self, k: int) -> None:
+        if self._pending[k] is None:
+            return
+        self._event[k].synchronize()
+        bufs, counts, n_real, n_atoms = self._pending[k]
+        for f, t in bufs.items():
+            if f == "partial_charges":
+                self.writer.append_ragged(f, t[:n_atoms].clone(), counts)
+            else:
+                self.writer.append(f, t[:n_real].clone())
+        self._pending[k] = None
+
+    def run(self, batches) -> int:
+        """``batches``: iterable of padded ``MolBatch`` or ``HostBatch`` objects accepted by the step.  Returns the number of
+        molecules written."""
+        import numpy as np
+        total = 0
+        for i, b in enumerate(batches):
+            k = i & 1
+            self._flush(k)                                  # the pinned buffers of two batches ago are free again
+            res = self.step(b)
+            slot = self.step.slot if hasattr(self.step, "slot") and self.step.slot is not None else b
+            gi = slot.graph_index
+            n_real = int(getattr(slot, "num_real_graphs", gi.num_graphs))
+            seg = gi.seg_ptr[: n_real + 1].cpu().numpy() if gi.seg_ptr.is_cuda else gi.seg_ptr[: n_real + 1].numpy()
+            bufs = {}
+            for f in self.fields:
+                t = res.get(f)
+                if t is None:
+                    continue
+                if self._host[k] is None:
+                    self._host[k] = {}
+                h = self._host[k].get(f)
+                if h is None or h.shape != t.shape or h.dtype != t.dtype:
+                    h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                    self._host[k][f] = h
+                h.copy_(t, non_blocking=True)
+                bufs[f] = h
+            ev = torch.cuda.Event()
+            ev.record()
+            self._event[k] = ev
+            self._pending[k] = (bufs, np.diff(seg), n_real, int(seg[-1]))
+            total += n_real
+        self._flush(0)
+        self._flush(1)
+        return total

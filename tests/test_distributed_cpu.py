@@ -89,6 +89,34 @@ def _worker(rank, world, port, q):
             assert np.array_equal(g, exp)
         else:
             assert g.size == 0
+        # device-resident variant (evaluation path): same result, dtype preserved (no float cast), tensors in / out
+        tg = D.gather_tensor_to_rank0(torch.from_numpy(arr).to(torch.float64))
+        ti = D.gather_tensor_to_rank0(torch.arange(rank + 1, dtype=torch.int64) + 10 * rank)
+        if rank == 0:
+            assert tg.dtype == torch.float64 and np.array_equal(tg.numpy(), exp.astype(np.float64))
+            assert ti.tolist() == [0, 10, 11]
+        else:
+            assert tg.shape == (0, 3) and ti.numel() == 0
+        # per-rank sharded output files, merged by rank 0 in rank order (replaces pickle merging / padded gathers)
+        import tempfile
+        from aimnet_x2d_b200.inference import ShardedOutputWriter, merge_rank_outputs
+        out_dir = D.broadcast_object(tempfile.mkdtemp() if rank == 0 else None)
+        wtr = ShardedOutputWriter(out_dir, rank, world)
+        for b in range(2):                                   # two batches per rank: 2 + rank molecules each
+            n_mol = 2 + rank
+            wtr.append("outputs", np.full((n_mol, 3), 100 * rank + b, dtype=np.float32))
+            counts = np.arange(1, n_mol + 1)
+            wtr.append_ragged("partial_charges", np.arange(counts.sum(), dtype=np.float32) + 1000 * rank, counts)
+        wtr.close()
+        D.barrier()
+        if rank == 0:
+            m = merge_rank_outputs(out_dir, world)
+            assert m["outputs"].shape == (2 * 2 + 2 * 3, 3)
+            assert m["outputs"][:, 0].tolist() == [0, 0, 1, 1, 100, 100, 100, 101, 101, 101]
+            ptr = m["partial_charges_ptr"]
+            assert ptr.tolist() == [0, 1, 3, 4, 6, 7, 9, 12, 13, 15] and len(m["partial_charges"]) == 18
+            assert m["partial_charges"][ptr[4]] == 1000.0          # first atom of rank 1's first molecule
+        D.barrier()
         s = D.gather_strings_to_rank0([f"r{rank}a", f"r{rank}b"])
         assert s == (["r0a", "r0b", "r1a", "r1b"] if rank == 0 else [])
         assert D.broadcast_object({"best": 1.5} if rank == 0 else None) == {"best": 1.5}
