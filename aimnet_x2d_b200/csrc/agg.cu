@@ -292,10 +292,11 @@ __device__ __forceinline__ uint32_t bf2_pack(float lo, float hi) {
 // (measured: ~33 issue slots per (row, edge); per-CTA %globaltimer stamps showed 2.3 us per 21-row tile, all of it
 // instruction issue).  Here one instruction serves a whole row: ~13 issue slots per (row, edge).  EDGES neighbour rows are
 // loaded before the first of them is added, the additions stay strictly in CSR order (bit-exact).
-constexpr int AGG2_WARPS = 8;             // consumer warps per CTA (+ 1 producer warp)
+constexpr int AGG2_WARPS = 8;             // consumer warps per CTA (+ 1 producer warp) when three CTAs share an SM
+constexpr int AGG2_MAX_WARPS = 24;        // ... and when large tiles (drug-like molecules) leave room for one CTA only
 constexpr int AGG2_EDGES = 4;             // neighbour rows in flight per warp
-template <int V, bool BF16>
-__global__ void __launch_bounds__(32 * (AGG2_WARPS + 1), 3) agg_rows_kernel(
+template <int V, bool BF16, int NW>
+__global__ void __launch_bounds__(32 * (NW + 1), NW == AGG2_WARPS ? 3 : 1) agg_rows_kernel(
     const uint32_t* __restrict__ x, uint32_t* __restrict__ out, int64_t ldo_w, const int32_t* __restrict__ rowptr,
     const int32_t* __restrict__ col, const uint32_t* __restrict__ addend, int64_t lda_w, const int4* __restrict__ tile_info,
     int n_tiles, int stages, int words, uint32_t x_bytes, uint32_t rp_bytes, uint32_t col_bytes, int dbg_flags) {
@@ -307,18 +308,19 @@ __global__ void __launch_bounds__(32 * (AGG2_WARPS + 1), 3) agg_rows_kernel(
   const int first = blockIdx.x, stride = gridDim.x;
   const int n_my = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int n_cw = NW;                                       // consumer warps; the last warp is the producer
 
   AGG_STAMP(0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], AGG2_WARPS);
+      mbar_init(&empty[s], n_cw);
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp == AGG2_WARPS) {
+  if (warp == n_cw) {
     // ================================================================= producer warp
     const uint32_t row_bytes = static_cast<uint32_t>(words) * 4u;
     for (int base = 0; base < n_my; base += 32) {
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(32 * (AGG2_WARPS + 1), 3) agg_rows_kernel(
     const uint32_t* xs = reinterpret_cast<const uint32_t*>(st) + lane;
     const int32_t* rp = reinterpret_cast<const int32_t*>(st + x_bytes) - (inf.x & ~3);             // indexed by global row
     const int32_t* cs = reinterpret_cast<const int32_t*>(st + x_bytes + rp_bytes) - (inf.z & ~3);  // indexed by global edge
-    for (int r = inf.x + warp; r < inf.y; r += AGG2_WARPS) {
+    for (int r = inf.x + warp; r < inf.y; r += n_cw) {
       const int beg = rp[r], end = rp[r + 1];
       uint32_t addw[V];
       if (addend != nullptr) {
@@ -461,19 +463,28 @@ static int launch_agg_rows(const void* x, void* out, int64_t ldo, const int32_t*
   stages = stages > AGG_STAGES ? AGG_STAGES : (stages < 1 ? 1 : stages);
   if (g_agg_debug_stages > 0 && g_agg_debug_stages <= stages) stages = g_agg_debug_stages;
   const size_t smem = stage * stages;
-  auto kern = agg_rows_kernel<V, BF16>;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    configured = smem;
+  // 8 consumer warps per CTA when two or three CTAs share an SM; large tiles (drug-like molecules) that leave room for one
+  // CTA only get 24, so that an SM always has 16-24 rows in flight
+  const bool wide = ctas_per_sm == 1;
+  static size_t configured[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > configured[wide]) {
+    if (wide) cudaFuncSetAttribute(agg_rows_kernel<V, BF16, AGG2_MAX_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    else cudaFuncSetAttribute(agg_rows_kernel<V, BF16, AGG2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured[wide] = smem;
   }
   int64_t grid = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
   grid = grid > n_tiles ? n_tiles : grid;
   const int esz = BF16 ? 2 : 4;
-  kern<<<static_cast<unsigned>(grid), 32 * (AGG2_WARPS + 1), smem, st>>>(
-      static_cast<const uint32_t*>(x), static_cast<uint32_t*>(out), ldo * esz / 4, rowptr, col, static_cast<const uint32_t*>(addend),
-      ld_addend * esz / 4, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles), stages, words,
-      static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb), g_agg_debug_flags);
+  if (wide)
+    agg_rows_kernel<V, BF16, AGG2_MAX_WARPS><<<static_cast<unsigned>(grid), 32 * (AGG2_MAX_WARPS + 1), smem, st>>>(
+        static_cast<const uint32_t*>(x), static_cast<uint32_t*>(out), ldo * esz / 4, rowptr, col, static_cast<const uint32_t*>(addend),
+        ld_addend * esz / 4, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles), stages, words,
+        static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb), g_agg_debug_flags);
+  else
+    agg_rows_kernel<V, BF16, AGG2_WARPS><<<static_cast<unsigned>(grid), 32 * (AGG2_WARPS + 1), smem, st>>>(
+        static_cast<const uint32_t*>(x), static_cast<uint32_t*>(out), ldo * esz / 4, rowptr, col, static_cast<const uint32_t*>(addend),
+        ld_addend * esz / 4, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles), stages, words,
+        static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb), g_agg_debug_flags);
   return launch_status("ax2d_agg");
 }
 

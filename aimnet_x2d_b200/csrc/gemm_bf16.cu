@@ -26,13 +26,14 @@ namespace ax2d {
 constexpr int BF_BM = 128;
 constexpr int BF_BK = 64;                 // bf16 per 128-byte swizzle row
 constexpr int BF_MAX_BN = 256;            // two accumulator buffers share the 512 TMEM columns
-constexpr int BF_EPI_WARPS = 8;           // two per TMEM lane quarter
+constexpr int BF_EPI_WARPS = 12;          // three per TMEM lane quarter
 constexpr int BF_THREADS = 32 * (2 + BF_EPI_WARPS);
 constexpr int BF_MAX_STAGES = 8;
 constexpr int BF_MAX_CT = 32;             // column tiles per row tile
 constexpr int BF_MAX_CSEG = 4;            // output / pre-activation segments
 constexpr int BF_MAX_RES = 3;
 constexpr int BF_CHUNK = 32;              // columns per epilogue chunk (= one tcgen05.ld 32x32b.x32)
+constexpr int BF_BIAS_SMEM = 2048;        // bias entries staged in shared memory
 
 struct BfMaps {
   CUtensorMap a[AX2D_MAX_SEG];
@@ -49,6 +50,7 @@ struct BfColTile {
   uint32_t flags;        // bit 0: activation, bit 1: activation-backward, bits 2..4: residual r covers the tile
 };
 struct BfArgs {
+  unsigned long long* dbg;               // development aid: %globaltimer stamps of CTA 0 (ax2d_debug_bf16_timing); normally null
   int64_t M;
   int N;
   const float* bias;
@@ -62,6 +64,7 @@ struct BfArgs {
   int seg_k0[AX2D_MAX_SEG];              // first K column of every A segment inside B
   int n_ct, total_tiles, stages;
   int bn_box;                            // rows of the B box (>= every tile's MMA N)
+  int in_double;                         // 1: the input staging tiles are double-buffered (next chunk's loads fly during this one)
   int n_in_max;                          // staging tiles per chunk: inputs (residuals + dact_pre) ...
   int n_out;                             // ... and outputs (c, pre)
   BfColTile ct[BF_MAX_CT];
@@ -222,18 +225,41 @@ __device__ __forceinline__ void stage_write_f32(uint32_t tile, int lane, const f
 
 constexpr uint32_t BF_IN_TILE = 2048;     // bytes of a bf16 staging tile
 
+// SiLU and its derivative through ONE special-function instruction (tanh.approx, ~2^-11 relative -- four times finer than
+// the bf16 rounding of the result): sigmoid(x) = 0.5 + 0.5 tanh(0.5 x).  The fp32 epilogues use ex2 + rcp (two MUFU ops per
+// element); in this kernel the 12 epilogue warps are throughput-bound on the MUFU and integer pipes.
+__device__ __forceinline__ float bf_sigmoid(float v) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+  return fmaf(0.5f, t, 0.5f);
+}
+template <int ACT>
+__device__ __forceinline__ float bf_act_fwd(float v) {
+  if constexpr (ACT == AX2D_ACT_SILU) return v * bf_sigmoid(v);
+  else return act_fwd_t<ACT>(v);
+}
+template <int ACT>
+__device__ __forceinline__ float bf_act_bwd(float v) {
+  if constexpr (ACT == AX2D_ACT_SILU) {
+    const float sg = bf_sigmoid(v);
+    return sg * fmaf(v, 1.f - sg, 1.f);
+  } else return act_bwd_t<ACT>(v);
+}
+
 // v <- epilogue(v) for one chunk; `in_base`: this chunk's input staging tiles in the order residuals.., dact_pre.
 // Returns with v = final values; pre-activation values (before activation) are written to pre_tile when has_pre.
 template <int ACT, int DACT, bool DROP>
 __device__ __forceinline__ void bf_chunk_math(const BfArgs& g, const EpiCtx& cx, const BfColTile& t, int col0, int64_t row, int lane,
-                                              uint32_t in_base, uint32_t pre_tile, bool has_pre, float* v) {
-  // bias (fp32, same 32 values for every lane: broadcast loads)
+                                              uint32_t in_base, uint32_t pre_tile, bool has_pre, float* v, const float* s_bias) {
+  // bias (fp32, same 32 values for every lane): broadcast reads of the copy staged in shared memory at kernel start (a
+  // global load here cost every chunk an exposed L2 round trip right at the top of its dependency chain)
   if (g.bias != nullptr) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int n = col0 + 4 * u;
       if (n + 3 < g.N) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        const float4 b4 = s_bias != nullptr ? *reinterpret_cast<const float4*>(s_bias + n)
+                                            : __ldg(reinterpret_cast<const float4*>(g.bias + n));
         v[4 * u] += b4.x; v[4 * u + 1] += b4.y; v[4 * u + 2] += b4.z; v[4 * u + 3] += b4.w;
       }
     }
@@ -241,14 +267,25 @@ __device__ __forceinline__ void bf_chunk_math(const BfArgs& g, const EpiCtx& cx,
   if (has_pre) stage_write_bf16(pre_tile, lane, v);
   float drop[32];
   if constexpr (DROP) {
-    const uint64_t base = static_cast<uint64_t>(row) * static_cast<uint32_t>(g.N) + static_cast<uint32_t>(col0);
+    // Counter-based like drop_scale4 (the backward pass regenerates the forward decisions from (seed, row, column)), but
+    // one avalanche hash per (row, 32-column chunk) and then one Weyl-step / multiply / xorshift word per TWO elements:
+    // ~5 instead of ~9 instructions per element in an epilogue that is bound by its instruction stream.
+    const uint32_t h0 = mix32(mix32(static_cast<uint32_t>(row) ^ cx.base0) + static_cast<uint32_t>(col0) * 0x9E3779B1u);
+    const uint32_t t16 = cx.thresh << 16;          // decisions compare the HIGH 16 bits of a word: no field extraction
 #pragma unroll
-    for (int u = 0; u < 8; ++u) drop_scale4(cx, base + 4u * u, drop + 4 * u);
+    for (int u = 0; u < 16; ++u) {
+      uint32_t w = h0 + static_cast<uint32_t>(u) * 0x9E3779B9u;      // Weyl step (compile-time addend)
+      w ^= w >> 15;
+      w *= 0x2C1B3C6Du;
+      w ^= w >> 12;
+      drop[2 * u] = w >= t16 ? cx.inv_keep : 0.f;
+      drop[2 * u + 1] = (w << 16) >= t16 ? cx.inv_keep : 0.f;
+    }
   }
   if constexpr (ACT != AX2D_ACT_NONE) {
     if (t.flags & 1u) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = act_fwd_t<ACT>(v[j]);
+      for (int j = 0; j < 32; ++j) v[j] = bf_act_fwd<ACT>(v[j]);
     }
   }
   if constexpr (DROP && DACT == AX2D_ACT_NONE) {
@@ -272,7 +309,7 @@ __device__ __forceinline__ void bf_chunk_math(const BfArgs& g, const EpiCtx& cx,
       stage_read_bf16(in_tile, lane, x);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float s = act_bwd_t<DACT>(x[j]);
+        float s = bf_act_bwd<DACT>(x[j]);
         if constexpr (DROP) s *= drop[j];
         v[j] *= s;
       }
@@ -290,13 +327,21 @@ __global__ void __launch_bounds__(BF_THREADS, 1) gemm_bf16_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = g.stages;
+  unsigned long long* dbg = (g.dbg != nullptr && blockIdx.x == 0) ? g.dbg : nullptr;
+  if (dbg != nullptr && threadIdx.x == 0) dbg[0] = gtime();
   constexpr uint32_t A_BYTES = BF_BM * BF_BK * 2;                                   // 16 KB
   const uint32_t b_bytes = static_cast<uint32_t>(g.bn_box) * BF_BK * 2;
   const uint32_t stage_bytes = A_BYTES + b_bytes;                                   // multiple of 1024 (bn_box % 16 == 0 -> 2 KB units)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t out_tile_bytes = g.c_f32 ? 4096u : 2048u;
-  const uint32_t warp_stage_bytes = 2u * (static_cast<uint32_t>(g.n_in_max) * BF_IN_TILE + static_cast<uint32_t>(g.n_out) * out_tile_bytes);
+  const uint32_t in_bufs = g.in_double ? 2u : 1u;
+  const uint32_t warp_stage_bytes = in_bufs * static_cast<uint32_t>(g.n_in_max) * BF_IN_TILE + 2u * static_cast<uint32_t>(g.n_out) * out_tile_bytes;
   unsigned char* epi_base = smem + static_cast<size_t>(S) * stage_bytes;
+  // bias copy behind the epilogue staging tiles (N <= BF_BIAS_SMEM floats; larger N reads it from global memory)
+  float* s_bias = (g.bias != nullptr && g.N <= BF_BIAS_SMEM)
+                      ? reinterpret_cast<float*>(epi_base + static_cast<size_t>(BF_EPI_WARPS) * warp_stage_bytes) : nullptr;
+  if (s_bias != nullptr)
+    for (int i = threadIdx.x; i < g.N; i += blockDim.x) s_bias[i] = __ldg(g.bias + i);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -319,6 +364,7 @@ __global__ void __launch_bounds__(BF_THREADS, 1) gemm_bf16_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const int n_ct = g.n_ct, total = g.total_tiles, num_kb = g.num_kb;
+  if (dbg != nullptr && threadIdx.x == 0) dbg[1] = gtime();
 
   if (warp == 0) {
     // ===================================================================== TMA producer (whole warp, elected issue)
@@ -353,41 +399,55 @@ __global__ void __launch_bounds__(BF_THREADS, 1) gemm_bf16_kernel(const __grid_c
         tc_fence_after();
         __syncwarp();
         const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        if (dbg != nullptr && lane == 0 && kb == 0 && j < 2) dbg[2 + j] = gtime();      // first k-block of tile j has landed
         umma_kblock_ss_w(d, smem_desc_k_sw128(sa), smem_desc_k_sw128(sa + A_BYTES), idesc, kb != 0 ? 1u : 0u, 2ull, &empty_bar[s]);
       }
       umma_commit_w(&acc_full[buf]);
+      if (dbg != nullptr && lane == 0 && j < 2) dbg[4 + j] = gtime();                    // all MMAs of tile j issued
     }
   } else {
     // ===================================================================== epilogue warps
     const int ew = warp - 2;
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int cp = ew >> 2;                  // chunk parity: this warp takes chunks cp, cp + 2, ...
+    const int cp = ew >> 2;                  // this warp takes chunks cp, cp + BF_EPI_WARPS / 4, ...
     const uint32_t stg = smem_u32(epi_base + static_cast<size_t>(ew) * warp_stage_bytes);
     const uint32_t in_bytes = static_cast<uint32_t>(g.n_in_max) * BF_IN_TILE;
     const uint32_t out_bytes = static_cast<uint32_t>(g.n_out) * out_tile_bytes;
-    // staging of item k: inputs at stg + (k & 1) * in_bytes, outputs at stg + 2 * in_bytes + (k & 1) * out_bytes
+    // staging of item k: inputs at stg + ib(k) * in_bytes, outputs at stg + in_bufs * in_bytes + (k & 1) * out_bytes,
+    // ib(k) = k & 1 with double-buffered inputs, 0 otherwise
+    const uint32_t dbl = g.in_double ? 1u : 0u;
     const EpiCtx cx = epi_ctx_seed(g.drop_p, g.drop_seed, g.drop_tick);
     const bool dropping = g.drop_p > 0.f;
     uint64_t* bars = in_bar[ew];
 
-    auto n_chunks = [&](int tile) { return (g.ct[tile % n_ct].w + BF_CHUNK - 1) / BF_CHUNK; };
-    auto first_item = [&](int& tile, int& ci) {          // first (tile, chunk) of this warp at or after (tile, ci)
-      while (tile < total) {
-        if (ci < n_chunks(tile)) return;
-        tile += gridDim.x;
-        ci = cp;
+    // Work items of this warp: (tile, chunk) pairs in tile order, chunks cp, cp + BF_EPI_WARPS / 4, ...  A position keeps the
+    // tile's row-tile / column-tile indices incrementally: no integer division in the loop (each costs ~50 instructions
+    // on a warp whose instruction stream is the bottleneck).
+    struct Pos { int tile, rt, ct, ci; };
+    const int step_rt = static_cast<int>(gridDim.x) / n_ct, step_ct = static_cast<int>(gridDim.x) % n_ct;
+    auto next_tile = [&](Pos& p) {
+      p.tile += gridDim.x;
+      p.rt += step_rt;
+      p.ct += step_ct;
+      if (p.ct >= n_ct) { p.ct -= n_ct; ++p.rt; }
+    };
+    auto first_item = [&](Pos& p) {          // first (tile, chunk) of this warp at or after p
+      while (p.tile < total) {
+        if (p.ci * BF_CHUNK < g.ct[p.ct].w) return;
+        next_tile(p);
+        p.ci = cp;
       }
     };
     // bulk loads of one chunk's input tiles (lane 0)
-    auto issue_inputs = [&](int tile, int ci, uint32_t k) {
-      const BfColTile& t = g.ct[tile % n_ct];
-      const int row0 = (tile / n_ct) * BF_BM + q * 32;
-      const int col = t.n0 + ci * BF_CHUNK;
-      uint32_t dst = stg + (k & 1u) * in_bytes;
+    auto issue_inputs = [&](const Pos& p, uint32_t k) {
+      const BfColTile& t = g.ct[p.ct];
+      const int row0 = p.rt * BF_BM + q * 32;
+      const int col = t.n0 + p.ci * BF_CHUNK;
+      uint32_t dst = stg + (k & dbl) * in_bytes;
       uint32_t n = 0;
       for (int r = 0; r < BF_MAX_RES; ++r) n += (t.flags >> (2 + r)) & 1u;
       n += (t.flags >> 1) & 1u;
-      uint64_t* bar = &bars[k & 1u];
+      uint64_t* bar = &bars[k & dbl];
       if (n == 0) {                       // keep the barrier protocol uniform: a plain arrival completes the phase
         mbar_arrive(bar);
         return;
@@ -402,65 +462,74 @@ __global__ void __launch_bounds__(BF_THREADS, 1) gemm_bf16_kernel(const __grid_c
     };
 
     const bool use_in = g.n_in_max > 0;
-    int cur_tile = blockIdx.x, cur_ci = cp;
-    first_item(cur_tile, cur_ci);
+    Pos cur{static_cast<int>(blockIdx.x), static_cast<int>(blockIdx.x) / n_ct, static_cast<int>(blockIdx.x) % n_ct, cp};
+    Pos tp = cur;                            // the tile loop's own position
+    first_item(cur);
     uint32_t k = 0;
-    if (use_in && cur_tile < total && lane == 0) issue_inputs(cur_tile, cur_ci, 0);
+    if (use_in && cur.tile < total && lane == 0) issue_inputs(cur, 0);
     int j = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++j) {
+    for (; tp.tile < total; next_tile(tp), ++j) {
+      const int tile = tp.tile;
       const int buf = j & 1;
-      const BfColTile& t = g.ct[tile % n_ct];
-      const int m0 = (tile / n_ct) * BF_BM;
+      const BfColTile& t = g.ct[tp.ct];
+      const int m0 = tp.rt * BF_BM;
       mbar_wait(&acc_full[buf], static_cast<uint32_t>(j >> 1) & 1u);
       tc_fence_after();
+      if (dbg != nullptr && ew == 0 && lane == 0 && j < 2) dbg[6 + 4 * j] = gtime();     // accumulator of tile j ready
       const uint32_t acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BF_MAX_BN);
-      while (cur_tile == tile) {
-        const int ci = cur_ci;
-        int nxt_tile = cur_tile, nxt_ci = cur_ci + 2;
-        first_item(nxt_tile, nxt_ci);
+      const bool has_pre = t.pseg >= 0;
+      while (cur.tile == tile) {
+        const int ci = cur.ci;
+        Pos nxt = cur;
+        nxt.ci += BF_EPI_WARPS / 4;
+        first_item(nxt);
         if (use_in) {
-          if (nxt_tile < total && lane == 0) issue_inputs(nxt_tile, nxt_ci, k + 1);
-          mbar_wait(&bars[k & 1u], (k >> 1) & 1u);
+          if (dbl && nxt.tile < total && lane == 0) issue_inputs(nxt, k + 1);
+          mbar_wait(&bars[k & dbl], dbl ? ((k >> 1) & 1u) : (k & 1u));
         }
+        if (dbg != nullptr && ew == 0 && lane == 0 && j < 2 && ci == cp) dbg[7 + 4 * j] = gtime();   // inputs of the first chunk here
         uint32_t r[32];
         tmem_ld32(acc + static_cast<uint32_t>(ci * BF_CHUNK), r);
+        if (dbg != nullptr && ew == 0 && lane == 0 && j < 2 && ci == cp) dbg[8 + 4 * j] = gtime();   // ... accumulators in registers
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        const uint32_t in_base = stg + (k & 1u) * in_bytes;
-        const uint32_t out_base = stg + 2u * in_bytes + (k & 1u) * out_bytes;
-        const bool has_pre = t.pseg >= 0;
+        const uint32_t in_base = stg + (k & dbl) * in_bytes;
+        const uint32_t out_base = stg + in_bufs * in_bytes + (k & 1u) * out_bytes;
         // the staging tiles of item k - 2 must have been read by their bulk stores before they are overwritten
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
         const int64_t row = static_cast<int64_t>(m0) + q * 32 + lane;
         const int col0 = t.n0 + ci * BF_CHUNK;
         AX2D_EPI_DISPATCH(g.act, g.dact, dropping, {
-          bf_chunk_math<ACT, DACT, DROP>(g, cx, t, col0, row, lane, in_base, out_base + out_tile_bytes, has_pre, v);
+          bf_chunk_math<ACT, DACT, DROP>(g, cx, t, col0, row, lane, in_base, out_base + out_tile_bytes, has_pre, v, s_bias);
         });
         if (g.c_f32) stage_write_f32(out_base, lane, v);
         else stage_write_bf16(out_base, lane, v);
         fence_proxy_async_smem();
         __syncwarp();
+        // single-buffered inputs: every lane has consumed this chunk's tiles (syncwarp above), the next chunk's may land
+        if (use_in && !dbl && nxt.tile < total && lane == 0) issue_inputs(nxt, k + 1);
         if (lane == 0) {
           const int row0 = m0 + q * 32;
           tma_store_2d(&maps.c[t.cseg], out_base, t.cn0 + ci * BF_CHUNK, row0);
-          if (has_pre)
-            tma_store_2d(&maps.pre[t.pseg], out_base + out_tile_bytes, t.pn0 + ci * BF_CHUNK, row0);
+          if (has_pre) tma_store_2d(&maps.pre[t.pseg], out_base + out_tile_bytes, t.pn0 + ci * BF_CHUNK, row0);
           bulk_commit();
+          if (dbg != nullptr && ew == 0 && j < 2 && ci == cp) dbg[9 + 4 * j] = gtime();               // first chunk stored
         }
-        cur_tile = nxt_tile;
-        cur_ci = nxt_ci;
+        cur = nxt;
         ++k;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
+    if (dbg != nullptr && ew == 0 && lane == 0) dbg[14] = gtime();                                    // last chunk of this warp issued
     if (lane == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
+  if (dbg != nullptr && threadIdx.x == 0) dbg[15] = gtime();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
@@ -587,7 +656,7 @@ __global__ void __launch_bounds__(BF_THREADS, 1) gemm_bf16_wgrad_kernel(const __
       const uint32_t acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
       const int n_ch = (BN + 31) / 32;
       uint32_t k = 0;
-      for (int ci = cp; ci < n_ch; ci += 2, ++k) {
+      for (int ci = cp; ci < n_ch; ci += BF_EPI_WARPS / 4, ++k) {
         if (n0 + ci * 32 >= g.Ki) break;
         uint32_t r[32];
         tmem_ld32(acc + static_cast<uint32_t>(ci * 32), r);
@@ -666,6 +735,10 @@ static const CUtensorMapDataType kBF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 
 using namespace ax2d;
 
+static unsigned long long* g_bf_dbg = nullptr;
+// development aid (not part of include/ax2d.h): 16 x u64 device buffer receiving %globaltimer stamps of CTA 0
+extern "C" void ax2d_debug_bf16_timing(unsigned long long* buf) { g_bf_dbg = buf; }
+
 extern "C" int ax2d_gemm_bf16_supported(const ax2d_cmat* a, int64_t M, int64_t N, int64_t K) {
   if (a == nullptr || M < 1 || N < 1 || K < 8) return 0;
   if (a->n_seg < 1 || a->n_seg > AX2D_MAX_SEG) return 0;
@@ -695,6 +768,7 @@ extern "C" int ax2d_gemm_bf16(const ax2d_cmat* a, const void* b, int64_t ldb, co
   memset(&g, 0, sizeof(g));
   BfMaps maps;
   memset(&maps, 0, sizeof(maps));
+  g.dbg = g_bf_dbg;
   g.M = M;
   g.N = static_cast<int>(N);
   g.c_f32 = c_dtype == AX2D_F32 ? 1 : 0;
@@ -840,8 +914,14 @@ extern "C" int ax2d_gemm_bf16(const ax2d_cmat* a, const void* b, int64_t ldb, co
   g.n_in_max = n_in_max;
   g.n_out = pre != nullptr ? 2 : 1;
   const size_t out_tile = g.c_f32 ? 4096 : 2048;
-  const size_t epi_bytes = static_cast<size_t>(BF_EPI_WARPS) * 2 * (n_in_max * BF_IN_TILE + g.n_out * out_tile);
   const size_t stage_bytes = static_cast<size_t>(BF_BM + bn_box) * BF_BK * 2;
+  g.in_double = 1;
+  size_t epi_bytes = static_cast<size_t>(BF_EPI_WARPS) * (2 * n_in_max * BF_IN_TILE + 2 * g.n_out * out_tile);
+  if (227 * 1024 - 2048 - BF_BIAS_SMEM * 4 < epi_bytes + 3 * stage_bytes) {       // keep >= 3 ring stages: single-buffer the inputs instead
+    g.in_double = 0;
+    epi_bytes = static_cast<size_t>(BF_EPI_WARPS) * (n_in_max * BF_IN_TILE + 2 * g.n_out * out_tile);
+  }
+  epi_bytes += BF_BIAS_SMEM * 4;
   const size_t budget = 227 * 1024 - 1024 - 1024 - epi_bytes;
   int stages = static_cast<int>(budget / stage_bytes);
   stages = stages > BF_MAX_STAGES ? BF_MAX_STAGES : stages;

@@ -213,6 +213,7 @@ class EmbeddingExtractor:
         molecules written."""
         import numpy as np
         total = 0
+        k = 1
         for i, b in enumerate(batches):
             k = i & 1
             self._flush(k)                                  # the pinned buffers of two batches ago are free again
@@ -239,6 +240,6 @@ class EmbeddingExtractor:
             self._event[k] = ev
             self._pending[k] = (bufs, np.diff(seg), n_real, int(seg[-1]))
             total += n_real
-        self._flush(0)
-        self._flush(1)
+        self._flush(1 - k)                                  # the older of the two outstanding batches first: input order
+        self._flush(k)
         return total

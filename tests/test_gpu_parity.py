@@ -515,6 +515,14 @@ def _train_step_pair(cfg, T, seed, batch, weights, lr=2.5e-4):
     return cuda, oracle
 
 
+def _f64_criterion_allowed(key):
+    """Full-size entries that may pass on the float64 criterion: bias gradients (column sums over ALL atoms of mixed-sign
+    terms) and the attention-pooling parameters (sums of dz[h, i] x_i, where dz sums to zero within every molecule).  In
+    both the result is orders of magnitude below the sum of the magnitudes of its terms, and the reference's own fp32 value
+    sits further than 1e-5 of the scale from the exact one."""
+    return key.endswith(".bias") or key.startswith("pooling.")
+
+
 def _exact_bias_grads(cfg, T, seed, batch, weights):
     """float64 evaluation of the oracle step (CPU): gradients of the bias vectors only, computed when one of them misses
     the primary bar (see _check_train_step)."""
@@ -525,7 +533,7 @@ def _exact_bias_grads(cfg, T, seed, batch, weights):
               final_cis_tensor=batch.final_cis_tensor, final_trans_tensor=batch.final_trans_tensor)
     out, _, _, _ = MP.gnn_forward(P, cfg, ob)
     MP.weighted_l1(out, batch.targets.double(), weights.double()).backward()
-    return {k: v.grad.numpy() for k, v in P.items() if k.endswith(".bias") and v.grad is not None}
+    return {k: v.grad.numpy() for k, v in P.items() if _f64_criterion_allowed(k) and v.grad is not None}
 
 
 def _check_train_step(cuda, oracle, lr, full_matrices, exact_bias=None):
@@ -542,18 +550,22 @@ def _check_train_step(cuda, oracle, lr, full_matrices, exact_bias=None):
             continue
         rn = float(np.linalg.norm(ref.astype(np.float64)))
         gn = float(np.linalg.norm(got.astype(np.float64)))
-        assert abs(gn - rn) <= RTOL_F32 * max(rn, 1e-30), f"gradient norm of {k}: {gn:.9e} vs {rn:.9e}"
+        fallback = _f64_criterion_allowed(k) and exact_bias is not None
+        if abs(gn - rn) > RTOL_F32 * max(rn, 1e-30):
+            assert fallback, f"gradient norm of {k}: {gn:.9e} vs {rn:.9e}"
+            en = float(np.linalg.norm(exact_bias()[k]))
+            assert abs(gn - en) <= RTOL_F32 * max(rn, 1e-30) + abs(rn - en), \
+                f"gradient norm of {k}: {gn:.9e} vs {rn:.9e} (float64 {en:.9e})"
         if any(s in k for s in full_matrices) or ref.size <= 1 << 16:
             try:
                 assert_close(got, ref, RTOL_F32, "grad (full size) " + k)
             except AssertionError:
-                # Bias gradients are column sums over ALL atoms of mixed-sign terms (|sum| << sum |terms|): the reference's
-                # own fp32 value is then further than 1e-5 of the scale from the exact sum.  For `.bias` entries ONLY the
-                # float64 criterion of close_or_as_exact_as_reference applies; everything else must meet the primary bar.
-                if not (k.endswith(".bias") and exact_bias is not None):
+                # ONLY the entries named by _f64_criterion_allowed may use the float64 criterion of
+                # close_or_as_exact_as_reference; everything else must meet the primary bar.
+                if not fallback:
                     raise
                 note = close_or_as_exact_as_reference(got, ref, exact_bias()[k], "grad (full size) " + k)
-                print("[float64 criterion, bias gradient]", note)
+                print("[float64 criterion]", note)
     # one clip + Adam step.  Adam's first update is lr * g / (|g| + 1e-8), i.e. +-lr wherever |g| >> 1e-8: entries whose
     # gradient is at the rounding level of the sum that produced it move by a noise-determined fraction of lr in the
     # reference as well, so they are excluded (|g_ref| < 1e-4 of the tensor's largest gradient) and counted.
