@@ -43,6 +43,9 @@ _SIGNATURES = {
     "ax2d_host_shell_edges": (c_int64, [c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64]),
     "ax2d_agg": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                          c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "ax2d_agg_tiles_mma_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "ax2d_agg_tiles_mma": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                   c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "ax2d_attn_pool_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ax2d_attn_pool_bwd_workspace": (c_int64, [c_int64, c_int, c_int]),
@@ -116,7 +119,7 @@ _lib = None
 # CUDA events on the launching stream (inside a CUDA-graph capture: external event-record nodes, so the durations are
 # those of the launches INSIDE the replayed step).  None: the calls go straight to the library.
 TIMER_HOOK = [None]
-_UNTIMED_MARKS = ("_host_", "_workspace", "_supported", "_splits", "abi_version", "error_string", "last_error",
+_UNTIMED_MARKS = ("_host_", "_workspace", "_supported", "_splits", "_config", "abi_version", "error_string", "last_error",
                   "launch_count")
 
 

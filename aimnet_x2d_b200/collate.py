@@ -52,6 +52,7 @@ class GraphIndex:
         self.num_rows = 0              # rows of the forward CSR: N if collapsed else H*N
         self.collapsed = True
         self.tile_local = False
+        self.unique_edges = False      # no (target, source) pair occurs twice (the dense tile product cannot count)
         self.n_tiles = 0
         self.max_tile_rows = 0
         self.max_tile_edges = 0
@@ -98,6 +99,11 @@ class GraphIndex:
             gi.collapsed = tmax < N
         R = N if gi.collapsed else num_hops * N
         gi.num_rows = R
+        if E:
+            keys = e_np[:, 0].astype(np.int64) * max(N, 1) + (e_np[:, 1].astype(np.int64) % max(N, 1))
+            gi.unique_edges = bool(np.unique(keys).size == E)
+        else:
+            gi.unique_edges = True
         slack = GraphIndex.INDEX_SLACK
         rowptr = np.zeros(R + 1 + slack, dtype=np.int32)
         col = np.zeros(max(E, 1) + slack, dtype=np.int32)
@@ -457,7 +463,7 @@ def static_signature(batch: MolBatch) -> tuple:
     gi = batch.graph_index
     return (gi.num_atoms, gi.num_graphs, gi.num_rows, gi.n_tiles, gi.max_tile_rows, gi.max_tile_edges, gi.max_seg,
             int(gi.col.numel()),
-            gi.collapsed, gi.tile_local, None if gi.tetra is None else gi.tetra[3],
+            gi.collapsed, gi.tile_local, gi.unique_edges, None if gi.tetra is None else gi.tetra[3],
             None if gi.cistrans is None else gi.cistrans[3], getattr(batch, "num_real_graphs", gi.num_graphs),
             tuple(sorted((k, v[2]) for k, v in gi.embed.items())))
 

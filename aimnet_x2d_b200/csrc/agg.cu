@@ -131,9 +131,15 @@ __device__ __forceinline__ unsigned long long agg_gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// (the register tests come FIRST: with the pointer test first every thread of every CTA loaded the __device__ variable
+// from L2 -- an exposed ~700-cycle round trip twice per tile on the critical path of every consumer warp, which is what
+// the first version of these kernels spent a third of its time on)
 #define AGG_STAMP(slot)                                                                  \
   do {                                                                                   \
-    if (g_agg_dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) g_agg_dbg[slot] = agg_gtime(); \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                           \
+      unsigned long long* dbg_ = g_agg_dbg;                                              \
+      if (dbg_ != nullptr) dbg_[slot] = agg_gtime();                                     \
+    }                                                                                    \
   } while (0)
 template <int V>
 __global__ void __launch_bounds__(AGG_CONSUMERS + 32, 2) agg_tiles_kernel(
@@ -488,6 +494,260 @@ static int launch_agg_rows(const void* x, void* out, int64_t ldo, const int32_t*
   return launch_status("ax2d_agg");
 }
 
+// ------------------------------------------------------------------------------------------------ tensor-core tiles
+// Third formulation of the tile kernel: the gather-reduce of a whole-molecule tile IS a small dense product
+//     out_tile[R, W] = A_tile[R, R] * x_tile[R, W],        A[r, c] = 1 iff the tile holds the edge (target r, source c),
+// because no edge leaves its tile.  The per-edge kernels above read one 640-byte row of x from shared memory and issue
+// ~13-33 instructions PER EDGE (E = 10 N): shared-memory wavefronts and instruction issue bound them at ~19 us per launch
+// whatever the data type (tools/agg_dbg.py: 8.6 us without the edge loop).  Here every staged row is read once per 16-row
+// output block by ldmatrix, and the sums are done by the tensor cores (mma.sync m16n8k16, bf16 operands, fp32 accumulation):
+//   * the consumers write the tile's 0/1 adjacency as a dense bf16 matrix (one store per edge) ...
+//   * ... and re-pack the staged rows into padded (ldmatrix conflict-free) bf16 planes: ONE plane for bf16 features, THREE
+//     for fp32 features -- x = b0 + b1 + b2 with bf16 terms is EXACT (8 + 8 + 8 significand bits), and 0/1 times a bf16
+//     term is exact, so the only difference to the sequential sum is the ORDER of the fp32 additions (~1e-7 relative; the
+//     per-edge kernels stay available for bit-exact results: ax2d_agg_config);
+//   * warp w owns (16-row block, 16-column pair) items; per item and 16-neighbour step: one ldmatrix.x4 of A, one
+//     ldmatrix.x4.trans of x per plane, two MMAs per plane.
+// Requires a duplicate-free edge list (a dense 0/1 matrix cannot count) -- checked at collation (GraphIndex.unique_edges).
+constexpr int AGG3_THREADS = 256;              // 8 consumer warps (+ 1 producer warp)
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void agg3_sync() { asm volatile("bar.sync 1, %0;" ::"n"(AGG3_THREADS) : "memory"); }
+
+template <bool BF16>
+__global__ void __launch_bounds__(AGG3_THREADS + 32) agg_mma_kernel(
+    const uint32_t* __restrict__ x, void* __restrict__ out, int64_t ldo, const int32_t* __restrict__ rowptr,
+    const int32_t* __restrict__ col, const void* __restrict__ addend, int64_t lda, const int4* __restrict__ tile_info,
+    int n_tiles, int stages, int width, int rpad, uint32_t x_bytes, uint32_t rp_bytes, uint32_t col_bytes) {
+  // width: columns (multiple of 16); rpad: tile-row capacity rounded up to 16 (rows and neighbours of the dense product)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[AGG_STAGES], empty[AGG_STAGES];
+  __shared__ int4 s_info[AGG_STAGES];
+  constexpr int P = BF16 ? 1 : 3;                         // bf16 planes of x
+  const uint32_t stage_bytes = x_bytes + rp_bytes + col_bytes;
+  const int SA = rpad + 8;                                // row pitch of the adjacency, bf16 elements (16-byte skew per row)
+  const int SX = width + 8;                               // row pitch of the x planes
+  unsigned char* work = smem_raw + static_cast<size_t>(stages) * stage_bytes;
+  uint16_t* As = reinterpret_cast<uint16_t*>(work);                                      // [rpad][SA]
+  uint16_t* Xp = As + static_cast<size_t>(rpad) * SA;                                     // [P][rpad][SX]
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_my = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  AGG_STAMP(0);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], AGG3_THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == AGG3_THREADS / 32) {
+    // ================================================================= producer warp (as in agg_rows_kernel)
+    const uint32_t row_bytes = static_cast<uint32_t>(width) * (BF16 ? 2u : 4u);
+    for (int base = 0; base < n_my; base += 32) {
+      int4 mine = make_int4(0, 0, 0, 0);
+      if (base + lane < n_my) mine = __ldg(tile_info + first + static_cast<int64_t>(base + lane) * stride);
+      const int cnt = n_my - base < 32 ? n_my - base : 32;
+      for (int j = 0; j < cnt; ++j) {
+        const int it = base + j;
+        int4 inf;
+        inf.x = __shfl_sync(0xffffffffu, mine.x, j);
+        inf.y = __shfl_sync(0xffffffffu, mine.y, j);
+        inf.z = __shfl_sync(0xffffffffu, mine.z, j);
+        inf.w = __shfl_sync(0xffffffffu, mine.w, j);
+        if (lane == 0) {
+          const int s = it % stages;
+          mbar_wait(&empty[s], (static_cast<uint32_t>(it / stages) & 1u) ^ 1u);
+          unsigned char* dst = smem_raw + static_cast<size_t>(s) * stage_bytes;
+          const uint32_t xb = static_cast<uint32_t>(inf.y - inf.x) * row_bytes;
+          const int rs = inf.x & ~3, es = inf.z & ~3;
+          const uint32_t rb = static_cast<uint32_t>((inf.y + 1 - rs + 3) & ~3) * 4;
+          const uint32_t cb = static_cast<uint32_t>((inf.w - es + 3) & ~3) * 4;
+          s_info[s] = inf;
+          mbar_expect_tx(&full[s], xb + rb + cb);
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(x) + static_cast<int64_t>(inf.x) * row_bytes;
+          for (uint32_t off = 0; off < xb; off += 16384) {
+            const uint32_t n = xb - off < 16384u ? xb - off : 16384u;
+            bulk_g2s(dst + off, src + off, n, &full[s]);
+          }
+          bulk_g2s(dst + x_bytes, rowptr + rs, rb, &full[s]);
+          if (cb > 0) bulk_g2s(dst + x_bytes + rp_bytes, col + es, cb, &full[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // =================================================================== consumers
+  const int tid = threadIdx.x;
+  const int lane8 = lane & 7, group = tid >> 3;          // 8 lanes per row when the adjacency is written
+  const int n_pairs = width >> 4;                        // 16-column pairs of n-blocks
+  const int m_blocks = rpad >> 4, k_steps = rpad >> 4;
+  const int n_items = m_blocks * n_pairs;
+  const int units = width >> 3;                          // 8-element units per row
+  for (int it = 0; it < n_my; ++it) {
+    const int s = it % stages;
+    mbar_wait(&full[s], static_cast<uint32_t>(it / stages) & 1u);
+    if (it < 3) AGG_STAMP(1 + 4 * it);
+    const int4 inf = s_info[s];
+    const int rows = inf.y - inf.x;
+    const unsigned char* st = smem_raw + static_cast<size_t>(s) * stage_bytes;
+    const int32_t* rp = reinterpret_cast<const int32_t*>(st + x_bytes) - (inf.x & ~3);
+    const int32_t* cs = reinterpret_cast<const int32_t*>(st + x_bytes + rp_bytes) - (inf.z & ~3);
+    // ---- (1) zero the adjacency, re-pack x into padded bf16 planes (rows beyond the tile: zeros -- 0 * NaN would poison)
+    for (int i = tid; i < rpad * (SA >> 3); i += AGG3_THREADS) reinterpret_cast<uint4*>(As)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < rpad * units; i += AGG3_THREADS) {
+      const int r = i / units, u = i - r * units;
+      if constexpr (BF16) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows) v = reinterpret_cast<const uint4*>(st)[r * units + u];
+        *reinterpret_cast<uint4*>(Xp + r * SX + u * 8) = v;
+      } else {
+        float f[8];
+        if (r < rows) {
+          const float4 a = reinterpret_cast<const float4*>(st)[(r * units + u) * 2], b = reinterpret_cast<const float4*>(st)[(r * units + u) * 2 + 1];
+          f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
+        uint32_t w[3][4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          // x = b0 + b1 + b2 exactly: every remainder is computed exactly in fp32 and has 8 significand bits fewer
+          float r0[2], r1[2];
+          uint32_t p0 = bf2_pack(f[e], f[e + 1]);
+          r0[0] = f[e] - __uint_as_float(p0 << 16);
+          r0[1] = f[e + 1] - __uint_as_float(p0 & 0xFFFF0000u);
+          uint32_t p1 = bf2_pack(r0[0], r0[1]);
+          r1[0] = r0[0] - __uint_as_float(p1 << 16);
+          r1[1] = r0[1] - __uint_as_float(p1 & 0xFFFF0000u);
+          w[0][e >> 1] = p0;
+          w[1][e >> 1] = p1;
+          w[2][e >> 1] = bf2_pack(r1[0], r1[1]);
+        }
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+          *reinterpret_cast<uint4*>(Xp + (p * rpad + r) * SX + u * 8) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+      }
+    }
+    agg3_sync();
+    if (it < 3) AGG_STAMP(2 + 4 * it);
+    // ---- (2) the tile's edges -> ones (8 lanes per row walk the row's edge list)
+    for (int r = group; r < rows; r += AGG3_THREADS / 8) {
+      const int beg = rp[inf.x + r], end = rp[inf.x + r + 1];
+      for (int k = beg + lane8; k < end; k += 8) As[r * SA + (cs[k] - inf.x)] = 0x3F80;
+    }
+    agg3_sync();
+    if (it < 3) AGG_STAMP(3 + 4 * it);
+    // the staged tile (raw rows, rowptr and col windows) is consumed: hand the stage back while the products run
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+    // ---- (3) products: item = (16-row block mb, 16-column pair np)
+    const uint32_t as_base = smem_u32(As), xp_base = smem_u32(Xp);
+    const int g = lane >> 2, t = lane & 3;
+    for (int item = warp; item < n_items; item += AGG3_THREADS / 32) {
+      const int mb = item % m_blocks, np = item / m_blocks;
+      if (mb * 16 >= rows) continue;
+      float acc_hi[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float acc_lo[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      for (int ks = 0; ks < k_steps; ++ks) {
+        if (ks * 16 >= rows) break;                              // neighbours live in [0, rows)
+        uint32_t a0, a1, a2, a3;
+        // ldmatrix.x4 row addresses: matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15) of the 16 x 16 block
+        ldsm_x4(as_base + 2u * static_cast<uint32_t>((mb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * SA + ks * 16 + (lane >> 4) * 8),
+                a0, a1, a2, a3);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          uint32_t b0, b1, b2, b3;
+          // .trans: stored rows = neighbours k, 8 contiguous columns each; matrices (k 0-7 | 8-15) x (n-block 0 | 1)
+          ldsm_x4_t(xp_base + 2u * static_cast<uint32_t>((p * rpad + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * SX + np * 16 + (lane >> 4) * 8),
+                    b0, b1, b2, b3);
+          float (*acc)[4] = (BF16 || p == 0) ? acc_hi : acc_lo;
+          mma_bf16(acc[0], a0, a1, a2, a3, b0, b1);
+          mma_bf16(acc[1], a0, a1, a2, a3, b2, b3);
+        }
+      }
+      // ---- (4) out[row, col .. col + 1] (+ addend): rows g and g + 8 of the block, columns np * 16 + nb * 8 + 2 t
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = mb * 16 + g + 8 * h;
+          if (r >= rows) continue;
+          const int64_t grow = static_cast<int64_t>(inf.x) + r;
+          const int c = np * 16 + nb * 8 + 2 * t;
+          float v0 = acc_hi[nb][2 * h] + acc_lo[nb][2 * h], v1 = acc_hi[nb][2 * h + 1] + acc_lo[nb][2 * h + 1];
+          if constexpr (BF16) {
+            if (addend != nullptr) {
+              const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint16_t*>(addend) + grow * lda + c));
+              v0 += __uint_as_float(a << 16);
+              v1 += __uint_as_float(a & 0xFFFF0000u);
+            }
+            *reinterpret_cast<uint32_t*>(static_cast<uint16_t*>(out) + grow * ldo + c) = bf2_pack(v0, v1);
+          } else {
+            if (addend != nullptr) {
+              const float2 a = __ldg(reinterpret_cast<const float2*>(static_cast<const float*>(addend) + grow * lda + c));
+              v0 += a.x;
+              v1 += a.y;
+            }
+            *reinterpret_cast<float2*>(static_cast<float*>(out) + grow * ldo + c) = make_float2(v0, v1);
+          }
+        }
+    }
+    if (it < 3) AGG_STAMP(4 + 4 * it);
+    agg3_sync();              // As / Xp are rewritten by the next tile
+  }
+  AGG_STAMP(15);
+}
+
+template <bool BF16>
+static int launch_agg_mma(const void* x, void* out, int64_t ldo, const int32_t* rowptr, const int32_t* col, const void* addend,
+                          int64_t ld_addend, const int32_t* tile_info, int64_t n_tiles, int max_tile_rows, int max_tile_edges,
+                          int width, cudaStream_t st, bool* handled) {
+  *handled = false;
+  const int rpad = (max_tile_rows + 15) / 16 * 16;
+  const size_t esz = BF16 ? 2 : 4;
+  const size_t xb = (static_cast<size_t>(max_tile_rows) * width * esz + 15) / 16 * 16;
+  const size_t rb = (static_cast<size_t>(max_tile_rows) + 8) * 4 / 16 * 16 + 16;
+  const size_t cb = (static_cast<size_t>(max_tile_edges) + 8) * 4 / 16 * 16 + 16;
+  const size_t stage = xb + rb + cb;
+  const size_t work = (static_cast<size_t>(rpad) * (rpad + 8) + static_cast<size_t>(BF16 ? 1 : 3) * rpad * (width + 8)) * 2 + 16;
+  if (width % 16 != 0 || rpad > 128) return AX2D_OK;               // not applicable: the caller takes the per-edge kernel
+  int ctas_per_sm = 4;
+  while (ctas_per_sm > 1 && (220 * 1024 / ctas_per_sm) < static_cast<int64_t>(work + 2 * stage)) --ctas_per_sm;
+  if (g_agg_debug_ctas > 0) ctas_per_sm = g_agg_debug_ctas;
+  const int64_t room = 220 * 1024 / ctas_per_sm - static_cast<int64_t>(work);
+  if (room < static_cast<int64_t>(stage)) return AX2D_OK;
+  int stages = static_cast<int>(room / stage);
+  stages = stages > AGG_STAGES ? AGG_STAGES : stages;
+  if (g_agg_debug_stages > 0 && g_agg_debug_stages <= stages) stages = g_agg_debug_stages;
+  const size_t smem = stage * stages + work;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(agg_mma_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = smem;
+  }
+  int64_t grid = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
+  grid = grid > n_tiles ? n_tiles : grid;
+  agg_mma_kernel<BF16><<<static_cast<unsigned>(grid), AGG3_THREADS + 32, smem, st>>>(
+      static_cast<const uint32_t*>(x), out, ldo, rowptr, col, addend, ld_addend, reinterpret_cast<const int4*>(tile_info),
+      static_cast<int>(n_tiles), stages, width, rpad, static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb));
+  *handled = true;
+  return launch_status("ax2d_agg");
+}
+
 // ------------------------------------------------------------------------------------------------ bf16 features
 // The same persistent tile pipeline for bf16 rows (BASELINE configs[3]): the staged tile is half the bytes, FOUR lanes own
 // one output row (lane j accumulates the 16-byte units j, j + 4, ... = 8 bf16 each, in fp32 registers, CSR order), the
@@ -757,8 +1017,9 @@ static int launch_agg(const float* x, int64_t ldx, float* out, int64_t ldo, int6
 
 }  // namespace ax2d
 
-// development aid (not part of include/ax2d.h): CTAs per SM / stages of the warp-per-row kernel (0 = automatic) and whether
-// it is used at all (0: the first-generation 8-lanes-per-row kernels)
+// development aid (not part of include/ax2d.h): CTAs per SM / stages of the warp-per-row kernel (0 = automatic) and which
+// per-edge kernel runs: 0 = first generation (8 / 4 lanes per row) for both types, 1 (default) = first generation for fp32
+// (same speed as the warp-per-row kernel on B200, measured) and warp-per-row for bf16 (1.4x faster), 2 = warp-per-row for both
 extern "C" void ax2d_debug_agg_config(int ctas_per_sm, int stages, int use_rows_kernel) {
   ax2d::g_agg_debug_ctas = ctas_per_sm;
   ax2d::g_agg_debug_stages = stages & 0xff;
@@ -768,6 +1029,52 @@ extern "C" void ax2d_debug_agg_config(int ctas_per_sm, int stages, int use_rows_
 // development aid (not part of include/ax2d.h): 16 x u64 device buffer receiving %globaltimer stamps of CTA 0
 extern "C" void ax2d_debug_agg_timing(unsigned long long* buf) {
   cudaMemcpyToSymbol(ax2d::g_agg_dbg, &buf, sizeof(buf));
+}
+
+// 1 iff the tensor-core tile kernel handles tiles of this shape (width % 16 == 0, tile capacity <= 128 rows, the dense
+// adjacency + the bf16 planes + two stages fit the shared memory)
+extern "C" int ax2d_agg_tiles_mma_supported(int width, int max_tile_rows, int max_tile_edges, int dtype) {
+  using namespace ax2d;
+  if (width <= 0 || width % 16 != 0 || max_tile_rows <= 0 || (dtype != AX2D_F32 && dtype != AX2D_BF16)) return 0;
+  const int rpad = (max_tile_rows + 15) / 16 * 16;
+  if (rpad > 128) return 0;
+  const size_t esz = dtype == AX2D_BF16 ? 2 : 4;
+  const size_t stage = (static_cast<size_t>(max_tile_rows) * width * esz + 15) / 16 * 16 + (static_cast<size_t>(max_tile_rows) + 8) * 4 / 16 * 16 +
+                       16 + (static_cast<size_t>(max_tile_edges) + 8) * 4 / 16 * 16 + 16;
+  const size_t work = (static_cast<size_t>(rpad) * (rpad + 8) + static_cast<size_t>(dtype == AX2D_BF16 ? 1 : 3) * rpad * (width + 8)) * 2 + 16;
+  return work + 2 * stage <= 220 * 1024 ? 1 : 0;
+}
+
+// a1 on the tensor cores: the same contract as the tiled mode of ax2d_agg (whole-molecule tiles, tile-local columns) PLUS a
+// duplicate-free edge list; fp32 results equal the sequential sums up to the order of the fp32 additions (see agg_mma_kernel).
+extern "C" int ax2d_agg_tiles_mma(const void* x, int64_t ldx, int64_t n_rows, void* out, int64_t ldo, const int32_t* rowptr,
+                                  const int32_t* col, const void* addend, int64_t ld_addend, int width, const int32_t* tile_info,
+                                  int64_t n_tiles, int max_tile_rows, int max_tile_edges, int dtype, ax2d_stream_t stream) {
+  using namespace ax2d;
+  AX2D_CHECK_ARG(ax2d_agg_tiles_mma_supported(width, max_tile_rows, max_tile_edges, dtype),
+                 "ax2d_agg_tiles_mma: unsupported tile shape (width %d, %d rows, %d edges, dtype %d)", width, max_tile_rows,
+                 max_tile_edges, dtype);
+  const int al = dtype == AX2D_BF16 ? 8 : 4;
+  AX2D_CHECK_ARG(ldx == width && ldo % al == 0 && ldo >= width && (addend == nullptr || (ld_addend % al == 0 && ld_addend >= width)),
+                 "ax2d_agg_tiles_mma: x must be contiguous (ldx == width); bad leading dimensions");
+  AX2D_CHECK_ARG(tile_info != nullptr && n_tiles > 0 && max_tile_edges >= 0, "ax2d_agg_tiles_mma: tile plan required");
+  AX2D_CHECK_ALIGN(x);
+  AX2D_CHECK_ALIGN(out);
+  AX2D_CHECK_ALIGN(addend);
+  AX2D_CHECK_ALIGN(tile_info);
+  AX2D_CHECK_ALIGN(rowptr);
+  AX2D_CHECK_ALIGN(col);
+  if (n_rows <= 0) return AX2D_OK;
+  bool handled = false;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = dtype == AX2D_BF16
+               ? launch_agg_mma<true>(x, out, ldo, rowptr, col, addend, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, width, st, &handled)
+               : launch_agg_mma<false>(x, out, ldo, rowptr, col, addend, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, width, st, &handled);
+  if (rc == AX2D_OK && !handled) {
+    set_error("ax2d_agg_tiles_mma: tile shape does not fit the shared memory");
+    return AX2D_ERR_UNSUPPORTED;
+  }
+  return rc;
 }
 
 extern "C" int ax2d_agg(const void* x, int64_t ldx, int64_t n_src_rows, void* out, int64_t ldo, int64_t n_out_rows,
@@ -840,7 +1147,7 @@ extern "C" int ax2d_agg(const void* x, int64_t ldx, int64_t n_src_rows, void* ou
     return launch_status("ax2d_agg");
   }
 #define AX2D_AGG_CASE(V) \
-  case V: return (tile_info != nullptr && g_agg_use_rows) \
+  case V: return (tile_info != nullptr && g_agg_use_rows == 2) \
       ? launch_agg_rows<V, false>(xf, of, ldo, rowptr, col, af, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, width, st) \
       : launch_agg<V>(xf, ldx, of, ldo, n_out_rows, rowptr, col, af, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, st);
   switch (width / 32) {

@@ -310,6 +310,13 @@ def split_k_for(M: int, N: int, K: int) -> int:
     return int(s)
 
 
+# Whole-molecule tiles as dense products on the tensor cores (ax2d_agg_tiles_mma).  Correct (tests/test_gpu_parity.py) but as
+# measured on B200 not faster than the per-edge kernels yet (C2 shapes, fwd / bwd: fp32 27.9 / 53.5 us against 18.1 / 19.4 us;
+# bf16 18.2 / 23.9 us against 19.1 / 20.6 us, profiles/r2e_agg_variants.txt), so it is OFF by default: the per-edge kernels
+# are also the ones that are bit-identical to the reference's sequential scatter_add.
+AGG_TENSOR_CORES = False
+
+
 def agg(x: torch.Tensor, gi, transpose: bool = False, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Forward (transpose=False): out[r] = sum x[col]; rows = gi.num_rows.  Backward: rows = N."""
     lib = _lib.load()
@@ -323,6 +330,18 @@ def agg(x: torch.Tensor, gi, transpose: bool = False, addend: Optional[torch.Ten
         raise RuntimeError(f"aggregation runs on fp32 or bf16 features, got {x.dtype}")
     tiled = (gi.tile_local and gi.collapsed and x.stride(0) == width and width % 32 == 0 and info is not None
              and gi.max_tile_rows * width * es + gi.max_tile_edges * 4 <= 200 * 1024 and gi.n_tiles > 0)
+    if (tiled and AGG_TENSOR_CORES and getattr(gi, "unique_edges", False)
+            and lib.ax2d_agg_tiles_mma_supported(width, gi.max_tile_rows, gi.max_tile_edges, DT_CODES[x.dtype])):
+        # whole-molecule tiles as dense products on the tensor cores (fp32: same sums, other order of the fp32 additions)
+        call = lambda: _lib.check(lib.ax2d_agg_tiles_mma(_p(x), x.stride(0), rows, _p(out), out.stride(0), _p(rowptr), _p(col),
+                                                         _p(addend), 0 if addend is None else addend.stride(0), width, _p(info),
+                                                         gi.n_tiles, gi.max_tile_rows, gi.max_tile_edges, DT_CODES[x.dtype],
+                                                         _stream()), "ax2d_agg_tiles_mma")
+        if TIMER is None:
+            call()
+        else:
+            TIMER.launch("agg", call, nbytes=agg_bytes(x.shape[0], rows, gi.num_edges, width, addend is not None, es))
+        return out
     call = lambda: _lib.check(lib.ax2d_agg(_p(x), x.stride(0), x.shape[0], _p(out), out.stride(0), rows, _p(rowptr),
                                            _p(col), _p(addend), 0 if addend is None else addend.stride(0), width,
                                            _p(info) if tiled else None, gi.n_tiles if tiled else 0,

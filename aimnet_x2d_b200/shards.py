@@ -40,7 +40,7 @@ from .trainer import HostBatch, _arena_layout, _batch_tensors
 MAGIC = b"AX2DSHRD"
 VERSION = 1
 _ALIGN = 4096
-_GI_SCALARS = ("num_atoms", "num_graphs", "num_edges", "num_hops", "num_rows", "collapsed", "tile_local", "n_tiles",
+_GI_SCALARS = ("num_atoms", "num_graphs", "num_edges", "num_hops", "num_rows", "collapsed", "tile_local", "unique_edges", "n_tiles",
                "max_tile_rows", "max_tile_edges", "max_seg")
 _DT = {"int32": torch.int32, "int64": torch.int64, "float32": torch.float32}
 

@@ -95,6 +95,18 @@ int ax2d_agg(const void* x, int64_t ldx, int64_t n_src_rows,
              const int32_t* tile_info, int64_t n_tiles, int max_tile_rows, int max_tile_edges,
              int dtype, ax2d_stream_t stream);
 
+/* The same operation for whole-molecule tiles as a dense product on the tensor cores: out_tile = A_tile x_tile with A the
+ * tile's 0/1 adjacency (models/layers.py:154-163 restricted to the shipped collation, where no edge leaves its molecule).
+ * Contract of the tiled mode of ax2d_agg PLUS: the edge list holds no duplicate (target, source) pair (checked at collation).
+ * bf16 features: fp32 accumulation, one rounding per output.  fp32 features: x is split into three bf16 terms (exact), so
+ * the result differs from the sequential sum only by the order of the fp32 additions (~1e-7 relative); ax2d_agg remains
+ * the bit-exact path.  ..._supported: 1 iff the tile shape fits (width % 16 == 0, <= 128 rows per tile, shared memory). */
+int ax2d_agg_tiles_mma_supported(int width, int max_tile_rows, int max_tile_edges, int dtype);
+int ax2d_agg_tiles_mma(const void* x, int64_t ldx, int64_t n_rows, void* out, int64_t ldo,
+                       const int32_t* rowptr, const int32_t* col, const void* addend, int64_t ld_addend, int width,
+                       const int32_t* tile_info, int64_t n_tiles, int max_tile_rows, int max_tile_edges,
+                       int dtype, ax2d_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * a7  MultiHeadAttentionPoolingLayer.forward  (models/pooling.py:122-172)
  *   z[h,n] = (w_h . x_n + b_h) / T ; a = per-(head,molecule) softmax ; pooled[g] = mean_h sum_n a[h,n] x_n

@@ -185,6 +185,15 @@ def test_bf16_aggregation_equals_rounded_fp32_aggregation(width, tiled):
     ref_b = ops.agg(x.float(), gi, transpose=True, addend=add.float())
     got_b = ops.agg(x, gi, transpose=True, addend=add)
     assert torch.equal(got_b, ref_b.to(torch.bfloat16))
+    # optional tensor-core tiles: other order of the fp32 additions -> at most the last bf16 bit of an output differs
+    ops.AGG_TENSOR_CORES = True
+    try:
+        for got_tc, want in ((ops.agg(x, gi), ref), (ops.agg(x, gi, transpose=True, addend=add), ref_b)):
+            assert got_tc.dtype == torch.bfloat16
+            err = (got_tc.float() - want).abs()
+            assert bool((err <= want.abs() * 2.0 ** -8 + 1e-6).all())
+    finally:
+        ops.AGG_TENSOR_CORES = False
 
 
 @pytest.mark.timeout(300)

@@ -116,8 +116,19 @@ def test_aggregation_is_bit_exact(width, tiled):
     gid = gi.to(DEV)
     if not tiled:
         gid.tile_local = False
-    out = ops.agg(torch.from_numpy(x).to(DEV), gid)
+    out = ops.agg(torch.from_numpy(x).to(DEV), gid)     # the per-edge kernels: sequential CSR order == the reference, bit for bit
     assert np.array_equal(out.cpu().numpy(), ref)
+    # optional: whole-molecule tiles as dense products on the tensor cores -- the same exact terms (x = b0 + b1 + b2 in bf16,
+    # 0/1 adjacency), only the order of the fp32 additions differs: 1e-6 of the tensor scale
+    ops.AGG_TENSOR_CORES = True
+    try:
+        out_tc = ops.agg(torch.from_numpy(x).to(DEV), gid)
+        assert_close(out_tc.cpu().numpy(), ref, 1e-6, "aggregation (tensor-core tiles)")
+        add = rng.normal(0, 1, size=(N, width)).astype(np.float32)
+        out_tc = ops.agg(torch.from_numpy(x).to(DEV), gid, addend=torch.from_numpy(add).to(DEV))
+        assert_close(out_tc.cpu().numpy(), ref + add, 1e-6, "aggregation + addend (tensor-core tiles)")
+    finally:
+        ops.AGG_TENSOR_CORES = False
     # backward operator (transposed CSR) == autograd of the reference gather/scatter
     xg = torch.from_numpy(x).requires_grad_(True)
     r = rng.normal(0, 1, size=(N, width)).astype(np.float32)
@@ -368,7 +379,14 @@ def test_full_size_c2_properties():
     e = batch.multi_hop_edge_indices
     ref = MP.message_passing(x, e[:, 0], e[:, 1], 3)
     out = ops.agg(x.to(DEV), gid)
-    assert np.array_equal(out.cpu().numpy(), ref[0].numpy())            # bit exact at full size
+    assert np.array_equal(out.cpu().numpy(), ref[0].numpy())            # per-edge kernel: bit exact at full size
+    assert gi.unique_edges
+    ops.AGG_TENSOR_CORES = True
+    try:
+        out_tc = ops.agg(x.to(DEV), gid)                                 # tensor-core tiles (optional path)
+        assert_close(out_tc.cpu().numpy(), ref[0].numpy(), 1e-6, "aggregation at full size (tensor-core tiles)")
+    finally:
+        ops.AGG_TENSOR_CORES = False
     assert float(ref[1].abs().max()) == 0.0                              # quirk Q1
     assert float(out[:, 153:].abs().max()) == 0.0                        # pad columns stay exact zeros
     # linearity + symmetry of the shell operator: <A x, y> == <x, A^T y>, and A^T == A for the shipped collation
