@@ -181,7 +181,10 @@ class GraphedTrainStep(StaticSlot):
     device scalar; ``__call__`` reads it back like ``trainer.py:169`` does.
     """
 
-    def __init__(self, model: torch.nn.Module, criterion: torch.nn.Module, optimizer: FlatAdam, device=None):
+    def __init__(self, model: torch.nn.Module, criterion: torch.nn.Module, optimizer: FlatAdam, device=None,
+                 single_graph: bool = False):
+        """``single_graph``: capture forward + backward, the NCCL all-reduce and the update into ONE graph (one launch per
+        step, no host round trip between backward and the collective).  Needs every rank to replay in lock step."""
         self.eager = TrainStep(model, criterion, optimizer, device)
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.device = self.eager.device
@@ -189,6 +192,7 @@ class GraphedTrainStep(StaticSlot):
         self.signature = None
         self.graph_fb = self.graph_opt = None
         self.loss = None
+        self.single_graph = bool(single_graph)
 
     def _fwd_bwd(self) -> torch.Tensor:
         bd, opt = self.slot, self.optimizer
@@ -221,17 +225,29 @@ class GraphedTrainStep(StaticSlot):
         torch.cuda.synchronize()
         self.graph_fb = torch.cuda.CUDAGraph()
         with (timer if timer is not None else contextlib.nullcontext()):
-            with torch.cuda.graph(self.graph_fb):
-                self.loss = self._fwd_bwd()
-            self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt):
-                opt.step()
+            if self.single_graph:
+                # thread-local capture mode: ProcessGroupNCCL's watchdog thread polls CUDA events while the capture runs
+                with torch.cuda.graph(self.graph_fb, capture_error_mode="thread_local"):
+                    self.loss = self._fwd_bwd()
+                    opt.all_reduce_grads()
+                    opt.step()
+                self.graph_opt = None
+            else:
+                with torch.cuda.graph(self.graph_fb):
+                    self.loss = self._fwd_bwd()
+                self.graph_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_opt):
+                    opt.step()
         with torch.no_grad():
             for dst, src in zip((opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.step_count), saved):
                 dst.copy_(src)
         torch.cuda.synchronize()
 
     def replay(self) -> torch.Tensor:
+        if self.graph_opt is None:           # single graph: backward -> all-reduce -> update in one launch
+            self.optimizer.sync_hyper()
+            self.graph_fb.replay()
+            return self.loss
         self.graph_fb.replay()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             self.optimizer.all_reduce_grads()

@@ -475,7 +475,7 @@ def ours_arm(args, wl):
     eager = TrainStep(model, crit, opt, device)
     launches_per_step = None
     if graphs:
-        stepper = GraphedTrainStep(model, crit, opt, device)
+        stepper = GraphedTrainStep(model, crit, opt, device, single_graph=args.single_graph)
         l0 = ops.launch_count()
         stepper.capture(host[0], warmup=2)
         launches_per_step = (ops.launch_count() - l0) // 3      # 2 eager warm-ups + 1 capture pass
@@ -499,9 +499,13 @@ def ours_arm(args, wl):
             nxt = [ds.host_batch(0, 0)]
 
             def host_step(i):
-                cur = nxt[0]
+                # launch the step on the batch whose H2D copy is already under way, THEN read the next record from the
+                # file (host memcpy into the pinned ring, overlapping the GPU step), start its H2D copy, and only then
+                # wait for the loss -- what a data-loader thread would do
+                loss = stepper(nxt[0], return_float=False)
                 nxt[0] = ds.host_batch((i + 1) % ring, (i + 1) % 3)
-                return stepper(cur, prefetch=nxt[0])
+                stepper.prefetch(nxt[0])
+                return float(loss.item())
         else:
             def host_step(i):  # public call: pinned host batch -> ONE H2D copy -> replay -> loss; the copy of the next
                 return stepper(packed[i % ring], prefetch=packed[(i + 1) % ring])  # batch overlaps this step
@@ -650,8 +654,9 @@ def ours_arm(args, wl):
                                       "pinned in-memory HostBatch ring",
                         "l2": f"ring of {ring} distinct batches per rank; per-step activations + saved tensors "
                               f"(> 1 GB) exceed the 126 MB L2, no explicit flush",
-                        "allreduce": "one ncclAllReduce of the flat fp32 gradient arena between the two graphs" if world > 1
-                        else "none (1 GPU)"},
+                        "allreduce": ("one ncclAllReduce of the flat fp32 gradient arena " +
+                                      ("captured inside the step graph" if args.single_graph else "between the two graphs"))
+                        if world > 1 else "none (1 GPU)"},
                 "e2e": {"value": mols / (ms_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "roofline": roof, "roofline_dense": roof_dense, "cpu_baseline": cpu,
@@ -748,6 +753,7 @@ def main():
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="weak: graphs per GPU fixed; strong: global batch fixed (default: strong for c4, weak otherwise)")
     ap.add_argument("--ring", type=int, default=0, help="distinct batches per rank (default: the workload's)")
+    ap.add_argument("--single-graph", action="store_true", help="capture backward + all-reduce + update into one CUDA graph")
     ap.add_argument("--shards", action="store_true", help="feed the e2e loop from a pre-collated shard file (default for c4)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload], name=args.workload)
