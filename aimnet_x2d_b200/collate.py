@@ -159,6 +159,9 @@ class GraphIndex:
             r = rp.numpy()
             info = np.stack([tp[:nt], tp[1:nt + 1], r[tp[:nt]], r[tp[1:nt + 1]]], axis=1).astype(np.int32)
             mx = max(mx, int((info[:, 3] - info[:, 2]).max()))
+            # largest tiles first: the kernel deals this list to its persistent CTAs in serpentine order, which balances
+            # the edges per CTA (tiles are independent, any order gives the same result)
+            info = info[np.argsort(-(info[:, 3] - info[:, 2]).astype(np.int64), kind="stable")]
             setattr(self, name, torch.from_numpy(np.ascontiguousarray(info)))
         self.max_tile_edges = mx
 

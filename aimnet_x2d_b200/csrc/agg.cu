@@ -141,6 +141,19 @@ __device__ __forceinline__ unsigned long long agg_gtime() {
       if (dbg_ != nullptr) dbg_[slot] = agg_gtime();                                     \
     }                                                                                    \
   } while (0)
+// Tiles are dealt to the persistent CTAs in SERPENTINE order: round k goes to the CTAs in ascending order when k is even and
+// in descending order when k is odd.  The tile plan lists the tiles by decreasing edge count (collate.refresh_tile_info), so
+// every CTA gets one tile of each size class and the per-CTA (and per-SM) work is balanced: with plain round-robin over
+// tiles in memory order the CTA lifetimes of one C2 launch ranged from 9.7 to 17.5 us (per-CTA %globaltimer stamps,
+// tools/agg_gen3.py; the end time of an SM is 4.5 us + 4.4 ns per edge it was dealt).
+__device__ __forceinline__ int agg_tile_of(int k, int first, int stride) {
+  return k * stride + ((k & 1) ? stride - 1 - first : first);
+}
+__device__ __forceinline__ int agg_my_tiles(int n_tiles, int first, int stride) {
+  const int full = n_tiles / stride, rem = n_tiles - full * stride;
+  const int pos = (full & 1) ? stride - 1 - first : first;
+  return full + (pos < rem ? 1 : 0);
+}
 template <int V>
 __global__ void __launch_bounds__(AGG_CONSUMERS + 32, 2) agg_tiles_kernel(
     const float* __restrict__ x, float* __restrict__ out, int64_t ldo, const int32_t* __restrict__ rowptr,
@@ -152,7 +165,7 @@ __global__ void __launch_bounds__(AGG_CONSUMERS + 32, 2) agg_tiles_kernel(
   constexpr int W4 = 8 * V;
   const uint32_t stage_bytes = x_bytes + rp_bytes + col_bytes;
   const int first = blockIdx.x, stride = gridDim.x;
-  const int n_my = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+  const int n_my = agg_my_tiles(n_tiles, first, stride);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   AGG_STAMP(0);
 
@@ -170,7 +183,7 @@ __global__ void __launch_bounds__(AGG_CONSUMERS + 32, 2) agg_tiles_kernel(
     // ================================================================= producer warp
     for (int base = 0; base < n_my; base += 32) {
       int4 mine = make_int4(0, 0, 0, 0);
-      if (base + lane < n_my) mine = __ldg(tile_info + first + static_cast<int64_t>(base + lane) * stride);
+      if (base + lane < n_my) mine = __ldg(tile_info + agg_tile_of(base + lane, first, stride));
       const int cnt = n_my - base < 32 ? n_my - base : 32;
       for (int j = 0; j < cnt; ++j) {
         const int it = base + j;
@@ -312,7 +325,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW == AGG2_WARPS ? 3 : 1) agg_r
   __shared__ int4 s_info[AGG_STAGES];
   const uint32_t stage_bytes = x_bytes + rp_bytes + col_bytes;
   const int first = blockIdx.x, stride = gridDim.x;
-  const int n_my = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+  const int n_my = agg_my_tiles(n_tiles, first, stride);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int n_cw = NW;                                       // consumer warps; the last warp is the producer
 
@@ -331,7 +344,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW == AGG2_WARPS ? 3 : 1) agg_r
     const uint32_t row_bytes = static_cast<uint32_t>(words) * 4u;
     for (int base = 0; base < n_my; base += 32) {
       int4 mine = make_int4(0, 0, 0, 0);
-      if (base + lane < n_my) mine = __ldg(tile_info + first + static_cast<int64_t>(base + lane) * stride);
+      if (base + lane < n_my) mine = __ldg(tile_info + agg_tile_of(base + lane, first, stride));
       const int cnt = n_my - base < 32 ? n_my - base : 32;
       for (int j = 0; j < cnt; ++j) {
         const int it = base + j;
@@ -494,6 +507,245 @@ static int launch_agg_rows(const void* x, void* out, int64_t ldo, const int32_t*
   return launch_status("ax2d_agg");
 }
 
+// ------------------------------------------------------------------------------------------------ packed-add consumers
+// Third-generation per-edge kernel (bit-exact, CSR order).  The warp-per-row kernel above is bound by instruction issue
+// (SASS: ~14 issue slots per (row, edge) + ~65 per row, 210 per QM9 row; fp32 and bf16 run at the same speed although bf16
+// moves half the bytes).  Blackwell halves the add count:
+//   * fp32: a lane owns 64-bit units (two adjacent columns) lane, lane + 32, ...: one LDS.64 + ONE packed add.rn.f32x2
+//     (SASS FADD2) per unit -- 3 + 3 instead of 5 + 5 instructions per neighbour row of 160 columns, same IEEE sums;
+//   * bf16: a lane owns 32-bit words (two columns): the mixed-precision add.rn.f32.bf16 (SASS FHADD.BF16 with a free
+//     .H0 / .H1 operand selector) adds a bf16 half straight into an fp32 accumulator -- no unpack shifts / masks;
+//   * the tail of a row's edge list runs as ONE predicated batch (no per-edge serial remainder loop);
+//   * rows go round-robin over the consumer warps ACROSS tiles (a 21-row QM9 tile on 8 warps otherwise leaves three warps
+//     idle for a third of every tile).
+template <bool BF16> struct AggAcc;
+template <> struct AggAcc<false> {
+  using unit = unsigned long long;
+  unsigned long long v;
+  __device__ __forceinline__ void zero() { v = 0ull; }
+  __device__ __forceinline__ void add(unit t) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(t)); }
+  __device__ __forceinline__ unit result() const { return v; }
+  static __device__ __forceinline__ unit ldg(const unit* p) {
+    unit r;
+    asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+  }
+  static __device__ __forceinline__ void stg(unit* p, unit w) {
+    asm volatile("st.global.L1::no_allocate.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+  }
+};
+template <> struct AggAcc<true> {
+  using unit = uint32_t;
+  float lo, hi;
+  __device__ __forceinline__ void zero() { lo = 0.f; hi = 0.f; }
+  __device__ __forceinline__ void add(unit w) {
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tadd.rn.f32.bf16 %0, l, %0;\n\tadd.rn.f32.bf16 %1, h, %1;\n\t}"
+        : "+f"(lo), "+f"(hi)
+        : "r"(w));
+  }
+  __device__ __forceinline__ unit result() const { return bf2_pack(lo, hi); }
+  static __device__ __forceinline__ unit ldg(const unit* p) {
+    unit r;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+  }
+  static __device__ __forceinline__ void stg(unit* p, unit w) {
+    asm volatile("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(p), "r"(w) : "memory");
+  }
+};
+
+template <int U, bool BF16, int NW>
+__global__ void __launch_bounds__(32 * (NW + 1), NW == AGG2_WARPS ? 3 : 1) agg_rows3_kernel(
+    const unsigned char* __restrict__ x, typename AggAcc<BF16>::unit* __restrict__ out, int64_t ldo_u,
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const typename AggAcc<BF16>::unit* __restrict__ addend,
+    int64_t lda_u, const int4* __restrict__ tile_info, int n_tiles, int stages, int units, uint32_t x_bytes, uint32_t rp_bytes,
+    uint32_t col_bytes, int dbg_flags) {
+  // units: units per row (fp32: width / 2 64-bit units, bf16: width / 2 32-bit words); U = ceil(units / 32) units per lane
+  using Acc = AggAcc<BF16>;
+  using unit = typename Acc::unit;
+  constexpr int EB = U <= 3 ? 4 : (U <= 6 ? 2 : 1);      // neighbour rows in flight per warp
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[AGG_STAGES], empty[AGG_STAGES];
+  __shared__ int4 s_info[AGG_STAGES];
+  const uint32_t stage_bytes = x_bytes + rp_bytes + col_bytes;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_my = agg_my_tiles(n_tiles, first, stride);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  AGG_STAMP(0);
+  if ((dbg_flags & 4) && threadIdx.x == 0) g_agg_dbg[16 + 2 * blockIdx.x] = agg_gtime();      // development: per-CTA start
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    // ================================================================= producer warp (as in agg_rows_kernel)
+    const uint32_t row_bytes = static_cast<uint32_t>(units) * sizeof(unit);
+    for (int base = 0; base < n_my; base += 32) {
+      int4 mine = make_int4(0, 0, 0, 0);
+      if (base + lane < n_my) mine = __ldg(tile_info + agg_tile_of(base + lane, first, stride));
+      const int cnt = n_my - base < 32 ? n_my - base : 32;
+      for (int j = 0; j < cnt; ++j) {
+        const int it = base + j;
+        int4 inf;
+        inf.x = __shfl_sync(0xffffffffu, mine.x, j);
+        inf.y = __shfl_sync(0xffffffffu, mine.y, j);
+        inf.z = __shfl_sync(0xffffffffu, mine.z, j);
+        inf.w = __shfl_sync(0xffffffffu, mine.w, j);
+        if (lane == 0) {
+          const int s = it % stages;
+          mbar_wait(&empty[s], (static_cast<uint32_t>(it / stages) & 1u) ^ 1u);
+          unsigned char* dst = smem_raw + static_cast<size_t>(s) * stage_bytes;
+          const uint32_t xb = static_cast<uint32_t>(inf.y - inf.x) * row_bytes;
+          const int rs = inf.x & ~3, es = inf.z & ~3;
+          const uint32_t rb = static_cast<uint32_t>((inf.y + 1 - rs + 3) & ~3) * 4;
+          const uint32_t cb = static_cast<uint32_t>((inf.w - es + 3) & ~3) * 4;
+          s_info[s] = inf;
+          mbar_expect_tx(&full[s], xb + rb + cb);
+          const unsigned char* src = x + static_cast<int64_t>(inf.x) * row_bytes;
+          for (uint32_t off = 0; off < xb; off += 16384) {
+            const uint32_t n = xb - off < 16384u ? xb - off : 16384u;
+            bulk_g2s(dst + off, src + off, n, &full[s]);
+          }
+          bulk_g2s(dst + x_bytes, rowptr + rs, rb, &full[s]);
+          if (cb > 0) bulk_g2s(dst + x_bytes + rp_bytes, col + es, cb, &full[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // =================================================================== consumers: one warp per row
+  const bool on_last = lane + 32 * (U - 1) < units;       // only the last unit slot of a lane can fall off the row
+  AGG_STAMP(1);
+  int rot = 0;                                            // rows handed out so far, modulo NW (identical in every warp)
+  for (int it = 0; it < n_my; ++it) {
+    const int s = it % stages;
+    mbar_wait(&full[s], static_cast<uint32_t>(it / stages) & 1u);
+    if (it < 6) AGG_STAMP(2 + 2 * it);
+    const int4 inf = s_info[s];
+    const unsigned char* st = smem_raw + static_cast<size_t>(s) * stage_bytes;
+    const unit* xs = reinterpret_cast<const unit*>(st) + lane;
+    const int32_t* rp = reinterpret_cast<const int32_t*>(st + x_bytes) - (inf.x & ~3);             // indexed by global row
+    const int32_t* cs = reinterpret_cast<const int32_t*>(st + x_bytes + rp_bytes) - (inf.z & ~3);  // indexed by global edge
+    int mine = warp - rot;
+    if (mine < 0) mine += NW;
+    rot = (rot + (inf.y - inf.x)) % NW;
+    for (int r = inf.x + mine; r < inf.y; r += NW) {
+      const int beg = rp[r], end = rp[r + 1];
+      unit addw[U];
+      if (addend != nullptr) {
+        const unit* a = addend + static_cast<int64_t>(r) * lda_u + lane;
+#pragma unroll
+        for (int u = 0; u < U; ++u) addw[u] = (u + 1 < U || on_last) ? Acc::ldg(a + 32 * u) : unit(0);
+      }
+      Acc acc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u].zero();
+      for (int k = beg; k < ((dbg_flags & 1) ? beg : end); k += 32) {
+        const int cnt = end - k < 32 ? end - k : 32;
+        const int my_off = lane < cnt ? (cs[k + lane] - inf.x) * units : 0;       // one coalesced index load per 32 edges
+        int j = 0;
+        for (; j + EB <= cnt; j += EB) {
+          unit t[EB][U];
+#pragma unroll
+          for (int e = 0; e < EB; ++e) {
+            const unit* row = xs + __shfl_sync(0xffffffffu, my_off, j + e);
+#pragma unroll
+            for (int u = 0; u < U; ++u) t[e][u] = (u + 1 < U || on_last) ? row[32 * u] : unit(0);
+          }
+#pragma unroll
+          for (int e = 0; e < EB; ++e)
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc[u].add(t[e][u]);
+        }
+        if (EB > 1 && j < cnt) {
+          // the remainder as one batch: warp-uniform predicates, the loads of all remaining rows before the first add
+          unit t[EB][U];
+#pragma unroll
+          for (int e = 0; e + 1 < EB; ++e) {
+            const unit* row = xs + __shfl_sync(0xffffffffu, my_off, (j + e) & 31);
+            if (j + e < cnt) {
+#pragma unroll
+              for (int u = 0; u < U; ++u) t[e][u] = (u + 1 < U || on_last) ? row[32 * u] : unit(0);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e + 1 < EB; ++e)
+            if (j + e < cnt) {
+#pragma unroll
+              for (int u = 0; u < U; ++u) acc[u].add(t[e][u]);
+            }
+        }
+      }
+      if (addend != nullptr) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[u].add(addw[u]);
+      }
+      unit* o = out + static_cast<int64_t>(r) * ldo_u + lane;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if ((u + 1 < U || on_last) && !(dbg_flags & 2)) Acc::stg(o + 32 * u, acc[u].result());
+    }
+    __syncwarp();
+    if (it < 6) AGG_STAMP(3 + 2 * it);
+    if (lane == 0) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+    }
+  }
+  AGG_STAMP(15);
+  if ((dbg_flags & 4) && threadIdx.x == 0) g_agg_dbg[17 + 2 * blockIdx.x] = agg_gtime();      // ... and end (consumer warp 0)
+}
+
+template <int U, bool BF16>
+static int launch_agg_rows3(const void* x, void* out, int64_t ldo, const int32_t* rowptr, const int32_t* col, const void* addend,
+                            int64_t ld_addend, const int32_t* tile_info, int64_t n_tiles, int max_tile_rows, int max_tile_edges,
+                            int width, cudaStream_t st) {
+  using unit = typename AggAcc<BF16>::unit;
+  const int esz = BF16 ? 2 : 4;
+  const int units = width / 2;                                   // two columns per unit in both types
+  const size_t xb = (static_cast<size_t>(max_tile_rows) * width * esz + 15) / 16 * 16;
+  const size_t rb = (static_cast<size_t>(max_tile_rows) + 8) * 4 / 16 * 16 + 16;
+  const size_t cb = (static_cast<size_t>(max_tile_edges) + 8) * 4 / 16 * 16 + 16;
+  const size_t stage = xb + rb + cb;
+  if (stage > 220 * 1024) {
+    set_error("ax2d_agg: tile of %d rows / %d edges needs %zu bytes of shared memory", max_tile_rows, max_tile_edges, stage);
+    return AX2D_ERR_UNSUPPORTED;
+  }
+  int ctas_per_sm = 3;
+  while (ctas_per_sm > 1 && (220 * 1024 / ctas_per_sm) / stage < 3) --ctas_per_sm;
+  if (g_agg_debug_ctas > 0 && g_agg_debug_ctas <= 3) ctas_per_sm = g_agg_debug_ctas;
+  int stages = static_cast<int>((220 * 1024 / ctas_per_sm) / stage);
+  stages = stages > AGG_STAGES ? AGG_STAGES : (stages < 1 ? 1 : stages);
+  if (g_agg_debug_stages > 0 && g_agg_debug_stages <= stages) stages = g_agg_debug_stages;
+  const size_t smem = stage * stages;
+  const bool wide = ctas_per_sm == 1;
+  static size_t configured[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > configured[wide]) {
+    if (wide) cudaFuncSetAttribute(agg_rows3_kernel<U, BF16, AGG2_MAX_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    else cudaFuncSetAttribute(agg_rows3_kernel<U, BF16, AGG2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured[wide] = smem;
+  }
+  int64_t grid = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
+  grid = grid > n_tiles ? n_tiles : grid;
+  if (wide)
+    agg_rows3_kernel<U, BF16, AGG2_MAX_WARPS><<<static_cast<unsigned>(grid), 32 * (AGG2_MAX_WARPS + 1), smem, st>>>(
+        static_cast<const unsigned char*>(x), static_cast<unit*>(out), ldo / 2, rowptr, col, static_cast<const unit*>(addend),
+        ld_addend / 2, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles), stages, units,
+        static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb), g_agg_debug_flags);
+  else
+    agg_rows3_kernel<U, BF16, AGG2_WARPS><<<static_cast<unsigned>(grid), 32 * (AGG2_WARPS + 1), smem, st>>>(
+        static_cast<const unsigned char*>(x), static_cast<unit*>(out), ldo / 2, rowptr, col, static_cast<const unit*>(addend),
+        ld_addend / 2, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles), stages, units,
+        static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb), g_agg_debug_flags);
+  return launch_status("ax2d_agg");
+}
+
 // ------------------------------------------------------------------------------------------------ tensor-core tiles
 // Third formulation of the tile kernel: the gather-reduce of a whole-molecule tile IS a small dense product
 //     out_tile[R, W] = A_tile[R, R] * x_tile[R, W],        A[r, c] = 1 iff the tile holds the edge (target r, source c),
@@ -540,7 +792,7 @@ __global__ void __launch_bounds__(AGG3_THREADS + 32) agg_mma_kernel(
   uint16_t* As = reinterpret_cast<uint16_t*>(work);                                      // [rpad][SA]
   uint16_t* Xp = As + static_cast<size_t>(rpad) * SA;                                     // [P][rpad][SX]
   const int first = blockIdx.x, stride = gridDim.x;
-  const int n_my = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+  const int n_my = agg_my_tiles(n_tiles, first, stride);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   AGG_STAMP(0);
@@ -558,7 +810,7 @@ __global__ void __launch_bounds__(AGG3_THREADS + 32) agg_mma_kernel(
     const uint32_t row_bytes = static_cast<uint32_t>(width) * (BF16 ? 2u : 4u);
     for (int base = 0; base < n_my; base += 32) {
       int4 mine = make_int4(0, 0, 0, 0);
-      if (base + lane < n_my) mine = __ldg(tile_info + first + static_cast<int64_t>(base + lane) * stride);
+      if (base + lane < n_my) mine = __ldg(tile_info + agg_tile_of(base + lane, first, stride));
       const int cnt = n_my - base < 32 ? n_my - base : 32;
       for (int j = 0; j < cnt; ++j) {
         const int it = base + j;
@@ -777,7 +1029,7 @@ __global__ void __launch_bounds__(AGG_CONSUMERS + 32, 2) agg_tiles_bf16_kernel(
   constexpr int U = 4 * V;                      // 16-byte units per row
   const uint32_t stage_bytes = x_bytes + rp_bytes + col_bytes;
   const int first = blockIdx.x, stride = gridDim.x;
-  const int n_my = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+  const int n_my = agg_my_tiles(n_tiles, first, stride);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -793,7 +1045,7 @@ __global__ void __launch_bounds__(AGG_CONSUMERS + 32, 2) agg_tiles_bf16_kernel(
     // ================================================================= producer warp (as in agg_tiles_kernel)
     for (int base = 0; base < n_my; base += 32) {
       int4 mine = make_int4(0, 0, 0, 0);
-      if (base + lane < n_my) mine = __ldg(tile_info + first + static_cast<int64_t>(base + lane) * stride);
+      if (base + lane < n_my) mine = __ldg(tile_info + agg_tile_of(base + lane, first, stride));
       const int cnt = n_my - base < 32 ? n_my - base : 32;
       for (int j = 0; j < cnt; ++j) {
         const int it = base + j;
@@ -1017,9 +1269,11 @@ static int launch_agg(const float* x, int64_t ldx, float* out, int64_t ldo, int6
 
 }  // namespace ax2d
 
-// development aid (not part of include/ax2d.h): CTAs per SM / stages of the warp-per-row kernel (0 = automatic) and which
-// per-edge kernel runs: 0 = first generation (8 / 4 lanes per row) for both types, 1 (default) = first generation for fp32
-// (same speed as the warp-per-row kernel on B200, measured) and warp-per-row for bf16 (1.4x faster), 2 = warp-per-row for both
+// development aid (not part of include/ax2d.h): CTAs per SM / stages of the warp-per-row kernels (0 = automatic) and which
+// per-edge kernel runs (all of them bit-identical): 0 = first generation (8 / 4 lanes per row) for both types, 1 (default) =
+// first generation for fp32 (the fp32 kernels are all bound by the shared-memory pipe and run at the same speed on B200,
+// measured) and the packed-add warp-per-row kernel for bf16 (1.15-1.25x faster than the second generation, 1.7x than the
+// first), 2 = second generation (warp per row) for both, 3 = packed-add kernel for both
 extern "C" void ax2d_debug_agg_config(int ctas_per_sm, int stages, int use_rows_kernel) {
   ax2d::g_agg_debug_ctas = ctas_per_sm;
   ax2d::g_agg_debug_stages = stages & 0xff;
@@ -1102,7 +1356,9 @@ extern "C" int ax2d_agg(const void* x, int64_t ldx, int64_t n_src_rows, void* ou
       AX2D_CHECK_ALIGN(rowptr);
       AX2D_CHECK_ALIGN(col);
 #define AX2D_AGG16_CASE(V) \
-  case V: return g_agg_use_rows \
+  case V: return (g_agg_use_rows == 3 || g_agg_use_rows == 1) \
+      ? launch_agg_rows3<(V + 1) / 2, true>(xh, oh, ldo, rowptr, col, ah, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, width, st16) \
+      : g_agg_use_rows \
       ? launch_agg_rows<(V + 1) / 2, true>(xh, oh, ldo, rowptr, col, ah, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, width, st16) \
       : launch_agg_bf16<V>(xh, oh, ldo, rowptr, col, ah, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, st16);
       switch (width / 32) {
@@ -1146,8 +1402,15 @@ extern "C" int ax2d_agg(const void* x, int64_t ldx, int64_t n_src_rows, void* ou
         xf, ldx, of, ldo, rowptr, col, af, ld_addend, n_out_rows, width / 4);
     return launch_status("ax2d_agg");
   }
+  // fp32, default configuration: small tiles (QM9-sized molecules, three CTAs per SM) run at the same speed in every
+  // generation (shared-memory pipe); LARGE tiles (drug-like molecules: one CTA with 24 consumer warps per SM) are 1.3x
+  // faster in the packed-add kernel than in the first generation (100 vs 132 us on 2048 drug-like molecules x 4 hops)
+  const bool big_tiles = tile_info != nullptr &&
+      (220 * 1024 / 3) / (static_cast<size_t>(max_tile_rows) * width * 4 + static_cast<size_t>(max_tile_rows + max_tile_edges) * 4 + 64) < 3;
 #define AX2D_AGG_CASE(V) \
-  case V: return (tile_info != nullptr && g_agg_use_rows == 2) \
+  case V: return (tile_info != nullptr && (g_agg_use_rows == 3 || (g_agg_use_rows == 1 && big_tiles))) \
+      ? launch_agg_rows3<(V + 1) / 2, false>(xf, of, ldo, rowptr, col, af, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, width, st) \
+      : (tile_info != nullptr && g_agg_use_rows == 2) \
       ? launch_agg_rows<V, false>(xf, of, ldo, rowptr, col, af, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, width, st) \
       : launch_agg<V>(xf, ldx, of, ldo, n_out_rows, rowptr, col, af, ld_addend, tile_info, n_tiles, max_tile_rows, max_tile_edges, st);
   switch (width / 32) {

@@ -458,6 +458,12 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_bwd_kernel(
           float4 wv[NH];
 #pragma unroll
           for (int h = 0; h < NH; ++h) wv[h] = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(h) * F) + c);
+          // two-level sums: dz sums to zero within a molecule, so sum_i dz[h,i] x_i cancels; the rows of this chunk go
+          // into a local accumulator that is added to the CTA's running sum once (a few molecule-sized terms per CTA
+          // instead of one add per atom into an ever larger partial sum)
+          float4 loc[NH];
+#pragma unroll
+          for (int h = 0; h < NH; ++h) loc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int i = 0; i < rows; ++i) {
             const float4 xv = reinterpret_cast<const float4*>(xs + static_cast<size_t>(i) * F)[c];
             const float cf = coef[i];
@@ -466,13 +472,18 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_bwd_kernel(
             for (int h = 0; h < NH; ++h) {
               const float dz = dzs[h * CH + i];
               t.x += dz * wv[h].x; t.y += dz * wv[h].y; t.z += dz * wv[h].z; t.w += dz * wv[h].w;
-              gw_acc[h][j].x += dz * xv.x; gw_acc[h][j].y += dz * xv.y;
-              gw_acc[h][j].z += dz * xv.z; gw_acc[h][j].w += dz * xv.w;
+              loc[h].x += dz * xv.x; loc[h].y += dz * xv.y;
+              loc[h].z += dz * xv.z; loc[h].w += dz * xv.w;
             }
             float4 o;
             o.x = cf * gv.x + invT * t.x; o.y = cf * gv.y + invT * t.y;
             o.z = cf * gv.z + invT * t.z; o.w = cf * gv.w + invT * t.w;
             reinterpret_cast<float4*>(gx + static_cast<int64_t>(n0 + c0 + i) * ldgx)[c] = o;
+          }
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            gw_acc[h][j].x += loc[h].x; gw_acc[h][j].y += loc[h].y;
+            gw_acc[h][j].z += loc[h].z; gw_acc[h][j].w += loc[h].w;
           }
         }
       }
@@ -499,22 +510,24 @@ __global__ void __launch_bounds__(256) attn_pool_bwd_reduce_kernel(const float* 
                                                                    int heads, const float* __restrict__ temperature,
                                                                    float* __restrict__ gw, float* __restrict__ gb,
                                                                    float* __restrict__ gT) {
-  __shared__ float red[8][32];
+  // (the per-CTA partials are summed in double: a few hundred terms per entry, and these sums cancel)
+  __shared__ double red[8][32];
   const int stride = pool_partial_stride(heads, F);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   const int total = heads * F + heads + 1;
-  float s = 0.f;
+  double sd = 0.0;
   if (i < total) {
 #pragma unroll 4
-    for (int p = warp; p < n_part; p += 8) s += __ldg(partials + static_cast<size_t>(p) * stride + i);
+    for (int p = warp; p < n_part; p += 8) sd += static_cast<double>(__ldg(partials + static_cast<size_t>(p) * stride + i));
   }
-  red[warp][lane] = s;
+  red[warp][lane] = sd;
   __syncthreads();
   if (warp != 0 || i >= total) return;
-  s = red[0][lane];
+  sd = red[0][lane];
 #pragma unroll
-  for (int w = 1; w < 8; ++w) s += red[w][lane];
+  for (int w = 1; w < 8; ++w) sd += red[w][lane];
+  const float s = static_cast<float>(sd);
   const float invT = 1.f / __ldg(temperature);
   if (i < heads * F) gw[i] = s * invT;
   else if (i < heads * F + heads) gb[i - heads * F] = s * invT;
