@@ -685,6 +685,28 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const _
 
   if (warp == 0) {
     // whole warp, elected issue (see "Warp-collective issue" above)
+    // The segment / column of every 32-column chunk is fixed for the CTA: resolved once, not per k-block (the producer's
+    // issue path is on the critical path of the three-stage ring: nine find_seg + TMA issues per k-block measured ~0.45 us).
+    // (Requesting the k-blocks beyond the ring into L2 ahead of time with cp.async.bulk.prefetch.tensor was measured and
+    // made the kernel SLOWER, 30 -> 38 us on 160 x 160: nine more issues per k-block on this warp, tools/bench_wgrad.py.)
+    constexpr int A_CH = TC_BM / 32, B_CH = WG_MAX_BN / 32;
+    const CUtensorMap* amap[A_CH];
+    const CUtensorMap* bmap[B_CH];
+    int acol[A_CH], bcol[B_CH];
+#pragma unroll
+    for (int c = 0; c < A_CH; ++c) {                // columns beyond the last segment: fully out-of-bounds box -> zeros
+      const int o = m0 + 32 * c;
+      const int sg = find_seg(g.a_start, g.a_nseg, o);
+      amap[c] = &maps.a[sg];
+      acol[c] = o - g.a_start[sg];
+    }
+#pragma unroll
+    for (int c = 0; c < B_CH; ++c) {
+      const int i = n0 + 32 * c;
+      const int sg = find_seg(g.b_start, g.b_nseg, i);
+      bmap[c] = &maps.b[sg];
+      bcol[c] = i - g.b_start[sg];
+    }
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
@@ -693,17 +715,12 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const _
       mbar_expect_tx_w(&full_bar[s], a_bytes + b_bytes);
       const int row = (kb0 + it) * WG_KB;
       unsigned char* dst = stage_a(s);
-      for (int c = 0; c < a_chunks; ++c) {          // columns beyond the last segment: fully out-of-bounds box -> zeros
-        const int o = m0 + 32 * c;
-        const int sg = find_seg(g.a_start, g.a_nseg, o);
-        tma_load_2d_w(dst + c * WG_CHUNK_BYTES, &maps.a[sg], &full_bar[s], o - g.a_start[sg], row);
-      }
+#pragma unroll
+      for (int c = 0; c < A_CH; ++c) tma_load_2d_w(dst + c * WG_CHUNK_BYTES, amap[c], &full_bar[s], acol[c], row);
       dst = stage_bhi(s);
-      for (int c = 0; c < b_chunks; ++c) {
-        const int i = n0 + 32 * c;
-        const int sg = find_seg(g.b_start, g.b_nseg, i);
-        tma_load_2d_w(dst + c * WG_CHUNK_BYTES, &maps.b[sg], &full_bar[s], i - g.b_start[sg], row);
-      }
+#pragma unroll
+      for (int c = 0; c < B_CH; ++c)
+        if (c < b_chunks) tma_load_2d_w(dst + c * WG_CHUNK_BYTES, bmap[c], &full_bar[s], bcol[c], row);
     }
   } else if (warp == 1) {
     // D = F32, A = B = TF32, A K-major from TMEM, B MN-major (bit 16) from shared memory, M = 128, N = BN

@@ -170,6 +170,17 @@ __device__ __forceinline__ void tma_load_2d_w(void* dst, const CUtensorMap* map,
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+// L2 prefetch of a 2-D tensor-map box (no shared-memory destination, no barrier): warp-collective, elected issue
+__device__ __forceinline__ void tma_prefetch_2d_w(const CUtensorMap* map, int c_inner, int c_outer) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n\t"
+      "}\n" ::"l"(reinterpret_cast<uint64_t>(map)),
+      "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx_w(uint64_t* bar, uint32_t bytes) {
   asm volatile(
       "{\n\t"

@@ -607,6 +607,13 @@ def ours_arm(args, wl):
             gi0 = host[0].graph_index
             fwd = ops.agg_bytes(gi0.num_atoms, gi0.num_atoms, gi0.num_edges, D, False, es)
             bwd = ops.agg_bytes(gi0.num_atoms, gi0.num_atoms, gi0.num_edges, D, True, es)
+            if wl["name"] == "c2":
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload's size, one ncu --set full
+                # capture per round (profiles/r2h_agg_f32_summary.txt): 25.6 MB forward, 51.0 MB backward with the fused
+                # addend -- below the algorithmic bytes because the 24 MB output stays in the 126 MB L2 (no re-reads)
+                roof["traffic"] = 0.5 * (25.603e6 + 50.996e6)
+                roof["traffic_note"] = ("ncu --set full capture of this round (profiles/r2h_agg_f32_summary.txt), mean of the "
+                                        "forward (25.6 MB) and backward (51.0 MB) launch: the output stays in L2")
             roof["achieved_padded_width"] = ach
             roof["in_step_avg_launch_us"] = a["ms_avg"] * 1e3          # in-graph event pair minus its calibrated overhead
             roof["in_step_bracket_overhead_us"] = ovh_us
@@ -637,6 +644,11 @@ def ours_arm(args, wl):
                           "share_of_step": dense_ms / kernel_ms, "share_source": "in-graph event pairs of this run",
                           "launches_per_step": sum(ks[k]["launches"] for k in dense),
                           "hbm_GBs_over_dense_launches": sum(ks[k]["bytes_total"] for k in dense) / (dense_ms * 1e-3) / 1e9}
+            if not bf16:
+                # the MMAs actually issued (three tf32 terms per useful product) against the same peak
+                roof_dense["issued_mma_frac"] = 3.0 * tf / tpeak
+            roof_dense["note"] = ("the N x 160 products are HBM-bound (72 MB per 160 -> 160 launch at 0.48 of the measured HBM rate, "
+                                  "tensor floor 8.4 us of 23 us), the wide ones tensor-bound: DESIGN.md section 5")
         h2d = packed[0].nbytes() if graphs else host[0].nbytes()
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
