@@ -41,6 +41,11 @@ _SIGNATURES = {
     "ax2d_host_tile_plan": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                     C.POINTER(c_int64), C.POINTER(c_int64), C.POINTER(C.c_int32)]),
     "ax2d_host_shell_edges": (c_int64, [c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64]),
+    "ax2d_host_shell_csr": (c_int64, [c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64]),
+    "ax2d_shell_csr_count": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
+    "ax2d_shell_csr_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "ax2d_agg": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                          c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "ax2d_agg_tiles_mma_supported": (c_int, [c_int, c_int, c_int, c_int]),

@@ -30,6 +30,69 @@ def _np(t, dtype=None) -> np.ndarray:
     return a if dtype is None else a.astype(dtype, copy=False)
 
 
+def shell_csr(atom_counts, bonds, num_hops: int, device=None):
+    """Shell-edge BFS (features.py:82-150) of a batch of molecules straight to the CSR pair of the aggregation kernels.
+    ``atom_counts`` [B]; ``bonds``: per molecule an [nb, 2] array of molecule-local atom indices (undirected, each bond
+    once).  Returns int32 tensors (rowptr [N + 1 + slack], col [E + slack], col_t [E + slack]): rows of ``col`` = sources
+    of a target in the reference's stable edge order (hop-major, BFS discovery order), rows of ``col_t`` = targets of a
+    source (hop-major, ascending); both share ``rowptr``.  ``device``: a CUDA device -> built on the GPU and returned there
+    (molecules of at most 256 atoms); None -> host."""
+    lib = _lib.load()
+    counts = _np(atom_counts, np.int64).reshape(-1)
+    B = int(counts.shape[0])
+    if len(bonds) != B:
+        raise ValueError("one bond array per molecule")
+    atom_ptr = np.zeros(B + 1, dtype=np.int64)
+    atom_ptr[1:] = np.cumsum(counts)
+    bond_ptr = np.zeros(B + 1, dtype=np.int64)
+    bond_ptr[1:] = np.cumsum([int(np.asarray(b).reshape(-1, 2).shape[0]) for b in bonds])
+    flat = (np.ascontiguousarray(np.concatenate([np.asarray(b).reshape(-1, 2) for b in bonds], 0).astype(np.int32))
+            if B and bond_ptr[-1] else np.zeros((0, 2), np.int32))
+    N = int(atom_ptr[-1])
+    slack = GraphIndex.INDEX_SLACK
+    if device is None:
+        rowptr = np.zeros(N + 1 + slack, dtype=np.int32)
+        E = int(lib.ax2d_host_shell_csr(B, _ptr(atom_ptr), _ptr(bond_ptr), _ptr(flat), int(num_hops), _ptr(rowptr), None, None, 0))
+        if E < 0:
+            _lib.check(E, "ax2d_host_shell_csr")
+        col = np.zeros(max(E, 1) + slack, dtype=np.int32)
+        col_t = np.zeros(max(E, 1) + slack, dtype=np.int32)
+        E2 = int(lib.ax2d_host_shell_csr(B, _ptr(atom_ptr), _ptr(bond_ptr), _ptr(flat), int(num_hops), _ptr(rowptr), _ptr(col),
+                                         _ptr(col_t), E))
+        if E2 != E:
+            _lib.check(E2 if E2 < 0 else -1, "ax2d_host_shell_csr")
+        rowptr[N + 1:] = E
+        return torch.from_numpy(rowptr), torch.from_numpy(col), torch.from_numpy(col_t)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("shell_csr: device must be a CUDA device (or None for the host path)")
+    max_atoms = int(counts.max()) if B else 0
+    if max_atoms > 256:
+        raise RuntimeError(f"shell_csr: a molecule of {max_atoms} atoms exceeds the device kernel's 256; use device=None")
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        d_atom = torch.from_numpy(atom_ptr.astype(np.int32)).to(dev)
+        d_bond = torch.from_numpy(bond_ptr.astype(np.int32)).to(dev)
+        d_flat = torch.from_numpy(flat).to(dev) if flat.size else torch.zeros((1, 2), dtype=torch.int32, device=dev)
+        rowptr = torch.zeros(N + 1 + slack, dtype=torch.int32, device=dev)
+        work = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(lib.ax2d_shell_csr_count(p(d_atom), p(d_bond), p(d_flat), B, N, max_atoms, int(num_hops), p(rowptr), p(work),
+                                            p(err), stream), "ax2d_shell_csr_count")
+        E, bad = int(rowptr[N].item()), int(err.item())
+        if bad:
+            raise RuntimeError(f"ax2d_shell_csr_count: inconsistent input (code {bad})")
+        col = torch.zeros(max(E, 1) + slack, dtype=torch.int32, device=dev)
+        col_t = torch.zeros(max(E, 1) + slack, dtype=torch.int32, device=dev)
+        _lib.check(lib.ax2d_shell_csr_fill(p(d_atom), p(d_bond), p(d_flat), B, max_atoms, int(num_hops), p(rowptr), p(col),
+                                           p(col_t), p(err), stream), "ax2d_shell_csr_fill")
+        if int(err.item()):
+            raise RuntimeError(f"ax2d_shell_csr_fill: inconsistent input (code {int(err.item())})")
+        rowptr[N + 1:] = E
+    return rowptr, col, col_t
+
+
 class GraphIndex:
     """Integer artefacts of one batch (all int32, built once at collation):
 
@@ -65,10 +128,29 @@ class GraphIndex:
 
     # ------------------------------------------------------------------ construction (host, exact integers)
     @staticmethod
+    def from_bonds(atom_counts, bonds, num_hops: int, atom_features: Optional[Dict[str, torch.Tensor]] = None,
+                   feature_sizes: Optional[Dict[str, int]] = None, tetra=None, cis=None, trans=None,
+                   tile_rows: int = DEFAULT_TILE_ROWS, device=None) -> "GraphIndex":
+        """Featurisation + collation of the graph structure in one step (SURVEY f-1): the shell-edge BFS
+        (features.py:82-150) emits the CSR pair directly from the molecules' bond lists -- on the host
+        (``ax2d_host_shell_csr``) or, with ``device``, on the GPU (``ax2d_shell_csr_count`` / ``_fill``) -- so no edge
+        list is built and nothing is sorted.  ``atom_counts`` [B]; ``bonds``: one [nb, 2] array of molecule-local atom
+        indices per molecule.  Bit-identical to ``build`` over the reference's collated edge list."""
+        counts = _np(atom_counts, np.int64).reshape(-1)
+        B = int(counts.shape[0])
+        rowptr, col, col_t = shell_csr(counts, bonds, num_hops, device=device)
+        bi = np.repeat(np.arange(B, dtype=np.int64), counts)
+        return GraphIndex.build(None, bi, B, num_hops, atom_features, feature_sizes, tetra, cis, trans, tile_rows,
+                                csr=(rowptr.cpu().numpy(), col.cpu().numpy(), col_t.cpu().numpy()))
+
+    @staticmethod
     def build(edges, batch_indices, num_graphs: int, num_hops: int,
               atom_features: Optional[Dict[str, torch.Tensor]] = None,
               feature_sizes: Optional[Dict[str, int]] = None,
-              tetra=None, cis=None, trans=None, tile_rows: int = DEFAULT_TILE_ROWS) -> "GraphIndex":
+              tetra=None, cis=None, trans=None, tile_rows: int = DEFAULT_TILE_ROWS, csr=None) -> "GraphIndex":
+        """``csr``: (rowptr [N+1+slack], col [E+slack], col_t [E+slack]) int32 arrays from ``shell_csr`` instead of
+        ``edges`` (shell relations are symmetric: both CSRs share rowptr; the edge list is duplicate-free and never
+        leaves a molecule by construction)."""
         lib = _lib.load()
         gi = GraphIndex()
         bi = _np(batch_indices, np.int64)
@@ -82,6 +164,8 @@ class GraphIndex:
             seg[1:] = np.cumsum(np.bincount(bi, minlength=B)).astype(np.int32)
         gi.max_seg = int(np.max(np.diff(seg))) if B else 0
 
+        if csr is not None and edges is not None:
+            raise ValueError("GraphIndex.build: pass either edges or csr")
         if edges is None:
             e_np = np.empty((0, 2), dtype=np.int64)
         elif isinstance(edges, torch.Tensor):
@@ -91,15 +175,17 @@ class GraphIndex:
         if e_np.dtype != np.int64:
             e_np = e_np.astype(np.int64)
         E = int(e_np.shape[0]) if e_np.ndim == 2 else 0
+        if csr is not None:
+            E = int(csr[0][N])
         gi.num_edges = E
-        if E:
+        if E and csr is None:
             tmax = int(e_np[:, 0].max())
             if tmax >= max(num_hops, 1) * N or int(e_np.min()) < 0:
                 raise ValueError("edge index out of range for message_passing (target must be < num_hops * N)")
             gi.collapsed = tmax < N
         R = N if gi.collapsed else num_hops * N
         gi.num_rows = R
-        if E:
+        if E and csr is None:
             keys = e_np[:, 0].astype(np.int64) * max(N, 1) + (e_np[:, 1].astype(np.int64) % max(N, 1))
             gi.unique_edges = bool(np.unique(keys).size == E)
         else:
@@ -109,7 +195,12 @@ class GraphIndex:
         col = np.zeros(max(E, 1) + slack, dtype=np.int32)
         rowptr_t = np.zeros(N + 1 + slack, dtype=np.int32)
         col_t = np.zeros(max(E, 1) + slack, dtype=np.int32)
-        if E:
+        if csr is not None:
+            rowptr[: N + 1] = csr[0][: N + 1]
+            rowptr_t[: N + 1] = csr[0][: N + 1]
+            col[:E] = csr[1][:E]
+            col_t[:E] = csr[2][:E]
+        elif E:
             se, sc = (s // 8 for s in e_np.strides)
             _lib.check(lib.ax2d_host_csr_build(_ptr(e_np), E, se, sc, N, R, 0, _ptr(rowptr), _ptr(col), None),
                        "ax2d_host_csr_build")

@@ -185,3 +185,87 @@ extern "C" int64_t ax2d_host_shell_edges(int64_t B, const int64_t* atom_ptr, con
   }
   return total;
 }
+
+// f-1: the shell-edge BFS emitting the CSR the aggregation kernels consume DIRECTLY (no edge list, no sort).
+// For a target row u the reference's stable edge order is hop-major and, inside a hop, the BFS discovery order of u's
+// frontier (features.py:97-150); the transposed row of a source w is hop-major with ASCENDING targets (the frontier lists
+// are grouped by ascending origin).  Shell relations are symmetric (distance(u, w) == distance(w, u)), so both CSRs share
+// one rowptr.  Equal, bit for bit, to ax2d_host_csr_build over the edge list of ax2d_host_shell_edges.
+extern "C" int64_t ax2d_host_shell_csr(int64_t B, const int64_t* atom_ptr, const int64_t* bond_ptr, const int32_t* bonds,
+                                       int num_hops, int32_t* rowptr, int32_t* col, int32_t* col_t, int64_t capacity) {
+  using namespace ax2d;
+  if (B < 0 || num_hops < 1 || atom_ptr == nullptr || bond_ptr == nullptr || rowptr == nullptr) {
+    set_error("ax2d_host_shell_csr: bad arguments");
+    return AX2D_ERR_ARG;
+  }
+  const bool fill = col != nullptr;
+  if (fill && col_t == nullptr) {
+    set_error("ax2d_host_shell_csr: col and col_t go together");
+    return AX2D_ERR_ARG;
+  }
+  int64_t total = 0;
+  rowptr[atom_ptr[0]] = 0;
+  std::vector<std::vector<int32_t>> nbr;
+  std::vector<int32_t> dist, order, next_order, hop_end;
+  for (int64_t g = 0; g < B; ++g) {
+    const int64_t n = atom_ptr[g + 1] - atom_ptr[g];
+    const int64_t off = atom_ptr[g];
+    if (n >= (1ll << 30) || off + n >= (1ll << 31)) {
+      set_error("ax2d_host_shell_csr: int32 index overflow");
+      return AX2D_ERR_ARG;
+    }
+    nbr.assign(static_cast<size_t>(n), {});
+    std::vector<uint8_t> adj(static_cast<size_t>(n * n), 0);
+    for (int64_t b = bond_ptr[g]; b < bond_ptr[g + 1]; ++b) {
+      const int32_t a0 = bonds[2 * b], a1 = bonds[2 * b + 1];
+      if (a0 < 0 || a1 < 0 || a0 >= n || a1 >= n) {
+        set_error("ax2d_host_shell_csr: bond %lld of molecule %lld out of range", (long long)b, (long long)g);
+        return AX2D_ERR_ARG;
+      }
+      if (a0 == a1) continue;
+      adj[a0 * n + a1] = adj[a1 * n + a0] = 1;
+    }
+    for (int64_t v = 0; v < n; ++v)
+      for (int64_t w = 0; w < n; ++w)
+        if (adj[v * n + w]) nbr[v].push_back(static_cast<int32_t>(w));
+    dist.assign(static_cast<size_t>(n), 0);
+    for (int64_t u = 0; u < n; ++u) {
+      // BFS from u in the reference's discovery order: hop h + 1 walks hop h in order, neighbours ascending
+      std::fill(dist.begin(), dist.end(), -1);
+      dist[u] = 0;
+      order.assign(nbr[u].begin(), nbr[u].end());
+      for (int32_t w : order) dist[w] = 1;
+      const int64_t row0 = total;
+      for (int h = 1; h <= num_hops && !order.empty(); ++h) {
+        if (fill) {
+          if (total + static_cast<int64_t>(order.size()) > capacity) {
+            set_error("ax2d_host_shell_csr: capacity %lld too small", (long long)capacity);
+            return AX2D_ERR_ARG;
+          }
+          for (size_t i = 0; i < order.size(); ++i) col[total + i] = static_cast<int32_t>(order[i] + off);
+          // transposed row of u: the same hop set with ascending targets
+          size_t k = 0;
+          for (int64_t w = 0; w < n; ++w)
+            if (dist[w] == h) col_t[total + k++] = static_cast<int32_t>(w + off);
+        }
+        total += static_cast<int64_t>(order.size());
+        if (h == num_hops) break;
+        next_order.clear();
+        for (int32_t v : order)
+          for (int32_t w : nbr[v])
+            if (dist[w] < 0) {
+              dist[w] = h + 1;
+              next_order.push_back(w);
+            }
+        order.swap(next_order);
+      }
+      (void)row0;
+      rowptr[off + u + 1] = static_cast<int32_t>(total);
+    }
+  }
+  if (total >= (1ll << 31)) {
+    set_error("ax2d_host_shell_csr: int32 index overflow");
+    return AX2D_ERR_ARG;
+  }
+  return total;
+}

@@ -76,6 +76,25 @@ int64_t ax2d_host_shell_edges(int64_t B, const int64_t* atom_ptr, const int64_t*
                               const int32_t* bonds, int num_hops,
                               int64_t* hop_counts, int64_t* edges_out, int64_t capacity);
 
+/* f-1: the same BFS emitting the CSR of the aggregation kernels DIRECTLY (features.py:82-150 + the collation of
+ * molecular.py:426-438 + the stable sort of ax2d_host_csr_build in one pass, no edge list): rowptr[N+1] (shared by both
+ * CSRs: shell relations are symmetric), col[E] = sources of every target row, hop-major and in BFS discovery order inside
+ * a hop (the reference's stable edge order), col_t[E] = targets of every source row, hop-major and ascending.  Call with
+ * col == NULL to get rowptr and E, then with col / col_t of capacity >= E.  Returns E (>= 0) or a negative error.
+ * Bit-identical to ax2d_host_csr_build over the edge list of ax2d_host_shell_edges. */
+int64_t ax2d_host_shell_csr(int64_t B, const int64_t* atom_ptr, const int64_t* bond_ptr, const int32_t* bonds, int num_hops,
+                            int32_t* rowptr, int32_t* col, int32_t* col_t, int64_t capacity);
+
+/* ... and on the device (one warp per molecule, adjacency bit matrices in shared memory, BFS on register bitsets; molecules
+ * of at most 256 atoms).  All pointers are device pointers: atom_ptr / bond_ptr [B+1] int32, bonds [nb,2] int32 (molecule-
+ * local indices), err one int32 zeroed by the caller (non-zero afterwards: 1 molecule larger than max_atoms, 2 bond index
+ * out of range, 3 more than 2^31 edges).  _count writes rowptr[N+1] (workspace: N int32); read E = rowptr[N], then _fill
+ * writes col / col_t [E].  Bit-identical to ax2d_host_shell_csr. */
+int ax2d_shell_csr_count(const int32_t* atom_ptr, const int32_t* bond_ptr, const int32_t* bonds, int64_t B, int64_t N,
+                         int max_atoms, int num_hops, int32_t* rowptr, int32_t* workspace, int32_t* err, ax2d_stream_t stream);
+int ax2d_shell_csr_fill(const int32_t* atom_ptr, const int32_t* bond_ptr, const int32_t* bonds, int64_t B, int max_atoms,
+                        int num_hops, const int32_t* rowptr, int32_t* col, int32_t* col_t, int32_t* err, ax2d_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * a1  ShellConvolutionLayer.message_passing  (models/layers.py:133-167): gather rows + scatter_add.
  *   out[r,:] = (addend ? addend[r,:] : 0) + sum_{k in [rowptr[r], rowptr[r+1])} x[col[k],:]

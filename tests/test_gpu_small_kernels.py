@@ -155,3 +155,43 @@ def test_attn_pool_fwd_direct_and_staged_kernels(hint):
     assert float((attn.double() - ref_attn).abs().max()) <= 1e-6
     assert float((pooled.double() - ref_pooled).abs().max()) <= 1e-5 * float(ref_pooled.abs().max())
     assert float((z.double() - zz.t()).abs().max()) <= 1e-5 * float(zz.abs().max())
+
+
+@pytest.mark.parametrize("kind,hops,count", [("qm9", 3, 300), ("drug", 4, 64), ("qm9", 1, 5)])
+def test_shell_csr_device_equals_host(kind, hops, count):
+    """f-1 on the device: the batched bitset BFS (one warp per molecule) writes the same rowptr / col / col_t as
+    ax2d_host_shell_csr, bit for bit -- including single atoms, molecules without bonds, duplicate and self bonds."""
+    from aimnet_x2d_b200 import collate as CL, molgen
+    rng = np.random.Generator(np.random.PCG64(91 + hops))
+    mols = [molgen.make_molecule(rng, kind, 4, False) for _ in range(count)]
+    mols.insert(3, dict(num_atoms=1, bonds=np.zeros((0, 2), np.int32)))
+    mols.insert(7, dict(num_atoms=6, bonds=np.zeros((0, 2), np.int32)))
+    mols.append(dict(num_atoms=4, bonds=np.array([[0, 1], [1, 0], [2, 2], [1, 3]], np.int32)))
+    counts, bonds = [m["num_atoms"] for m in mols], [m["bonds"] for m in mols]
+    h_rowptr, h_col, h_col_t = CL.shell_csr(counts, bonds, hops)
+    d_rowptr, d_col, d_col_t = CL.shell_csr(counts, bonds, hops, device=DEV)
+    assert d_rowptr.is_cuda and d_col.is_cuda
+    N = sum(counts)
+    E = int(h_rowptr[N])
+    assert int(d_rowptr[N]) == E and E > 0
+    assert torch.equal(d_rowptr.cpu()[: N + 1], h_rowptr[: N + 1])
+    assert torch.equal(d_col.cpu()[:E], h_col[:E])
+    assert torch.equal(d_col_t.cpu()[:E], h_col_t[:E])
+    a = CL.GraphIndex.from_bonds(counts, bonds, hops)
+    b = CL.GraphIndex.from_bonds(counts, bonds, hops, device=DEV)
+    for k in CL.GraphIndex._TENSORS:
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_shell_csr_device_full_batch_feeds_the_aggregation():
+    """A whole C2-sized batch: CSR built on the device from the bond lists == the collated batch's GraphIndex, and the
+    aggregation over it equals the aggregation over the collated index."""
+    from aimnet_x2d_b200 import collate as CL, ops, synthetic as S
+    mols = S.make_molecules(77, 2048, 3, "qm9", 4)
+    batch = CL.MolBatch.from_data_list([S.to_data(m) for m in mols], S.FEATURE_SIZES)
+    gi = CL.GraphIndex.from_bonds([m["num_atoms"] for m in mols], [m["bonds"] for m in mols], 3, device=DEV)
+    ref = batch.graph_index
+    for k in CL.GraphIndex._TENSORS:
+        assert torch.equal(getattr(gi, k), getattr(ref, k)), k
+    x = torch.randn(gi.num_atoms, 160, device=DEV)
+    assert torch.equal(ops.agg(x, gi.to(DEV)), ops.agg(x, ref.to(DEV)))

@@ -156,6 +156,56 @@ def test_collation_matches_reference_golden():
     assert MolBatch.from_data_list([]).multi_hop_edge_indices is None
 
 
+def _csr_from_reference_edges(mols, num_hops):
+    """Reference route: BFS edge lists (oracle, features.py:97-150) -> collation (molecular.py:427-438) -> stable sort."""
+    for m in mols:
+        m["hops"] = GP.shell_edges_bfs(m["num_atoms"], m["bonds"], num_hops)
+    e = GP.collate(mols)["multi_hop_edge_indices"]
+    N = sum(m["num_atoms"] for m in mols)
+    return GP.csr_artefacts(np.ascontiguousarray(e), N, num_hops), N, int(e.shape[0])
+
+
+@pytest.mark.parametrize("kind,hops", [("qm9", 3), ("drug", 4), ("qm9", 1)])
+def test_shell_csr_host_equals_bfs_collation_and_stable_sort(kind, hops):
+    """f-1: ax2d_host_shell_csr emits, straight from the bond lists, the CSR pair that the reference route (BFS edge lists ->
+    collation -> stable sort by target / by source) produces -- bit for bit, incl. the golden BFS fixtures, single atoms,
+    molecules without bonds and duplicate / self bonds."""
+    from aimnet_x2d_b200 import collate as CL, molgen
+    rng = np.random.Generator(np.random.PCG64(17 + hops))
+    mols = [molgen.make_molecule(rng, kind, 4, False) for _ in range(23)]
+    mols.append(dict(num_atoms=1, bonds=np.zeros((0, 2), np.int32)))                      # single atom
+    mols.append(dict(num_atoms=5, bonds=np.zeros((0, 2), np.int32)))                      # no bonds at all
+    mols.append(dict(num_atoms=4, bonds=np.array([[0, 1], [1, 0], [2, 2], [1, 3]], np.int32)))   # duplicate + self bond
+    g = load_golden("bfs_random")
+    mols += [dict(num_atoms=int(g[f"n_{i}"]), bonds=g[f"bonds_{i}"].astype(np.int32)) for i in range(int(g["count"]))]
+    feats = {k: v for k, v in mols[0].get("features", {}).items()}
+    for m in mols:                                           # collate() of the oracle wants the full molecule records
+        m.setdefault("features", {k: np.zeros(m["num_atoms"], dtype=v.dtype) for k, v in feats.items()})
+        m.setdefault("target", np.zeros(4, np.float32))
+        m.setdefault("total_charge", 0.0)
+        for k in ("chiral", "cis", "trans"):
+            m.setdefault(k, [])
+        m.setdefault("atomic_numbers", np.ones(m["num_atoms"], np.int64))
+    ref, N, E = _csr_from_reference_edges(mols, hops)
+    rowptr, col, col_t = CL.shell_csr([m["num_atoms"] for m in mols], [m["bonds"] for m in mols], hops)
+    assert int(rowptr[N]) == E
+    assert np.array_equal(rowptr.numpy()[: N + 1], ref["rowptr"][: N + 1])
+    assert np.array_equal(col.numpy()[:E], ref["col"])
+    assert np.array_equal(rowptr.numpy()[: N + 1], ref["rowptr_t"][: N + 1])               # shell relations are symmetric
+    assert np.array_equal(col_t.numpy()[:E], ref["col_t"])
+    # ... and the whole GraphIndex built from bonds equals the one built from the collated edge list
+    from aimnet_x2d_b200.collate import GraphIndex
+    e = GP.collate(mols)["multi_hop_edge_indices"]
+    bi = np.repeat(np.arange(len(mols)), [m["num_atoms"] for m in mols])
+    a = GraphIndex.build(e, bi, len(mols), hops)
+    b = GraphIndex.from_bonds([m["num_atoms"] for m in mols], [m["bonds"] for m in mols], hops)
+    for k in GraphIndex._TENSORS:
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    for k in ("num_atoms", "num_edges", "num_rows", "collapsed", "tile_local", "unique_edges", "n_tiles", "max_tile_rows",
+              "max_tile_edges", "max_seg"):
+        assert getattr(a, k) == getattr(b, k), k
+
+
 def test_collation_matches_oracle_on_synthetic_batch():
     from aimnet_x2d_b200 import synthetic as S
     mols = S.make_molecules(31, 17, 3, "drug", stereo=True)
