@@ -17,7 +17,7 @@ from .collate import GraphIndex, MolBatch, MolData, collate_fn  # noqa: E402
 from .gnn import GNN, GNNConfig  # noqa: E402
 from .layers import LinearBlock, MultiLayerPerceptron, ShellConvolutionLayer  # noqa: E402
 from .losses import WeightedL1Loss, WeightedMSELoss  # noqa: E402
-from .inference import (EmbeddingExtractor, GraphedInferenceStep, InferenceStep, ShardedOutputWriter,  # noqa: E402
+from .inference import (EmbeddingExtractor, GraphedInferenceStep, InferenceStep, OutputFetcher, ShardedOutputWriter,  # noqa: E402
                         merge_rank_outputs)
 from .shards import ShardDataset, ShardWriter, shard_batch_indices, write_shard  # noqa: E402
 from .optim import FlatAdam  # noqa: E402
@@ -29,5 +29,5 @@ __all__ = ["GNN", "GNNConfig", "ShellConvolutionLayer", "LinearBlock", "MultiLay
            "MaxPoolingLayer", "SumPoolingLayer", "MultiHeadAttentionPoolingLayer", "create_pooling_layer",
            "WeightedL1Loss", "WeightedMSELoss", "GraphIndex", "MolBatch", "MolData", "collate_fn", "FlatAdam",
            "get_activation_function", "InferenceStep", "GraphedInferenceStep", "TrainStep",
-           "GraphedTrainStep", "EmbeddingExtractor", "ShardedOutputWriter", "merge_rank_outputs", "ShardDataset",
+           "GraphedTrainStep", "EmbeddingExtractor", "OutputFetcher", "ShardedOutputWriter", "merge_rank_outputs", "ShardDataset",
            "ShardWriter", "shard_batch_indices", "write_shard"]

@@ -184,23 +184,72 @@ def merge_rank_outputs(directory: str, world_size: int) -> Dict[str, "np.ndarray
     return out
 
 
+class OutputFetcher:
+    """Device -> host copies of a step's result tensors that OVERLAP the next forward pass: the static result buffers of a
+    graph-replayed step are snapshotted into one of two device staging sets on the compute stream (a ~3 us copy), the
+    device-to-host copy of the snapshot runs on a side stream into pinned memory, and the compute stream only waits (on the
+    device, never the host) before it overwrites a staging set whose copy is still in flight two steps later."""
+
+    def __init__(self, device, fields=("outputs", "embeddings", "partial_charges"), depth: int = 2):
+        self.device = torch.device(device)
+        self.fields = tuple(fields)
+        self.depth = int(depth)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._stage = [dict() for _ in range(self.depth)]
+        self._host = [dict() for _ in range(self.depth)]
+        self._done = [None] * self.depth
+        self._i = 0
+
+    def fetch(self, res: Dict[str, Optional[torch.Tensor]]) -> int:
+        """Start the copy of ``res`` (result dict of the step just enqueued); returns a handle for ``wait``."""
+        k = self._i % self.depth
+        self._i += 1
+        cur = torch.cuda.current_stream(self.device)
+        if self._done[k] is not None:
+            cur.wait_event(self._done[k])                   # the staging set is free again (device-side wait)
+        for f in self.fields:
+            t = res.get(f)
+            if t is None:
+                continue
+            st = self._stage[k].get(f)
+            if st is None or st.shape != t.shape or st.dtype != t.dtype:
+                st = torch.empty_like(t)
+                self._stage[k][f] = st
+                self._host[k][f] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            st.copy_(t, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            for f, st in self._stage[k].items():
+                self._host[k][f].copy_(st, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._done[k] = done
+        return k
+
+    def wait(self, handle: int) -> Dict[str, torch.Tensor]:
+        """Host tensors (pinned, valid until ``depth`` more ``fetch`` calls) of the copy started by ``fetch``."""
+        self._done[handle].synchronize()
+        return self._host[handle]
+
+
 class EmbeddingExtractor:
     """Forward-only pass over a sequence of (padded) batches with results streamed to a ``ShardedOutputWriter``: ONE forward
     per batch yields predictions, pooled embeddings and partial charges (the reference runs the model twice per batch for
-    embeddings, ``inference/embeddings.py:109-119``), device-to-host copies go through two pinned buffers so that the copy of
-    batch i overlaps the forward of batch i + 1, and nothing is gathered across ranks."""
+    embeddings, ``inference/embeddings.py:109-119``), device-to-host copies run on a side stream from a snapshot of the result
+    (``OutputFetcher``) so that the copy of batch i overlaps the forward of batch i + 1, and nothing is gathered across ranks."""
 
     def __init__(self, step, writer: ShardedOutputWriter, fields=("outputs", "embeddings", "partial_charges")):
         self.step, self.writer, self.fields = step, writer, tuple(fields)
-        self._host = [None, None]
-        self._event = [None, None]
+        self._fetcher = None
         self._pending = [None, None]
 
     def _flush(self, k: int) -> None:
         if self._pending[k] is None:
             return
-        self._event[k].synchronize()
-        bufs, counts, n_real, n_atoms = self._pending[k]
+        handle, counts, n_real, n_atoms = self._pending[k]
+        bufs = self._fetcher.wait(handle)
         for f, t in bufs.items():
             if f == "partial_charges":
                 self.writer.append_ragged(f, t[:n_atoms].clone(), counts)
@@ -222,23 +271,11 @@ class EmbeddingExtractor:
             gi = slot.graph_index
             n_real = int(getattr(slot, "num_real_graphs", gi.num_graphs))
             seg = gi.seg_ptr[: n_real + 1].cpu().numpy() if gi.seg_ptr.is_cuda else gi.seg_ptr[: n_real + 1].numpy()
-            bufs = {}
-            for f in self.fields:
-                t = res.get(f)
-                if t is None:
-                    continue
-                if self._host[k] is None:
-                    self._host[k] = {}
-                h = self._host[k].get(f)
-                if h is None or h.shape != t.shape or h.dtype != t.dtype:
-                    h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-                    self._host[k][f] = h
-                h.copy_(t, non_blocking=True)
-                bufs[f] = h
-            ev = torch.cuda.Event()
-            ev.record()
-            self._event[k] = ev
-            self._pending[k] = (bufs, np.diff(seg), n_real, int(seg[-1]))
+            if self._fetcher is None:
+                dev = next(t for t in res.values() if t is not None).device
+                self._fetcher = OutputFetcher(dev, self.fields, depth=2)
+            handle = self._fetcher.fetch(res)               # snapshot + device-to-host copy on a side stream
+            self._pending[k] = (handle, np.diff(seg), n_real, int(seg[-1]))
             total += n_real
         self._flush(1 - k)                                  # the older of the two outstanding batches first: input order
         self._flush(k)
