@@ -678,6 +678,14 @@ def ours_arm(args, wl):
                                       "share": v["ms_total"] / kernel_ms} for k, v in sorted(ks.items(), key=lambda kv: -kv[1]["ms_total"])}}
         print(json.dumps(line), flush=True)
     if world > 1:
+        if args.single_graph:
+            # ProcessGroupNCCL cannot be destroyed while a live CUDA graph holds captured collectives of its communicator
+            # (the call blocks: observed at 2 and 8 ranks); every rank has finished its work, leave without the tear-down
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

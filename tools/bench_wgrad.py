@@ -33,8 +33,8 @@ def timed(fn, reps=30):
 
 
 for dtype in (torch.float32, torch.bfloat16):
-    for (no, ki) in [(160, 160), (160, 640), (160, 320), (512, 512)]:
-        rows = M if no == 160 else 2048
+    for (no, ki) in [(160, 160), (128, 160), (160, 128), (128, 320), (160, 640), (160, 320), (512, 512)]:
+        rows = 2048 if no == 512 else M
         gs = [torch.randn(rows, no, device="cuda").to(dtype) for _ in range(NBUF)]
         xs = [torch.randn(rows, ki, device="cuda").to(dtype) for _ in range(NBUF)]
         outs = [torch.empty(no, ki, device="cuda") for _ in range(NBUF)]
