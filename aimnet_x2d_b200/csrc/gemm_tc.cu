@@ -820,6 +820,287 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const _
   }
 }
 
+// ---------------------------------------------------------------------------------------------- weight gradients, 160 rows
+// Most weight matrices of the model have 160 output features = one 128-row UMMA tile + a 32-row strip.  gemm_tc_wgrad_kernel
+// gives the strip its own CTAs, which run the whole k-loop (all of X again, a full M = 128 MMA per term) for a quarter of a
+// tile of output: half of the CTA-k-blocks of a 160 x 160 launch.  Here ONE CTA owns all 160 rows of its column tile:
+//   * rows 0..127: as before -- G columns 0..127 split into the TMEM A ring by warps 2..5, MMAs with the A operand from
+//     tensor memory;
+//   * rows 128..159 are computed TRANSPOSED, strip^T[i, o] = sum_m X[m, i] G[m, 128 + o]: the M side of the MMA is the
+//     column tile of X (already in shared memory, split into hi / lo by warps 6..9), the N side the strip's G chunk
+//     [32 contraction rows x 32 columns] -- one more TMA box per k-block, split in shared memory by warps 2..5 -- so a strip
+//     MMA has N = 32 and costs a fifth of a main-tile MMA instead of as much (an M = 128 MMA over the strip's 32 valid rows
+//     costs the same as a full tile).  Two such products per term: X columns 0..127 and 128..159 (the second reads past the
+//     tile's X chunks into the following shared memory: finite garbage in accumulator lanes the epilogue never stores);
+//   * TMEM: [0, 160) accumulator of rows 0..127, [160, 192) / [192, 224) the two transposed strip accumulators, [320, 512)
+//     the A ring.  The three terms of a k-step go to ONE accumulator (like the projection kernel: 128 + 64 columns more for
+//     separate small-term accumulators do not fit next to the ring), compensated by tc_acc_scale;
+//   * the strip's epilogue needs no transpose: lane = column i of X, register j = row 128 + j, so every store instruction
+//     of a warp writes 32 consecutive floats of one output row.
+// Half the CTAs per split means twice the splits on the same machine: 8 instead of 16 k-blocks per CTA on 160 x 160.
+constexpr int WGM_ACC_SA = 160, WGM_ACC_SB = 192;
+constexpr int WGM_STRIP_BYTES = WG_CHUNK_BYTES;       // one [32 x 32] fp32 box
+
+// One k-block of the merged kernel: per k-step three MMAs into the main tile (A from TMEM, N = BN) and 2 x 3 into the
+// transposed strip tiles (A = X from shared memory, B = the strip chunk, N = 32), and the commit, under one election.
+__device__ __forceinline__ void umma_kblock_wgm_w(uint32_t t0, uint32_t ts, uint32_t a_hi, uint32_t a_lo, uint64_t dsh, uint64_t dsl,
+                                                  uint64_t dbh, uint64_t dbl, uint32_t idesc_ts, uint32_t idesc_s,
+                                                  uint32_t acc_first, uint64_t* free_bar) {
+  static_assert(WG_KB == 32, "four k-steps of 8 per k-block");
+  // %0 main accumulator, %1 strip accumulator A (B = %1 + 32), %2 / %3 TMEM A (hi / lo), %4 / %5 strip chunk (hi / lo),
+  // %6 / %7 X (hi / lo), %8 / %9 instruction descriptors, %10 accumulate flag of the first k-step, %11 barrier
+#define AX2D_WGM_STEP(AH, AL, SH, SL, BH, BL, BH2, BL2, PF)                                \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [" AL "], " BH ", %8, " PF ";\n\t"         \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [" AH "], " BL ", %8, pt;\n\t"             \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [" AH "], " BH ", %8, pt;\n\t"             \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], " BL ", " SH ", %9, " PF ";\n\t"           \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], " BH ", " SL ", %9, pt;\n\t"               \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], " BH ", " SH ", %9, pt;\n\t"               \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [tsb], " BL2 ", " SH ", %9, " PF ";\n\t"         \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [tsb], " BH2 ", " SL ", %9, pt;\n\t"             \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [tsb], " BH2 ", " SH ", %9, pt;\n\t"
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, pf, pt;\n\t"
+      ".reg .b32 ah1, al1, ah2, al2, ah3, al3, tsb;\n\t"
+      ".reg .b64 sh1, sl1, sh2, sl2, sh3, sl3, bh1, bl1, bh2, bl2, bh3, bl3;\n\t"
+      ".reg .b64 ch0, cl0, ch1, cl1, ch2, cl2, ch3, cl3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %10, 0;\n\t"
+      "setp.eq.b32 pt, %8, %8;\n\t"
+      "add.u32 tsb, %1, 32;\n\t"
+      "add.u32 ah1, %2, 8;\n\t add.u32 al1, %3, 8;\n\t add.u64 bh1, %6, 64;\n\t add.u64 bl1, %7, 64;\n\t"
+      "add.u32 ah2, %2, 16;\n\t add.u32 al2, %3, 16;\n\t add.u64 bh2, %6, 128;\n\t add.u64 bl2, %7, 128;\n\t"
+      "add.u32 ah3, %2, 24;\n\t add.u32 al3, %3, 24;\n\t add.u64 bh3, %6, 192;\n\t add.u64 bl3, %7, 192;\n\t"
+      "add.u64 sh1, %4, 64;\n\t add.u64 sl1, %5, 64;\n\t add.u64 sh2, %4, 128;\n\t add.u64 sl2, %5, 128;\n\t"
+      "add.u64 sh3, %4, 192;\n\t add.u64 sl3, %5, 192;\n\t"
+      // X columns 128 ..: four 4 KB chunks further on (descriptor addresses are in 16-byte units)
+      "add.u64 ch0, %6, 1024;\n\t add.u64 cl0, %7, 1024;\n\t add.u64 ch1, bh1, 1024;\n\t add.u64 cl1, bl1, 1024;\n\t"
+      "add.u64 ch2, bh2, 1024;\n\t add.u64 cl2, bl2, 1024;\n\t add.u64 ch3, bh3, 1024;\n\t add.u64 cl3, bl3, 1024;\n\t"
+      AX2D_WGM_STEP("%2", "%3", "%4", "%5", "%6", "%7", "ch0", "cl0", "pf")
+      AX2D_WGM_STEP("ah1", "al1", "sh1", "sl1", "bh1", "bl1", "ch1", "cl1", "pt")
+      AX2D_WGM_STEP("ah2", "al2", "sh2", "sl2", "bh2", "bl2", "ch2", "cl2", "pt")
+      AX2D_WGM_STEP("ah3", "al3", "sh3", "sl3", "bh3", "bl3", "ch3", "cl3", "pt")
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
+      "}\n" ::"r"(t0),
+      "r"(ts), "r"(a_hi), "r"(a_lo), "l"(dsh), "l"(dsl), "l"(dbh), "l"(dbl), "r"(idesc_ts), "r"(idesc_s), "r"(acc_first),
+      "r"(smem_u32(free_bar))
+      : "memory");
+#undef AX2D_WGM_STEP
+}
+
+__global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad160_kernel(const __grid_constant__ WgMaps maps,
+                                                                         const __grid_constant__ WgArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[WG_MAX_STAGES], split_bar[WG_MAX_STAGES], empty_bar[WG_MAX_STAGES], acc_bar;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_strip_sum[4][32];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = g.BN, S = g.stages;
+  constexpr int a_chunks = TC_BM / 32;
+  const int b_chunks = BN / 32;
+  constexpr uint32_t a_bytes = a_chunks * WG_CHUNK_BYTES;
+  const uint32_t b_bytes = static_cast<uint32_t>(b_chunks) * WG_CHUNK_BYTES;
+  // stage: [raw G chunks 0..3 | strip hi | X hi chunks | strip lo | X lo chunks]
+  const uint32_t stage_bytes = a_bytes + 2 * WGM_STRIP_BYTES + 2 * b_bytes;
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  auto stage_a = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };
+  auto stage_shi = [&](int s) { return stage_a(s) + a_bytes; };
+  auto stage_bhi = [&](int s) { return stage_a(s) + a_bytes + WGM_STRIP_BYTES; };
+  auto stage_slo = [&](int s) { return stage_a(s) + a_bytes + WGM_STRIP_BYTES + b_bytes; };
+  auto stage_blo = [&](int s) { return stage_a(s) + a_bytes + 2 * WGM_STRIP_BYTES + b_bytes; };
+
+  const int n0 = blockIdx.y * BN;
+  const int kb0 = blockIdx.z * g.kb_per_split;
+  int kb1 = kb0 + g.kb_per_split;
+  kb1 = kb1 < g.num_kb ? kb1 : g.num_kb;
+  const int nkb = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], TC_WORKERS / 32);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    constexpr int A_CH = a_chunks + 1, B_CH = WG_MAX_BN / 32;          // four chunks of the main tile + the strip
+    const CUtensorMap* amap[A_CH];
+    const CUtensorMap* bmap[B_CH];
+    int acol[A_CH], bcol[B_CH];
+#pragma unroll
+    for (int c = 0; c < A_CH; ++c) {
+      const int o = 32 * c;
+      const int sg = find_seg(g.a_start, g.a_nseg, o);
+      amap[c] = &maps.a[sg];
+      acol[c] = o - g.a_start[sg];
+    }
+#pragma unroll
+    for (int c = 0; c < B_CH; ++c) {
+      const int i = n0 + 32 * c;
+      const int sg = find_seg(g.b_start, g.b_nseg, i);
+      bmap[c] = &maps.b[sg];
+      bcol[c] = i - g.b_start[sg];
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      __syncwarp();
+      mbar_expect_tx_w(&full_bar[s], a_bytes + WGM_STRIP_BYTES + b_bytes);
+      const int row = (kb0 + it) * WG_KB;
+      unsigned char* dst = stage_a(s);
+#pragma unroll
+      for (int c = 0; c < a_chunks; ++c) tma_load_2d_w(dst + c * WG_CHUNK_BYTES, amap[c], &full_bar[s], acol[c], row);
+      tma_load_2d_w(stage_shi(s), amap[a_chunks], &full_bar[s], acol[a_chunks], row);
+      dst = stage_bhi(s);
+#pragma unroll
+      for (int c = 0; c < B_CH; ++c)
+        if (c < b_chunks) tma_load_2d_w(dst + c * WG_CHUNK_BYTES, bmap[c], &full_bar[s], bcol[c], row);
+    }
+  } else if (warp == 1) {
+    // main tile: A K-major from TMEM, B MN-major (bit 16), N = BN; strip tiles: A = X, MN-major from shared memory (bit 15),
+    // B = the strip chunk, MN-major, N = 32
+    const uint32_t idesc_ts = idesc_tf32(BN) | (1u << 16);
+    const uint32_t idesc_s = idesc_tf32(32) | (1u << 15) | (1u << 16);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
+      mbar_wait(&full_bar[s], ph);
+      mbar_wait(&split_bar[s], ph);
+      tc_fence_after();
+      __syncwarp();
+      const uint32_t a_hi = tmem_base + static_cast<uint32_t>(WG_A_TMEM + s * 2 * WG_KB);
+      umma_kblock_wgm_w(tmem_base, tmem_base + WGM_ACC_SA, a_hi, a_hi + WG_KB, smem_desc_mn_sw128_32b(smem_u32(stage_shi(s))),
+                        smem_desc_mn_sw128_32b(smem_u32(stage_slo(s))), smem_desc_mn_sw128_32b(smem_u32(stage_bhi(s))),
+                        smem_desc_mn_sw128_32b(smem_u32(stage_blo(s))), idesc_ts, idesc_s, it != 0 ? 1u : 0u, &empty_bar[s]);
+    }
+    umma_commit_w(&acc_bar);
+  } else {
+    const int t = threadIdx.x - 64;
+    const bool a_side = warp < 6;
+    const bool want_db = g.db != nullptr && blockIdx.y == 0;
+    float colsum = 0.f, strip_sum = 0.f;
+    int s = 0;
+    uint32_t ph = 0;
+    if (a_side) {
+      const int q = warp & 3;
+      const float* chunk0 = reinterpret_cast<const float*>(stage_a(0)) + q * (WG_CHUNK_BYTES / 4);
+      for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
+        mbar_wait(&full_bar[s], ph);
+        const float* chunk = chunk0 + static_cast<size_t>(s) * (stage_bytes / 4);
+        const uint32_t slot = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(WG_A_TMEM + s * 2 * WG_KB);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr) {
+            const int r = 16 * half + rr;
+            const float v = chunk[r * 32 + (2 * ((lane >> 3) ^ (r & 3)) + ((lane >> 2) & 1)) * 4 + (lane & 3)];
+            colsum += v;
+            float h, o;
+            split_tf32(v, h, o);
+            hi[rr] = __float_as_uint(h);
+            lo[rr] = __float_as_uint(o);
+          }
+          tmem_st16(slot + 16 * half, hi);
+          tmem_st16(slot + WG_KB + 16 * half, lo);
+        }
+        // the strip chunk: this warp splits contraction rows 8 q .. 8 q + 7 of it in shared memory (lane = column)
+        float* shi = reinterpret_cast<float*>(stage_shi(s));
+        float* slo = reinterpret_cast<float*>(stage_slo(s));
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = 8 * q + rr;
+          const int idx = r * 32 + (2 * ((lane >> 3) ^ (r & 3)) + ((lane >> 2) & 1)) * 4 + (lane & 3);
+          const float v = shi[idx];
+          strip_sum += v;
+          float h, o;
+          split_tf32(v, h, o);
+          shi[idx] = h;
+          slo[idx] = o;
+        }
+        fence_proxy_async_smem();
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);
+      }
+      if (want_db) {
+        const int64_t o = static_cast<int64_t>(q) * 32 + lane;
+        g.db[static_cast<int64_t>(blockIdx.z) * g.e.M + o] = colsum;
+      }
+      s_strip_sum[q][lane] = strip_sum;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (want_db && q == 0 && 128 + lane < g.e.M)
+        g.db[static_cast<int64_t>(blockIdx.z) * g.e.M + 128 + lane] =
+            ((s_strip_sum[0][lane] + s_strip_sum[1][lane]) + s_strip_sum[2][lane]) + s_strip_sum[3][lane];
+    } else {
+      const int tb = t - 128;
+      const int n4 = static_cast<int>(b_bytes / 16);
+      for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
+        mbar_wait(&full_bar[s], ph);
+        float4* h4 = reinterpret_cast<float4*>(stage_bhi(s));
+        float4* l4 = reinterpret_cast<float4*>(stage_blo(s));
+#pragma unroll 5
+        for (int i = tb; i < n4; i += 128) {
+          const float4 v = h4[i];
+          float4 h, o;
+          split_tf32(v.x, h.x, o.x);
+          split_tf32(v.y, h.y, o.y);
+          split_tf32(v.z, h.z, o.z);
+          split_tf32(v.w, h.w, o.w);
+          h4[i] = h;
+          l4[i] = o;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);
+      }
+    }
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 32);     // stage memory is free now
+    const EpiCtx cx = epi_ctx(g.e);
+    float* ws = g.ws != nullptr ? g.ws + static_cast<int64_t>(blockIdx.z) * g.e.M * g.e.N : nullptr;
+    const float scale = tc_acc_scale(4 * nkb * 3);                 // three terms per k-step into one accumulator
+    tc_epilogue<AX2D_ACT_NONE, AX2D_ACT_NONE, false>(g.e, BN, ws, cx, tmem_base, stg, 0, n0, warp & 3, lane, (warp - 2) >> 2, 0u,
+                                                     scale);
+    // the strip, transposed in tensor memory: lane = X column i, register j = output row 128 + j
+    {
+      const int q = warp & 3, second = (warp - 2) >> 2;            // warps 2..5: X columns 0..127, warp 8: columns 128..159
+      if (second == 0 || q == 0) {
+        const int i = second == 0 ? q * 32 + lane : TC_BM + lane;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(second == 0 ? WGM_ACC_SA : WGM_ACC_SB), r);
+        const int64_t N = g.e.N;
+        const int rows = static_cast<int>(g.e.M) - TC_BM;          // valid strip rows (<= 32)
+        if (i < BN && n0 + i < N) {
+          float* dst = ws + static_cast<int64_t>(TC_BM) * N + n0 + i;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < rows) dst[static_cast<int64_t>(j) * N] = __uint_as_float(r[j]) * scale;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
 // elementwise (hi, lo) split of a weight matrix, optionally transposed: out[r, c] = split(w[c, r]) if transpose.
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, int64_t ldw, int rows, int cols,
                                                          int transpose, float* __restrict__ hi, float* __restrict__ lo,
@@ -1022,14 +1303,25 @@ static int wgrad_split(int64_t tiles, int64_t num_kb) {
   return static_cast<int>(best);
 }
 
+// 128 < M <= 160 output features: one CTA per column tile owns all rows (gemm_tc_wgrad160_kernel) instead of a full tile
+// plus a strip tile.  Needs the three-term split (one accumulator per tile, no room for a fourth term's bookkeeping).
+static int g_wg_merged = 1;
+// development aid (not part of include/ax2d.h): 0 = always the two-tile kernel
+extern "C" void ax2d_debug_wgrad_merged(int on) { g_wg_merged = on; }
+// (only with several splits, i.e. long contractions: its strip epilogue writes partial tiles)
+static bool wgrad_merged(int64_t M, int64_t K) {
+  return g_wg_merged != 0 && AX2D_TC_TERMS == 3 && M > TC_BM && M <= TC_BM + 32 && K >= 64 * WG_KB;
+}
+static int64_t wgrad_m_tiles(int64_t M, int64_t K) { return wgrad_merged(M, K) ? 1 : (M + TC_BM - 1) / TC_BM; }
+
 extern "C" int ax2d_gemm_tc_wgrad_splits(int64_t M, int64_t N, int64_t K) {
   const int64_t n_tiles = (N + WG_MAX_BN - 1) / WG_MAX_BN;
-  return wgrad_split(((M + TC_BM - 1) / TC_BM) * n_tiles, (K + WG_KB - 1) / WG_KB);
+  return wgrad_split(wgrad_m_tiles(M, K) * n_tiles, (K + WG_KB - 1) / WG_KB);
 }
 
 extern "C" int64_t ax2d_gemm_tc_wgrad_workspace(int64_t M, int64_t N, int64_t K) {
   const int64_t n_tiles = (N + WG_MAX_BN - 1) / WG_MAX_BN;
-  const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * n_tiles;
+  const int64_t tiles = wgrad_m_tiles(M, K) * n_tiles;
   const int64_t num_kb = (K + WG_KB - 1) / WG_KB;
   const int64_t split = wgrad_split(tiles, num_kb);
   return split > 1 ? split * (M * N + M) * 4 : 0;       // partial tiles + partial bias-gradient vectors
@@ -1075,7 +1367,8 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
   g.BN = BN;
   g.tmem_cols = 512;        // one CTA per SM: main + small-term accumulator + the A ring
   g.acc2 = WG_ACC2;
-  const int m_tiles = static_cast<int>((M + TC_BM - 1) / TC_BM);
+  const bool merged = wgrad_merged(M, K);
+  const int m_tiles = static_cast<int>(wgrad_m_tiles(M, K));
   g.num_kb = static_cast<int>((K + WG_KB - 1) / WG_KB);
   int split = wgrad_split(static_cast<int64_t>(m_tiles) * n_tiles, g.num_kb);
   g.kb_per_split = (g.num_kb + split - 1) / split;
@@ -1089,7 +1382,7 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
   } else {
     g.db = bias_grad;
   }
-  const size_t stage_bytes = static_cast<size_t>(TC_BM / 32 + 2 * (BN / 32)) * WG_CHUNK_BYTES;
+  const size_t stage_bytes = static_cast<size_t>(TC_BM / 32 + (merged ? 2 : 0) + 2 * (BN / 32)) * WG_CHUNK_BYTES;
   int stages = static_cast<int>((224 * 1024) / stage_bytes);
   stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
   stages = stages > g.kb_per_split ? g.kb_per_split : stages;
@@ -1100,20 +1393,24 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
   if (smem < epi_bytes) smem = epi_bytes;
   if (smem < 120 * 1024) smem = 120 * 1024;        // never two CTAs on an SM: each allocates all 512 TMEM columns
   smem += 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (merged) smem += static_cast<size_t>(8 - BN / 32) * WG_CHUNK_BYTES;   // the second strip product reads X chunks 4..7:
+                                                                           // up to here past the last stage's X lo
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[merged]) {
+    cudaError_t e = merged ? cudaFuncSetAttribute(gemm_tc_wgrad160_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                           : cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
       set_error("ax2d_gemm_tc_wgrad: cannot raise the dynamic shared memory limit to %zu: %s", smem, cudaGetErrorString(e));
       return AX2D_ERR_LAUNCH;
     }
-    configured = smem;
+    configured[merged] = smem;
   }
   AX2D_CHECK_ARG(accumulate != 2 || split > 1, "ax2d_gemm_tc_wgrad: accumulate == 2 (leave the partials) needs more than one split "
                                               "(ax2d_gemm_tc_wgrad_splits)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), static_cast<unsigned>(split));
-  gemm_tc_wgrad_kernel<<<grid, TC_WG_THREADS, smem, st>>>(maps, g);
+  if (merged) gemm_tc_wgrad160_kernel<<<grid, TC_WG_THREADS, smem, st>>>(maps, g);
+  else gemm_tc_wgrad_kernel<<<grid, TC_WG_THREADS, smem, st>>>(maps, g);
   rc = launch_status("ax2d_gemm_tc_wgrad");
   if (rc != AX2D_OK || split == 1 || accumulate == 2) return rc;
   return splitk_reduce(g.ws, split, M, N, g.e.c, accumulate == 1, g.db, bias_grad, st);
