@@ -569,6 +569,8 @@ constexpr int WG_CHUNK_BYTES = WG_KB * 128;      // one [32 x 32] fp32 box
 struct WgMaps {
   CUtensorMap a[AX2D_MAX_SEG];
   CUtensorMap b[AX2D_MAX_SEG];
+  CUtensorMap a3;                  // merged kernel: 3-D chunk view of the G segment that holds columns 0..159 ...
+  CUtensorMap b3[AX2D_MAX_SEG];    // ... and of every X segment
 };
 struct WgArgs {
   EpiArgs e;                       // M = No, N = Ki; used directly when there is a single split
@@ -576,6 +578,8 @@ struct WgArgs {
   int b_start[AX2D_MAX_SEG + 1], b_nseg;
   int num_kb, kb_per_split;
   int BN, stages, tmem_cols;
+  int a3_chunk0, b3_on;            // merged kernel: first chunk of the G tile in maps.a3 (-1: per-chunk boxes); X tiles that
+                                   // lie inside one segment go through maps.b3[segment] (0: per-chunk boxes)
   int acc2;                        // column offset of the small-term accumulator
   float* ws;                       // [splits][No][Ki] or nullptr
   float* db;                       // optional fused bias gradient: column sums of G, [splits][No] partials (or the
@@ -838,6 +842,10 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const _
 //   * the strip's epilogue needs no transpose: lane = column i of X, register j = row 128 + j, so every store instruction
 //     of a warp writes 32 consecutive floats of one output row.
 // Half the CTAs per split means twice the splits on the same machine: 8 instead of 16 k-blocks per CTA on 160 x 160.
+// Where a tile lies inside one column segment its chunks arrive as ONE 3-D TMA box per operand (make_map_chunks) instead of
+// one box per 32-column chunk.  Measured (tools/bench_wgrad.py): ~1.15 us per k-block whatever the number of TMA
+// instructions (2 or 10) and with or without an L2 prefetch of the k-blocks beyond the ring -- what is left is the MMA
+// stream itself: 12 MMAs of N = 160 (0.5 us) + 24 of N = 32, which cost far more than a fifth of a wide one.
 constexpr int WGM_ACC_SA = 160, WGM_ACC_SB = 192;
 constexpr int WGM_STRIP_BYTES = WG_CHUNK_BYTES;       // one [32 x 32] fp32 box
 
@@ -951,6 +959,11 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad160_kernel(cons
       bmap[c] = &maps.b[sg];
       bcol[c] = i - g.b_start[sg];
     }
+    // this CTA's X tile through the 3-D view of its segment: only if it lies inside ONE segment
+    const int b_sg0 = find_seg(g.b_start, g.b_nseg, n0);
+    const bool b3_ok = g.b3_on != 0 && find_seg(g.b_start, g.b_nseg, n0 + BN - 1) == b_sg0 &&
+                       n0 + BN <= g.b_start[b_sg0 + 1];
+    const int b3_chunk0 = (n0 - g.b_start[b_sg0]) >> 5;
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < nkb; ++it, ph ^= (s + 1 == S ? 1u : 0u), s = (s + 1 == S ? 0 : s + 1)) {
@@ -959,13 +972,22 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad160_kernel(cons
       mbar_expect_tx_w(&full_bar[s], a_bytes + WGM_STRIP_BYTES + b_bytes);
       const int row = (kb0 + it) * WG_KB;
       unsigned char* dst = stage_a(s);
+      if (g.a3_chunk0 >= 0) {
+        // the four chunks of the main tile and the strip chunk are contiguous in shared memory: one 3-D box
+        tma_load_3d_w(dst, &maps.a3, &full_bar[s], 0, row, g.a3_chunk0);
+      } else {
 #pragma unroll
-      for (int c = 0; c < a_chunks; ++c) tma_load_2d_w(dst + c * WG_CHUNK_BYTES, amap[c], &full_bar[s], acol[c], row);
-      tma_load_2d_w(stage_shi(s), amap[a_chunks], &full_bar[s], acol[a_chunks], row);
+        for (int c = 0; c < a_chunks; ++c) tma_load_2d_w(dst + c * WG_CHUNK_BYTES, amap[c], &full_bar[s], acol[c], row);
+        tma_load_2d_w(stage_shi(s), amap[a_chunks], &full_bar[s], acol[a_chunks], row);
+      }
       dst = stage_bhi(s);
+      if (b3_ok) {
+        tma_load_3d_w(dst, &maps.b3[b_sg0], &full_bar[s], 0, row, b3_chunk0);
+      } else {
 #pragma unroll
-      for (int c = 0; c < B_CH; ++c)
-        if (c < b_chunks) tma_load_2d_w(dst + c * WG_CHUNK_BYTES, bmap[c], &full_bar[s], bcol[c], row);
+        for (int c = 0; c < B_CH; ++c)
+          if (c < b_chunks) tma_load_2d_w(dst + c * WG_CHUNK_BYTES, bmap[c], &full_bar[s], bcol[c], row);
+      }
     }
   } else if (warp == 1) {
     // main tile: A K-major from TMEM, B MN-major (bit 16), N = BN; strip tiles: A = X, MN-major from shared memory (bit 15),
@@ -1305,7 +1327,9 @@ static int wgrad_split(int64_t tiles, int64_t num_kb) {
 
 // 128 < M <= 160 output features: one CTA per column tile owns all rows (gemm_tc_wgrad160_kernel) instead of a full tile
 // plus a strip tile.  Needs the three-term split (one accumulator per tile, no room for a fourth term's bookkeeping).
-static int g_wg_merged = 1;
+static int g_wg_merged = 1, g_wg_box3 = 1;
+// development aid (not part of include/ax2d.h): 0 = per-chunk 2-D boxes in the merged kernel
+extern "C" void ax2d_debug_wgrad_box3(int on) { g_wg_box3 = on; }
 // development aid (not part of include/ax2d.h): 0 = always the two-tile kernel
 extern "C" void ax2d_debug_wgrad_merged(int on) { g_wg_merged = on; }
 // (only with several splits, i.e. long contractions: its strip epilogue writes partial tiles)
@@ -1368,6 +1392,18 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
   g.tmem_cols = 512;        // one CTA per SM: main + small-term accumulator + the A ring
   g.acc2 = WG_ACC2;
   const bool merged = wgrad_merged(M, K);
+  g.a3_chunk0 = -1;
+  g.b3_on = 0;
+  if (merged && g_wg_box3 != 0) {
+    // one 3-D box per operand and k-block where the tile lies inside one segment (see make_map_chunks)
+    if (a->width[0] >= TC_BM + 32) {
+      if ((rc = make_map_chunks(&maps.a3, a->ptr[0], a->width[0], K, a->ld[0], WG_KB, TC_BM / 32 + 1)) != AX2D_OK) return rc;
+      g.a3_chunk0 = 0;
+    }
+    for (int s = 0; s < b->n_seg; ++s)
+      if ((rc = make_map_chunks(&maps.b3[s], b->ptr[s], b->width[s], K, b->ld[s], WG_KB, BN / 32)) != AX2D_OK) return rc;
+    g.b3_on = 1;
+  }
   const int m_tiles = static_cast<int>(wgrad_m_tiles(M, K));
   g.num_kb = static_cast<int>((K + WG_KB - 1) / WG_KB);
   int split = wgrad_split(static_cast<int64_t>(m_tiles) * n_tiles, g.num_kb);

@@ -170,15 +170,14 @@ __device__ __forceinline__ void tma_load_2d_w(void* dst, const CUtensorMap* map,
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
-// L2 prefetch of a 2-D tensor-map box (no shared-memory destination, no barrier): warp-collective, elected issue
-__device__ __forceinline__ void tma_prefetch_2d_w(const CUtensorMap* map, int c_inner, int c_outer) {
+__device__ __forceinline__ void tma_load_3d_w(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "{\n\t"
       ".reg .pred e;\n\t"
       "elect.sync _|e, 0xffffffff;\n\t"
-      "@e cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n\t"
-      "}\n" ::"l"(reinterpret_cast<uint64_t>(map)),
-      "r"(c_inner), "r"(c_outer)
+      "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_w(uint64_t* bar, uint32_t bytes) {
@@ -308,5 +307,29 @@ static inline int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int
   return AX2D_OK;
 }
 
+// The same fp32 row-major matrix seen as [column chunks of 32][rows][32 columns]: ONE box {32, rows, chunks} lands `chunks`
+// consecutive [rows x 32] blocks in shared memory, each in the canonical 128-byte-swizzled MN-major layout -- one TMA
+// instruction per operand and k-block instead of one per 32-column chunk.
+static inline int make_map_chunks(CUtensorMap* map, const void* ptr, int64_t cols, int64_t rows, int64_t ld, int box_rows,
+                                  int box_chunks) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("ax2d_gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+    return AX2D_ERR_UNSUPPORTED;
+  }
+  cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(cols / 32)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4u, 128u};
+  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_chunks)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("ax2d_gemm_tc: cuTensorMapEncodeTiled (3-D chunk view) failed (%d) for a [%lld x %lld] matrix, ld %lld", (int)r,
+              (long long)rows, (long long)cols, (long long)ld);
+    return AX2D_ERR_ARG;
+  }
+  return AX2D_OK;
+}
 
 }  // namespace ax2d
