@@ -17,6 +17,25 @@ from .collate import MolBatch, static_signature
 from .optim import FlatAdam
 
 
+NVTX = bool(int(__import__("os").environ.get("AX2D_NVTX", "0")))      # AX2D_NVTX=1: NVTX ranges around the phases of a step
+
+
+class _Range:
+    """``with _Range("name"):`` -- an NVTX range when AX2D_NVTX=1 (for nsys / ncu --nvtx timelines), nothing otherwise."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class TrainStep:
     def __init__(self, model: torch.nn.Module, criterion: torch.nn.Module, optimizer: FlatAdam, device=None):
         self.model = model
@@ -32,14 +51,18 @@ class TrainStep:
     def device_step(self, bd: MolBatch) -> torch.Tensor:
         """One optimisation step on a device-resident batch; returns the loss as a device scalar (no sync)."""
         opt = self.optimizer
-        opt.zero_grad()                                                     # trainer.py:130
-        out, _, _ = self.model(bd.atom_features_map, bd.multi_hop_edge_indices, bd.batch_indices, bd.total_charges,
-                               bd.final_tetrahedral_chiral_tensor, bd.final_cis_tensor, bd.final_trans_tensor,
-                               graph_index=bd.graph_index)                  # trainer.py:151-159
-        loss = self.criterion(out, bd.targets)                              # trainer.py:162
-        loss.backward()                                                     # trainer.py:163
-        opt.all_reduce_grads()                                              # DDP reducer (runner.py:703-707)
-        opt.step()                                                          # trainer.py:164-165
+        with _Range("ax2d.forward"):
+            opt.zero_grad()                                                 # trainer.py:130
+            out, _, _ = self.model(bd.atom_features_map, bd.multi_hop_edge_indices, bd.batch_indices, bd.total_charges,
+                                   bd.final_tetrahedral_chiral_tensor, bd.final_cis_tensor, bd.final_trans_tensor,
+                                   graph_index=bd.graph_index)              # trainer.py:151-159
+            loss = self.criterion(out, bd.targets)                          # trainer.py:162
+        with _Range("ax2d.backward"):
+            loss.backward()                                                 # trainer.py:163
+        with _Range("ax2d.allreduce"):
+            opt.all_reduce_grads()                                          # DDP reducer (runner.py:703-707)
+        with _Range("ax2d.clip_adam"):
+            opt.step()                                                      # trainer.py:164-165
         return loss.detach()
 
     def __call__(self, batch: MolBatch, return_float: bool = True):
@@ -246,26 +269,31 @@ class GraphedTrainStep(StaticSlot):
     def replay(self) -> torch.Tensor:
         if self.graph_opt is None:           # single graph: backward -> all-reduce -> update in one launch
             self.optimizer.sync_hyper()
-            self.graph_fb.replay()
+            with _Range("ax2d.graph(forward+backward+allreduce+clip_adam)"):
+                self.graph_fb.replay()
             return self.loss
-        self.graph_fb.replay()
+        with _Range("ax2d.graph(forward+backward)"):
+            self.graph_fb.replay()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            self.optimizer.all_reduce_grads()
+            with _Range("ax2d.allreduce"):
+                self.optimizer.all_reduce_grads()
         self.optimizer.sync_hyper()          # LR schedulers: the captured update reads its hyper-parameters from device memory
-        self.graph_opt.replay()
+        with _Range("ax2d.graph(clip_adam)"):
+            self.graph_opt.replay()
         return self.loss
 
     def __call__(self, padded, return_float: bool = True, prefetch: Optional[HostBatch] = None):
         """``padded``: a padded ``MolBatch`` (one copy per tensor) or a ``HostBatch`` from ``pack`` (one copy, possibly
         already under way).  ``prefetch``: the ``HostBatch`` of a later call, copied while this step runs."""
-        if isinstance(padded, HostBatch):
-            if self.graph_fb is None:
-                raise RuntimeError("capture() with a padded MolBatch before passing HostBatch objects")
-            self._load_host(padded)
-        else:
-            if self.graph_fb is None:
-                self.capture(padded)
-            self.load(padded)
+        with _Range("ax2d.h2d"):
+            if isinstance(padded, HostBatch):
+                if self.graph_fb is None:
+                    raise RuntimeError("capture() with a padded MolBatch before passing HostBatch objects")
+                self._load_host(padded)
+            else:
+                if self.graph_fb is None:
+                    self.capture(padded)
+                self.load(padded)
         loss = self.replay()
         if prefetch is not None:
             self.prefetch(prefetch)
