@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_fwd_kernel(
 // latency-bound kernel (a few dependent phases over ~36 KB per molecule) needs.  The head weights (8 KB, the same for
 // every CTA) are read through L1 instead of being copied to shared memory first.
 constexpr int kDirectRows = 256;
+// MAXH: compile-time bound of the head loops (the number of heads rounded up to 1 / 2 / 4 / 8): with the generic bound of 8
+// half of the issued instructions of the default 4-head layer were predicated-off head iterations.
+template <int MAXH>
 __global__ void __launch_bounds__(kPoolThreads) attn_pool_fwd_direct_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ seg_ptr, int64_t N, int F, int heads,
     const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ temperature,
@@ -204,22 +207,22 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_fwd_direct_kernel(
   // ---- pass 1: scores z[h,i] = (w_h . x_i + b_h) / T            (pooling.py:134-140)
   const float4* xg = reinterpret_cast<const float4*>(x + static_cast<int64_t>(n0) * F);
   for (int i = warp; i < n; i += kPoolThreads / 32) {
-    float dot[kMaxHeads];
+    float dot[MAXH];
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) dot[h] = 0.f;
+    for (int h = 0; h < MAXH; ++h) dot[h] = 0.f;
     const float4* xr = xg + static_cast<size_t>(i) * F4;
     // (unrolling this loop so that the row's four loads issue together costs 90 registers and occupancy: 75 vs 60 us)
     for (int c = lane; c < F4; c += 32) {
       const float4 xv = __ldg(xr + c);
 #pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h)
+      for (int h = 0; h < MAXH; ++h)
         if (h < heads) {
           const float4 wv = __ldg(w4 + h * F4 + c);
           dot[h] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
         }
     }
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h)
+    for (int h = 0; h < MAXH; ++h)
       if (h < heads) {
         const float s = warp_sum(dot[h]);
         if (lane == 0) {
@@ -622,10 +625,19 @@ extern "C" int ax2d_attn_pool_fwd(const float* x, int64_t ldx, const int32_t* se
   if (B <= 0) return AX2D_OK;
   if (max_rows_hint > 0 && max_rows_hint <= kDirectRows) {       // every molecule fits the score buffer: no x staging
     const size_t smem_d = static_cast<size_t>(heads + 1) * kDirectRows * 4;
-    if (smem_d > 48 * 1024)
-      cudaFuncSetAttribute(attn_pool_fwd_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_d));
-    attn_pool_fwd_direct_kernel<<<static_cast<unsigned>(B), kPoolThreads, smem_d, reinterpret_cast<cudaStream_t>(stream)>>>(
-        x, seg_ptr, N, F, heads, w, b, temperature, pooled, attn, z);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define AX2D_POOL_DIRECT(MH)                                                                                                   \
+  do {                                                                                                                         \
+    if (smem_d > 48 * 1024)                                                                                                    \
+      cudaFuncSetAttribute(attn_pool_fwd_direct_kernel<MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_d)); \
+    attn_pool_fwd_direct_kernel<MH><<<static_cast<unsigned>(B), kPoolThreads, smem_d, st>>>(x, seg_ptr, N, F, heads, w, b,      \
+                                                                                            temperature, pooled, attn, z);     \
+  } while (0)
+    if (heads <= 1) AX2D_POOL_DIRECT(1);
+    else if (heads <= 2) AX2D_POOL_DIRECT(2);
+    else if (heads <= 4) AX2D_POOL_DIRECT(4);
+    else AX2D_POOL_DIRECT(8);
+#undef AX2D_POOL_DIRECT
     return launch_status("ax2d_attn_pool_fwd");
   }
   const int CH = pool_chunk_rows(F, heads, max_rows_hint, false);
