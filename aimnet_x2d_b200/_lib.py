@@ -36,6 +36,7 @@ _SIGNATURES = {
     "ax2d_error_string": (C.c_char_p, [c_int]),
     "ax2d_last_error": (C.c_char_p, []),
     "ax2d_launch_count": (C.c_uint64, []),
+    "ax2d_set_pdl": (c_int, [c_int]),
     "ax2d_host_csr_build": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
                                     c_void_p, c_void_p, c_void_p]),
     "ax2d_host_tile_plan": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256) agg_kernel(const float* __restrict__ x, i
                                                   const int32_t* __restrict__ col, const float* __restrict__ addend,
                                                   int64_t ld_addend, const int32_t* __restrict__ tile_ptr,
                                                   int64_t n_out_rows, int rows_per_cta) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   constexpr int W4 = 8 * V;                 // float4 per row
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(AGG_CONSUMERS + 32, 2) agg_tiles_kernel(
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_enter();      // the barrier set-up above overlaps the previous kernel's tail; no global access before this
   AGG_STAMP(1);
 
   if (warp == AGG_CONSUMERS / 32) {
@@ -338,6 +340,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW == AGG2_WARPS ? 3 : 1) agg_r
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_enter();      // the barrier set-up above overlaps the previous kernel's tail; no global access before this
 
   if (warp == n_cw) {
     // ================================================================= producer warp
@@ -495,12 +498,12 @@ static int launch_agg_rows(const void* x, void* out, int64_t ldo, const int32_t*
   grid = grid > n_tiles ? n_tiles : grid;
   const int esz = BF16 ? 2 : 4;
   if (wide)
-    agg_rows_kernel<V, BF16, AGG2_MAX_WARPS><<<static_cast<unsigned>(grid), 32 * (AGG2_MAX_WARPS + 1), smem, st>>>(
+    launch_k(agg_rows_kernel<V, BF16, AGG2_MAX_WARPS>, dim3(static_cast<unsigned>(grid)), dim3(32 * (AGG2_MAX_WARPS + 1)), smem, st, 
         static_cast<const uint32_t*>(x), static_cast<uint32_t*>(out), ldo * esz / 4, rowptr, col, static_cast<const uint32_t*>(addend),
         ld_addend * esz / 4, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles), stages, words,
         static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb), g_agg_debug_flags);
   else
-    agg_rows_kernel<V, BF16, AGG2_WARPS><<<static_cast<unsigned>(grid), 32 * (AGG2_WARPS + 1), smem, st>>>(
+    launch_k(agg_rows_kernel<V, BF16, AGG2_WARPS>, dim3(static_cast<unsigned>(grid)), dim3(32 * (AGG2_WARPS + 1)), smem, st, 
         static_cast<const uint32_t*>(x), static_cast<uint32_t*>(out), ldo * esz / 4, rowptr, col, static_cast<const uint32_t*>(addend),
         ld_addend * esz / 4, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles), stages, words,
         static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb), g_agg_debug_flags);
@@ -584,6 +587,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), NW == AGG2_WARPS ? 3 : 1) agg_r
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_enter();      // the barrier set-up above overlaps the previous kernel's tail; no global access before this
 
   if (warp == NW) {
     // ================================================================= producer warp (as in agg_rows_kernel)
@@ -736,12 +740,12 @@ static int launch_agg_rows3(const void* x, void* out, int64_t ldo, const int32_t
   int64_t grid = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
   grid = grid > n_tiles ? n_tiles : grid;
   if (wide)
-    agg_rows3_kernel<U, BF16, AGG2_MAX_WARPS><<<static_cast<unsigned>(grid), 32 * (AGG2_MAX_WARPS + 1), smem, st>>>(
+    launch_k(agg_rows3_kernel<U, BF16, AGG2_MAX_WARPS>, dim3(static_cast<unsigned>(grid)), dim3(32 * (AGG2_MAX_WARPS + 1)), smem, st, 
         static_cast<const unsigned char*>(x), static_cast<unit*>(out), ldo / 2, rowptr, col, static_cast<const unit*>(addend),
         ld_addend / 2, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles), stages, units,
         static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb), g_agg_debug_flags);
   else
-    agg_rows3_kernel<U, BF16, AGG2_WARPS><<<static_cast<unsigned>(grid), 32 * (AGG2_WARPS + 1), smem, st>>>(
+    launch_k(agg_rows3_kernel<U, BF16, AGG2_WARPS>, dim3(static_cast<unsigned>(grid)), dim3(32 * (AGG2_WARPS + 1)), smem, st, 
         static_cast<const unsigned char*>(x), static_cast<unit*>(out), ldo / 2, rowptr, col, static_cast<const unit*>(addend),
         ld_addend / 2, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles), stages, units,
         static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb), g_agg_debug_flags);
@@ -806,6 +810,7 @@ __global__ void __launch_bounds__(AGG3_THREADS + 32) agg_mma_kernel(
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_enter();      // the barrier set-up above overlaps the previous kernel's tail; no global access before this
 
   if (warp == AGG3_THREADS / 32) {
     // ================================================================= producer warp (as in agg_rows_kernel)
@@ -995,7 +1000,7 @@ static int launch_agg_mma(const void* x, void* out, int64_t ldo, const int32_t* 
   }
   int64_t grid = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
   grid = grid > n_tiles ? n_tiles : grid;
-  agg_mma_kernel<BF16><<<static_cast<unsigned>(grid), AGG3_THREADS + 32, smem, st>>>(
+  launch_k(agg_mma_kernel<BF16>, dim3(static_cast<unsigned>(grid)), dim3(AGG3_THREADS + 32), smem, st, 
       static_cast<const uint32_t*>(x), out, ldo, rowptr, col, addend, ld_addend, reinterpret_cast<const int4*>(tile_info),
       static_cast<int>(n_tiles), stages, width, rpad, static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb));
   *handled = true;
@@ -1042,6 +1047,7 @@ __global__ void __launch_bounds__(AGG_CONSUMERS + 32, 2) agg_tiles_bf16_kernel(
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_enter();      // the barrier set-up above overlaps the previous kernel's tail; no global access before this
 
   if (warp == AGG_CONSUMERS / 32) {
     // ================================================================= producer warp (as in agg_tiles_kernel)
@@ -1152,6 +1158,7 @@ __global__ void __launch_bounds__(256) agg_generic_bf16_kernel(const uint16_t* _
                                                                int64_t ldo, const int32_t* __restrict__ rowptr,
                                                                const int32_t* __restrict__ col, const uint16_t* __restrict__ addend,
                                                                int64_t ld_addend, int64_t n_out_rows, int w8) {
+  pdl_enter();
   const int warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * warps + (threadIdx.x >> 5);
@@ -1195,7 +1202,7 @@ static int launch_agg_bf16(const uint16_t* x, uint16_t* out, int64_t ldo, const 
   }
   int64_t grid = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
   grid = grid > n_tiles ? n_tiles : grid;
-  kern<<<static_cast<unsigned>(grid), AGG_CONSUMERS + 32, smem, st>>>(
+  launch_k(kern, dim3(static_cast<unsigned>(grid)), dim3(AGG_CONSUMERS + 32), smem, st, 
       x, out, ldo, rowptr, col, addend, ld_addend, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles), stages,
       static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb));
   return launch_status("ax2d_agg");
@@ -1208,6 +1215,7 @@ __global__ void __launch_bounds__(256) agg_generic_kernel(const float* __restric
                                                           const int32_t* __restrict__ col,
                                                           const float* __restrict__ addend, int64_t ld_addend,
                                                           int64_t n_out_rows, int w4) {
+  pdl_enter();
   const int warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * warps + (threadIdx.x >> 5);
@@ -1257,13 +1265,13 @@ static int launch_agg(const float* x, int64_t ldx, float* out, int64_t ldo, int6
     }
     int64_t grid = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
     grid = grid > n_tiles ? n_tiles : grid;
-    kern<<<static_cast<unsigned>(grid), AGG_CONSUMERS + 32, smem, st>>>(
+    launch_k(kern, dim3(static_cast<unsigned>(grid)), dim3(AGG_CONSUMERS + 32), smem, st, 
         x, out, ldo, rowptr, col, addend, ld_addend, reinterpret_cast<const int4*>(tile_info), static_cast<int>(n_tiles),
         stages, static_cast<uint32_t>(xb), static_cast<uint32_t>(rb), static_cast<uint32_t>(cb));
   } else {
     const int rows_per_cta = 32;
     const int64_t grid = (n_out_rows + rows_per_cta - 1) / rows_per_cta;
-    agg_kernel<V, false><<<static_cast<unsigned>(grid), 256, 0, st>>>(x, ldx, out, ldo, rowptr, col, addend,
+    launch_k(agg_kernel<V, false>, dim3(static_cast<unsigned>(grid)), dim3(256), 0, st, x, ldx, out, ldo, rowptr, col, addend,
                                                                        ld_addend, nullptr, n_out_rows, rows_per_cta);
   }
   return launch_status("ax2d_agg");
@@ -1371,7 +1379,7 @@ extern "C" int ax2d_agg(const void* x, int64_t ldx, int64_t n_src_rows, void* ou
 #undef AX2D_AGG16_CASE
     }
     const int warps = 8;
-    agg_generic_bf16_kernel<<<static_cast<unsigned>((n_out_rows + warps - 1) / warps), warps * 32, 0, st16>>>(
+    launch_k(agg_generic_bf16_kernel, dim3(static_cast<unsigned>((n_out_rows + warps - 1) / warps)), dim3(warps * 32), 0, st16, 
         xh, ldx, oh, ldo, rowptr, col, ah, ld_addend, n_out_rows, width / 8);
     return launch_status("ax2d_agg");
   }
@@ -1400,7 +1408,7 @@ extern "C" int ax2d_agg(const void* x, int64_t ldx, int64_t n_src_rows, void* ou
   }
   if (width % 32 != 0 || width > 32 * 16) {
     const int warps = 8;
-    agg_generic_kernel<<<static_cast<unsigned>((n_out_rows + warps - 1) / warps), warps * 32, 0, st>>>(
+    launch_k(agg_generic_kernel, dim3(static_cast<unsigned>((n_out_rows + warps - 1) / warps)), dim3(warps * 32), 0, st, 
         xf, ldx, of, ldo, rowptr, col, af, ld_addend, n_out_rows, width / 4);
     return launch_status("ax2d_agg");
   }

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(128) charge_eq_fwd_kernel(const float* __restr
                                                             const float* __restrict__ total_charges,
                                                             float* __restrict__ out, int64_t ldo,
                                                             float* __restrict__ stats) {
+  pdl_enter();
   __shared__ float red[4];
   const int g = blockIdx.x;
   const int n0 = seg_ptr[g], n1 = seg_ptr[g + 1];
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(128) charge_eq_bwd_kernel(const float* __restr
                                                             const float* __restrict__ stats,
                                                             const float* __restrict__ g_out, int64_t ldg,
                                                             float* __restrict__ gx, int64_t ldgx) {
+  pdl_enter();
   __shared__ float red[4];
   const int g = blockIdx.x;
   const int n0 = seg_ptr[g], n1 = seg_ptr[g + 1];
@@ -120,6 +122,7 @@ __device__ __forceinline__ void tetra_load(const float* __restrict__ x, int64_t 
 __global__ void __launch_bounds__(128) tetra_contrib_kernel(const float* __restrict__ x, int64_t ldx, int true_width,
                                                             int width, const int32_t* __restrict__ idx, int64_t M,
                                                             float* __restrict__ contrib) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t m = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(256) tetra_apply_kernel(const float* __restric
                                                           const int32_t* __restrict__ slot_idx,
                                                           const float* __restrict__ rows, float* __restrict__ out,
                                                           int64_t ldo) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t a = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (a >= N) return;
@@ -169,6 +173,7 @@ __global__ void __launch_bounds__(128) tetra_bwd_rows_kernel(const float* __rest
                                                              int width, const int32_t* __restrict__ idx, int64_t M,
                                                              const float* __restrict__ g_out, int64_t ldg,
                                                              float* __restrict__ g_rows) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t m = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -233,6 +238,7 @@ __global__ void __launch_bounds__(256) cistrans_kernel(const float* __restrict__
                                                        const int32_t* __restrict__ u_tgt,
                                                        const float* __restrict__ u_sign, int n_upd, int transpose,
                                                        float* __restrict__ out, int64_t ldo) {
+  pdl_enter();
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= N * W4) return;
   const int64_t r = t / W4;
@@ -261,7 +267,7 @@ extern "C" int ax2d_charge_eq_fwd(const float* x, int64_t ldx, const int32_t* se
   AX2D_CHECK_ALIGN(x);
   AX2D_CHECK_ALIGN(out);
   if (B <= 0) return AX2D_OK;
-  charge_eq_fwd_kernel<<<static_cast<unsigned>(B), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(charge_eq_fwd_kernel, dim3(static_cast<unsigned>(B)), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, ldx, seg_ptr, width / 4, total_charges, out, ldo, stats);
   return launch_status("ax2d_charge_eq_fwd");
 }
@@ -273,7 +279,7 @@ extern "C" int ax2d_charge_eq_bwd(const float* x, int64_t ldx, const float* out,
   AX2D_CHECK_ALIGN(g_out);
   AX2D_CHECK_ALIGN(gx);
   if (B <= 0) return AX2D_OK;
-  charge_eq_bwd_kernel<<<static_cast<unsigned>(B), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(charge_eq_bwd_kernel, dim3(static_cast<unsigned>(B)), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, ldx, out, ldo, seg_ptr, width / 4, stats, g_out, ldg, gx, ldgx);
   return launch_status("ax2d_charge_eq_bwd");
 }
@@ -289,12 +295,12 @@ extern "C" int ax2d_tetra_fwd(const float* x, int64_t ldx, int64_t N, int width,
   AX2D_CHECK_ALIGN(contrib);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (M > 0) {
-    tetra_contrib_kernel<<<static_cast<unsigned>((M + 3) / 4), 128, 0, st>>>(x, ldx, true_width, width, idx, M, contrib);
+    launch_k(tetra_contrib_kernel, dim3(static_cast<unsigned>((M + 3) / 4)), dim3(128), 0, st, x, ldx, true_width, width, idx, M, contrib);
     int rc = launch_status("ax2d_tetra_fwd(contrib)");
     if (rc != AX2D_OK) return rc;
   }
   if (N > 0)
-    tetra_apply_kernel<<<static_cast<unsigned>((N + 7) / 8), 256, 0, st>>>(x, ldx, N, width / 4, slot_ptr, slot_idx,
+    launch_k(tetra_apply_kernel, dim3(static_cast<unsigned>((N + 7) / 8)), dim3(256), 0, st, x, ldx, N, width / 4, slot_ptr, slot_idx,
                                                                            contrib, out, ldo);
   return launch_status("ax2d_tetra_fwd(apply)");
 }
@@ -310,13 +316,13 @@ extern "C" int ax2d_tetra_bwd(const float* x, int64_t ldx, int64_t N, int width,
   AX2D_CHECK_ALIGN(g_rows);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (M > 0) {
-    tetra_bwd_rows_kernel<<<static_cast<unsigned>((M + 3) / 4), 128, 0, st>>>(x, ldx, true_width, width, idx, M, g_out,
+    launch_k(tetra_bwd_rows_kernel, dim3(static_cast<unsigned>((M + 3) / 4)), dim3(128), 0, st, x, ldx, true_width, width, idx, M, g_out,
                                                                               ldg, g_rows);
     int rc = launch_status("ax2d_tetra_bwd(rows)");
     if (rc != AX2D_OK) return rc;
   }
   if (N > 0)
-    tetra_apply_kernel<<<static_cast<unsigned>((N + 7) / 8), 256, 0, st>>>(g_out, ldg, N, width / 4, slot_ptr, slot_idx,
+    launch_k(tetra_apply_kernel, dim3(static_cast<unsigned>((N + 7) / 8)), dim3(256), 0, st, g_out, ldg, N, width / 4, slot_ptr, slot_idx,
                                                                            g_rows, gx, ldgx);
   return launch_status("ax2d_tetra_bwd(apply)");
 }
@@ -330,7 +336,7 @@ extern "C" int ax2d_cistrans(const float* x, int64_t ldx, int64_t N, int width, 
   AX2D_CHECK_ALIGN(out);
   if (N <= 0) return AX2D_OK;
   const int64_t total = N * (width / 4);
-  cistrans_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(cistrans_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, ldx, N, width / 4, upd_src, upd_tgt, upd_sign, n_upd, transpose, out, ldo);
   return launch_status("ax2d_cistrans");
 }

@@ -14,6 +14,7 @@ struct EmbedArgs {
 constexpr int kEmbedRowsPerCta = 32;
 __global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedArgs a, int n_tables, int E4, int64_t N,
                                                         float* __restrict__ out, int64_t ldo) {
+  pdl_enter();
   const int per_row = n_tables * E4;
   const int64_t n0 = static_cast<int64_t>(blockIdx.x) * kEmbedRowsPerCta;
   for (int c = threadIdx.x; c < per_row; c += 64) {
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedArgs a, int n_table
 // bf16 output (BASELINE configs[3]): the fp32 table rows are rounded on the way out; 8 columns (16 bytes) per thread
 __global__ void __launch_bounds__(256) embed_fwd_bf16_kernel(EmbedArgs a, int n_tables, int E8, int64_t N,
                                                              uint16_t* __restrict__ out, int64_t ldo) {
+  pdl_enter();
   const int per_row = n_tables * E8;
   const int64_t n0 = static_cast<int64_t>(blockIdx.x) * kEmbedRowsPerCta;
   for (int c = threadIdx.x; c < per_row; c += 64) {
@@ -68,6 +70,7 @@ __device__ __forceinline__ float embed_g(const uint16_t* p) { return __uint_as_f
 template <typename GT>
 __global__ void __launch_bounds__(256) embed_bwd_all_kernel(EmbedBwdArgs a, const GT* __restrict__ g, int64_t ldg, int n_tables,
                                                             int E, int64_t N, int64_t rows_per_cta, float* __restrict__ ws) {
+  pdl_enter();
   extern __shared__ float tab[];          // [total_rows][E]
   const int total = a.row_off[n_tables] * E;
   for (int i = threadIdx.x; i < total; i += blockDim.x) tab[i] = 0.f;
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(256) embed_bwd_all_kernel(EmbedBwdArgs a, cons
 // eight lanes per output element: lane z sums the partials z, z + 8, ..., a shuffle tree combines them (fixed order)
 __global__ void __launch_bounds__(256) embed_bwd_all_final_kernel(EmbedBwdArgs a, const float* __restrict__ ws, int n_tables, int E,
                                                                   int n_part) {
+  pdl_enter();
   const int total = a.row_off[n_tables] * E;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const int z0 = threadIdx.x & 7;
@@ -123,6 +127,7 @@ __global__ void __launch_bounds__(256) embed_bwd_partial_kernel(const float* __r
                                                                 int col0, int E4, const int32_t* __restrict__ order,
                                                                 const int32_t* __restrict__ ptr, int splits,
                                                                 float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float4 red[16][16];
   const int v = blockIdx.x, s = blockIdx.y;
   const int beg = ptr[v], end = ptr[v + 1];
@@ -157,6 +162,7 @@ __global__ void __launch_bounds__(256) embed_bwd_partial_kernel(const float* __r
 }
 __global__ void embed_bwd_final_kernel(const float* __restrict__ partial, int splits, int E, int64_t vocab,
                                        float* __restrict__ g_table) {
+  pdl_enter();
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= vocab * E) return;
   const int64_t v = t / E;
@@ -170,6 +176,7 @@ __global__ void embed_bwd_final_kernel(const float* __restrict__ partial, int sp
 constexpr int kNormBlocks = 1024;
 __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __restrict__ g, int64_t n,
                                                              float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float red[8];
   float s = 0.f;
   const int64_t n4 = n >> 2;
@@ -193,6 +200,7 @@ __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __rest
 }
 __global__ void __launch_bounds__(256) sqnorm_final_kernel(const float* __restrict__ partial, int n_part,
                                                            float* __restrict__ norm2) {
+  pdl_enter();
   __shared__ float red[8];
   float s = 0.f;
   for (int i = threadIdx.x; i < n_part; i += blockDim.x) s += partial[i];
@@ -206,13 +214,15 @@ __global__ void __launch_bounds__(256) sqnorm_final_kernel(const float* __restri
   }
 }
 
-__global__ void step_inc_kernel(int64_t* step) { step[0] += 1; }
+__global__ void step_inc_kernel(int64_t* step) {
+  pdl_enter(); step[0] += 1; }
 
 __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                         const float* __restrict__ norm2, float grad_scale,
                                                         float max_norm, float lr, float beta1, float beta2, float eps,
                                                         const int64_t* __restrict__ step) {
+  pdl_enter();
   __shared__ float s_coef, s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0) {
     const double t = static_cast<double>(step[0]);
@@ -250,6 +260,7 @@ __global__ void __launch_bounds__(256) clip_adam_dev_kernel(float* __restrict__ 
                                                             float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                             const float* __restrict__ norm2, const float* __restrict__ hyper,
                                                             const int64_t* __restrict__ step) {
+  pdl_enter();
   __shared__ float s_coef, s_step_size, s_bc2_sqrt;
   const float grad_scale = hyper[0], max_norm = hyper[1], lr = hyper[2], beta1 = hyper[3], beta2 = hyper[4], eps = hyper[5];
   if (threadIdx.x == 0) {
@@ -287,6 +298,7 @@ __global__ void __launch_bounds__(1024) weighted_loss_kernel(const float* __rest
                                                              const float* __restrict__ weights, int64_t B, int T,
                                                              int kind, float* __restrict__ loss,
                                                              float* __restrict__ g_pred) {
+  pdl_enter();
   __shared__ float red[32];
   const float invB = 1.f / static_cast<float>(B);
   float s = 0.f;
@@ -332,8 +344,7 @@ extern "C" int ax2d_embed_fwd(const float* const* tables, const int64_t* const* 
     a.table[t] = tables[t];
     a.index[t] = indices[t];
   }
-  embed_fwd_kernel<<<static_cast<unsigned>((N + kEmbedRowsPerCta - 1) / kEmbedRowsPerCta), dim3(64, 4), 0,
-                     reinterpret_cast<cudaStream_t>(stream)>>>(a, n_tables, emb_dim / 4, N, out, ldo);
+  launch_k(embed_fwd_kernel, dim3(static_cast<unsigned>((N + kEmbedRowsPerCta - 1) / kEmbedRowsPerCta)), dim3(64, 4), 0, reinterpret_cast<cudaStream_t>(stream), a, n_tables, emb_dim / 4, N, out, ldo);
   return launch_status("ax2d_embed_fwd");
 }
 
@@ -349,8 +360,7 @@ extern "C" int ax2d_embed_fwd_bf16(const float* const* tables, const int64_t* co
     a.table[t] = tables[t];
     a.index[t] = indices[t];
   }
-  embed_fwd_bf16_kernel<<<static_cast<unsigned>((N + kEmbedRowsPerCta - 1) / kEmbedRowsPerCta), dim3(64, 4), 0,
-                          reinterpret_cast<cudaStream_t>(stream)>>>(a, n_tables, emb_dim / 8, N, static_cast<uint16_t*>(out), ldo);
+  launch_k(embed_fwd_bf16_kernel, dim3(static_cast<unsigned>((N + kEmbedRowsPerCta - 1) / kEmbedRowsPerCta)), dim3(64, 4), 0, reinterpret_cast<cudaStream_t>(stream), a, n_tables, emb_dim / 8, N, static_cast<uint16_t*>(out), ldo);
   return launch_status("ax2d_embed_fwd_bf16");
 }
 
@@ -394,15 +404,15 @@ static int embed_bwd_all_impl(const void* g_out, int g_bf16, int64_t ldg, int n_
   const int ctas = embed_bwd_all_ctas(N);
   const int64_t rows_per_cta = (N + ctas - 1) / ctas;
   if (g_bf16)
-    embed_bwd_all_kernel<uint16_t><<<ctas, 256, smem, st>>>(a, static_cast<const uint16_t*>(g_out), ldg, n_tables, emb_dim, N,
+    launch_k(embed_bwd_all_kernel<uint16_t>, dim3(ctas), dim3(256), smem, st, a, static_cast<const uint16_t*>(g_out), ldg, n_tables, emb_dim, N,
                                                             rows_per_cta, static_cast<float*>(workspace));
   else
-    embed_bwd_all_kernel<float><<<ctas, 256, smem, st>>>(a, static_cast<const float*>(g_out), ldg, n_tables, emb_dim, N, rows_per_cta,
+    launch_k(embed_bwd_all_kernel<float>, dim3(ctas), dim3(256), smem, st, a, static_cast<const float*>(g_out), ldg, n_tables, emb_dim, N, rows_per_cta,
                                                          static_cast<float*>(workspace));
   int rc = launch_status("ax2d_embed_bwd_all(partial)");
   if (rc != AX2D_OK) return rc;
   const int total = rows * emb_dim;
-  embed_bwd_all_final_kernel<<<(8 * total + 255) / 256, 256, 0, st>>>(a, static_cast<const float*>(workspace), n_tables, emb_dim,
+  launch_k(embed_bwd_all_final_kernel, dim3((8 * total + 255) / 256), dim3(256), 0, st, a, static_cast<const float*>(workspace), n_tables, emb_dim,
                                                                       ctas);
   return launch_status("ax2d_embed_bwd_all(final)");
 }
@@ -431,12 +441,12 @@ extern "C" int ax2d_embed_bwd(const float* g_out, int64_t ldg, int table, int em
   AX2D_CHECK_ALIGN(workspace);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(static_cast<unsigned>(vocab), kEmbedSplits);
-  embed_bwd_partial_kernel<<<grid, 256, 0, st>>>(g_out, ldg, table * emb_dim, emb_dim / 4, order, ptr, kEmbedSplits,
+  launch_k(embed_bwd_partial_kernel, dim3(grid), dim3(256), 0, st, g_out, ldg, table * emb_dim, emb_dim / 4, order, ptr, kEmbedSplits,
                                                 static_cast<float*>(workspace));
   int rc = launch_status("ax2d_embed_bwd(partial)");
   if (rc != AX2D_OK) return rc;
   const int64_t total = vocab * emb_dim;
-  embed_bwd_final_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+  launch_k(embed_bwd_final_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 
       static_cast<const float*>(workspace), kEmbedSplits, emb_dim, vocab, g_table);
   return launch_status("ax2d_embed_bwd(final)");
 }
@@ -452,9 +462,9 @@ extern "C" int ax2d_sqnorm(const float* g, int64_t n, float* norm2, int64_t* ste
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int64_t blocks = (n / 4 + 255) / 256;
   blocks = blocks < 1 ? 1 : (blocks > kNormBlocks ? kNormBlocks : blocks);
-  sqnorm_partial_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(g, n, static_cast<float*>(workspace));
-  sqnorm_final_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(workspace), static_cast<int>(blocks), norm2);
-  if (step_inc != nullptr) step_inc_kernel<<<1, 1, 0, st>>>(step_inc);
+  launch_k(sqnorm_partial_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, g, n, static_cast<float*>(workspace));
+  launch_k(sqnorm_final_kernel, dim3(1), dim3(256), 0, st, static_cast<const float*>(workspace), static_cast<int>(blocks), norm2);
+  if (step_inc != nullptr) launch_k(step_inc_kernel, dim3(1), dim3(1), 0, st, step_inc);
   return launch_status("ax2d_sqnorm", step_inc != nullptr ? 3 : 2);
 }
 
@@ -465,7 +475,7 @@ extern "C" int ax2d_clip_adam(float* p, const float* g, float* m, float* v, int6
   if (n == 0) return AX2D_OK;
   int64_t blocks = (n + 255) / 256;
   blocks = blocks > kNumSMs * 8 ? kNumSMs * 8 : blocks;
-  clip_adam_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(clip_adam_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       p, g, m, v, n, norm2, grad_scale, max_norm, lr, beta1, beta2, eps, step);
   return launch_status("ax2d_clip_adam");
 }
@@ -476,7 +486,7 @@ extern "C" int ax2d_clip_adam_dev(float* p, const float* g, float* m, float* v, 
   if (n == 0) return AX2D_OK;
   int64_t blocks = (n + 255) / 256;
   blocks = blocks > kNumSMs * 8 ? kNumSMs * 8 : blocks;
-  clip_adam_dev_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, norm2,
+  launch_k(clip_adam_dev_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p, g, m, v, n, norm2,
                                                                                                             hyper, step);
   return launch_status("ax2d_clip_adam_dev");
 }
@@ -484,7 +494,7 @@ extern "C" int ax2d_clip_adam_dev(float* p, const float* g, float* m, float* v, 
 extern "C" int ax2d_weighted_loss(const float* pred, const float* target, const float* weights, int64_t B, int T,
                                   int kind, float* loss, float* g_pred, ax2d_stream_t stream) {
   AX2D_CHECK_ARG(B > 0 && T > 0 && (kind == 0 || kind == 1) && B * T < (1ll << 31), "ax2d_weighted_loss: bad arguments");
-  weighted_loss_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, target, weights, B, T, kind, loss,
+  launch_k(weighted_loss_kernel, dim3(1), dim3(1024), 0, reinterpret_cast<cudaStream_t>(stream), pred, target, weights, B, T, kind, loss,
                                                                                g_pred);
   return launch_status("ax2d_weighted_loss");
 }
@@ -519,6 +529,7 @@ __device__ __forceinline__ float pk_round_tf32(float v) {
 }
 // 32 x 32 tiles through shared memory so that the transposed copies are written as coalesced rows too
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackDesc* __restrict__ table) {
+  pdl_enter();
   __shared__ float tile[32][33];
   const PackDesc d = table[blockIdx.y];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -561,6 +572,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackDesc* __res
   }
 }
 __global__ void __launch_bounds__(256) unpack_grads_kernel(const PackDesc* __restrict__ table) {
+  pdl_enter();
   const PackDesc d = table[blockIdx.y];
   if (d.grad_dst == nullptr) return;
   // four consecutive columns per thread: the split-K partials (the bulk of the traffic) are read as float4 whenever the
@@ -604,7 +616,7 @@ extern "C" int ax2d_pack_weights(const void* table, int n_blocks, int max_block_
   int gx = (max_block_elems + 1023) / 1024;       // one CTA per 32 x 32 tile of the largest block (rough: ragged
   gx = gx > 128 ? 128 : (gx < 1 ? 1 : gx);        // blocks loop)
   dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(n_blocks));
-  pack_weights_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<const PackDesc*>(table));
+  launch_k(pack_weights_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), static_cast<const PackDesc*>(table));
   return launch_status("ax2d_pack_weights");
 }
 extern "C" int ax2d_unpack_grads(const void* table, int n_blocks, int max_block_elems, ax2d_stream_t stream) {
@@ -613,6 +625,6 @@ extern "C" int ax2d_unpack_grads(const void* table, int n_blocks, int max_block_
   int gx = (max_block_elems / 4 + 255) / 256;
   gx = gx > 100 ? 100 : (gx < 1 ? 1 : gx);     // ~one quad per thread for the large blocks: their partial sums are latency-bound
   dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(n_blocks));
-  unpack_grads_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<const PackDesc*>(table));
+  launch_k(unpack_grads_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), static_cast<const PackDesc*>(table));
   return launch_status("ax2d_unpack_grads");
 }

@@ -35,6 +35,7 @@ __device__ __forceinline__ float4 load_op(const SegView& v, int64_t r, int64_t r
 
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constant__ GemmArgs g) {
+  pdl_enter();
   __shared__ __align__(16) float As[2][BK][AS_LD];
   __shared__ __align__(16) float Bs[2][BK][BS_LD];
   const int tid = threadIdx.x;
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const __grid_constan
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int split, int64_t M,
                                                             int64_t N, SegOut c, int accumulate,
                                                             const float* __restrict__ vec_ws, float* __restrict__ vec_out) {
+  pdl_enter();
   const int64_t t = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;   // float4 index
   const int z0 = threadIdx.x & 7;
   const int64_t N4 = N >> 2;
@@ -228,6 +230,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // are combined through shared memory in warp order.
 constexpr int kColsumRows = 256;
 __global__ void __launch_bounds__(256) colsum_partial_kernel(SegView a, int64_t M, int N4, float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float4 red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(SegView a, int64_t 
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int n_part, int N, float* __restrict__ out,
                                     int accumulate) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= N) return;
   float s = 0.f;
@@ -268,6 +272,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int n_par
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ gr, int64_t ldg,
                                                       const float* __restrict__ pre, int64_t ldp,
                                                       float* __restrict__ out, int64_t ldo, int64_t M, int W4, int act) {
+  pdl_enter();
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= M * W4) return;
   const int64_t m = t / W4;
@@ -277,7 +282,8 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
   reinterpret_cast<float4*>(out + m * ldo)[c] = make_float4(gv.x * act_bwd(act, pv.x), gv.y * act_bwd(act, pv.y),
                                                             gv.z * act_bwd(act, pv.z), gv.w * act_bwd(act, pv.w));
 }
-__global__ void tick_kernel(unsigned long long* c) { c[0] += 1ull; }
+__global__ void tick_kernel(unsigned long long* c) {
+  pdl_enter(); c[0] += 1ull; }
 
 int to_view(const ax2d_cmat* m, SegView* v, int64_t total, const char* what) {
   int acc = 0;
@@ -343,7 +349,7 @@ int to_out(const ax2d_mat* m, SegOut* v, int64_t total, const char* what, bool a
 int splitk_reduce(const float* ws, int split, int64_t M, int64_t N, const SegOut& c, int accumulate, const float* vec_ws,
                   float* vec_out, cudaStream_t st) {
   const int64_t total = 8 * (M * (N / 4) + (vec_ws != nullptr ? (M + 3) / 4 : 0));      // 8 lanes per float4
-  splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(ws, split, M, N, c, accumulate, vec_ws,
+  launch_k(splitk_reduce_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, ws, split, M, N, c, accumulate, vec_ws,
                                                                                   vec_out);
   return launch_status("split-k reduce");
 }
@@ -441,15 +447,15 @@ extern "C" int ax2d_gemm(const ax2d_cmat* a, int trans_a, const ax2d_cmat* b, in
   AX2D_CHECK_ARG(!trans_a || (g.e.act == AX2D_ACT_NONE && g.e.dact == AX2D_ACT_NONE && g.e.mask == nullptr &&
                               g.e.drop_p == 0.f),
                  "ax2d_gemm: trans_a (weight-gradient) products support only bias / residual / accumulate epilogues");
-  if (trans_a && trans_b) gemm_kernel<true, true><<<grid, GEMM_THREADS, 0, st>>>(g);
-  else if (trans_a) gemm_kernel<true, false><<<grid, GEMM_THREADS, 0, st>>>(g);
-  else if (trans_b) gemm_kernel<false, true><<<grid, GEMM_THREADS, 0, st>>>(g);
-  else gemm_kernel<false, false><<<grid, GEMM_THREADS, 0, st>>>(g);
+  if (trans_a && trans_b) launch_k(gemm_kernel<true, true>, dim3(grid), dim3(GEMM_THREADS), 0, st, g);
+  else if (trans_a) launch_k(gemm_kernel<true, false>, dim3(grid), dim3(GEMM_THREADS), 0, st, g);
+  else if (trans_b) launch_k(gemm_kernel<false, true>, dim3(grid), dim3(GEMM_THREADS), 0, st, g);
+  else launch_k(gemm_kernel<false, false>, dim3(grid), dim3(GEMM_THREADS), 0, st, g);
   rc = launch_status("ax2d_gemm");
   if (rc != AX2D_OK) return rc;
   if (split_k > 1) {
     const int64_t total = 8 * M * (N / 4);
-    splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+    launch_k(splitk_reduce_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, 
         g.ws, static_cast<int>(grid.z), M, N, g.e.c, g.e.accumulate, nullptr, nullptr);
     rc = launch_status("ax2d_gemm(split-k reduce)");
   }
@@ -470,9 +476,9 @@ extern "C" int ax2d_colsum(const ax2d_cmat* a, int64_t M, int64_t N, float* out,
   const int n_part = static_cast<int>((M + kColsumRows - 1) / kColsumRows);
   if (n_part > 0) {
     dim3 grid(static_cast<unsigned>((N / 4 + 31) / 32), static_cast<unsigned>(n_part));
-    colsum_partial_kernel<<<grid, 256, 0, st>>>(v, M, static_cast<int>(N / 4), static_cast<float*>(workspace));
+    launch_k(colsum_partial_kernel, dim3(grid), dim3(256), 0, st, v, M, static_cast<int>(N / 4), static_cast<float*>(workspace));
   }
-  colsum_final_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, st>>>(static_cast<const float*>(workspace), n_part,
+  launch_k(colsum_final_kernel, dim3(static_cast<unsigned>((N + 127) / 128)), dim3(128), 0, st, static_cast<const float*>(workspace), n_part,
                                                                                static_cast<int>(N), out, accumulate);
   return launch_status("ax2d_colsum", n_part > 0 ? 2 : 1);
 }
@@ -485,13 +491,13 @@ extern "C" int ax2d_act_bwd(const float* gr, int64_t ldg, const float* pre, int6
   AX2D_CHECK_ALIGN(out);
   if (M <= 0) return AX2D_OK;
   const int64_t total = M * (width / 4);
-  act_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(act_bwd_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       gr, ldg, pre, ldp, out, ldo, M, width / 4, act);
   return launch_status("ax2d_act_bwd");
 }
 
 extern "C" int ax2d_tick(uint64_t* counter, ax2d_stream_t stream) {
   AX2D_CHECK_ARG(counter != nullptr, "ax2d_tick: null counter");
-  tick_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(counter));
+  launch_k(tick_kernel, dim3(1), dim3(1), 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<unsigned long long*>(counter));
   return launch_status("ax2d_tick");
 }

@@ -340,8 +340,6 @@ __global__ void __launch_bounds__(BF_THREADS, 1) gemm_bf16_kernel(const __grid_c
   // bias copy behind the epilogue staging tiles (N <= BF_BIAS_SMEM floats; larger N reads it from global memory)
   float* s_bias = (g.bias != nullptr && g.N <= BF_BIAS_SMEM)
                       ? reinterpret_cast<float*>(epi_base + static_cast<size_t>(BF_EPI_WARPS) * warp_stage_bytes) : nullptr;
-  if (s_bias != nullptr)
-    for (int i = threadIdx.x; i < g.N; i += blockDim.x) s_bias[i] = __ldg(g.bias + i);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -362,6 +360,11 @@ __global__ void __launch_bounds__(BF_THREADS, 1) gemm_bf16_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();      // nothing above touches global memory: the prologue overlaps the previous kernel's tail
+  if (s_bias != nullptr) {                       // CTA-uniform
+    for (int i = threadIdx.x; i < g.N; i += blockDim.x) s_bias[i] = __ldg(g.bias + i);
+    __syncthreads();
+  }
   const uint32_t tmem_base = tmem_base_smem;
   const int n_ct = g.n_ct, total = g.total_tiles, num_kb = g.num_kb;
   if (dbg != nullptr && threadIdx.x == 0) dbg[1] = gtime();
@@ -600,6 +603,7 @@ __global__ void __launch_bounds__(BF_THREADS, 1) gemm_bf16_wgrad_kernel(const __
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();      // nothing above touches global memory: the prologue overlaps the previous kernel's tail
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t ones_col = static_cast<uint32_t>((BN + 15) & ~15);              // TMEM column of the bias accumulator
 
@@ -695,6 +699,7 @@ __global__ void __launch_bounds__(BF_THREADS, 1) gemm_bf16_wgrad_kernel(const __
 template <bool TO_BF16>
 __global__ void __launch_bounds__(256) convert_kernel(const void* __restrict__ in, int64_t ldi, void* __restrict__ out, int64_t ldo,
                                                       int64_t M, int w8) {
+  pdl_enter();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= M * w8) return;
   const int64_t m = i / w8;
@@ -715,6 +720,7 @@ __global__ void __launch_bounds__(256) convert_kernel(const void* __restrict__ i
 __global__ void __launch_bounds__(256) act_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ gr, int64_t ldg,
                                                            const __nv_bfloat16* __restrict__ pre, int64_t ldp,
                                                            __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t M, int w8, int act) {
+  pdl_enter();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= M * w8) return;
   const int64_t m = i / w8;
@@ -939,7 +945,7 @@ extern "C" int ax2d_gemm_bf16(const ax2d_cmat* a, const void* b, int64_t ldb, co
     configured = smem;
   }
   dim3 grid(static_cast<unsigned>(g.total_tiles < kNumSMs ? g.total_tiles : kNumSMs));
-  gemm_bf16_kernel<<<grid, BF_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, g);
+  launch_k(gemm_bf16_kernel, dim3(grid), dim3(BF_THREADS), smem, reinterpret_cast<cudaStream_t>(stream), maps, g);
   return launch_status("ax2d_gemm_bf16");
 }
 
@@ -1043,7 +1049,7 @@ extern "C" int ax2d_gemm_bf16_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, cons
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), static_cast<unsigned>(split));
-  gemm_bf16_wgrad_kernel<<<grid, BF_THREADS, smem, st>>>(maps, g);
+  launch_k(gemm_bf16_wgrad_kernel, dim3(grid), dim3(BF_THREADS), smem, st, maps, g);
   rc = launch_status("ax2d_gemm_bf16_wgrad");
   if (rc != AX2D_OK || accumulate == 2) return rc;
   SegOut out;
@@ -1063,8 +1069,8 @@ extern "C" int ax2d_convert(const void* in, int64_t ldi, int in_dtype, void* out
   const int64_t total = M * (width / 8);
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (out_dtype == AX2D_BF16) convert_kernel<true><<<blocks, 256, 0, st>>>(in, ldi, out, ldo, M, width / 8);
-  else convert_kernel<false><<<blocks, 256, 0, st>>>(in, ldi, out, ldo, M, width / 8);
+  if (out_dtype == AX2D_BF16) launch_k(convert_kernel<true>, dim3(blocks), dim3(256), 0, st, in, ldi, out, ldo, M, width / 8);
+  else launch_k(convert_kernel<false>, dim3(blocks), dim3(256), 0, st, in, ldi, out, ldo, M, width / 8);
   return launch_status("ax2d_convert");
 }
 
@@ -1076,7 +1082,7 @@ extern "C" int ax2d_act_bwd_bf16(const void* g, int64_t ldg, const void* pre, in
   AX2D_CHECK_ALIGN(out);
   if (M <= 0) return AX2D_OK;
   const int64_t total = M * (width / 8);
-  act_bwd_bf16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(act_bwd_bf16_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(g), ldg, static_cast<const __nv_bfloat16*>(pre), ldp, static_cast<__nv_bfloat16*>(out), ldo, M,
       width / 8, act);
   return launch_status("ax2d_act_bwd_bf16");

@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();      // nothing above touches global memory: the prologue overlaps the previous kernel's tail
   const uint32_t tmem_base = tmem_base_smem;
   const int n_tiles = g.n_tiles, total = g.total_tiles, num_kb = g.num_kb;
 
@@ -685,6 +686,7 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad_kernel(const _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();      // nothing above touches global memory: the prologue overlaps the previous kernel's tail
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
@@ -938,6 +940,7 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad160_kernel(cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();      // nothing above touches global memory: the prologue overlaps the previous kernel's tail
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
@@ -1127,6 +1130,7 @@ __global__ void __launch_bounds__(TC_WG_THREADS, 1) gemm_tc_wgrad160_kernel(cons
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, int64_t ldw, int rows, int cols,
                                                          int transpose, float* __restrict__ hi, float* __restrict__ lo,
                                                          int64_t ldo) {
+  pdl_enter();
   // out is [rows, cols]; source is w[rows, cols] or, transposed, w[cols, rows]
   __shared__ float tile[32][33];
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
@@ -1177,7 +1181,7 @@ extern "C" int ax2d_split_tf32(const float* w, int64_t ldw, int rows, int cols, 
   AX2D_CHECK_ARG(w != nullptr && hi != nullptr && lo != nullptr && rows > 0 && cols > 0 && ldo >= cols,
                  "ax2d_split_tf32: bad arguments");
   dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
-  split_tf32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, ldw, rows, cols, transpose, hi, lo, ldo);
+  launch_k(split_tf32_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), w, ldw, rows, cols, transpose, hi, lo, ldo);
   return launch_status("ax2d_split_tf32");
 }
 
@@ -1289,8 +1293,8 @@ extern "C" int ax2d_gemm_tc(const ax2d_cmat* a, const float* b_hi, const float* 
     configured[wide] = smem;
   }
   dim3 grid(static_cast<unsigned>(g.total_tiles < kNumSMs ? g.total_tiles : kNumSMs));
-  if (wide) gemm_tc_kernel<TC_BK_WIDE><<<grid, TC_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, g);
-  else gemm_tc_kernel<TC_BK><<<grid, TC_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, g);
+  if (wide) launch_k(gemm_tc_kernel<TC_BK_WIDE>, dim3(grid), dim3(TC_THREADS), smem, reinterpret_cast<cudaStream_t>(stream), maps, g);
+  else launch_k(gemm_tc_kernel<TC_BK>, dim3(grid), dim3(TC_THREADS), smem, reinterpret_cast<cudaStream_t>(stream), maps, g);
   return launch_status("ax2d_gemm_tc");
 }
 
@@ -1445,8 +1449,8 @@ extern "C" int ax2d_gemm_tc_wgrad(const ax2d_cmat* a, const ax2d_cmat* b, const 
                                               "(ax2d_gemm_tc_wgrad_splits)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), static_cast<unsigned>(split));
-  if (merged) gemm_tc_wgrad160_kernel<<<grid, TC_WG_THREADS, smem, st>>>(maps, g);
-  else gemm_tc_wgrad_kernel<<<grid, TC_WG_THREADS, smem, st>>>(maps, g);
+  if (merged) launch_k(gemm_tc_wgrad160_kernel, dim3(grid), dim3(TC_WG_THREADS), smem, st, maps, g);
+  else launch_k(gemm_tc_wgrad_kernel, dim3(grid), dim3(TC_WG_THREADS), smem, st, maps, g);
   rc = launch_status("ax2d_gemm_tc_wgrad");
   if (rc != AX2D_OK || split == 1 || accumulate == 2) return rc;
   return splitk_reduce(g.ws, split, M, N, g.e.c, accumulate == 1, g.db, bias_grad, st);

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_fwd_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ seg_ptr, int64_t N, int F, int heads,
     const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ temperature,
     float* __restrict__ pooled, float* __restrict__ attn, float* __restrict__ zbuf, int CH) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   float* xs = reinterpret_cast<float*>(smem_raw);                 // [CH, F]
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_fwd_direct_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ seg_ptr, int64_t N, int F, int heads,
     const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ temperature,
     float* __restrict__ pooled, float* __restrict__ attn, float* __restrict__ zbuf) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* as = reinterpret_cast<float*>(smem_raw);                 // [heads, kDirectRows]  scores then weights
   float* abar = as + static_cast<size_t>(heads) * kDirectRows;    // [kDirectRows]
@@ -293,6 +295,7 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_bwd_kernel(
     const float* __restrict__ w, const float* __restrict__ temperature, const float* __restrict__ attn,
     const float* __restrict__ zbuf, const float* __restrict__ g_pooled, const float* __restrict__ g_attn,
     float* __restrict__ gx, int64_t ldgx, float* __restrict__ partials, int CH) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ float red[kPoolThreads / 32][NH + 1];
@@ -513,6 +516,7 @@ __global__ void __launch_bounds__(256) attn_pool_bwd_reduce_kernel(const float* 
                                                                    int heads, const float* __restrict__ temperature,
                                                                    float* __restrict__ gw, float* __restrict__ gb,
                                                                    float* __restrict__ gT) {
+  pdl_enter();
   // (the per-CTA partials are summed in double: a few hundred terms per entry, and these sums cancel)
   __shared__ double red[8][32];
   const int stride = pool_partial_stride(heads, F);
@@ -554,6 +558,7 @@ constexpr int kPoolBwdMaxGrid = kNumSMs * 3;
 __global__ void __launch_bounds__(128) seg_reduce_fwd_kernel(const float* __restrict__ x, int64_t ldx,
                                                              const int32_t* __restrict__ seg_ptr, int F4, int mode,
                                                              float* __restrict__ out, int32_t* __restrict__ arg) {
+  pdl_enter();
   const int g = blockIdx.x;
   const int n0 = seg_ptr[g], n1 = seg_ptr[g + 1];
   for (int c = threadIdx.x; c < F4; c += blockDim.x) {
@@ -587,6 +592,7 @@ __global__ void __launch_bounds__(128) seg_reduce_bwd_kernel(const float* __rest
                                                              const int32_t* __restrict__ seg_ptr, int F4, int mode,
                                                              const int32_t* __restrict__ arg, float* __restrict__ gx,
                                                              int64_t ldgx) {
+  pdl_enter();
   const int g = blockIdx.x;
   const int n0 = seg_ptr[g], n1 = seg_ptr[g + 1];
   for (int c = threadIdx.x; c < F4; c += blockDim.x) {
@@ -630,7 +636,7 @@ extern "C" int ax2d_attn_pool_fwd(const float* x, int64_t ldx, const int32_t* se
   do {                                                                                                                         \
     if (smem_d > 48 * 1024)                                                                                                    \
       cudaFuncSetAttribute(attn_pool_fwd_direct_kernel<MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_d)); \
-    attn_pool_fwd_direct_kernel<MH><<<static_cast<unsigned>(B), kPoolThreads, smem_d, st>>>(x, seg_ptr, N, F, heads, w, b,      \
+    launch_k(attn_pool_fwd_direct_kernel<MH>, dim3(static_cast<unsigned>(B)), dim3(kPoolThreads), smem_d, st, x, seg_ptr, N, F, heads, w, b,      \
                                                                                             temperature, pooled, attn, z);     \
   } while (0)
     if (heads <= 1) AX2D_POOL_DIRECT(1);
@@ -644,7 +650,7 @@ extern "C" int ax2d_attn_pool_fwd(const float* x, int64_t ldx, const int32_t* se
   const size_t smem = (static_cast<size_t>(CH) * F + static_cast<size_t>(heads) * F + static_cast<size_t>(heads) * CH + CH) * 4;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(attn_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  attn_pool_fwd_kernel<<<static_cast<unsigned>(B), kPoolThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(attn_pool_fwd_kernel, dim3(static_cast<unsigned>(B)), dim3(kPoolThreads), smem, reinterpret_cast<cudaStream_t>(stream), 
       x, seg_ptr, N, F, heads, w, b, temperature, pooled, attn, z, CH);
   return launch_status("ax2d_attn_pool_fwd");
 }
@@ -664,12 +670,12 @@ static int launch_pool_bwd(const float* x, const int32_t* seg_ptr, int64_t B, in
   auto kern = attn_pool_bwd_kernel<NH>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   const int grid = B < kPoolBwdMaxGrid ? static_cast<int>(B) : kPoolBwdMaxGrid;
-  kern<<<grid, kPoolThreads, smem, st>>>(x, seg_ptr, B, N, F, w, temperature, attn, z, g_pooled, g_attn, gx, ldgx,
+  launch_k(kern, dim3(grid), dim3(kPoolThreads), smem, st, x, seg_ptr, B, N, F, w, temperature, attn, z, g_pooled, g_attn, gx, ldgx,
                                          static_cast<float*>(ws), CH);
   int rc = launch_status("ax2d_attn_pool_bwd");
   if (rc != AX2D_OK) return rc;
   const int total = NH * F + NH + 1;
-  attn_pool_bwd_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(static_cast<const float*>(ws), grid, F, NH,
+  launch_k(attn_pool_bwd_reduce_kernel, dim3((total + 31) / 32), dim3(256), 0, st, static_cast<const float*>(ws), grid, F, NH,
                                                                     temperature, gw, gb, gT);
   return launch_status("ax2d_attn_pool_bwd(reduce)");
 }
@@ -709,7 +715,7 @@ extern "C" int ax2d_seg_reduce_fwd(const float* x, int64_t ldx, const int32_t* s
   AX2D_CHECK_ALIGN(out);
   AX2D_CHECK_ALIGN(arg);
   if (B <= 0) return AX2D_OK;
-  seg_reduce_fwd_kernel<<<static_cast<unsigned>(B), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(seg_reduce_fwd_kernel, dim3(static_cast<unsigned>(B)), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, ldx, seg_ptr, F / 4, mode, out, arg);
   return launch_status("ax2d_seg_reduce_fwd");
 }
@@ -721,7 +727,7 @@ extern "C" int ax2d_seg_reduce_bwd(const float* g_out, const int32_t* seg_ptr, i
   AX2D_CHECK_ALIGN(g_out);
   AX2D_CHECK_ALIGN(gx);
   if (B <= 0) return AX2D_OK;
-  seg_reduce_bwd_kernel<<<static_cast<unsigned>(B), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(seg_reduce_bwd_kernel, dim3(static_cast<unsigned>(B)), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), 
       g_out, seg_ptr, F / 4, mode, arg, gx, ldgx);
   return launch_status("ax2d_seg_reduce_bwd");
 }

@@ -33,6 +33,8 @@ class KernelTimer:
     def __enter__(self):
         global TIMER
         self._prev = (_lib.TIMER_HOOK[0], TIMER)
+        # event records between the launches: programmatic dependent launch off while the brackets are in place
+        self._pdl = _lib.load().ax2d_set_pdl(0)
         _lib.TIMER_HOOK[0] = self
         TIMER = self
         return self
@@ -40,6 +42,7 @@ class KernelTimer:
     def __exit__(self, *exc):
         global TIMER
         _lib.TIMER_HOOK[0], TIMER = self._prev
+        _lib.load().ax2d_set_pdl(self._pdl)
         return False
 
     def bracket(self, name, fn, args):

@@ -42,6 +42,10 @@ const char* ax2d_error_string(int code);
 const char* ax2d_last_error(void);
 /* number of CUDA kernels this library has enqueued in this process so far (bench.py's gpu_launches). */
 uint64_t    ax2d_launch_count(void);
+/* Programmatic dependent launch of the step's kernels (off unless AX2D_PDL=1 or ax2d_set_pdl(1)): inside a captured step
+ * graph the next kernel's prologue overlaps the tail of the current one; every kernel waits (griddepcontrol.wait)
+ * before it touches memory, so results do not depend on the setting.  Returns the previous setting. */
+int         ax2d_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * Collation-time integer work (HOST).  Replaces the Python loops of

@@ -195,3 +195,78 @@ def test_shell_csr_device_full_batch_feeds_the_aggregation():
         assert torch.equal(getattr(gi, k), getattr(ref, k)), k
     x = torch.randn(gi.num_atoms, 160, device=DEV)
     assert torch.equal(ops.agg(x, gi.to(DEV)), ops.agg(x, ref.to(DEV)))
+
+
+# ------------------------------------------------------------------------------------------------ a5: stereo kernels
+def _stereo_index(N, tetra, cis, trans):
+    from aimnet_x2d_b200.collate import GraphIndex
+    gi = GraphIndex()
+    gi.num_atoms = N
+    gi.set_stereo(tetra, cis, trans)
+    if gi.tetra is not None:
+        i, sp, si, M = gi.tetra
+        gi.tetra = (i.to(DEV), sp.to(DEV), si.to(DEV), M)
+    if gi.cistrans is not None:
+        s, t, sg, n = gi.cistrans
+        gi.cistrans = (s.to(DEV), t.to(DEV), sg.to(DEV), n)
+    return gi
+
+
+@pytest.mark.parametrize("N,D,Dp,M,seed", [(64, 12, 12, 9, 0), (200, 30, 32, 70, 1), (5, 4, 4, 1, 2), (900, 153, 160, 400, 3)])
+def test_tetra_kernels_match_oracle(N, D, Dp, M, seed):
+    """Stand-alone ax2d_tetra_fwd / ax2d_tetra_bwd against the oracle's restatement of gnn.py:387-462 in float64:
+    atoms shared by several centres (index_add_ order), repeated atoms inside one centre, atoms in no centre (zeroed,
+    quirk Q4), padded feature columns; forward values and the gradient with respect to x at 1e-5 of the largest entry."""
+    from aimnet_x2d_b200 import ops
+    from oracle import model_port
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tetra = rng.integers(0, max(N // 2, 4), size=(M, 4)).astype(np.int64)           # upper half of the atoms: never used
+    if M > 2:
+        tetra[1, 1] = tetra[1, 0]                                                       # a repeated neighbour
+        tetra[2] = tetra[0]                                                             # two centres on the same atoms
+    x = np.zeros((N, Dp), dtype=np.float32)
+    x[:, :D] = rng.normal(size=(N, D)).astype(np.float32)
+    x[3 % N, :D] *= 1e-4                                                                # a nearly zero row (normalize eps path)
+    g = rng.normal(size=(N, Dp)).astype(np.float32)
+    gi = _stereo_index(N, tetra, None, None)
+    xd = torch.from_numpy(x).to(DEV).requires_grad_(True)
+    out = ops.TetraFn.apply(xd, D, gi)
+    out.backward(torch.from_numpy(g).to(DEV))
+    xr = torch.from_numpy(x[:, :D]).double().requires_grad_(True)
+    ref = model_port.tetrahedral(xr, torch.from_numpy(tetra))
+    ref.backward(torch.from_numpy(g[:, :D]).double())
+    o, gx = out.detach().cpu().double(), xd.grad.cpu().double()
+    assert float((o[:, :D] - ref.detach()).abs().max()) <= 1e-5 * float(ref.detach().abs().max())
+    assert float((gx[:, :D] - xr.grad).abs().max()) <= 1e-5 * float(xr.grad.abs().max())
+    untouched = np.setdiff1d(np.arange(N), np.unique(tetra))
+    assert torch.all(o[untouched, :D] == 0)                                             # quirk Q4: exact zeros
+    # fp32 oracle (the reference's own arithmetic): same bar
+    ref32 = model_port.tetrahedral(torch.from_numpy(x[:, :D]), torch.from_numpy(tetra))
+    assert float((o[:, :D] - ref32.double()).abs().max()) <= 1e-5 * float(ref32.abs().max())
+
+
+@pytest.mark.parametrize("N,D,Dp,Kc,Kt,seed", [(50, 12, 12, 3, 2, 0), (300, 153, 160, 40, 25, 1), (10, 8, 8, 0, 2, 2), (10, 8, 8, 1, 0, 3)])
+def test_cistrans_kernel_matches_oracle(N, D, Dp, Kc, Kt, seed):
+    """Stand-alone ax2d_cistrans (forward and its transposed backward) against the oracle's gnn.py:465-509 restatement:
+    only rows 0 and 1 of the [2K, 2] index tensors are used (quirk Q3), cis subtracts, trans adds, repeated targets
+    accumulate."""
+    from aimnet_x2d_b200 import ops
+    from oracle import model_port
+    rng = np.random.Generator(np.random.PCG64(100 + seed))
+    cis = rng.integers(0, N, size=(2 * Kc, 2)).astype(np.int64) if Kc else np.zeros((0, 2), dtype=np.int64)
+    trans = rng.integers(0, N, size=(2 * Kt, 2)).astype(np.int64) if Kt else np.zeros((0, 2), dtype=np.int64)
+    if Kc and Kt:
+        trans[1] = cis[1]                                                               # the same targets from both lists
+    x = np.zeros((N, Dp), dtype=np.float32)
+    x[:, :D] = rng.normal(size=(N, D)).astype(np.float32)
+    g = rng.normal(size=(N, Dp)).astype(np.float32)
+    gi = _stereo_index(N, None, cis, trans)
+    xd = torch.from_numpy(x).to(DEV).requires_grad_(True)
+    out = ops.CisTransFn.apply(xd, gi)
+    out.backward(torch.from_numpy(g).to(DEV))
+    xr = torch.from_numpy(x[:, :D]).double().requires_grad_(True)
+    ref = model_port.cis_trans(xr, torch.from_numpy(cis), torch.from_numpy(trans))
+    ref.backward(torch.from_numpy(g[:, :D]).double())
+    o, gx = out.detach().cpu().double(), xd.grad.cpu().double()
+    assert float((o[:, :D] - ref.detach()).abs().max()) <= 1e-5 * float(ref.detach().abs().max())
+    assert float((gx[:, :D] - xr.grad).abs().max()) <= 1e-5 * float(xr.grad.abs().max())
