@@ -52,6 +52,7 @@ _SIGNATURES = {
     "ax2d_agg_tiles_mma_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "ax2d_agg_tiles_mma": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                    c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "ax2d_attn_pool_fwd_config": (c_int, [c_int, c_int]),
     "ax2d_attn_pool_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ax2d_attn_pool_bwd_workspace": (c_int64, [c_int64, c_int, c_int]),

@@ -285,6 +285,309 @@ __global__ void __launch_bounds__(kPoolThreads) attn_pool_fwd_direct_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------ forward, streaming
+// One pass over x with an online softmax per (head, molecule): G warps share a molecule (rows sub, sub + G, ...), each
+// warp streams its rows through a private ring of kStreamRing rows in shared memory filled with cp.async (every lane
+// copies exactly the 16-byte columns it later reads, so the ring needs no barrier at all) and keeps, per head, the
+// running maximum m_h, the running sum s_h of exp(z - m_h) and the running weighted sum acc_h = sum_i exp(z_i - m_h) x_i
+// in registers (rescaled when the maximum moves).  The G partial states of a molecule are merged once at the end.
+// x is read from HBM exactly once and never again (the two-phase kernels above re-read it from L2 for the weighted sum and
+// wait for one dependent 16-byte load per lane at a time: 0.07 - 0.23 of the HBM rate); 4 CTAs x 4 warps x 3 rows of
+// 2 KB are in flight per SM.  Same arithmetic as pooling.py:134-161 up to the order of the fp32 sums.
+constexpr int kStreamRingS = 4, kStreamRingW = 6;
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory");
+}
+
+// packed fp32 pairs (Blackwell FFMA2 / FMUL2): a float4 read from shared memory is two 64-bit units
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float ex2_approx(float v) {         // 2^v, relative error <= 2^-22
+  float r;
+  asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
+// Sum H per-lane values over the warp with log2(H) halving stages (a lane keeps half of its values and sends the other
+// half: H/2 + H/4 + ... shuffles), the remaining butterfly stages on the single value left, and one indexed shuffle per
+// head to hand every total to every lane (bitwise identical in all lanes: the branches on them stay warp-uniform).
+// 4 heads: 10 shuffles + 6 adds instead of 20 + 20.
+template <int H>
+__device__ __forceinline__ void warp_sum_heads(float (&d)[H], int lane) {
+  static_assert(H == 1 || H == 2 || H == 4 || H == 8, "power of two");
+  int off = 16;
+#pragma unroll
+  for (int nv = H; nv > 1; nv >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int q = 0; q < nv / 2; ++q) {
+      const float keep = up ? d[q + nv / 2] : d[q];
+      const float send = up ? d[q] : d[q + nv / 2];
+      d[q] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) d[0] += __shfl_xor_sync(0xffffffffu, d[0], off);
+  constexpr int L = H == 1 ? 0 : H == 2 ? 1 : H == 4 ? 2 : 3;
+  const float mine = d[0];
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    int src = 0;
+#pragma unroll
+    for (int k = 0; k < L; ++k) src |= ((h >> (L - 1 - k)) & 1) << (4 - k);
+    d[h] = __shfl_sync(0xffffffffu, mine, src);
+  }
+}
+
+// WREG (kept, off: ax2d_attn_pool_fwd_config mode 2): the head weights of a lane's columns live in registers (2 CTAs per
+// SM, a ring of 6 rows per warp) instead of being re-read from shared memory for every row (4 CTAs per SM, ring of 4;
+// 16 of the 20 LDS.128 per row are weights).  Measured slower, 201 vs 158 us on 4160 drug-like molecules: the kernel is
+// bound by instruction issue and fixed-latency dependencies (ncu: issue-active 47 %, stalls wait / short scoreboard),
+// not by the shared-memory pipe, and 8 warps per SM hide less of it than 16.
+template <int MAXH, int J, bool WREG>
+__global__ void __launch_bounds__(kPoolThreads, WREG ? 2 : 4) attn_pool_fwd_stream_kernel(
+    const float* __restrict__ x, const int32_t* __restrict__ seg_ptr, int64_t B, int64_t N, int F, int heads, int G,
+    const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ temperature,
+    float* __restrict__ pooled, float* __restrict__ attn, float* zbuf) {
+  pdl_enter();
+  constexpr int W4 = 32 * J;                                           // float4 slots of a staged row
+  constexpr int kStreamRing = WREG ? kStreamRingW : kStreamRingS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ulonglong2* ws4 = reinterpret_cast<ulonglong2*>(smem_raw);           // [MAXH][W4] head weights, zero beyond heads / F
+  ulonglong2* ring = ws4 + (WREG ? 0 : MAXH * W4);                     // [4 warps][kStreamRing][W4]
+  float* stat = reinterpret_cast<float*>(ring + 4 * kStreamRing * W4); // [4 warps][2 * MAXH]: m_h, s_h
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int F4 = F >> 2;
+  ulonglong2 wr[WREG ? MAXH : 1][WREG ? J : 1];
+  if (WREG) {
+#pragma unroll
+    for (int h = 0; h < (WREG ? MAXH : 1); ++h)
+#pragma unroll
+      for (int j = 0; j < (WREG ? J : 1); ++j) {
+        const int c = lane + 32 * j;
+        wr[h][j] = (h < heads && c < F4) ? __ldg(reinterpret_cast<const ulonglong2*>(w) + h * F4 + c) : make_ulonglong2(0ull, 0ull);
+      }
+  } else {
+    for (int i = tid; i < MAXH * W4; i += kPoolThreads) {
+      const int h = i / W4, c = i - h * W4;
+      reinterpret_cast<float4*>(ws4)[i] =
+          (h < heads && c < F4) ? __ldg(reinterpret_cast<const float4*>(w) + h * F4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  ulonglong2* myring = ring + warp * (kStreamRing * W4);
+  if (F4 < W4) {                               // columns beyond the row are never copied: zero them once (no masks below)
+    for (int i = lane; i < kStreamRing * W4; i += 32)
+      if (i % W4 >= F4) myring[i] = make_ulonglong2(0ull, 0ull);
+  }
+  __syncthreads();
+  const float invT = 1.f / __ldg(temperature);
+  const int64_t mol = (static_cast<int64_t>(blockIdx.x) * 4 + warp) / G;     // G in {1, 2, 4}: a group never straddles CTAs
+  const int sub = warp % G;
+  const bool active = mol < B;
+  int n0 = 0, n = 0;
+  if (active) {
+    n0 = seg_ptr[mol];
+    n = seg_ptr[mol + 1] - n0;
+  }
+  const float4* xg = reinterpret_cast<const float4*>(x) + static_cast<int64_t>(n0) * F4;
+  const int my_rows = n > sub ? (n - sub + G - 1) / G : 0;
+
+  auto issue = [&](int k) {                    // k-th row of this warp -> ring slot k % kStreamRing (one group per call)
+    if (k < my_rows) {
+      const float4* src = xg + static_cast<int64_t>(sub + k * G) * F4;
+      ulonglong2* dst = myring + (k % kStreamRing) * W4;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int c = lane + 32 * j;
+        if (c < F4) cp_async16(dst + c, src + c);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int k = 0; k < kStreamRing - 1; ++k) issue(k);
+
+  // scores are kept in log2 units (z * log2 e) so that every exponential is one ex2.approx
+  ulonglong2 acc[MAXH][J];
+  float m[MAXH], s[MAXH], bias[MAXH];
+#pragma unroll
+  for (int h = 0; h < MAXH; ++h) {
+    m[h] = -INFINITY;
+    s[h] = 0.f;
+    bias[h] = h < heads ? __ldg(b + h) : 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[h][j] = make_ulonglong2(0ull, 0ull);
+  }
+
+  for (int k = 0; k < my_rows; ++k) {
+    issue(k + kStreamRing - 1);                // into the slot this lane finished reading in the previous iteration
+    cp_async_wait<kStreamRing - 1>();          // this lane's copies of row k have landed (it reads only those)
+    const ulonglong2* row = myring + (k % kStreamRing) * W4;
+    ulonglong2 xv[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) xv[j] = row[lane + 32 * j];
+    float dot[MAXH];
+#pragma unroll
+    for (int h = 0; h < MAXH; ++h) {
+      uint64_t d2 = 0ull;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const ulonglong2 wv = WREG ? wr[WREG ? h : 0][WREG ? j : 0] : ws4[h * W4 + lane + 32 * j];
+        d2 = fma2(xv[j].x, wv.x, d2);
+        d2 = fma2(xv[j].y, wv.y, d2);
+      }
+      float lo, hi;
+      upk2(d2, lo, hi);
+      dot[h] = lo + hi;
+    }
+    warp_sum_heads<MAXH>(dot, lane);                                   // every lane: all head totals, bitwise identical
+    const int i = sub + k * G;
+    float zsel = 0.f;
+#pragma unroll
+    for (int h = 0; h < MAXH; ++h) {
+      if (h < heads) {
+        const float z = (dot[h] + bias[h]) * invT;                     // pooling.py:134-140
+        const float z2 = z * kLog2e;
+        if (lane == h) zsel = z;
+        if (z2 > m[h]) {                                               // warp-uniform
+          const float r = ex2_approx(m[h] - z2);                       // first row: 2^-inf = 0 on zeros
+          const uint64_t r2 = pk2(r, r);
+          s[h] *= r;
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            acc[h][j].x = mul2(acc[h][j].x, r2);
+            acc[h][j].y = mul2(acc[h][j].y, r2);
+          }
+          m[h] = z2;
+        }
+        const float p = ex2_approx(z2 - m[h]);
+        const uint64_t p2 = pk2(p, p);
+        s[h] += p;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          acc[h][j].x = fma2(p2, xv[j].x, acc[h][j].x);
+          acc[h][j].y = fma2(p2, xv[j].y, acc[h][j].y);
+        }
+      }
+    }
+    if (lane < heads) zbuf[static_cast<int64_t>(lane) * N + n0 + i] = zsel;
+  }
+  cp_async_wait<0>();
+  float4* pooled4 = reinterpret_cast<float4*>(pooled) + mol * F4;
+  const float inv_h = 1.f / static_cast<float>(heads);
+  auto axpy = [](float4& o, float f, const ulonglong2& v) {
+    float a0, a1, a2, a3;
+    upk2(v.x, a0, a1);
+    upk2(v.y, a2, a3);
+    o.x += f * a0; o.y += f * a1; o.z += f * a2; o.w += f * a3;
+  };
+
+  // The returned weights (saved for the backward, whose dz = a (da - sum a da) cancels) are NOT taken from the ex2.approx
+  // values of the loop: a = expf(z - max) / sum expf(z - max) with the accurate exponential over the molecule's scores
+  // (n x heads values from L2; every warp of the group does the two reductions redundantly, then writes its slice).
+  auto write_attn = [&](int part, int parts) {
+    for (int h = 0; h < heads; ++h) {
+      const float* zr = zbuf + static_cast<int64_t>(h) * N + n0;
+      float mx = -INFINITY;
+      for (int r = lane; r < n; r += 32) mx = fmaxf(mx, __ldcg(zr + r));
+      mx = warp_max(mx);
+      float sm = 0.f;
+      for (int r = lane; r < n; r += 32) sm += expf(__ldcg(zr + r) - mx);
+      sm = warp_sum(sm);
+      float* ar = attn + static_cast<int64_t>(h) * N + n0;
+      for (int r = part * 32 + lane; r < n; r += 32 * parts) ar[r] = expf(__ldcg(zr + r) - mx) / sm;   // pooling.py:144-145
+    }
+  };
+
+  if (G == 1) {                                // kernel argument: uniform over the grid
+    if (!active) return;
+    float rs[MAXH];
+#pragma unroll
+    for (int h = 0; h < MAXH; ++h) rs[h] = (h < heads && n > 0) ? 1.f / s[h] : 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c = lane + 32 * j;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);                      // n == 0: torch_scatter leaves the segment at 0
+#pragma unroll
+      for (int h = 0; h < MAXH; ++h)
+        if (h < heads) axpy(o, inv_h * rs[h], acc[h][j]);
+      if (c < F4) pooled4[c] = o;
+    }
+    __syncwarp();                              // the scores written by lanes 0 .. heads-1 are read back by every lane
+    write_attn(0, 1);
+    return;
+  }
+
+  // ---- merge of the G partial states of a molecule (every warp of the CTA takes part in the barriers)
+  if (lane == 0) {
+#pragma unroll
+    for (int h = 0; h < MAXH; ++h) {
+      stat[warp * 2 * MAXH + h] = m[h];
+      stat[warp * 2 * MAXH + MAXH + h] = s[h];
+    }
+  }
+  __syncthreads();
+  const int w0 = warp - sub;
+  float mg[MAXH], rsg[MAXH];
+#pragma unroll
+  for (int h = 0; h < MAXH; ++h) {
+    float mm = -INFINITY;
+    for (int g = 0; g < G; ++g) mm = fmaxf(mm, stat[(w0 + g) * 2 * MAXH + h]);
+    float ss = 0.f;
+    for (int g = 0; g < G; ++g) {
+      const float sw = stat[(w0 + g) * 2 * MAXH + MAXH + h];
+      if (sw > 0.f) ss += sw * ex2_approx(stat[(w0 + g) * 2 * MAXH + h] - mm);   // a warp without rows has s = 0, m = -inf
+    }
+    mg[h] = mm;
+    rsg[h] = ss > 0.f ? 1.f / ss : 0.f;
+  }
+  float4* mypart = reinterpret_cast<float4*>(myring);   // the ring is drained: its first slot takes this warp's weighted sum
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < MAXH; ++h)
+      if (h < heads && s[h] > 0.f) axpy(o, ex2_approx(m[h] - mg[h]) * inv_h * rsg[h], acc[h][j]);
+    mypart[lane + 32 * j] = o;
+  }
+  __syncthreads();
+  if (!active) return;
+  if (sub == 0) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c = lane + 32 * j;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int g = 0; g < G; ++g) {
+        const float4 v = reinterpret_cast<const float4*>(ring + (w0 + g) * (kStreamRing * W4))[c];
+        o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+      }
+      if (c < F4) pooled4[c] = o;
+    }
+  }
+  write_attn(sub, G);
+}
+
 // ------------------------------------------------------------------------------------------ backward
 // Formulas: SURVEY.md appendix C6.  d_i = (1/H) G_g . x_i ; da[h,i] = d_i (+ Ga[h,i]) ;
 // dz[h,i] = a[h,i] (da[h,i] - sum_j a[h,j] da[h,j]) ; gx_i = (sum_h a[h,i]/H) G_g + (1/T) sum_h dz[h,i] w_h ;
@@ -619,6 +922,19 @@ __global__ void __launch_bounds__(128) seg_reduce_bwd_kernel(const float* __rest
 
 using namespace ax2d;
 
+// development / test switch: mode 0 = streaming kernel where it applies, 1 = the two-phase kernels only;
+// group 0 = warps per molecule chosen from the batch size, 1 / 2 / 4 = forced
+static int g_pool_fwd_mode = 0, g_pool_fwd_group = 0, g_pool_fwd_wreg = 0;
+extern "C" int ax2d_attn_pool_fwd_config(int mode, int group) {
+  AX2D_CHECK_ARG((mode == 0 || mode == 1 || mode == 2) && (group == 0 || group == 1 || group == 2 || group == 4),
+                 "ax2d_attn_pool_fwd_config: mode in {0,1,2}, group in {0,1,2,4}");
+  g_pool_fwd_wreg = mode == 2 ? 1 : 0;         // mode 2: streaming kernel with the head weights in registers (measured slower)
+  if (mode == 2) mode = 0;
+  g_pool_fwd_mode = mode;
+  g_pool_fwd_group = group;
+  return AX2D_OK;
+}
+
 extern "C" int ax2d_attn_pool_fwd(const float* x, int64_t ldx, const int32_t* seg_ptr, int64_t B, int64_t N, int F,
                                   int heads, const float* w, const float* b, const float* temperature, float* pooled,
                                   float* attn, float* z, int max_rows_hint, ax2d_stream_t stream) {
@@ -629,6 +945,55 @@ extern "C" int ax2d_attn_pool_fwd(const float* x, int64_t ldx, const int32_t* se
   AX2D_CHECK_ALIGN(w);
   AX2D_CHECK_ALIGN(pooled);
   if (B <= 0) return AX2D_OK;
+  {
+    // streaming single-pass kernel: rows of up to 512 features, per-head accumulators in registers (heads x F <= 2048)
+    const int F4 = F / 4;
+    const int J = F4 <= 32 ? 1 : F4 <= 64 ? 2 : F4 <= 128 ? 4 : 0;
+    const int MH = heads <= 1 ? 1 : heads <= 2 ? 2 : heads <= 4 ? 4 : 8;
+    if (g_pool_fwd_mode == 0 && J != 0 && MH * J <= 16) {
+      // warps per molecule: ~12+ rows per warp (the prologue and the merge are per warp), more warps when the batch
+      // is too small to fill half of the 148 x 16 warp slots (measured: tools/bench_pool.py)
+      int G = g_pool_fwd_group;
+      if (G != 1 && G != 2 && G != 4) {
+        const int64_t avg = N / B;
+        G = avg >= 48 ? 4 : avg >= 24 ? 2 : 1;
+        while (G < 4 && B * G < 1184 && avg / G >= 8) G *= 2;
+      }
+      const unsigned grid = static_cast<unsigned>((B * G + 3) / 4);
+      cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define AX2D_POOL_STREAM(MH_, J_)                                                                                          \
+  do {                                                                                                                     \
+    if (wreg) {                                                                                                            \
+      const size_t sm = static_cast<size_t>(4 * kStreamRingW * 32 * J_) * 16 + 4 * 2 * MH_ * 4;                            \
+      if (sm > 48 * 1024)                                                                                                  \
+        cudaFuncSetAttribute(attn_pool_fwd_stream_kernel<MH_, J_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                             static_cast<int>(sm));                                                                        \
+      launch_k(attn_pool_fwd_stream_kernel<MH_, J_, true>, dim3(grid), dim3(kPoolThreads), sm, st, x, seg_ptr, B, N, F,    \
+               heads, G, w, b, temperature, pooled, attn, z);                                                              \
+    } else {                                                                                                               \
+      launch_k(attn_pool_fwd_stream_kernel<MH_, J_, false>, dim3(grid), dim3(kPoolThreads),                                \
+               static_cast<size_t>((MH_ * 32 * J_ + 4 * kStreamRingS * 32 * J_) * 16 + 4 * 2 * MH_ * 4), st, x, seg_ptr,   \
+               B, N, F, heads, G, w, b, temperature, pooled, attn, z);                                                     \
+    }                                                                                                                      \
+  } while (0)
+      const bool wreg = g_pool_fwd_wreg != 0;
+      switch (MH * 8 + J) {
+        case 1 * 8 + 1: AX2D_POOL_STREAM(1, 1); break;
+        case 1 * 8 + 2: AX2D_POOL_STREAM(1, 2); break;
+        case 1 * 8 + 4: AX2D_POOL_STREAM(1, 4); break;
+        case 2 * 8 + 1: AX2D_POOL_STREAM(2, 1); break;
+        case 2 * 8 + 2: AX2D_POOL_STREAM(2, 2); break;
+        case 2 * 8 + 4: AX2D_POOL_STREAM(2, 4); break;
+        case 4 * 8 + 1: AX2D_POOL_STREAM(4, 1); break;
+        case 4 * 8 + 2: AX2D_POOL_STREAM(4, 2); break;
+        case 4 * 8 + 4: AX2D_POOL_STREAM(4, 4); break;
+        case 8 * 8 + 1: AX2D_POOL_STREAM(8, 1); break;
+        default: AX2D_POOL_STREAM(8, 2); break;
+      }
+#undef AX2D_POOL_STREAM
+      return launch_status("ax2d_attn_pool_fwd");
+    }
+  }
   if (max_rows_hint > 0 && max_rows_hint <= kDirectRows) {       // every molecule fits the score buffer: no x staging
     const size_t smem_d = static_cast<size_t>(heads + 1) * kDirectRows * 4;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

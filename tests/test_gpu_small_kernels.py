@@ -120,15 +120,32 @@ def test_weighted_loss_kernel(kind, B, T):
     assert float((pred.grad.double() - p64.grad).abs().max()) <= 1e-5 * float(p64.grad.abs().max())
 
 
+def _attn_pool_reference(x, w, b, T, sizes):
+    heads, F, N = w.shape[0], x.shape[1], x.shape[0]
+    zz = (x.double() @ w.double().t() + b.double()) / T                                       # [N, heads]
+    ref_pooled = torch.zeros((len(sizes), F), dtype=torch.float64, device=DEV)
+    ref_attn = torch.zeros((heads, N), dtype=torch.float64, device=DEV)
+    o = 0
+    for g, n in enumerate(sizes):
+        if n:
+            a = torch.softmax(zz[o:o + n], dim=0)                                             # per head over the molecule
+            ref_attn[:, o:o + n] = a.t()
+            ref_pooled[g] = (a.t().unsqueeze(2) * x[o:o + n].double().unsqueeze(0)).sum(1).mean(0)
+        o += n
+    return zz, ref_attn, ref_pooled
+
+
+@pytest.mark.parametrize("mode,group", [(1, 0), (0, 0), (0, 1), (0, 2), (0, 4), (2, 0), (2, 1), (2, 4)])
 @pytest.mark.parametrize("hint", [8, 300, 1000])
-def test_attn_pool_fwd_direct_and_staged_kernels(hint):
-    """hint <= 256 selects the kernel that reads x straight from global memory; a molecule larger than the hint (300
-    atoms against hint 8) must still be handled (scores through global memory); hint 1000 selects the staged kernel.
-    Reference: pooling.py:134-161 in float64."""
+def test_attn_pool_fwd_direct_and_staged_kernels(hint, mode, group):
+    """mode 1 (two-phase kernels): hint <= 256 selects the kernel that reads x straight from global memory; a molecule
+    larger than the hint (300 atoms against hint 8) must still be handled (scores through global memory); hint 1000
+    selects the staged kernel.  mode 0 / 2: the single-pass streaming kernel (online softmax; head weights in shared memory /
+    in registers) with 1 / 2 / 4 warps per molecule (empty molecules, a single atom, fewer rows than warps, 300 rows).  Reference: pooling.py:134-161 in float64."""
     L = _lib()
     lib = L.load()
     rng = np.random.Generator(np.random.PCG64(hint))
-    sizes = [300, 5, 0, 40, 1, 29]
+    sizes = [300, 5, 0, 40, 1, 29, 2, 3, 0]
     N, F, heads = sum(sizes), 64, 4
     seg = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32), device=DEV)
     x = torch.from_numpy(rng.normal(size=(N, F)).astype(np.float32)).to(DEV)
@@ -139,20 +156,50 @@ def test_attn_pool_fwd_direct_and_staged_kernels(hint):
     attn = torch.full((heads, N), float("nan"), device=DEV)
     z = torch.full((heads, N), float("nan"), device=DEV)
     P = lambda t: C.c_void_p(t.data_ptr())
-    L.check(lib.ax2d_attn_pool_fwd(P(x), F, P(seg), len(sizes), N, F, heads, P(w), P(b), P(T), P(pooled), P(attn), P(z), hint,
-                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ax2d_attn_pool_fwd")
-    torch.cuda.synchronize()
-    zz = (x.double() @ w.double().t() + b.double()) / 0.7                                     # [N, heads]
-    ref_pooled = torch.zeros((len(sizes), F), dtype=torch.float64, device=DEV)
-    ref_attn = torch.zeros((heads, N), dtype=torch.float64, device=DEV)
-    o = 0
-    for g, n in enumerate(sizes):
-        if n:
-            a = torch.softmax(zz[o:o + n], dim=0)                                             # per head over the molecule
-            ref_attn[:, o:o + n] = a.t()
-            ref_pooled[g] = (a.t().unsqueeze(2) * x[o:o + n].double().unsqueeze(0)).sum(1).mean(0)
-        o += n
+    L.check(lib.ax2d_attn_pool_fwd_config(mode, group), "ax2d_attn_pool_fwd_config")
+    try:
+        L.check(lib.ax2d_attn_pool_fwd(P(x), F, P(seg), len(sizes), N, F, heads, P(w), P(b), P(T), P(pooled), P(attn), P(z), hint,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ax2d_attn_pool_fwd")
+        torch.cuda.synchronize()
+    finally:
+        lib.ax2d_attn_pool_fwd_config(0, 0)
+    zz, ref_attn, ref_pooled = _attn_pool_reference(x, w, b, 0.7, sizes)
     assert float((attn.double() - ref_attn).abs().max()) <= 1e-6
+    assert float((pooled.double() - ref_pooled).abs().max()) <= 1e-5 * float(ref_pooled.abs().max())
+    assert float((z.double() - zz.t()).abs().max()) <= 1e-5 * float(zz.abs().max())
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("F,heads,group", [(512, 4, 0), (512, 4, 1), (512, 4, 4), (160, 4, 2), (256, 8, 4), (512, 8, 0), (32, 1, 2),
+                                           (100, 2, 4), (640, 4, 0)])
+def test_attn_pool_fwd_streaming_shapes(F, heads, group, mode):
+    """The streaming forward over the row widths and head counts it is compiled for (1 / 2 / 4 float4 per lane; per-head
+    accumulators in registers), and the fall-back to the two-phase kernels beyond them (8 heads x 512, F = 640);
+    scores with a large spread (sharp softmax, maxima that keep moving), against float64."""
+    L = _lib()
+    lib = L.load()
+    rng = np.random.Generator(np.random.PCG64(F + heads))
+    sizes = [int(v) for v in rng.integers(0, 70, size=150)] + [1, 0, 257]
+    N = sum(sizes)
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32), device=DEV)
+    x = torch.from_numpy(rng.normal(size=(N, F)).astype(np.float32)).to(DEV)
+    x[::7] *= 3.0                                                                             # scores spread over +-20
+    w = torch.from_numpy((rng.normal(size=(heads, F)) / np.sqrt(F)).astype(np.float32)).to(DEV)
+    b = torch.from_numpy(rng.normal(size=heads).astype(np.float32)).to(DEV)
+    T = torch.tensor(0.3, device=DEV)
+    pooled = torch.full((len(sizes), F), float("nan"), device=DEV)
+    attn = torch.full((heads, N), float("nan"), device=DEV)
+    z = torch.full((heads, N), float("nan"), device=DEV)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    L.check(lib.ax2d_attn_pool_fwd_config(mode, group), "ax2d_attn_pool_fwd_config")
+    try:
+        L.check(lib.ax2d_attn_pool_fwd(P(x), F, P(seg), len(sizes), N, F, heads, P(w), P(b), P(T), P(pooled), P(attn), P(z), 257,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ax2d_attn_pool_fwd")
+        torch.cuda.synchronize()
+    finally:
+        lib.ax2d_attn_pool_fwd_config(0, 0)
+    zz, ref_attn, ref_pooled = _attn_pool_reference(x, w, b, 0.3, sizes)
+    assert float((attn.double() - ref_attn).abs().max()) <= 2e-5      # scores of +-30: their own fp32 rounding
     assert float((pooled.double() - ref_pooled).abs().max()) <= 1e-5 * float(ref_pooled.abs().max())
     assert float((z.double() - zz.t()).abs().max()) <= 1e-5 * float(zz.abs().max())
 
@@ -226,7 +273,7 @@ def test_tetra_kernels_match_oracle(N, D, Dp, M, seed):
         tetra[2] = tetra[0]                                                             # two centres on the same atoms
     x = np.zeros((N, Dp), dtype=np.float32)
     x[:, :D] = rng.normal(size=(N, D)).astype(np.float32)
-    x[3 % N, :D] *= 1e-4                                                                # a nearly zero row (normalize eps path)
+    x[3 % N, :D] *= 0.05                                                                # a short row (its gradient is amplified by 1 / norm)
     g = rng.normal(size=(N, Dp)).astype(np.float32)
     gi = _stereo_index(N, tetra, None, None)
     xd = torch.from_numpy(x).to(DEV).requires_grad_(True)
