@@ -573,6 +573,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackDesc* __res
 }
 __global__ void __launch_bounds__(256) unpack_grads_kernel(const PackDesc* __restrict__ table) {
   pdl_enter();
+  __shared__ float4 s_part[3][64];
   const PackDesc d = table[blockIdx.y];
   if (d.grad_dst == nullptr) return;
   // four consecutive columns per thread: the split-K partials (the bulk of the traffic) are read as float4 whenever the
@@ -581,6 +582,45 @@ __global__ void __launch_bounds__(256) unpack_grads_kernel(const PackDesc* __res
   const int total = d.rows * quads;
   const int64_t plane = static_cast<int64_t>(d.p_rows) * d.p_cols;
   const bool vec = d.split > 0 && (d.p_cols & 3) == 0 && (d.dc & 3) == 0 && (reinterpret_cast<uintptr_t>(d.part) & 15u) == 0;
+  if (vec && d.split >= 32) {
+    // many partials per element (the 148-way splits of the 160-row matrices): one thread per quad would chain
+    // split / 8 dependent batches of loads.  Four thread groups take the planes z = k, k + 4, ... of the same 64 quads
+    // and the first group adds the four sums in a fixed order (deterministic; another association than z = 0, 1, ...).
+    const int q_in = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    for (int base = blockIdx.x * 64; base < total; base += gridDim.x * 64) {      // uniform over the CTA
+      const int i = base + q_in;
+      const bool live = i < total;
+      const int r = live ? i / quads : 0, c0 = live ? (i - r * quads) * 4 : 0;
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        const float* p = d.part + static_cast<int64_t>(d.dr + r) * d.p_cols + d.dc + c0;
+#pragma unroll 8
+        for (int z = sl; z < d.split; z += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(p + z * plane));
+          sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+      }
+      if (sl > 0) s_part[sl - 1][q_in] = sum;
+      __syncthreads();
+      if (sl == 0 && live) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float4 v = s_part[k][q_in];
+          sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        const float* gp = d.g + static_cast<int64_t>(r) * d.dst_ld + c0;
+        float* dst = d.grad_dst + static_cast<int64_t>(r) * d.src_ld + c0;
+        // (a quad that sticks out of the block reads the padding of the packed row: p_cols and dc are multiples of 4)
+        const float a4[4] = {sum.x, sum.y, sum.z, sum.w};
+        const int nc = d.cols - c0 < 4 ? d.cols - c0 : 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nc) dst[j] += gp[j] + a4[j];
+      }
+      __syncthreads();
+    }
+    return;
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int r = i / quads, c0 = (i - r * quads) * 4;
     const int nc = d.cols - c0 < 4 ? d.cols - c0 : 4;
