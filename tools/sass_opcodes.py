@@ -7,7 +7,7 @@ import re
 import subprocess
 
 LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "aimnet_x2d_b200", "libax2d.so")
-OPS = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "FADD2", "FHADD", "REDUX"]
+OPS = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "FADD2", "FFMA2", "FHADD", "LDGSTS", "ACQBULK", "REDUX"]
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 counts = collections.OrderedDict()
 cur = None
@@ -24,7 +24,7 @@ for line in sass.splitlines():
             counts[cur][op] += 1
 print("# SASS opcode counts per kernel (cuobjdump -sass aimnet_x2d_b200/libax2d.so); UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st,")
 print("# UTMALDG / UTMASTG = TMA tensor load / store, UBLKCP = cp.async.bulk, UTCBAR = tcgen05.commit, SYNCS = mbarrier ops,")
-print("# FADD2 = add.f32x2, FHADD = add.f32.bf16 (mixed precision), REDUX = warp reduction")
+print("# FADD2 / FFMA2 = add / fma .f32x2, FHADD = add.f32.bf16 (mixed precision), LDGSTS = cp.async, ACQBULK = griddepcontrol.wait, REDUX = warp reduction")
 print(f"{'kernel':70s} " + " ".join(f"{o:>8s}" for o in OPS))
 tot = collections.Counter()
 for k, c in counts.items():
