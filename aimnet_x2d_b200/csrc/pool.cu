@@ -1,10 +1,11 @@
 // a7 / a8 -- graph pooling (models/pooling.py).
 //
-// Attention pooling is ONE kernel per direction: a CTA owns a molecule, stages its rows of x in shared
-// memory with a bulk async copy, and does score -> per-(head,molecule) softmax -> weighted sum from
-// there, so x is read from HBM exactly once and the reference's [heads, N, F] temporary
-// (pooling.py:150-154) never exists.  Molecules with more rows than the shared-memory chunk are
-// processed in chunks (second pass re-reads x, served by L2).
+// Attention pooling is ONE kernel per direction; the reference's [heads, N, F] temporary (pooling.py:150-154) never
+// exists.  Forward (default, attn_pool_fwd_stream_kernel): one pass over x with an online softmax per (head, molecule),
+// 1 / 2 / 4 warps per molecule, rows streamed through per-warp cp.async rings.  Two-phase forward kernels (rows wider
+// than 512 features or heads x F > 2048) and the backward: a CTA owns a molecule, stages its rows of x in shared memory
+// with a bulk async copy and does score -> per-(head, molecule) softmax -> weighted sum from there; molecules with more
+// rows than the shared-memory chunk are processed in chunks (second pass re-reads x, served by L2).
 // Parameter gradients are reduced in two passes with a fixed order (no atomics).
 #include "common.cuh"
 

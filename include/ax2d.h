@@ -136,15 +136,17 @@ int ax2d_agg_tiles_mma(const void* x, int64_t ldx, int64_t n_rows, void* out, in
  * x [N,F] (ld), seg_ptr[B+1], w [heads,F], b [heads], temperature: device scalar.
  * Outputs pooled [B,F], attn [heads,N], z [heads,N] (saved scores for backward).
  * x must be contiguous (ldx == F).  max_rows_hint: largest molecule of the batch (known at collation;
- * 0 = unknown) -- sizes the shared-memory chunk; larger molecules are still handled (chunked).
+ * 0 = unknown) -- sizes the shared-memory chunk of the backward and of the two-phase forward kernels; larger
+ * molecules are still handled (chunked).  The default forward (F <= 512, heads x F <= 2048) streams the rows
+ * once and does not use it.
  * ---------------------------------------------------------------------------------------------- */
 int ax2d_attn_pool_fwd(const float* x, int64_t ldx, const int32_t* seg_ptr, int64_t B, int64_t N,
                        int F, int heads, const float* w, const float* b, const float* temperature,
                        float* pooled, float* attn, float* z, int max_rows_hint, ax2d_stream_t stream);
 /* Development / test switch of the forward: mode 0 (default) = single-pass streaming kernel (online softmax, x read once)
  * whenever F <= 512 and heads x F <= 2048, 1 = the two-phase kernels only, 2 = the streaming kernel with the head weights
- * in registers instead of shared memory (measured slower); group = warps per molecule of the streaming kernel (0 = chosen from the batch,
- * or 1 / 2 / 4). */
+ * in registers instead of shared memory (measured slower); group = warps per molecule of the streaming kernel
+ * (0 = chosen from the batch, or 1 / 2 / 4). */
 int ax2d_attn_pool_fwd_config(int mode, int group);
 int64_t ax2d_attn_pool_bwd_workspace(int64_t B, int F, int heads);
 /* g_attn may be NULL (no gradient flows into the returned attention weights).  gx [N,F] (ld gx).
