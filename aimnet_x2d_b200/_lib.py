@@ -39,6 +39,7 @@ _SIGNATURES = {
     "ax2d_set_pdl": (c_int, [c_int]),
     "ax2d_host_csr_build": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
                                     c_void_p, c_void_p, c_void_p]),
+    "ax2d_host_csr_rows_unique": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "ax2d_host_tile_plan": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                     C.POINTER(c_int64), C.POINTER(c_int64), C.POINTER(C.c_int32)]),
     "ax2d_host_shell_edges": (c_int64, [c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64]),

@@ -90,6 +90,26 @@ extern "C" int ax2d_host_csr_build(const int64_t* edges, int64_t E, int64_t stri
   return AX2D_OK;
 }
 
+// unique[0] = 1 iff no (row, column) pair occurs twice in the CSR (one stamp per column: O(E)).
+extern "C" int ax2d_host_csr_rows_unique(const int32_t* rowptr, const int32_t* col, int64_t R, int64_t N, int32_t* unique) {
+  using namespace ax2d;
+  AX2D_CHECK_ARG(rowptr != nullptr && unique != nullptr && R >= 0 && N >= 0, "ax2d_host_csr_rows_unique: bad arguments");
+  unique[0] = 1;
+  std::vector<int32_t> stamp(static_cast<size_t>(N), -1);
+  for (int64_t r = 0; r < R; ++r) {
+    for (int32_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+      const int32_t c = col[e];
+      AX2D_CHECK_ARG(c >= 0 && c < N, "ax2d_host_csr_rows_unique: column %d out of range at entry %d", c, e);
+      if (stamp[c] == static_cast<int32_t>(r)) {
+        unique[0] = 0;
+        return AX2D_OK;
+      }
+      stamp[c] = static_cast<int32_t>(r);
+    }
+  }
+  return AX2D_OK;
+}
+
 extern "C" int ax2d_host_tile_plan(const int32_t* seg_ptr, int64_t B, int64_t cap, const int32_t* rowptr,
                                    const int32_t* col, int32_t* tile_ptr, int64_t* n_tiles, int64_t* max_rows,
                                    int32_t* tile_local) {

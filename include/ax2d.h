@@ -61,6 +61,9 @@ int ax2d_host_csr_build(const int64_t* edges, int64_t E, int64_t stride_e, int64
                         int64_t N, int64_t R, int transpose,
                         int32_t* rowptr, int32_t* col, int32_t* perm);
 
+/* unique[0] = 1 iff no (row, column) pair occurs twice in the CSR, i.e. no (target, source) edge of
+ * multi_hop_edge_indices is repeated (a dense tile product could not count a repeated edge twice). */
+int ax2d_host_csr_rows_unique(const int32_t* rowptr, const int32_t* col, int64_t R, int64_t N, int32_t* unique);
 /* Greedy packing of whole molecules into row tiles of at most `cap` rows (a molecule larger than cap
  * gets a tile of its own).  seg_ptr[B+1] are the molecule row offsets.  tile_ptr must hold B+1 entries.
  * On return *n_tiles tiles, *max_rows = largest tile.  If rowptr/col are given (R == N rows), *tile_local
