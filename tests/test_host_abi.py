@@ -71,6 +71,28 @@ def test_host_csr_rejects_out_of_range():
         GraphIndex.build(torch.tensor([[0, 1]]), np.array([1, 0, 0]), 2, 3)        # unsorted batch_indices
 
 
+def test_csr_rows_unique_flags_repeated_edges():
+    """GraphIndex.unique_edges (an O(E) stamp pass over the CSR) against np.unique over the (target, source) keys:
+    random edge lists with and without a repeated pair, hop-offset targets, the flag through collation."""
+    from aimnet_x2d_b200.collate import GraphIndex
+    rng = np.random.Generator(np.random.PCG64(11))
+    N, hops = 50, 3
+    for trial in range(20):
+        E = int(rng.integers(1, 400))
+        offset = trial % 2 == 1                                           # targets in [0, hops * N): one row per (hop, atom)
+        t = rng.integers(0, hops * N if offset else N, size=E)
+        s_ = rng.integers(0, N, size=E)
+        if trial % 3 == 0 and E > 1:
+            t[-1], s_[-1] = t[0], s_[0]                                   # at least one repeated pair
+        want = np.unique(t * N + s_).size == E
+        edges = torch.from_numpy(np.stack([t, s_], 1).astype(np.int64))
+        bi = np.repeat(np.arange(5), N // 5)
+        gi = GraphIndex.build(edges, bi, 5, hops, None, None, None, None, None, 32)
+        assert gi.unique_edges == bool(want), trial
+    gi = GraphIndex.build(torch.empty((0, 2), dtype=torch.long), np.repeat(np.arange(5), 10), 5, hops, None, None, None, None, None, 32)
+    assert gi.unique_edges
+
+
 def test_tile_plan_properties():
     from aimnet_x2d_b200 import synthetic as S
     b = S.make_batch(9, 64, 3, "qm9", tile_rows=32)
